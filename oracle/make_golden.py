@@ -1,0 +1,204 @@
+"""Generate `tests/golden/*.npz` by running the UNMODIFIED reference and pin the oracle against it.
+
+Run in the build container only (needs `/root/reference`):
+
+    python -m oracle.make_golden            # all cases
+    python -m oracle.make_golden hulc_b2s8  # one case
+
+For every case the script
+  1. builds the reference `Hulc`/`GCBC` LightningModule from the resolved config tree (`synthetic.model_config`) under
+     the dependency shims of `oracle/ref_stubs.py`,
+  2. overwrites its parameters with `synthetic.fill_state_dict_`, builds the seeded batch (`synthetic.make_batch`),
+  3. injects the run's randomness (categorical sample via a patched `torch.multinomial`, Normal noise via a patched
+     `_standard_normal`, dropout keep-masks via patched `F.dropout`/`F.scaled_dot_product_attention`),
+  4. runs `training_step` + `backward` of the reference, and the oracle on the same tensors,
+  5. asserts oracle == reference (losses, logits, every parameter gradient) and writes the reference's numbers
+     to the fixture.  Fixtures hold outputs only; inputs and weights are regenerated from seeds by the tests.
+"""
+from __future__ import annotations
+
+import contextlib
+import copy
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_stubs  # noqa: E402
+
+ref_stubs.install()
+
+from hulc_b200.utils import synthetic  # noqa: E402
+from oracle import hulc_oracle as O  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+
+CASES = {
+    # name: (model, rnn_model, B, S, dropout_p)
+    "hulc_b2s8": ("hulc", "rnn_decoder", 2, 8, 0.0),  # BASELINE config 1
+    "hulc_b2s8_drop": ("hulc", "rnn_decoder", 2, 8, 0.1),
+    "hulc_gru_b2s8": ("hulc", "gru_decoder", 2, 8, 0.0),
+    "gcbc_b2s8": ("gcbc", "rnn_decoder", 2, 8, 0.0),
+    "mcil_b2s8": ("mcil", "rnn_decoder", 2, 8, 0.0),
+    "hulc_b4s32": ("hulc", "rnn_decoder", 4, 32, 0.0),  # full window, small batch
+    "hulc_b32s32": ("hulc", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 2 shape
+}
+
+
+def build_reference(model, rnn_model, dropout_p, max_window):
+    import importlib
+
+    cfg = synthetic.model_config(model, rnn_model, max_window, dropout_p, target_root="hulc")
+    cfg = copy.deepcopy(cfg)
+    target = cfg.pop("_target_")
+    cfg.pop("_recursive_")
+    mod, _, name = target.rpartition(".")
+    cls = getattr(importlib.import_module(mod), name)
+    torch.manual_seed(0)
+    net = cls(**cfg)
+    synthetic.fill_state_dict_(net.state_dict())
+    net.train()
+    return net
+
+
+@contextlib.contextmanager
+def injected_randomness(u_queue, eps_queue, mask_queue, p):
+    """Route the reference's three RNG consumers to seeded tensors."""
+    import torch.distributions.normal as tdn
+    import torch.nn.functional as F
+
+    orig_mn, orig_sn, orig_do, orig_sdpa = torch.multinomial, tdn._standard_normal, F.dropout, F.scaled_dot_product_attention
+
+    def multinomial(probs_2d, n, replacement=False, **kw):
+        u = u_queue.pop(0).reshape(-1, 1)
+        assert n == 1 and u.shape[0] == probs_2d.shape[0]
+        c = torch.cumsum(probs_2d, -1)
+        return (c <= u).sum(-1, keepdim=True).clamp(max=probs_2d.shape[-1] - 1)
+
+    def standard_normal(shape, dtype, device):
+        e = eps_queue.pop(0)
+        assert tuple(e.shape) == tuple(shape), (e.shape, shape)
+        return e.to(dtype)
+
+    def dropout(x, p_=0.5, training=True, inplace=False):
+        if not training or p_ == 0.0:
+            return x
+        name, keep = mask_queue.pop(0)
+        if keep.dim() == 3 and tuple(keep.shape) != tuple(x.shape):  # (B,S,D) recipe -> seq-first (S,B,D) reference
+            keep = keep.permute(1, 0, 2)
+        assert tuple(keep.shape) == tuple(x.shape), (name, keep.shape, x.shape)
+        return x * keep.to(x.dtype) / (1.0 - p_)
+
+    def sdpa(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, **kw):
+        assert attn_mask is None and not is_causal
+        a = torch.softmax(q @ k.transpose(-1, -2) / (q.shape[-1] ** 0.5), -1)
+        return dropout(a, dropout_p, True) @ v
+
+    torch.multinomial, tdn._standard_normal = multinomial, standard_normal
+    F.dropout, F.scaled_dot_product_attention = dropout, sdpa
+    try:
+        yield
+    finally:
+        torch.multinomial, tdn._standard_normal = orig_mn, orig_sn
+        F.dropout, F.scaled_dot_product_attention = orig_do, orig_sdpa
+
+
+def run_case(name):
+    model, rnn_model, B, S, p = CASES[name]
+    t0 = time.time()
+    net = build_reference(model, rnn_model, p, 32)
+    batch = synthetic.make_batch(B, S, seed=1)
+    noise = {m: synthetic.plan_noise(B, S, m) for m in batch}
+    masks = {m: synthetic.dropout_masks(B, S, m, p) for m in batch} if p > 0 else None
+
+    # --- reference -------------------------------------------------------------------------------------------------
+    u_q, eps_q, m_q = [], [], []
+    for m in batch:
+        if model == "hulc":
+            u_q.append(noise[m]["u"])
+        if model == "mcil":
+            eps_q.append(noise[m]["eps"])
+        if masks is not None:
+            order = ["in"] + [f"l{i}.{s}" for i in range(2) for s in ("attn", "drop1", "ffn", "drop2")]
+            m_q += [(k, masks[m][k]) for k in order]
+
+    captured = {}
+    dec = net.action_decoder
+    orig_loss = dec._loss
+
+    def spy_loss(logit_probs, log_scales, means, gripper_act, actions):
+        captured[net.modality_scope] = (logit_probs, log_scales, means, gripper_act, actions)
+        return orig_loss(logit_probs, log_scales, means, gripper_act, actions)
+
+    dec._loss = spy_loss
+    with injected_randomness(u_q, eps_q, m_q, p):
+        loss_ref = net.training_step(batch, 0)
+    assert not u_q and not eps_q and not m_q, "injected randomness not fully consumed"
+    loss_ref.backward()
+    ref_grads = {k: (v.grad.detach().clone() if v.grad is not None else None) for k, v in net.named_parameters()}
+    logged = net.logged
+
+    # --- oracle ----------------------------------------------------------------------------------------------------
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and k in ref_grads) for k, v in net.state_dict().items()}
+    out = O.training_step(
+        sd, batch, model=model, rnn_model=rnn_model, dropout_p=p,
+        plan_u={m: noise[m]["u"] for m in batch}, plan_eps={m: noise[m]["eps"] for m in batch}, dropout_masks=masks,
+    )
+    out["total_loss"].backward()
+
+    def close(a, b, what, rtol=1e-4, atol=1e-5):
+        if not torch.allclose(a, b, rtol=rtol, atol=atol):
+            raise AssertionError(f"{name}: oracle != reference for {what}: max|d|={float((a - b).abs().max()):.3e}")
+
+    close(out["total_loss"].detach(), loss_ref.detach(), "total_loss", 1e-5, 1e-6)
+    fx = {"total_loss": loss_ref.detach()}
+    for k in ("train/kl_loss", "train/action_loss", "train/lang_clip_loss", "train/kl_loss_scaled_vis", "train/kl_loss_scaled_lang",
+              "train/action_loss_vis", "train/action_loss_lang"):
+        if k in logged:
+            fx[k.replace("train/", "")] = logged[k]
+    close(out["action_loss"].detach(), logged["train/action_loss"], "action_loss", 1e-5, 1e-6)
+    if model == "hulc":
+        close(out["kl_loss"].detach(), logged["train/kl_loss"], "kl_loss", 1e-5, 1e-7)
+    if model != "mcil":
+        close(3.0 * out["lang_clip_loss"].detach(), logged["train/lang_clip_loss"], "clip", 1e-5, 1e-6)
+    nseq = min(B, 2)
+    for m in batch:
+        lp, ls, mu, grip, act = captured[m]
+        close(out[f"logit_probs_{m}"].detach(), lp.detach(), f"logit_probs_{m}")
+        close(out[f"log_scales_{m}"].detach(), ls.detach(), f"log_scales_{m}")
+        close(out[f"means_{m}"].detach(), mu.detach(), f"means_{m}")
+        fx[f"logit_probs_{m}"], fx[f"log_scales_{m}"], fx[f"means_{m}"] = lp[:nseq].detach(), ls[:nseq].detach(), mu[:nseq].detach()
+        if grip is not None:
+            close(out[f"gripper_act_{m}"].detach(), grip.detach(), f"gripper_act_{m}")
+            close(out[f"actions_tcp_{m}"], act, f"actions_tcp_{m}", 1e-5, 2e-5)
+            fx[f"gripper_act_{m}"], fx[f"actions_tcp_{m}"] = grip[:nseq].detach(), act[:nseq].detach()
+        if f"plan_idx_{m}" in out:
+            fx[f"plan_idx_{m}"] = out[f"plan_idx_{m}"]
+    worst = 0.0
+    for k, g in ref_grads.items():
+        og = sd[k].grad
+        if g is None:
+            assert og is None or float(og.abs().max()) == 0.0, f"{name}: oracle has a gradient for unused parameter {k}"
+            fx[f"gradnorm/{k}"] = torch.tensor(-1.0)
+            continue
+        denom = float(g.norm()) + 1e-12
+        rel = float((og - g).norm()) / denom
+        worst = max(worst, rel)
+        assert rel < 1e-3, f"{name}: oracle grad != reference grad for {k}: rel {rel:.3e}"
+        fx[f"gradnorm/{k}"] = g.norm()
+        fx[f"gradhead/{k}"] = g.reshape(-1)[:16].clone()
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLDEN / f"{name}.npz", **{k: np.asarray(v.detach().cpu().numpy()) for k, v in fx.items()})
+    print(f"[golden] {name}: total_loss={float(loss_ref):.6f} params={sum(p.numel() for p in net.parameters())} "
+          f"worst oracle-vs-reference grad rel err={worst:.2e}  ({time.time() - t0:.1f}s)")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        run_case(n)
