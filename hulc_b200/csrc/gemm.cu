@@ -1,0 +1,341 @@
+// gemm.cu — fp32 GEMM with fused epilogues (bias / broadcast addend / beta*C / ReLU / ReLU-gate / dropout) and a
+// deterministic split-K for the skinny shapes of the HULC step (M = 32..64 sequences against 2048-wide weights).
+//
+// This is the exact-fp32 path (CUDA-core FFMA); it is what config 2 (fp32, rtol 1e-3) is validated on.  The tcgen05
+// path (gemm_tc.cu) reuses the same C-ABI.
+//
+//   C[M,N] = epi( alpha * op(A)[M,K] * op(B)[K,N] )
+//   transA = 0: A is M x K row-major (lda), 1: A is stored K x M row-major (lda)        [wgrad: dY^T]
+//   transB = 0: B is K x N row-major (ldb), 1: B is stored N x K row-major (ldb)        [torch Linear weight]
+#include "common.cuh"
+
+namespace {
+
+struct GemmParams {
+  const float* A; const float* B; float* C;
+  int M, N, K, lda, ldb, ldc;
+  float alpha, beta;
+  const float* bias;            // [N] or null
+  const float* addend;          // null or [*, N]: C += addend[(add_mod ? m % add_mod : m) * ldadd + n]
+  int ldadd, add_mod;
+  int act;                      // 0 none, 1 relu
+  const float* gate; int ldg;   // null or [M,N]: C = gate > 0 ? C : 0
+  DropSpec drop;                // applied last, element index m*N+n
+  // split-K
+  int splits, k_per_split;
+  float* partial;               // [splits][tiles][BM*BN]
+  unsigned* counters;           // [tiles], zero on entry, zero on exit
+};
+
+__device__ __forceinline__ float epilogue(const GemmParams& p, float acc, int m, int n) {
+  float v = p.alpha * acc;
+  if (p.bias) v += p.bias[n];
+  if (p.addend) v += p.addend[(size_t)(p.add_mod ? m % p.add_mod : m) * p.ldadd + n];
+  if (p.beta != 0.f) v += p.beta * p.C[(size_t)m * p.ldc + n];
+  if (p.act == 1) v = fmaxf(v, 0.f);
+  if (p.gate) v = p.gate[(size_t)m * p.ldg + n] > 0.f ? v : 0.f;
+  v *= drop_factor(p.drop, (unsigned long long)m * p.N + n);
+  return v;
+}
+
+template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmParams p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int PAD = 4;
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  __shared__ unsigned s_ticket;
+
+  const int tid = threadIdx.x;
+  const int tn = tid % (BN / TN), tm = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kend = min(p.K, kbeg + p.k_per_split);
+
+  // ---- global -> register staging -------------------------------------------------------------------------------
+  // A tile: BM x BK.  !TA: vectors run along k (4 per row);  TA: vectors run along m.
+  constexpr int A_V = BM * BK / 4 / NT;  // float4 per thread
+  constexpr int B_V = BN * BK / 4 / NT;
+  static_assert(A_V >= 1 && B_V >= 1, "tile too small for the thread count");
+  float4 ra[A_V], rb[B_V];
+  const bool a_vec = ((reinterpret_cast<size_t>(p.A) & 15) == 0) && (p.lda % 4 == 0);
+  const bool b_vec = ((reinterpret_cast<size_t>(p.B) & 15) == 0) && (p.ldb % 4 == 0);
+
+  auto load_a = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < A_V; ++j) {
+      int v = tid + j * NT;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!TA) {
+        int row = v / (BK / 4), kq = (v % (BK / 4)) * 4;
+        int m = m0 + row, k = k0 + kq;
+        if (m < p.M) {
+          const float* src = p.A + (size_t)m * p.lda + k;
+          if (a_vec && k + 3 < kend) r = *reinterpret_cast<const float4*>(src);
+          else {
+            if (k < kend) r.x = src[0];
+            if (k + 1 < kend) r.y = src[1];
+            if (k + 2 < kend) r.z = src[2];
+            if (k + 3 < kend) r.w = src[3];
+          }
+        }
+      } else {
+        int kk = v / (BM / 4), mq = (v % (BM / 4)) * 4;
+        int m = m0 + mq, k = k0 + kk;
+        if (k < kend) {
+          const float* src = p.A + (size_t)k * p.lda + m;
+          if (a_vec && m + 3 < p.M) r = *reinterpret_cast<const float4*>(src);
+          else {
+            if (m < p.M) r.x = src[0];
+            if (m + 1 < p.M) r.y = src[1];
+            if (m + 2 < p.M) r.z = src[2];
+            if (m + 3 < p.M) r.w = src[3];
+          }
+        }
+      }
+      ra[j] = r;
+    }
+  };
+  auto load_b = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < B_V; ++j) {
+      int v = tid + j * NT;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (TB) {
+        int row = v / (BK / 4), kq = (v % (BK / 4)) * 4;
+        int n = n0 + row, k = k0 + kq;
+        if (n < p.N) {
+          const float* src = p.B + (size_t)n * p.ldb + k;
+          if (b_vec && k + 3 < kend) r = *reinterpret_cast<const float4*>(src);
+          else {
+            if (k < kend) r.x = src[0];
+            if (k + 1 < kend) r.y = src[1];
+            if (k + 2 < kend) r.z = src[2];
+            if (k + 3 < kend) r.w = src[3];
+          }
+        }
+      } else {
+        int kk = v / (BN / 4), nq = (v % (BN / 4)) * 4;
+        int n = n0 + nq, k = k0 + kk;
+        if (k < kend) {
+          const float* src = p.B + (size_t)k * p.ldb + n;
+          if (b_vec && n + 3 < p.N) r = *reinterpret_cast<const float4*>(src);
+          else {
+            if (n < p.N) r.x = src[0];
+            if (n + 1 < p.N) r.y = src[1];
+            if (n + 2 < p.N) r.z = src[2];
+            if (n + 3 < p.N) r.w = src[3];
+          }
+        }
+      }
+      rb[j] = r;
+    }
+  };
+  auto store_a = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < A_V; ++j) {
+      int v = tid + j * NT;
+      if (!TA) {
+        int row = v / (BK / 4), kq = (v % (BK / 4)) * 4;
+        As[buf][kq + 0][row] = ra[j].x; As[buf][kq + 1][row] = ra[j].y;
+        As[buf][kq + 2][row] = ra[j].z; As[buf][kq + 3][row] = ra[j].w;
+      } else {
+        int kk = v / (BM / 4), mq = (v % (BM / 4)) * 4;
+        *reinterpret_cast<float4*>(&As[buf][kk][mq]) = ra[j];
+      }
+    }
+  };
+  auto store_b = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < B_V; ++j) {
+      int v = tid + j * NT;
+      if (TB) {
+        int row = v / (BK / 4), kq = (v % (BK / 4)) * 4;
+        Bs[buf][kq + 0][row] = rb[j].x; Bs[buf][kq + 1][row] = rb[j].y;
+        Bs[buf][kq + 2][row] = rb[j].z; Bs[buf][kq + 3][row] = rb[j].w;
+      } else {
+        int kk = v / (BN / 4), nq = (v % (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[buf][kk][nq]) = rb[j];
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // Each thread owns TM rows as TM/4 groups of 4 spaced BM/(TM/4) apart (conflict-free LDS.128), same for columns.
+  constexpr int GM = TM / 4, GN = TN / 4;
+  constexpr int SM_STRIDE = BM / GM, SN_STRIDE = BN / GN;
+
+  const int nk = (kend - kbeg + BK - 1) / BK;
+  if (nk > 0) {
+    load_a(kbeg); load_b(kbeg);
+    store_a(0); store_b(0);
+  }
+  __syncthreads();
+  for (int it = 0; it < nk; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < nk) { load_a(kbeg + (it + 1) * BK); load_b(kbeg + (it + 1) * BK); }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < GM; ++g) {
+        float4 t = *reinterpret_cast<const float4*>(&As[buf][k][g * SM_STRIDE + tm * 4]);
+        a[g * 4 + 0] = t.x; a[g * 4 + 1] = t.y; a[g * 4 + 2] = t.z; a[g * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int g = 0; g < GN; ++g) {
+        float4 t = *reinterpret_cast<const float4*>(&Bs[buf][k][g * SN_STRIDE + tn * 4]);
+        b[g * 4 + 0] = t.x; b[g * 4 + 1] = t.y; b[g * 4 + 2] = t.z; b[g * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (it + 1 < nk) { store_a(buf ^ 1); store_b(buf ^ 1); }
+    __syncthreads();
+  }
+
+  // ---- epilogue -------------------------------------------------------------------------------------------------
+  if (p.splits > 1) {
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int ntiles = gridDim.x * gridDim.y;
+    float* mine = p.partial + ((size_t)blockIdx.z * ntiles + tile) * (BM * BN);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int g = 0; g < GN; ++g) {
+        int lm = (i / 4) * SM_STRIDE + tm * 4 + (i % 4), ln = g * SN_STRIDE + tn * 4;
+        *reinterpret_cast<float4*>(&mine[lm * BN + ln]) = make_float4(acc[i][g * 4], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
+      }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&p.counters[tile], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(p.splits - 1)) return;
+    __threadfence();
+    // last CTA of this tile: fixed-order reduction over the splits -> bit-reproducible
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int z = 0; z < p.splits; ++z) {
+      const float* src = p.partial + ((size_t)z * ntiles + tile) * (BM * BN);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int g = 0; g < GN; ++g) {
+          int lm = (i / 4) * SM_STRIDE + tm * 4 + (i % 4), ln = g * SN_STRIDE + tn * 4;
+          float4 t = __ldcg(reinterpret_cast<const float4*>(&src[lm * BN + ln]));
+          acc[i][g * 4] += t.x; acc[i][g * 4 + 1] += t.y; acc[i][g * 4 + 2] += t.z; acc[i][g * 4 + 3] += t.w;
+        }
+    }
+    if (tid == 0) p.counters[tile] = 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + (i / 4) * SM_STRIDE + tm * 4 + (i % 4);
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + (j / 4) * SN_STRIDE + tn * 4 + (j % 4);
+      if (n < p.N) p.C[(size_t)m * p.ldc + n] = epilogue(p, acc[i][j], m, n);
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_cfg(GemmParams p, int transA, int transB, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+  constexpr int BK = 16;
+  constexpr int NT = (BM / TM) * (BN / TN);
+  int gm = hulc_cdiv(p.M, BM), gn = hulc_cdiv(p.N, BN);
+  int tiles = gm * gn;
+  // split-K when the tile grid cannot fill the 148 SMs and K is deep enough to be worth a second pass
+  int splits = 1;
+  if (workspace && tiles < kNumSMs && p.K >= 8 * BK) {
+    splits = min(hulc_cdiv(2 * kNumSMs, tiles), p.K / (4 * BK));
+    splits = max(1, min(splits, 32));
+    size_t need = 4096 + (size_t)splits * tiles * BM * BN * sizeof(float);
+    while (splits > 1 && (need > workspace_bytes || tiles > 1024)) {
+      --splits;
+      need = 4096 + (size_t)splits * tiles * BM * BN * sizeof(float);
+    }
+  }
+  int kps = hulc_cdiv(hulc_cdiv(p.K, splits), BK) * BK;
+  splits = hulc_cdiv(p.K, kps);
+  p.splits = splits; p.k_per_split = kps;
+  if (splits > 1) {
+    p.counters = reinterpret_cast<unsigned*>(workspace);
+    p.partial = workspace + 1024;
+  }
+  dim3 grid(gn, gm, splits), block(NT);
+  void (*kfn)(GemmParams);
+  if (!transA && !transB) kfn = sgemm_kernel<BM, BN, BK, TM, TN, false, false>;
+  else if (!transA && transB) kfn = sgemm_kernel<BM, BN, BK, TM, TN, false, true>;
+  else if (transA && !transB) kfn = sgemm_kernel<BM, BN, BK, TM, TN, true, false>;
+  else kfn = sgemm_kernel<BM, BN, BK, TM, TN, true, true>;
+  HULC_LAUNCH(kfn, grid, block, 0, st, p);
+  HULC_RETURN_LAST();
+}
+
+// out[c] = beta*out[c] + sum_r X[r*ldx + c]
+__global__ void colsum_kernel(const float* __restrict__ X, int rows, int cols, int ldx, float* __restrict__ out, float beta, int rows_per_block) {
+  __shared__ float red[8][33];
+  int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  int ry = threadIdx.x >> 5;  // 8 row lanes
+  int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < cols)
+    for (int r = r0 + ry; r < r1; r += 8) s += X[(size_t)r * ldx + c];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    if (gridDim.y == 1) out[c] = beta * out[c] + t;
+    else atomicAdd(&out[c], t);
+  }
+}
+__global__ void scale_vec_kernel(float* x, int n, float s) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= s;
+}
+
+}  // namespace
+
+// See include/hulc_b200.h for the contract.
+HULC_API int hulc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA,
+                       int transB, float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act,
+                       const float* gate, int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site,
+                       const unsigned char* drop_keep, float* workspace, size_t workspace_bytes, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (K < 0 || !A || !B || !C) return (int)cudaErrorInvalidValue;
+  GemmParams p;
+  p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.alpha = alpha; p.beta = beta; p.bias = bias; p.addend = addend; p.ldadd = ldadd; p.add_mod = add_mod;
+  p.act = act; p.gate = gate; p.ldg = ldg; p.drop = make_drop(drop_p, drop_seed, drop_site, drop_keep);
+  p.splits = 1; p.k_per_split = K; p.partial = nullptr; p.counters = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M >= 256 && N >= 96) return launch_cfg<128, 128, 8, 8>(p, transA, transB, workspace, workspace_bytes, st);
+  return launch_cfg<64, 64, 4, 4>(p, transA, transB, workspace, workspace_bytes, st);
+}
+
+HULC_API int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, void* stream) {
+  if (cols <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int gy = 1, rpb = rows;
+  if (rows >= 4096) {  // long reductions: spread rows over CTAs, combine with atomics
+    gy = min(64, rows / 1024);
+    rpb = hulc_cdiv(rows, gy);
+    if (beta == 0.f) cudaMemsetAsync(out, 0, sizeof(float) * cols, st);
+    else if (beta != 1.f) HULC_LAUNCH(scale_vec_kernel, dim3(hulc_cdiv(cols, 256)), dim3(256), 0, st, out, cols, beta);
+  }
+  HULC_LAUNCH(colsum_kernel, dim3(hulc_cdiv(cols, 32), gy), dim3(256), 0, st, X, rows, cols, ldx, out, beta, rpb);
+  HULC_RETURN_LAST();
+}

@@ -16,3 +16,5 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+from emu_fixture import emu, emu_lib_path  # noqa: E402,F401
