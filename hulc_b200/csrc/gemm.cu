@@ -18,8 +18,8 @@ struct GemmParams {
   const float* bias;            // [N] or null
   const float* addend;          // null or [*, N]: C += addend[(add_mod ? m % add_mod : m) * ldadd + n]
   int ldadd, add_mod;
-  int act;                      // 0 none, 1 relu
-  const float* gate; int ldg;   // null or [M,N]: C = gate > 0 ? C : 0
+  int act;                      // bits 0-1: 0 none, 1 relu, 2 tanh;  bit 2: the gate is a tanh output
+  const float* gate; int ldg;   // null or [M,N]: C = gate > 0 ? C : 0   (bit 2 set: C *= 1 - gate^2)
   DropSpec drop;                // applied last, element index m*N+n
   // split-K
   int splits, k_per_split;
@@ -32,8 +32,12 @@ __device__ __forceinline__ float epilogue(const GemmParams& p, float acc, int m,
   if (p.bias) v += p.bias[n];
   if (p.addend) v += p.addend[(size_t)(p.add_mod ? m % p.add_mod : m) * p.ldadd + n];
   if (p.beta != 0.f) v += p.beta * p.C[(size_t)m * p.ldc + n];
-  if (p.act == 1) v = fmaxf(v, 0.f);
-  if (p.gate) v = p.gate[(size_t)m * p.ldg + n] > 0.f ? v : 0.f;
+  if ((p.act & 3) == 1) v = fmaxf(v, 0.f);
+  else if ((p.act & 3) == 2) v = tanhf(v);
+  if (p.gate) {
+    float g = p.gate[(size_t)m * p.ldg + n];
+    v = (p.act & 4) ? v * (1.f - g * g) : (g > 0.f ? v : 0.f);
+  }
   v *= drop_factor(p.drop, (unsigned long long)m * p.N + n);
   return v;
 }
@@ -298,7 +302,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, int rows, int cols, i
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    if (gridDim.y == 1) out[c] = beta * out[c] + t;
+    if (gridDim.y == 1) out[c] = (beta != 0.f ? beta * out[c] : 0.f) + t;
     else atomicAdd(&out[c], t);
   }
 }

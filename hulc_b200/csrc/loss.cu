@@ -1,0 +1,474 @@
+// loss.cu — the scalar-producing ends of the step, each as ONE fused forward+backward kernel:
+//   world_to_tcp_frame, discretised-logistic-mixture NLL + gripper cross-entropy, latent-plan sampling + balanced KL
+//   (discrete 32x32 categorical and continuous Gaussian), CLIP-style contrastive loss.
+// The reference runs each of these as dozens of elementwise aten kernels plus host syncs (SURVEY.md §2.3 K13,K17-K19).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// world_to_tcp_frame (decoders/utils/gripper_control.py:16-36)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+// R = Rx(a) Ry(b) Rz(c)  (pytorch3d_transforms.py:162-218, convention "XYZ")
+__device__ __forceinline__ void euler_xyz(float a, float b, float c, float* R) {
+  float sa, ca, sb, cb, sc, cc;
+  sincosf(a, &sa, &ca); sincosf(b, &sb, &cb); sincosf(c, &sc, &cc);
+  float Rx[9] = {1, 0, 0, 0, ca, -sa, 0, sa, ca};
+  float Ry[9] = {cb, 0, sb, 0, 1, 0, -sb, 0, cb};
+  float Rz[9] = {cc, -sc, 0, sc, cc, 0, 0, 0, 1};
+  float T[9];
+  mat3_mul(Rx, Ry, T);
+  mat3_mul(T, Rz, R);
+}
+// general 3x3 inverse by cofactors (the reference calls torch.inverse)
+__device__ __forceinline__ void mat3_inv(const float* m, float* o) {
+  float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  float det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  float id = 1.f / det;
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+__global__ void world_to_tcp_kernel(const float* __restrict__ act, const float* __restrict__ robot_obs, int obs_dim, float* __restrict__ out, int n,
+                                    int* __restrict__ nan_flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* a = act + (size_t)i * 7;
+  const float* o = robot_obs + (size_t)i * obs_dim;
+  const float PI = 3.14159265358979323846f;
+  float R[9], Rinv[9], Rn[9], Rninv[9], M[9];
+  euler_xyz(o[3], o[4], o[5], R);
+  mat3_inv(R, Rinv);
+  float r[7];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r[k] = Rinv[k * 3] * a[0] + Rinv[k * 3 + 1] * a[1] + Rinv[k * 3 + 2] * a[2];
+  euler_xyz(o[3] + a[3] * 0.01f, o[4] + a[4] * 0.01f, o[5] + a[5] * 0.01f, Rn);
+  mat3_inv(Rn, Rninv);
+  mat3_mul(Rninv, R, M);
+  // matrix_to_euler_angles(M, "XYZ") (pytorch3d_transforms.py:264-303)
+  float e[3] = {atan2f(-M[5], M[8]), asinf(M[2]), atan2f(-M[1], M[0])};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = e[k];
+    if (v < -PI) v += 2.f * PI;
+    if (v > PI) v -= 2.f * PI;
+    r[3 + k] = v * 100.f;
+  }
+  r[6] = a[6];
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { out[(size_t)i * 7 + k] = r[k]; bad |= (r[k] != r[k]); }
+  if (bad && nan_flag) atomicOr(nan_flag, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Discretised logistic mixture NLL + gripper CE (decoders/logistic_decoder_rnn.py:136-155,184-231), forward + gradient
+// w.r.t. the head pre-activations in one pass.  One thread per (token, action dim).  heads holds B sequences (rows
+// b*S+t, or t*B+b when time_major); the loss is taken over sequences [b0, b0+Bm) only and dheads is written for those.
+//   heads row layout: [logit_probs n_dims*n_mix | means n_dims*n_mix | raw log_scales n_dims*n_mix | gripper 2]
+//   losses[0] = mean_tokens sum_dims NLL, losses[1] = mean_tokens CE;   dheads = grad_scale * d(losses[0] + alpha*losses[1]) / d heads
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxMix = 16;
+
+__global__ void __launch_bounds__(256) logistic_loss_kernel(const float* __restrict__ heads, int ldh, const float* __restrict__ actions, int act_dim,
+                                                            float* __restrict__ dheads, float* __restrict__ partial, unsigned* __restrict__ counter,
+                                                            float* __restrict__ losses, int B, int S, int b0, int Bm, int time_major, int n_dims,
+                                                            int n_mix, int num_classes, float log_scale_min, float act_min, float act_max,
+                                                            int has_gripper, float gripper_alpha, float grad_scale) {
+  __shared__ float red[32];
+  __shared__ unsigned s_ticket;
+  const int T = Bm * S;  // tokens of the sequences [b0, b0+Bm) — one modality of the batched step
+  const int per_tok = n_dims + (has_gripper ? 1 : 0);
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  float nll = 0.f, ce = 0.f;
+  if (gid < T * per_tok) {
+    int tok = gid / per_tok, d = gid % per_tok;
+    int b = b0 + (time_major ? tok % Bm : tok / S), t = time_major ? tok / Bm : tok % S;
+    int row = time_major ? t * B + b : b * S + t;
+    const float* a_tok = actions + ((size_t)b * S + t) * act_dim;
+    const float* h = heads + (size_t)row * ldh;
+    float* dh = dheads + (size_t)row * ldh;
+    const float inv_T = grad_scale / (float)T;
+    const int NM = n_dims * n_mix;
+    if (d < n_dims) {
+      float a = a_tok[d];
+      const float* lp = h + d * n_mix;
+      const float* mu = h + NM + d * n_mix;
+      const float* lsr = h + 2 * NM + d * n_mix;
+      float half_bin = (act_max - act_min) * 0.5f / (float)(num_classes - 1);
+      float log_half_classes = logf((float)(num_classes - 1) * 0.5f);
+      float tot[kMaxMix], dmu[kMaxMix], dls[kMaxMix];
+      float mlp = -FLT_MAX;
+      for (int k = 0; k < n_mix; ++k) mlp = fmaxf(mlp, lp[k]);
+      float selp = 0.f;
+      for (int k = 0; k < n_mix; ++k) selp += expf(lp[k] - mlp);
+      float lse_p = mlp + logf(selp);
+      float mt = -FLT_MAX;
+      for (int k = 0; k < n_mix; ++k) {
+        float ls = fmaxf(lsr[k], log_scale_min);
+        float c = a - mu[k];
+        float inv = expf(-ls);
+        float u = inv * (c + half_bin), v = inv * (c - half_bin), m = inv * c;
+        float su = sigmoidf(u), sv = sigmoidf(v);
+        float delta = su - sv;
+        float f, fu = 0.f, fv = 0.f, fm = 0.f, fls = 0.f;  // f and its partials w.r.t. u, v, m and (direct) ls
+        if (a < act_min + 1e-3f) { f = u - softplusf(u); fu = 1.f - su; }
+        else if (a > act_max - 1e-3f) { f = -softplusf(v); fv = -sv; }
+        else if (delta > 1e-5f) { f = logf(fmaxf(delta, 1e-12f)); fu = su * (1.f - su) / delta; fv = -sv * (1.f - sv) / delta; }
+        else { f = m - ls - 2.f * softplusf(m) - log_half_classes; fm = 1.f - 2.f * sigmoidf(m); fls = -1.f; }
+        dmu[k] = -inv * (fu + fv + fm);
+        dls[k] = -(u * fu + v * fv + m * fm) + fls;
+        tot[k] = f + lp[k] - lse_p;
+        mt = fmaxf(mt, tot[k]);
+      }
+      float se = 0.f;
+      for (int k = 0; k < n_mix; ++k) se += expf(tot[k] - mt);
+      float L = mt + logf(se);
+      nll = -L;
+      for (int k = 0; k < n_mix; ++k) {
+        float w = expf(tot[k] - L);
+        float pi = expf(lp[k] - lse_p);
+        dh[d * n_mix + k] = (pi - w) * inv_T;
+        dh[NM + d * n_mix + k] = -w * dmu[k] * inv_T;
+        dh[2 * NM + d * n_mix + k] = (lsr[k] >= log_scale_min) ? -w * dls[k] * inv_T : 0.f;
+      }
+    } else {
+      float g0 = h[3 * NM], g1 = h[3 * NM + 1];
+      int label = (a_tok[act_dim - 1] == -1.f) ? 0 : 1;
+      float mx = fmaxf(g0, g1);
+      float lse = mx + logf(expf(g0 - mx) + expf(g1 - mx));
+      ce = lse - (label ? g1 : g0);
+      float p0 = expf(g0 - lse), p1 = expf(g1 - lse);
+      dh[3 * NM] = gripper_alpha * (p0 - (label == 0 ? 1.f : 0.f)) * inv_T;
+      dh[3 * NM + 1] = gripper_alpha * (p1 - (label == 1 ? 1.f : 0.f)) * inv_T;
+    }
+  }
+  // deterministic two-level reduction: per-block partials, last block sums them in order
+  float bn = block_sum(nll, red);
+  float bc = block_sum(ce, red);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = bn; partial[2 * blockIdx.x + 1] = bc;
+    __threadfence();
+    s_ticket = atomicAdd(counter, 1u);
+  }
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1 && threadIdx.x == 0) {
+    __threadfence();
+    float sn = 0.f, sc = 0.f;
+    for (unsigned i = 0; i < gridDim.x; ++i) { sn += __ldcg(&partial[2 * i]); sc += __ldcg(&partial[2 * i + 1]); }
+    losses[0] = sn / (float)T; losses[1] = sc / (float)T;
+    *counter = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Discrete latent plan (hulc/utils/distributions.py:23-41, hulc/models/hulc.py:289-291,539-561).
+// One warp per (sequence, category); lane = class (class_size must be 32).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plan_discrete_fwd_kernel(const float* __restrict__ pr_logit, const float* __restrict__ pp_logit,
+                                                                const float* __restrict__ u_in, const int* __restrict__ idx_in,
+                                                                float* __restrict__ plan, int* __restrict__ idx_out, float* __restrict__ kl_rows,
+                                                                int rows, unsigned long long seed, unsigned site) {
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float lq = pr_logit[(size_t)row * 32 + lane];
+  float lp = pp_logit ? pp_logit[(size_t)row * 32 + lane] : 0.f;
+  float mq = warp_max(lq), mp = warp_max(lp);
+  float eq = expf(lq - mq), ep = expf(lp - mp);
+  float sq = warp_sum(eq), sp = warp_sum(ep);
+  float q = eq / sq;
+  float logq = lq - mq - logf(sq), logp = lp - mp - logf(sp);
+  if (kl_rows) {
+    float kl = warp_sum(q * (logq - logp));
+    if (lane == 0) kl_rows[row] = kl;
+  }
+  int idx;
+  if (idx_in) idx = idx_in[row];
+  else {
+    float u = u_in ? u_in[row] : philox_uniform(seed, site, (unsigned long long)row);
+    // sequential inclusive prefix sum (same association as torch.cumsum) -> #{j : c_j <= u}
+    float c = 0.f;
+    int cnt = 0;
+    for (int j = 0; j < 32; ++j) {
+      c += __shfl_sync(0xffffffffu, q, j);
+      cnt += (c <= u) ? 1 : 0;
+    }
+    idx = min(cnt, 31);
+  }
+  if (plan) plan[(size_t)row * 32 + lane] = (lane == idx) ? 1.f : 0.f;
+  if (idx_out && lane == 0) idx_out[row] = idx;
+}
+
+// d pr = q (g - sum q g)  [straight-through]  +  c_rhs * q ((log q - log p) - KL)     d pp = c_lhs * (p - q)
+__global__ void __launch_bounds__(256) plan_discrete_bwd_kernel(const float* __restrict__ pr_logit, const float* __restrict__ pp_logit,
+                                                                const float* __restrict__ dplan, const float* __restrict__ dkl, float coef_lhs,
+                                                                float coef_rhs, float* __restrict__ d_pr, float* __restrict__ d_pp, int rows) {
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float lq = pr_logit[(size_t)row * 32 + lane];
+  float mq = warp_max(lq);
+  float eq = expf(lq - mq);
+  float sq = warp_sum(eq);
+  float q = eq / sq;
+  float g = dplan ? dplan[(size_t)row * 32 + lane] : 0.f;
+  float gq = warp_sum(q * g);
+  float dq = q * (g - gq);
+  if (pp_logit) {
+    float up = dkl ? *dkl : 1.f;
+    float lp = pp_logit[(size_t)row * 32 + lane];
+    float mp = warp_max(lp);
+    float ep = expf(lp - mp);
+    float sp = warp_sum(ep);
+    float p = ep / sp;
+    float logq = lq - mq - logf(sq), logp = lp - mp - logf(sp);
+    float t = logq - logp;
+    float kl = warp_sum(q * t);
+    dq += up * coef_rhs * q * (t - kl);
+    d_pp[(size_t)row * 32 + lane] = up * coef_lhs * (p - q);
+  }
+  d_pr[(size_t)row * 32 + lane] = dq;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Continuous latent plan (distributions.py:28-29,55-59): state = [mean | raw_std], std = softplus(raw) + 1e-4,
+// plan = mean + std * eps, KL(N_q || N_p) summed over dims.  One thread per (sequence, dim).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void plan_cont_fwd_kernel(const float* __restrict__ pr, const float* __restrict__ pp, const float* __restrict__ eps_in,
+                                     float* __restrict__ plan, float* __restrict__ kl_elem, int Bn, int P, unsigned long long seed, unsigned site) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * P) return;
+  int b = i / P, d = i % P;
+  float mq = pr[(size_t)b * 2 * P + d], sq = softplusf(pr[(size_t)b * 2 * P + P + d]) + 1e-4f;
+  float e;
+  if (eps_in) e = eps_in[i];
+  else {  // Box-Muller on two philox uniforms
+    float u1 = fmaxf(philox_uniform(seed, site, 2ull * i), 1e-7f), u2 = philox_uniform(seed, site, 2ull * i + 1);
+    e = sqrtf(-2.f * logf(u1)) * cosf(6.283185307179586f * u2);
+  }
+  plan[i] = mq + sq * e;
+  if (kl_elem) {
+    float mp = pp[(size_t)b * 2 * P + d], sp = softplusf(pp[(size_t)b * 2 * P + P + d]) + 1e-4f;
+    float vr = (sq / sp) * (sq / sp), t1 = (mq - mp) / sp;
+    kl_elem[i] = 0.5f * (vr + t1 * t1 - 1.f - logf(vr));
+  }
+}
+__global__ void plan_cont_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ pp, const float* __restrict__ eps_in,
+                                     const float* __restrict__ dplan, const float* __restrict__ dkl, float coef_lhs, float coef_rhs,
+                                     float* __restrict__ d_pr, float* __restrict__ d_pp, int Bn, int P, unsigned long long seed, unsigned site) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * P) return;
+  int b = i / P, d = i % P;
+  float rq = pr[(size_t)b * 2 * P + P + d], rp = pp[(size_t)b * 2 * P + P + d];
+  float mq = pr[(size_t)b * 2 * P + d], sq = softplusf(rq) + 1e-4f;
+  float mp = pp[(size_t)b * 2 * P + d], sp = softplusf(rp) + 1e-4f;
+  float e;
+  if (eps_in) e = eps_in[i];
+  else {
+    float u1 = fmaxf(philox_uniform(seed, site, 2ull * i), 1e-7f), u2 = philox_uniform(seed, site, 2ull * i + 1);
+    e = sqrtf(-2.f * logf(u1)) * cosf(6.283185307179586f * u2);
+  }
+  float g = dplan ? dplan[i] : 0.f;
+  float up = dkl ? *dkl : 1.f;
+  // KL = 0.5 (sq^2/sp^2 + (mq-mp)^2/sp^2 - 1 - 2 log sq + 2 log sp)
+  float dmq = (mq - mp) / (sp * sp), dsq = sq / (sp * sp) - 1.f / sq;
+  float dmp = -dmq, dsp = -(sq * sq) / (sp * sp * sp) - (mq - mp) * (mq - mp) / (sp * sp * sp) + 1.f / sp;
+  float gmq = g + up * coef_rhs * dmq, gsq = g * e + up * coef_rhs * dsq;
+  d_pr[(size_t)b * 2 * P + d] = gmq;
+  d_pr[(size_t)b * 2 * P + P + d] = gsq * sigmoidf(rq);
+  d_pp[(size_t)b * 2 * P + d] = up * coef_lhs * dmp;
+  d_pp[(size_t)b * 2 * P + P + d] = up * coef_lhs * dsp * sigmoidf(rp);
+}
+
+// out[0] = scale * sum_i x[i], fixed order (single block)
+__global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ x, int n, float* __restrict__ out, float scale) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CLIP-style contrastive loss (hulc/models/hulc.py:650-695) on already projected features, forward + gradients, one CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clip_loss_kernel(const float* __restrict__ im, const float* __restrict__ tx, const float* __restrict__ logit_scale,
+                                                        const unsigned char* __restrict__ mask, float* __restrict__ loss, float* __restrict__ d_im,
+                                                        float* __restrict__ d_tx, float* __restrict__ d_logit_scale, int n, int D, float grad_scale) {
+  HULC_DYN_SMEM(float, sm);
+  __shared__ int s_nv;
+  __shared__ float red[32];
+  int* sel = reinterpret_cast<int*>(sm);       // [n] compacted indices of selected rows
+  float* a = sm + n;                           // [n][D] normalised image features
+  float* t = a + (size_t)n * D;                // [n][D] normalised text features
+  float* na = t + (size_t)n * D;               // [n] norms
+  float* nt = na + n;                          // [n]
+  float* L = nt + n;                           // [n][n] logits, then gradient G
+  float* rlse = L + (size_t)n * n;             // [n] row logsumexp
+  float* clse = rlse + n;                      // [n] column logsumexp
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int c = 0;
+    for (int i = 0; i < n; ++i)
+      if (!mask || mask[i]) sel[c++] = i;
+    s_nv = c;
+  }
+  __syncthreads();
+  const int nv = s_nv;
+  for (int i = tid; i < n * D; i += blockDim.x) { d_im[i] = 0.f; d_tx[i] = 0.f; }
+  if (nv == 0) {  // reference: dummy pass scaled by 0 -> zero loss, zero gradients
+    if (tid == 0) { loss[0] = 0.f; d_logit_scale[0] = 0.f; }
+    return;
+  }
+  const float s = expf(logit_scale[0]);
+  for (int r = tid; r < nv; r += blockDim.x) {
+    const float* pi = im + (size_t)sel[r] * D;
+    const float* pt = tx + (size_t)sel[r] * D;
+    float qi = 0.f, qt = 0.f;
+    for (int k = 0; k < D; ++k) { qi += pi[k] * pi[k]; qt += pt[k] * pt[k]; }
+    qi = sqrtf(qi); qt = sqrtf(qt);
+    na[r] = qi; nt[r] = qt;
+    for (int k = 0; k < D; ++k) { a[r * D + k] = pi[k] / qi; t[r * D + k] = pt[k] / qt; }
+  }
+  __syncthreads();
+  for (int e = tid; e < nv * nv; e += blockDim.x) {
+    int i = e / nv, j = e % nv;
+    float dot = 0.f;
+    for (int k = 0; k < D; ++k) dot += a[i * D + k] * t[j * D + k];
+    L[i * nv + j] = s * dot;
+  }
+  __syncthreads();
+  for (int r = tid; r < 2 * nv; r += blockDim.x) {
+    bool col = r >= nv;
+    int i = col ? r - nv : r;
+    float mx = -FLT_MAX;
+    for (int j = 0; j < nv; ++j) mx = fmaxf(mx, col ? L[j * nv + i] : L[i * nv + j]);
+    float se = 0.f;
+    for (int j = 0; j < nv; ++j) se += expf((col ? L[j * nv + i] : L[i * nv + j]) - mx);
+    (col ? clse : rlse)[i] = mx + logf(se);
+  }
+  __syncthreads();
+  float part = 0.f;
+  for (int i = tid; i < nv; i += blockDim.x) part += (rlse[i] - L[i * nv + i]) + (clse[i] - L[i * nv + i]);
+  part = block_sum(part, red);
+  if (tid == 0) loss[0] = 0.5f * part / (float)nv;
+  __syncthreads();
+  // G = dloss/dL ; d s accumulates sum G * (a.t)
+  float ds = 0.f;
+  const float c = grad_scale * 0.5f / (float)nv;
+  for (int e = tid; e < nv * nv; e += blockDim.x) {
+    int i = e / nv, j = e % nv;
+    float l = L[e];
+    float g = c * (expf(l - rlse[i]) + expf(l - clse[j]) - (i == j ? 2.f : 0.f));
+    ds += g * (l / s);
+    L[e] = g;
+  }
+  ds = block_sum(ds, red);
+  if (tid == 0) d_logit_scale[0] = ds * s;
+  __syncthreads();
+  // d a_i = s * sum_j G_ij t_j ; d t_j = s * sum_i G_ij a_i ; then through the L2 normalisation
+  for (int r = tid; r < 2 * nv; r += blockDim.x) {
+    bool is_t = r >= nv;
+    int i = is_t ? r - nv : r;
+    const float* self = (is_t ? t : a) + i * D;
+    const float* other = is_t ? a : t;
+    float nrm = is_t ? nt[i] : na[i];
+    float* dst = (is_t ? d_tx : d_im) + (size_t)sel[i] * D;
+    float proj = 0.f;
+    for (int k = 0; k < D; ++k) {
+      float gk = 0.f;
+      for (int j = 0; j < nv; ++j) gk += (is_t ? L[j * nv + i] : L[i * nv + j]) * other[j * D + k];
+      gk *= s;
+      dst[k] = gk;  // stash un-normalised gradient
+      proj += gk * self[k];
+    }
+    for (int k = 0; k < D; ++k) dst[k] = (dst[k] - self[k] * proj) / nrm;
+  }
+}
+
+}  // namespace
+
+HULC_API int hulc_world_to_tcp(const float* actions, const float* robot_obs, int obs_dim, float* out, int n_tokens, int* nan_flag, void* stream) {
+  if (n_tokens <= 0) return 0;
+  HULC_LAUNCH(world_to_tcp_kernel, dim3(hulc_cdiv(n_tokens, 128)), dim3(128), 0, (cudaStream_t)stream, actions, robot_obs, obs_dim, out, n_tokens,
+              nan_flag);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_logistic_loss(const float* heads, int ldh, const float* actions, int act_dim, float* dheads, float* losses, int B, int S,
+                                int b0, int Bm, int time_major, int n_dims, int n_mix, int num_classes, float log_scale_min, float act_min,
+                                float act_max, int has_gripper, float gripper_alpha, float grad_scale, float* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (Bm * S <= 0) return 0;
+  if (b0 < 0 || b0 + Bm > B) return (int)cudaErrorInvalidValue;
+  if (n_mix > kMaxMix) return (int)cudaErrorInvalidValue;
+  int total = Bm * S * (n_dims + (has_gripper ? 1 : 0));
+  int blocks = hulc_cdiv(total, 256);
+  if (workspace_bytes < 4096 + sizeof(float) * 2 * (size_t)blocks) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(logistic_loss_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, heads, ldh, actions, act_dim, dheads, workspace + 1024,
+              reinterpret_cast<unsigned*>(workspace) + 1023, losses, B, S, b0, Bm, time_major, n_dims, n_mix, num_classes, log_scale_min, act_min,
+              act_max, has_gripper, gripper_alpha, grad_scale);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_plan_discrete_fwd(const float* pr_logit, const float* pp_logit, const float* u, const int* idx_in, float* plan, int* idx_out,
+                                    float* kl_rows, int rows, int class_size, unsigned long long seed, unsigned site, void* stream) {
+  if (rows <= 0) return 0;
+  if (class_size != 32) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(plan_discrete_fwd_kernel, dim3(hulc_cdiv(rows, 8)), dim3(256), 0, (cudaStream_t)stream, pr_logit, pp_logit, u, idx_in, plan, idx_out,
+              kl_rows, rows, seed, site);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_plan_discrete_bwd(const float* pr_logit, const float* pp_logit, const float* dplan, const float* dkl, float coef_lhs,
+                                    float coef_rhs, float* d_pr, float* d_pp, int rows, int class_size, void* stream) {
+  if (rows <= 0) return 0;
+  if (class_size != 32) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(plan_discrete_bwd_kernel, dim3(hulc_cdiv(rows, 8)), dim3(256), 0, (cudaStream_t)stream, pr_logit, pp_logit, dplan, dkl, coef_lhs,
+              coef_rhs, d_pr, d_pp, rows);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_plan_cont_fwd(const float* pr_state, const float* pp_state, const float* eps, float* plan, float* kl_elem, int batch,
+                                int plan_features, unsigned long long seed, unsigned site, void* stream) {
+  int n = batch * plan_features;
+  if (n <= 0) return 0;
+  HULC_LAUNCH(plan_cont_fwd_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, pr_state, pp_state, eps, plan, kl_elem, batch,
+              plan_features, seed, site);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_plan_cont_bwd(const float* pr_state, const float* pp_state, const float* eps, const float* dplan, const float* dkl,
+                                float coef_lhs, float coef_rhs, float* d_pr, float* d_pp, int batch, int plan_features, unsigned long long seed,
+                                unsigned site, void* stream) {
+  int n = batch * plan_features;
+  if (n <= 0) return 0;
+  HULC_LAUNCH(plan_cont_bwd_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, pr_state, pp_state, eps, dplan, dkl, coef_lhs,
+              coef_rhs, d_pr, d_pp, batch, plan_features, seed, site);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_sum(const float* x, int n, float* out, float scale, void* stream) {
+  HULC_LAUNCH(sum_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, x, n, out, scale);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_clip_loss(const float* im, const float* tx, const float* logit_scale, const unsigned char* mask, float* loss, float* d_im,
+                            float* d_tx, float* d_logit_scale, int n, int D, float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  size_t smem = sizeof(float) * ((size_t)n + 2 * (size_t)n * D + 2 * n + (size_t)n * n + 2 * n);
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  auto kfn = clip_loss_kernel;
+  if (smem > 48 * 1024) HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HULC_LAUNCH(kfn, dim3(1), dim3(256), smem, (cudaStream_t)stream, im, tx, logit_scale, mask, loss, d_im, d_tx, d_logit_scale, n, D, grad_scale);
+  HULC_RETURN_LAST();
+}

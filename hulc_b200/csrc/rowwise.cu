@@ -1,0 +1,354 @@
+// rowwise.cu — warp-per-row kernels: LayerNorm (+residual +dropout) fwd/bwd, spatial softmax fwd/bwd,
+// position-embedding add, strided copies/reductions, fused Adam.  All HBM-bound; rows map to warps, lanes stride the
+// row so global accesses are coalesced; reductions are warp shuffles.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm:  z = res + drop(x)   (z = x when res == null);   y = (z - mean) * rstd * w + b
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MAXV>  // elements per lane held in registers: D <= 32*MAXV
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_fwd_kernel(
+    const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldres, const float* __restrict__ w,
+    const float* __restrict__ b, float* __restrict__ y, int ldy, float* __restrict__ z, int ldz, float* __restrict__ stats,
+    int rows, int D, float eps, DropSpec drop) {
+  int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    float t = 0.f;
+    if (c < D) {
+      t = x[(size_t)row * ldx + c];
+      if (res) t = res[(size_t)row * ldres + c] + t * drop_factor(drop, (unsigned long long)row * D + c);
+    }
+    v[i] = t; s += t;
+  }
+  float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    float d = (c < D) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    if (c < D) {
+      y[(size_t)row * ldy + c] = (v[i] - mean) * rstd * w[c] + b[c];
+      if (z) z[(size_t)row * ldz + c] = v[i];
+    }
+  }
+  if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+}
+
+// dz = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*w;   dx = dz * drop;   dw += sum dy*xhat;  db += sum dy
+template <int MAXV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_bwd_kernel(
+    const float* __restrict__ dy, int lddy, const float* __restrict__ z, int ldz, const float* __restrict__ stats,
+    const float* __restrict__ w, float* __restrict__ dz, int lddz, float* __restrict__ dx, int lddx, float* __restrict__ dw,
+    float* __restrict__ db, int rows, int D, int rows_per_block, DropSpec drop) {
+  __shared__ float s_dw[kWarpsPerBlock][32 * MAXV];
+  __shared__ float s_db[kWarpsPerBlock][32 * MAXV];
+  int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float aw[MAXV], ab[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) aw[i] = ab[i] = 0.f;
+  int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int row = r0 + wid; row < r1; row += kWarpsPerBlock) {
+    float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float g[MAXV], xh[MAXV];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane + 32 * i;
+      g[i] = xh[i] = 0.f;
+      if (c < D) {
+        float d = dy[(size_t)row * lddy + c];
+        xh[i] = (z[(size_t)row * ldz + c] - mean) * rstd;
+        g[i] = d * w[c];
+        aw[i] += d * xh[i]; ab[i] += d;
+        sg += g[i]; sgx += g[i] * xh[i];
+      }
+    }
+    sg = warp_sum(sg) / D; sgx = warp_sum(sgx) / D;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane + 32 * i;
+      if (c < D) {
+        float t = rstd * (g[i] - sg - xh[i] * sgx);
+        if (dz) dz[(size_t)row * lddz + c] = t;
+        if (dx) dx[(size_t)row * lddx + c] = t * drop_factor(drop, (unsigned long long)row * D + c);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { s_dw[wid][lane + 32 * i] = aw[i]; s_db[wid][lane + 32 * i] = ab[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWarpsPerBlock; ++k) { tw += s_dw[k][c]; tb += s_db[k][c]; }
+    atomicAdd(&dw[c], tw); atomicAdd(&db[c], tb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Spatial softmax over H*W positions of one (frame, channel) row.  out[row] = (E[x_map], E[y_map]), x_map follows the
+// row index of the feature map, y_map the column index, both linspace(-1, 1).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lin_coord(int i, int n) { return n > 1 ? -1.0f + 2.0f * (float)i / (float)(n - 1) : -1.0f; }
+
+template <int MAXV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) spatial_softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                              int rows, int H, int W, float inv_temp) {
+  int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int P = H * W;
+  const float* xr = x + (size_t)row * P;
+  float v[MAXV];
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int p = lane + 32 * i;
+    v[i] = (p < P) ? xr[p] * inv_temp : -FLT_MAX;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float s = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int p = lane + 32 * i;
+    if (p < P) {
+      float e = expf(v[i] - mx);
+      s += e; sx += e * lin_coord(p / W, H); sy += e * lin_coord(p % W, W);
+    }
+  }
+  s = warp_sum(s); sx = warp_sum(sx); sy = warp_sum(sy);
+  if (lane == 0) { out[2 * (size_t)row] = sx / s; out[2 * (size_t)row + 1] = sy / s; }
+}
+
+// dx_p = a_p * inv_temp * ((gx*xm_p + gy*ym_p) - (gx*ex + gy*ey)), optionally gated by x_p > 0 (the ReLU that produced x)
+template <int MAXV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) spatial_softmax_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                                                              float* __restrict__ dx, int rows, int H, int W, float inv_temp,
+                                                                              int relu_gate) {
+  int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int P = H * W;
+  const float* xr = x + (size_t)row * P;
+  float v[MAXV];
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int p = lane + 32 * i;
+    v[i] = (p < P) ? xr[p] * inv_temp : -FLT_MAX;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float gx = dout[2 * (size_t)row], gy = dout[2 * (size_t)row + 1];
+  float s = 0.f, sc = 0.f;
+  float e[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int p = lane + 32 * i;
+    e[i] = 0.f;
+    if (p < P) {
+      e[i] = expf(v[i] - mx);
+      s += e[i]; sc += e[i] * (gx * lin_coord(p / W, H) + gy * lin_coord(p % W, W));
+    }
+  }
+  s = warp_sum(s); sc = warp_sum(sc);
+  float inv_s = 1.f / s, mean_c = sc * inv_s;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int p = lane + 32 * i;
+    if (p < P) {
+      float c = gx * lin_coord(p / W, H) + gy * lin_coord(p % W, W);
+      float g = e[i] * inv_s * inv_temp * (c - mean_c);
+      if (relu_gate && !(v[i] > 0.f)) g = 0.f;
+      dx[(size_t)row * P + p] = g;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// y[b,s,:] = drop(x[b,s,:] + pos[s,:])   and the generic dropout re-application used by its backward
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void add_posemb_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ y, long long n, int S, int D,
+                                  DropSpec drop) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int d = (int)(i % D), s = (int)((i / D) % S);
+  y[i] = (x[i] + pos[(size_t)s * D + d]) * drop_factor(drop, (unsigned long long)i);
+}
+__global__ void dropout_apply_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, DropSpec drop) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * drop_factor(drop, (unsigned long long)i);
+}
+
+// dst[i0,i1,i2] (+)= alpha * src[i0,i1,i2] with arbitrary element strides (slices, transposes, broadcasts via stride 0)
+__global__ void strided_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int n0, int n1, int n2, long long d0, long long d1,
+                                    long long d2, long long s0, long long s1, long long s2, float alpha, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)n0 * n1 * n2;
+  if (i >= n) return;
+  int i2 = (int)(i % n2), i1 = (int)((i / n2) % n1), i0 = (int)(i / ((long long)n1 * n2));
+  float v = alpha * src[i0 * s0 + i1 * s1 + i2 * s2];
+  float* p = dst + i0 * d0 + i1 * d1 + i2 * d2;
+  *p = accumulate ? *p + v : v;
+}
+
+// out[b,d] = scale * sum_s x[b,s,d]   (x contiguous [B,S,D])
+__global__ void reduce_mid_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int S, int D, float scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  int b = i / D, d = i % D;
+  const float* p = x + (size_t)b * S * D + d;
+  float s = 0.f;
+  for (int t = 0; t < S; ++t) s += p[(size_t)t * D];
+  out[i] = s * scale;
+}
+
+// out[c] += sum_{n,p} x[n,c,p]  (NCHW bias gradient, accumulated); one block per (channel, chunk of n)
+__global__ void __launch_bounds__(256) nchw_channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C, int P, int n_per_block) {
+  __shared__ float red[32];
+  int c = blockIdx.x;
+  int n0 = blockIdx.y * n_per_block, n1 = min(N, n0 + n_per_block);
+  float s = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    const float* p = x + ((size_t)n * C + c) * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s += p[i];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(&out[c], s);
+}
+
+// torch.optim.Adam (no weight decay, no amsgrad): one launch over the flat parameter buffer
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                            float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float gi = g[i] * grad_scale;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+__global__ void scale_kernel(float* __restrict__ x, long long n, float alpha) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= alpha;
+}
+
+}  // namespace
+
+HULC_API int hulc_layernorm_fwd(const float* x, int ldx, const float* res, int ldres, const float* w, const float* b, float* y, int ldy,
+                                float* z, int ldz, float* stats, int rows, int D, float eps, float drop_p, unsigned long long drop_seed,
+                                unsigned drop_site, const unsigned char* drop_keep, void* stream) {
+  if (rows <= 0) return 0;
+  if (D > 128 || D <= 0) return (int)cudaErrorInvalidValue;
+  DropSpec d = make_drop(drop_p, drop_seed, drop_site, drop_keep);
+  dim3 grid(hulc_cdiv(rows, kWarpsPerBlock)), block(kWarpsPerBlock * 32);
+  HULC_LAUNCH(layernorm_fwd_kernel<4>, grid, block, 0, (cudaStream_t)stream, x, ldx, res, ldres, w, b, y, ldy, z, ldz, stats, rows, D, eps, d);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_layernorm_bwd(const float* dy, int lddy, const float* z, int ldz, const float* stats, const float* w, float* dz, int lddz,
+                                float* dx, int lddx, float* dw, float* db, int rows, int D, float drop_p, unsigned long long drop_seed,
+                                unsigned drop_site, const unsigned char* drop_keep, void* stream) {
+  if (rows <= 0) return 0;
+  if (D > 128 || D <= 0) return (int)cudaErrorInvalidValue;
+  DropSpec d = make_drop(drop_p, drop_seed, drop_site, drop_keep);
+  int nblk = min(2 * kNumSMs, hulc_cdiv(rows, kWarpsPerBlock));
+  int rpb = hulc_cdiv(rows, nblk);
+  nblk = hulc_cdiv(rows, rpb);
+  HULC_LAUNCH(layernorm_bwd_kernel<4>, dim3(nblk), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, dy, lddy, z, ldz, stats, w, dz, lddz, dx,
+              lddx, dw, db, rows, D, rpb, d);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_spatial_softmax_fwd(const float* x, float* out, int rows, int H, int W, float inv_temp, void* stream) {
+  if (rows <= 0) return 0;
+  if (H * W > 32 * 16) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(spatial_softmax_fwd_kernel<16>, dim3(hulc_cdiv(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, x, out, rows,
+              H, W, inv_temp);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_spatial_softmax_bwd(const float* x, const float* dout, float* dx, int rows, int H, int W, float inv_temp, int relu_gate,
+                                      void* stream) {
+  if (rows <= 0) return 0;
+  if (H * W > 32 * 16) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(spatial_softmax_bwd_kernel<16>, dim3(hulc_cdiv(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, x, dout, dx,
+              rows, H, W, inv_temp, relu_gate);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_add_posemb_fwd(const float* x, const float* pos, float* y, int B, int S, int D, float drop_p, unsigned long long drop_seed,
+                                 unsigned drop_site, const unsigned char* drop_keep, void* stream) {
+  long long n = (long long)B * S * D;
+  if (n <= 0) return 0;
+  HULC_LAUNCH(add_posemb_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, pos, y, n, S, D,
+              make_drop(drop_p, drop_seed, drop_site, drop_keep));
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_dropout_apply(const float* x, float* y, long long n, float drop_p, unsigned long long drop_seed, unsigned drop_site,
+                                const unsigned char* drop_keep, void* stream) {
+  if (n <= 0) return 0;
+  HULC_LAUNCH(dropout_apply_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n,
+              make_drop(drop_p, drop_seed, drop_site, drop_keep));
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_strided_copy(float* dst, const float* src, int n0, int n1, int n2, long long d0, long long d1, long long d2, long long s0,
+                               long long s1, long long s2, float alpha, int accumulate, void* stream) {
+  long long n = (long long)n0 * n1 * n2;
+  if (n <= 0) return 0;
+  HULC_LAUNCH(strided_copy_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, dst, src, n0, n1, n2, d0, d1, d2, s0, s1, s2, alpha,
+              accumulate);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_reduce_mid(const float* x, float* out, int B, int S, int D, float scale, void* stream) {
+  if (B * D <= 0) return 0;
+  HULC_LAUNCH(reduce_mid_kernel, dim3(hulc_cdiv((long long)B * D, 128)), dim3(128), 0, (cudaStream_t)stream, x, out, B, S, D, scale);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_nchw_channel_sum(const float* x, float* out, int N, int C, int P, void* stream) {
+  if (N <= 0 || C <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int gy = max(1, min(N, (4 * kNumSMs) / C));
+  int npb = hulc_cdiv(N, gy);
+  gy = hulc_cdiv(N, npb);
+  HULC_LAUNCH(nchw_channel_sum_kernel, dim3(C, gy), dim3(256), 0, st, x, out, N, C, P, npb);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, int step,
+                            float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  int blocks = (int)min((long long)kNumSMs * 8, (n + 255) / 256);
+  HULC_LAUNCH(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_scale(float* x, long long n, float alpha, void* stream) {
+  if (n <= 0) return 0;
+  HULC_LAUNCH(scale_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, n, alpha);
+  HULC_RETURN_LAST();
+}

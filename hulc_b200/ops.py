@@ -107,3 +107,246 @@ def colsum(X, out=None, beta=0.0):
         out = empty(cols, like=X)
     _L().hulc_colsum(_ptr(X), rows, cols, _rowmajor(X), _ptr(out), float(beta), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GRU gates
+# ----------------------------------------------------------------------------------------------------------------------
+def gru_gates_fwd(gi, gh, hprev, h, saved):
+    _chk(gi, gh, hprev, h, saved)
+    B, H = h.shape
+    _L().hulc_gru_gates_fwd(_ptr(gi), _rowmajor(gi), _ptr(gh), _rowmajor(gh), _ptr(hprev), _rowmajor(hprev) if hprev is not None else 0,
+                            _ptr(h), _rowmajor(h), _ptr(saved), B, H, _stream())
+
+
+def gru_gates_bwd(dh_above, dh_rec, saved, hprev, dgi, dgh, dh_carry):
+    _chk(dh_above, dh_rec, saved, hprev, dgi, dgh, dh_carry)
+    B, H = dh_carry.shape
+    ld = lambda t: _rowmajor(t) if t is not None else 0
+    _L().hulc_gru_gates_bwd(_ptr(dh_above), ld(dh_above), _ptr(dh_rec), ld(dh_rec), _ptr(saved), _ptr(hprev), ld(hprev), _ptr(dgi), ld(dgi),
+                            _ptr(dgh), ld(dgh), _ptr(dh_carry), ld(dh_carry), B, H, _stream())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# convolutions
+# ----------------------------------------------------------------------------------------------------------------------
+def _conv_out(n, k, s):
+    return (n - k) // s + 1
+
+
+def conv2d_fwd(x, w, b, stride, y=None, relu=True):
+    _chk(x, w, b, y)
+    assert x.is_contiguous() and w.is_contiguous()
+    N, CIN, H, W = x.shape
+    COUT, _, KS, _ = w.shape
+    if y is None:
+        y = empty(N, COUT, _conv_out(H, KS, stride), _conv_out(W, KS, stride), like=x)
+    assert y.is_contiguous()
+    ws = workspace(x.device)
+    _L().hulc_conv2d_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, CIN, H, W, COUT, KS, stride, int(relu), _ptr(ws), ws.numel() * 4, _stream())
+    return y
+
+
+def conv2d_dgrad(dy, w, x_shape, stride, gate=None, dx=None):
+    _chk(dy, w, gate, dx)
+    N, CIN, H, W = x_shape
+    COUT, _, KS, _ = w.shape
+    if dx is None:
+        dx = empty(N, CIN, H, W, like=dy)
+    assert dy.is_contiguous() and dx.is_contiguous() and (gate is None or gate.is_contiguous())
+    ws = workspace(dy.device)
+    _L().hulc_conv2d_dgrad(_ptr(dy), _ptr(w), _ptr(gate), _ptr(dx), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
+    return dx
+
+
+def conv2d_wgrad(x, dy, dw, stride, beta=0.0):
+    _chk(x, dy, dw)
+    N, CIN, H, W = x.shape
+    COUT, _, KS, _ = dw.shape
+    assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
+    ws = workspace(x.device)
+    _L().hulc_conv2d_wgrad(_ptr(x), _ptr(dy), _ptr(dw), float(beta), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
+    return dw
+
+
+def nchw_channel_sum(x, out):
+    _chk(x, out)
+    N, C = x.shape[:2]
+    P = x[0, 0].numel()
+    assert x.is_contiguous()
+    _L().hulc_nchw_channel_sum(_ptr(x), _ptr(out), N, C, P, _stream())
+    return out
+
+
+def spatial_softmax_fwd(x, out=None, temperature=1.0):
+    _chk(x, out)
+    N, C, H, W = x.shape
+    if out is None:
+        out = empty(N, 2 * C, like=x)
+    assert x.is_contiguous() and out.is_contiguous()
+    _L().hulc_spatial_softmax_fwd(_ptr(x), _ptr(out), N * C, H, W, 1.0 / float(temperature), _stream())
+    return out
+
+
+def spatial_softmax_bwd(x, dout, dx=None, temperature=1.0, relu_gate=True):
+    _chk(x, dout, dx)
+    N, C, H, W = x.shape
+    if dx is None:
+        dx = empty(N, C, H, W, like=x)
+    assert x.is_contiguous() and dout.is_contiguous() and dx.is_contiguous()
+    _L().hulc_spatial_softmax_bwd(_ptr(x), _ptr(dout), _ptr(dx), N * C, H, W, 1.0 / float(temperature), int(relu_gate), _stream())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# LayerNorm / transformer pieces
+# ----------------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, w, b, y, stats, res=None, z=None, eps=1e-5, drop: Drop = NO_DROP):
+    """y = LN(res + drop(x)) (res None: LN(x)); z receives the pre-norm sum when given; stats [rows,2]."""
+    _chk(x, w, b, y, stats, res, z)
+    rows, D = x.shape
+    ld = lambda t: _rowmajor(t) if t is not None else 0
+    _L().hulc_layernorm_fwd(_ptr(x), ld(x), _ptr(res), ld(res), _ptr(w), _ptr(b), _ptr(y), ld(y), _ptr(z), ld(z), _ptr(stats), rows, D, float(eps),
+                            *drop.args(), _stream())
+    return y
+
+
+def layernorm_bwd(dy, z, stats, w, dw, db, dz=None, dx=None, drop: Drop = NO_DROP):
+    """dz = dLN/dz (goes to the residual branch), dx = dz * dropout factor; dw, db are ACCUMULATED into."""
+    _chk(dy, z, stats, w, dw, db, dz, dx)
+    rows, D = dy.shape
+    ld = lambda t: _rowmajor(t) if t is not None else 0
+    _L().hulc_layernorm_bwd(_ptr(dy), ld(dy), _ptr(z), ld(z), _ptr(stats), _ptr(w), _ptr(dz), ld(dz), _ptr(dx), ld(dx), _ptr(dw), _ptr(db), rows, D,
+                            *drop.args(), _stream())
+
+
+def add_posemb_fwd(x, pos, y, drop: Drop = NO_DROP):
+    _chk(x, pos, y)
+    B, S, D = x.shape
+    assert x.is_contiguous() and y.is_contiguous() and pos.is_contiguous() and pos.shape[0] >= S
+    _L().hulc_add_posemb_fwd(_ptr(x), _ptr(pos), _ptr(y), B, S, D, *drop.args(), _stream())
+    return y
+
+
+def dropout_apply(x, y, drop: Drop):
+    _chk(x, y)
+    assert x.is_contiguous() and y.is_contiguous()
+    _L().hulc_dropout_apply(_ptr(x), _ptr(y), x.numel(), *drop.args(), _stream())
+    return y
+
+
+def attention_fwd(qkv, out, probs, B, S, H, drop: Drop = NO_DROP):
+    _chk(qkv, out, probs)
+    dh = qkv.shape[1] // (3 * H)
+    assert qkv.is_contiguous() and out.is_contiguous() and probs.is_contiguous()
+    _L().hulc_attention_fwd(_ptr(qkv), _ptr(out), _ptr(probs), B, S, H, dh, *drop.args(), _stream())
+    return out
+
+
+def attention_bwd(qkv, probs, dout, dqkv, B, S, H, drop: Drop = NO_DROP):
+    _chk(qkv, probs, dout, dqkv)
+    dh = qkv.shape[1] // (3 * H)
+    assert dout.is_contiguous() and dqkv.is_contiguous()
+    _L().hulc_attention_bwd(_ptr(qkv), _ptr(probs), _ptr(dout), _ptr(dqkv), B, S, H, dh, *drop.args(), _stream())
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# data movement
+# ----------------------------------------------------------------------------------------------------------------------
+def strided_copy(dst, src, alpha=1.0, accumulate=False):
+    """dst (+)= alpha * src for <=3-D views of fp32 storage (src may be an expanded/permuted view)."""
+    _chk(dst, src)
+    assert dst.shape == src.shape and dst.dim() <= 3
+    shape = [1] * (3 - dst.dim()) + list(dst.shape)
+    ds = [0] * (3 - dst.dim()) + list(dst.stride())
+    ss = [0] * (3 - src.dim()) + list(src.stride())
+    _L().hulc_strided_copy(_ptr(dst), _ptr(src), *shape, *ds, *ss, float(alpha), int(accumulate), _stream())
+    return dst
+
+
+def reduce_mid(x, out, scale=1.0):
+    _chk(x, out)
+    B, S, D = x.shape
+    assert x.is_contiguous() and out.is_contiguous()
+    _L().hulc_reduce_mid(_ptr(x), _ptr(out), B, S, D, float(scale), _stream())
+    return out
+
+
+def sum_to(x, out, scale=1.0):
+    _chk(x, out)
+    assert x.is_contiguous()
+    _L().hulc_sum(_ptr(x), x.numel(), _ptr(out), float(scale), _stream())
+    return out
+
+
+def scale_(x, alpha):
+    _chk(x)
+    assert x.is_contiguous()
+    _L().hulc_scale(_ptr(x), x.numel(), float(alpha), _stream())
+    return x
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------------------
+def world_to_tcp(actions, robot_obs, out, nan_flag):
+    _chk(actions, robot_obs, out)
+    _chk(nan_flag, dtype=torch.int32)
+    assert actions.is_contiguous() and robot_obs.is_contiguous() and actions.shape[-1] == 7
+    _L().hulc_world_to_tcp(_ptr(actions), _ptr(robot_obs), robot_obs.shape[-1], _ptr(out), actions.numel() // 7, _ptr(nan_flag), _stream())
+    return out
+
+
+def logistic_loss(heads, actions, dheads, losses, B, S, b0, Bm, *, time_major, n_dims, n_mix, num_classes, log_scale_min=-7.0, act_min=-1.0,
+                  act_max=1.0, has_gripper=True, gripper_alpha=1.0, grad_scale=1.0):
+    _chk(heads, actions, dheads, losses)
+    assert actions.is_contiguous() and _rowmajor(heads) == _rowmajor(dheads)
+    ws = workspace(heads.device)
+    _L().hulc_logistic_loss(_ptr(heads), _rowmajor(heads), _ptr(actions), actions.shape[-1], _ptr(dheads), _ptr(losses), B, S, b0, Bm,
+                            int(time_major), n_dims, n_mix, num_classes, float(log_scale_min), float(act_min), float(act_max), int(has_gripper),
+                            float(gripper_alpha), float(grad_scale), _ptr(ws), ws.numel() * 4, _stream())
+
+
+def plan_discrete_fwd(pr_logit, pp_logit, plan, kl_rows, *, u=None, idx_in=None, idx_out=None, class_size=32, seed=0, site=0):
+    _chk(pr_logit, pp_logit, plan, kl_rows, u)
+    _chk(idx_in, idx_out, dtype=torch.int32)
+    rows = pr_logit.numel() // class_size
+    _L().hulc_plan_discrete_fwd(_ptr(pr_logit), _ptr(pp_logit), _ptr(u), _ptr(idx_in), _ptr(plan), _ptr(idx_out), _ptr(kl_rows), rows, class_size,
+                                int(seed), int(site), _stream())
+
+
+def plan_discrete_bwd(pr_logit, pp_logit, dplan, d_pr, d_pp, coef_lhs, coef_rhs, class_size=32, dkl=None):
+    _chk(pr_logit, pp_logit, dplan, d_pr, d_pp, dkl)
+    rows = pr_logit.numel() // class_size
+    _L().hulc_plan_discrete_bwd(_ptr(pr_logit), _ptr(pp_logit), _ptr(dplan), _ptr(dkl), float(coef_lhs), float(coef_rhs), _ptr(d_pr), _ptr(d_pp),
+                                rows, class_size, _stream())
+
+
+def plan_cont_fwd(pr_state, pp_state, plan, kl_elem, *, eps=None, seed=0, site=0):
+    _chk(pr_state, pp_state, plan, kl_elem, eps)
+    Bn, P = plan.shape
+    _L().hulc_plan_cont_fwd(_ptr(pr_state), _ptr(pp_state), _ptr(eps), _ptr(plan), _ptr(kl_elem), Bn, P, int(seed), int(site), _stream())
+
+
+def plan_cont_bwd(pr_state, pp_state, dplan, d_pr, d_pp, coef_lhs, coef_rhs, *, eps=None, seed=0, site=0, dkl=None):
+    _chk(pr_state, pp_state, dplan, d_pr, d_pp, eps, dkl)
+    Bn, P2 = pr_state.shape
+    _L().hulc_plan_cont_bwd(_ptr(pr_state), _ptr(pp_state), _ptr(eps), _ptr(dplan), _ptr(dkl), float(coef_lhs), float(coef_rhs), _ptr(d_pr),
+                            _ptr(d_pp), Bn, P2 // 2, int(seed), int(site), _stream())
+
+
+def clip_loss(im, tx, logit_scale, mask, loss, d_im, d_tx, d_logit_scale, grad_scale=1.0):
+    _chk(im, tx, logit_scale, loss, d_im, d_tx, d_logit_scale)
+    _chk(mask, dtype=torch.uint8)
+    n, D = im.shape
+    assert im.is_contiguous() and tx.is_contiguous() and d_im.is_contiguous() and d_tx.is_contiguous()
+    _L().hulc_clip_loss(_ptr(im), _ptr(tx), _ptr(logit_scale), _ptr(mask), _ptr(loss), _ptr(d_im), _ptr(d_tx), _ptr(d_logit_scale), n, D,
+                        float(grad_scale), _stream())
+
+
+def adam_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, grad_scale=1.0):
+    _chk(p, g, m, v)
+    assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    _L().hulc_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                        float(grad_scale), _stream())

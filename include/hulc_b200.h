@@ -38,6 +38,114 @@ int hulc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int
 /* out[c] = beta*out[c] + sum_r X[r*ldx + c]  (bias gradients). */
 int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, void* stream);
 
+/* activation / gate selectors for hulc_gemm's `act` argument */
+#define HULC_ACT_NONE 0
+#define HULC_ACT_RELU 1
+#define HULC_ACT_TANH 2
+#define HULC_GATE_TANH 4 /* OR-ed in: `gate` holds tanh outputs, C *= 1 - gate^2 (default: C = gate > 0 ? C : 0) */
+
+/* ---- GRU gate math ---------------------------------------------------------------------------------------------------
+ * torch.nn.GRU built at decoders/utils/rnn.py:27-36 (gate order r|z|n).  gi = x W_ih^T + b_ih, gh = h_prev W_hh^T + b_hh
+ * (both [B,3H], produced by hulc_gemm); fwd writes h and saved[B,4H] = r|z|n|gh_n; bwd takes dh = dh_above + dh_rec and
+ * writes dgi, dgh and dh_carry = dh*z (the caller adds dgh W_hh). */
+int hulc_gru_gates_fwd(const float* gi, int ldgi, const float* gh, int ldgh, const float* hprev, int ldhp, float* h, int ldh,
+                       float* saved, int B, int H, void* stream);
+int hulc_gru_gates_bwd(const float* dh_above, int lda, const float* dh_rec, int ldr, const float* saved, const float* hprev,
+                       int ldhp, float* dgi, int ldgi, float* dgh, int ldgh, float* dh_carry, int ldc, int B, int H, void* stream);
+
+/* ---- convolutions of the perceptual encoders -------------------------------------------------------------------------
+ * perceptual_encoders/vision_network.py:36-47 and vision_network_gripper.py:11-17: nn.Conv2d (valid, NCHW) + ReLU for
+ * the three layer shapes (3->32 k8 s4, 32->64 k4 s2, 64->64 k3 s1).  x [N,CIN,H,W], w [COUT,CIN,KS,KS], y [N,COUT,HO,WO].
+ * dgrad gates dx by (gate > 0) when gate != NULL (the ReLU output that fed this conv); wgrad: dw = beta*dw + grad. */
+int hulc_conv2d_fwd(const float* x, const float* w, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                    int relu, float* workspace, size_t workspace_bytes, void* stream);
+int hulc_conv2d_dgrad(const float* dy, const float* w, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int KS,
+                      int S, float* workspace, size_t workspace_bytes, void* stream);
+int hulc_conv2d_wgrad(const float* x, const float* dy, float* dw, float beta, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                      float* workspace, size_t workspace_bytes, void* stream);
+/* out[c] += sum_{n,p} x[n,c,p] (conv bias gradient; accumulates like the other parameter-gradient outputs) */
+int hulc_nchw_channel_sum(const float* x, float* out, int N, int C, int P, void* stream);
+
+/* ---- SpatialSoftmax (vision_network.py:74-108) ------------------------------------------------------------------------
+ * rows = N*C feature maps of H*W; out[row] = (E[x_map], E[y_map]) interleaved, i.e. the (N, 2C) tensor of the reference.
+ * bwd with relu_gate=1 also applies the mask of the ReLU that produced x (x > 0). */
+int hulc_spatial_softmax_fwd(const float* x, float* out, int rows, int H, int W, float inv_temp, void* stream);
+int hulc_spatial_softmax_bwd(const float* x, const float* dout, float* dx, int rows, int H, int W, float inv_temp, int relu_gate,
+                             void* stream);
+
+/* ---- LayerNorm (+ residual + dropout) ----------------------------------------------------------------------------------
+ * nn.LayerNorm at vision_network.py:53, goal_encoders.py:29, and the post-norm residual blocks of
+ * nn.TransformerEncoderLayer (plan_recognition_net.py:83-85): z = res + dropout(x) (z = x when res == NULL),
+ * y = (z - mean) * rstd * w + b; stats[row] = (mean, rstd).  bwd: dz (to the residual), dx = dz*dropout, dw/db ACCUMULATE. */
+int hulc_layernorm_fwd(const float* x, int ldx, const float* res, int ldres, const float* w, const float* b, float* y, int ldy,
+                       float* z, int ldz, float* stats, int rows, int D, float eps, float drop_p, unsigned long long drop_seed,
+                       unsigned drop_site, const unsigned char* drop_keep, void* stream);
+int hulc_layernorm_bwd(const float* dy, int lddy, const float* z, int ldz, const float* stats, const float* w, float* dz, int lddz,
+                       float* dx, int lddx, float* dw, float* db, int rows, int D, float drop_p, unsigned long long drop_seed,
+                       unsigned drop_site, const unsigned char* drop_keep, void* stream);
+
+/* ---- posterior transformer pieces (plan_encoders/plan_recognition_net.py:94-117) ----------------------------------------
+ * add_posemb: y[b,s,:] = dropout(x[b,s,:] + pos[s,:]) (:101-111).  attention: packed qkv [B*S, 3*H*dh] batch-first,
+ * softmax(q k^T / sqrt(dh)) with dropout on the probabilities, out [B*S, H*dh]; probs [B,H,S,S] saved for bwd. */
+int hulc_add_posemb_fwd(const float* x, const float* pos, float* y, int B, int S, int D, float drop_p, unsigned long long drop_seed,
+                        unsigned drop_site, const unsigned char* drop_keep, void* stream);
+int hulc_dropout_apply(const float* x, float* y, long long n, float drop_p, unsigned long long drop_seed, unsigned drop_site,
+                       const unsigned char* drop_keep, void* stream);
+int hulc_attention_fwd(const float* qkv, float* out, float* probs, int B, int S, int H, int dh, float drop_p,
+                       unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, void* stream);
+int hulc_attention_bwd(const float* qkv, const float* probs, const float* dout, float* dqkv, int B, int S, int H, int dh,
+                       float drop_p, unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, void* stream);
+
+/* ---- data movement helpers -------------------------------------------------------------------------------------------------
+ * strided_copy: dst[i0,i1,i2] (+)= alpha*src[i0,i1,i2] with element strides (torch slicing / permute / expand at
+ * logistic_decoder_rnn.py:267-272, concat_encoders.py:103-107); reduce_mid: out[b,d] = scale*sum_s x[b,s,d] (the mean over
+ * time at plan_recognition_net.py:114); sum: out[0] = scale*sum x; scale: x *= alpha. */
+int hulc_strided_copy(float* dst, const float* src, int n0, int n1, int n2, long long d0, long long d1, long long d2, long long s0,
+                      long long s1, long long s2, float alpha, int accumulate, void* stream);
+int hulc_reduce_mid(const float* x, float* out, int B, int S, int D, float scale, void* stream);
+int hulc_sum(const float* x, int n, float* out, float scale, void* stream);
+int hulc_scale(float* x, long long n, float alpha, void* stream);
+
+/* ---- world_to_tcp_frame (decoders/utils/gripper_control.py:16-36) ----------------------------------------------------------
+ * actions [n,7], robot_obs [n,obs_dim] (euler XYZ at 3:6) -> out [n,7].  *nan_flag is OR-ed with 1 if any output is NaN
+ * (the reference asserts on the host, :35; the flag is checked without stalling the stream). */
+int hulc_world_to_tcp(const float* actions, const float* robot_obs, int obs_dim, float* out, int n_tokens, int* nan_flag, void* stream);
+
+/* ---- discretised logistic mixture NLL + gripper CE (decoders/logistic_decoder_rnn.py:136-155,184-231) ---------------------
+ * heads rows: [logit_probs n_dims*n_mix | means | raw log_scales | gripper 2]; B sequences of S tokens, row = b*S+t or
+ * t*B+b (time_major); the loss covers sequences [b0,b0+Bm).  losses[0] = NLL, losses[1] = CE (means over Bm*S tokens);
+ * dheads = grad_scale * d(losses[0] + gripper_alpha*losses[1])/d heads, written in the same pass. */
+int hulc_logistic_loss(const float* heads, int ldh, const float* actions, int act_dim, float* dheads, float* losses, int B, int S,
+                       int b0, int Bm, int time_major, int n_dims, int n_mix, int num_classes, float log_scale_min, float act_min,
+                       float act_max, int has_gripper, float gripper_alpha, float grad_scale, float* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- latent plan: sample + KL (hulc/utils/distributions.py:23-60, hulc/models/hulc.py:289-291,539-561) ---------------------
+ * discrete: rows = batch*category_size rows of class_size (=32) logits; the sample index is idx_in[row] if given, else the
+ * inverse CDF of u[row], else of Philox(seed, site, row); plan = one-hot (straight-through: the bwd adds the softmax
+ * Jacobian); kl_rows[row] = KL(post || prior) of that category.  bwd: d_pr = ST(dplan) + dkl*coef_rhs*dKL/dpost,
+ * d_pp = dkl*coef_lhs*dKL/dprior (dkl == NULL -> 1).  continuous: state = [mean | raw_std], plan = mean + std*eps. */
+int hulc_plan_discrete_fwd(const float* pr_logit, const float* pp_logit, const float* u, const int* idx_in, float* plan, int* idx_out,
+                           float* kl_rows, int rows, int class_size, unsigned long long seed, unsigned site, void* stream);
+int hulc_plan_discrete_bwd(const float* pr_logit, const float* pp_logit, const float* dplan, const float* dkl, float coef_lhs,
+                           float coef_rhs, float* d_pr, float* d_pp, int rows, int class_size, void* stream);
+int hulc_plan_cont_fwd(const float* pr_state, const float* pp_state, const float* eps, float* plan, float* kl_elem, int batch,
+                       int plan_features, unsigned long long seed, unsigned site, void* stream);
+int hulc_plan_cont_bwd(const float* pr_state, const float* pp_state, const float* eps, const float* dplan, const float* dkl,
+                       float coef_lhs, float coef_rhs, float* d_pr, float* d_pp, int batch, int plan_features,
+                       unsigned long long seed, unsigned site, void* stream);
+
+/* ---- CLIP-style auxiliary loss (hulc/models/hulc.py:650-695) on the ProjVisLang outputs --------------------------------------
+ * im, tx [n,D]; rows with mask[i]==0 are left out (all masked -> loss 0, zero grads, :669-676).  Writes the loss and
+ * grad_scale * its gradients w.r.t. im, tx and logit_scale. */
+int hulc_clip_loss(const float* im, const float* tx, const float* logit_scale, const unsigned char* mask, float* loss, float* d_im,
+                   float* d_tx, float* d_logit_scale, int n, int D, float grad_scale, void* stream);
+
+/* ---- optimizer: torch.optim.Adam(lr, betas, eps), no weight decay (hulc/models/hulc.py:239-252) over a flat buffer ---------
+ * g is multiplied by grad_scale first (1/world after the all-reduce); `step` is the 1-based step count. */
+int hulc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, int step,
+                   float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,4 +17,5 @@ def pytest_configure(config):
 def golden_dir():
     return ROOT / "tests" / "golden"
 
+sys.path.insert(0, str(ROOT / "tests"))
 from emu_fixture import emu, emu_lib_path  # noqa: E402,F401
