@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — training sequences/sec of the HULC per-step hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+
+A step = forward + backward + (gradient all-reduce) + Adam over one synthetic batch of 32 vision + 32 language
+sequences of 32 frames per GPU (BASELINE config 2 shape, fp32).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "training sequences/sec (B=32, seq_len=32)"
+UNIT = "seq/s"
+B_PER_MODALITY, SEQ_LEN = 32, 32
+GFLOP_PER_SEQ = 13.03  # fwd+bwd, SURVEY.md §8(d) / BASELINE.md §3
+MB_PER_SEQ = 41.6      # mandatory HBM bytes per sequence, ibid.
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_step_fn(B, S, threads):
+    """The oracle (CPU restatement of the reference, oracle/hulc_oracle.py) as a training step: forward + autograd
+    backward + torch.optim.Adam, fp32 — BASELINE.md §4's CPU-baseline recipe."""
+    import torch
+
+    from hulc_b200.utils import synthetic
+    from oracle import hulc_oracle as O
+
+    torch.set_num_threads(threads)
+    sd = {k: v.requires_grad_(True) for k, v in synthetic.make_state_dict("hulc").items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=2e-4)
+    batch = synthetic.make_batch(B, S, seed=1)
+    noise = {m: synthetic.plan_noise(B, S, m) for m in batch}
+    masks = {m: synthetic.dropout_masks(B, S, m, 0.1) for m in batch}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = O.training_step(sd, batch, dropout_p=0.1, plan_u={m: noise[m]["u"] for m in batch}, dropout_masks=masks)
+        out["total_loss"].backward()
+        opt.step()
+        return float(out["total_loss"].detach())
+
+    return step
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's algorithm on the host cores.  The reference is pure Python/PyTorch and is not
+    present on the GPU box, so this arm times the oracle port with every host thread (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    Bs = 8  # bounded sample: 8 + 8 sequences of 32 frames per step (the workload has 32 + 32)
+    step = oracle_step_fn(Bs, SEQ_LEN, cores)
+    for _ in range(max(1, args.warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = 2 * Bs / dt
+    sample = f"{Bs}+{Bs} sequences x {SEQ_LEN} frames per step (1/4 of the workload's batch), fwd+bwd+Adam, fp32, torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "HULC full model, batch=32+32 seq_len=32, 200x200+84x84 RGB, fp32 (BASELINE config 2)", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
+    """Time the conv kernels of the static-camera encoder (the bulk of the step's FLOPs) one by one with CUDA events on
+    the launching stream and report the roofline of the one that takes the largest share of the step."""
+    from hulc_b200 import ops
+
+    P = eng.ps.p
+    pre = "perceptual_encoder.rgb_static_encoder"
+    x = batch["vis"]["rgb_obs"]["rgb_static"].flatten(0, 1)  # one modality: 1024 frames
+    n_mod = len(batch)
+    a1, a2, a3 = eng._bufs["static.a1"], eng._bufs["static.a2"], eng._bufs["static.a3"]
+    da1, da2, da3 = eng._bufs["static.da1"], eng._bufs["static.da2"], eng._bufs["static.da3"]
+    n1 = x.shape[0]
+    scratch = torch.empty_like(P[f"{pre}.conv_model.2.weight"])
+    scratch0 = torch.empty_like(P[f"{pre}.conv_model.0.weight"])
+    scratch4 = torch.empty_like(P[f"{pre}.conv_model.4.weight"])
+    mac = lambda n, co, ho, k: 2.0 * n * co * ho * ho * k  # flops
+    N = a1.shape[0]
+    cands = {
+        "conv1_fwd": (lambda: ops.conv2d_fwd(x, P[f"{pre}.conv_model.0.weight"], P[f"{pre}.conv_model.0.bias"], 4, a1[:n1]), mac(n1, 32, 49, 192), n_mod),
+        "conv2_fwd": (lambda: ops.conv2d_fwd(a1, P[f"{pre}.conv_model.2.weight"], P[f"{pre}.conv_model.2.bias"], 2, a2), mac(N, 64, 23, 512), 1),
+        "conv3_fwd": (lambda: ops.conv2d_fwd(a2, P[f"{pre}.conv_model.4.weight"], P[f"{pre}.conv_model.4.bias"], 1, a3), mac(N, 64, 21, 576), 1),
+        "conv3_dgrad": (lambda: ops.conv2d_dgrad(da3, P[f"{pre}.conv_model.4.weight"], a2.shape, 1, gate=a2, dx=da2), mac(N, 64, 21, 576), 1),
+        "conv2_dgrad": (lambda: ops.conv2d_dgrad(da2, P[f"{pre}.conv_model.2.weight"], a1.shape, 2, gate=a1, dx=da1), mac(N, 64, 23, 512), 1),
+        "conv3_wgrad": (lambda: ops.conv2d_wgrad(a2, da3, scratch4, 1), mac(N, 64, 21, 576), 1),
+        "conv2_wgrad": (lambda: ops.conv2d_wgrad(a1, da2, scratch, 2), mac(N, 64, 23, 512), 1),
+        "conv1_wgrad": (lambda: ops.conv2d_wgrad(x, da1[:n1], scratch0, 4), mac(n1, 32, 49, 192), n_mod),
+    }
+    res = {}
+    for name, (fn, flops, per_step) in cands.items():
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 5
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = dict(ms=ms, flops=flops, per_step=per_step, share=ms * per_step / step_ms)
+    top = max(res, key=lambda k: res[k]["ms"] * res[k]["per_step"])
+    r = res[top]
+    achieved = r["flops"] / (r["ms"] * 1e-3) / 1e12
+    return {
+        "bound": "tensor", "kernel": top, "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
+        "traffic": None, "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); this kernel is exact-fp32 on CUDA cores",
+        "ms_per_launch": r["ms"], "share_of_step": r["share"],
+        "kernels": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "share_of_step": round(v["share"], 4)} for k, v in res.items()},
+        "step": {"tensor_frac": None, "hbm_frac": None},
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from hulc_b200 import ops
+    from hulc_b200.models.hulc import Hulc
+    from hulc_b200.utils import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hulc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+
+    cfg = synthetic.model_config("hulc", target_root="hulc_b200")
+    cfg.pop("_target_"); cfg.pop("_recursive_")
+    model = Hulc(**cfg, device=dev)
+    model.load_state_dict(synthetic.make_state_dict("hulc"), strict=False)  # identical weights on every rank
+    eng = model.engine
+    opt = model.configure_optimizers()["optimizer"]
+
+    host = synthetic.make_batch(B_PER_MODALITY, SEQ_LEN, seed=1 + rank)  # per-rank data (weak scaling)
+    batch = synthetic._to(host, dev)
+
+    def allreduce_and_adam():
+        if world > 1:
+            dist.all_reduce(eng.ps.grad)  # the one per-step collective: 188 MB fp32 gradient over NVLink
+        eng.ps.adam_step(lr=eng.lr, grad_scale=1.0 / world)
+
+    def step(i, b):
+        out = eng.step(b, seed=i)
+        allreduce_and_adam()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------------------------------
+    for i in range(max(3, args.warmup)):
+        step(i, batch)
+    barrier()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            out = step(100 + i, batch)
+        e1.record()
+        barrier()
+    launches = ops.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    seqs = 2 * B_PER_MODALITY * world
+    value = seqs / (ms * 1e-3)
+    eng.check_nan_flag()
+    loss = float(out["total_loss"].item())
+
+    # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, through the public model API ---------------------------
+    def pin(d):
+        if isinstance(d, dict):
+            return {k: pin(v) for k, v in d.items()}
+        return d.pin_memory() if torch.is_tensor(d) else d
+
+    def tensors(d):
+        for v in d.values():
+            if isinstance(v, dict):
+                yield from tensors(v)
+            elif torch.is_tensor(v):
+                yield v
+
+    hostp = pin(host)
+    h2d_bytes = sum(t_.numel() * t_.element_size() for t_ in tensors(hostp))
+    copy_stream = torch.cuda.Stream()
+    stage = [synthetic._to(host, dev), synthetic._to(host, dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for dst, src in zip(tensors(stage[slot]), tensors(hostp)):
+                dst.copy_(src, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n):
+        losses = []
+        upload(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                upload(slot ^ 1)  # next step's inputs stream in while this step computes
+            torch.cuda.current_stream().wait_event(ready[slot])
+            loss_t = model.training_step(stage[slot], i, seed=1000 + i)
+            consumed[slot].record()
+            allreduce_and_adam()
+            losses.append(loss_t.item())  # device -> host read of the step's result
+        return losses
+
+    for ev in consumed:
+        ev.record()
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        e2e_loop(args.steps)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = seqs / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        roof = dominant_kernel_roofline(torch, eng, batch, peaks, ms)
+        per_gpu = value / world
+        roof["step"] = {
+            "tensor_frac": per_gpu * GFLOP_PER_SEQ * 1e9 / (peaks["tf_sustained"] * 1e12),
+            "hbm_frac": per_gpu * MB_PER_SEQ * 1e6 / (peaks["hbm"] * 1e9),
+            "note": "whole step vs SURVEY.md §8(d) bounds: 13.03 GFLOP and 41.6 MB per sequence; sustained bf16 peak",
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            Bs = 8
+            ostep = oracle_step_fn(Bs, SEQ_LEN, cores)
+            ostep()
+            t0 = time.perf_counter()
+            n = 2
+            for _ in range(n):
+                ostep()
+            dt = (time.perf_counter() - t0) / n
+            cpu = {"value": 2 * Bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{Bs}+{Bs} sequences x {SEQ_LEN} frames, fwd+bwd+Adam fp32, 1 warm-up + {n} timed steps of the oracle (torch CPU, {cores} threads)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "HULC full model, batch=32 vis + 32 lang sequences per GPU, seq_len=32, 200x200 + 84x84 RGB fp32 frames, 384-d lang emb (BASELINE config 2), fwd+bwd+Adam",
+                       "parallelism": f"dp{world}", "l2": "per-step inputs are 1.16 GB per GPU (> 126 MB L2); no explicit flush", "dropout_p": 0.1},
+            "clocks": clk.summary(), "gpu_launches": launches, "launches_per_step": launches / args.steps, "loss": loss,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "api": "hulc_b200.models.hulc.Hulc.training_step + fused Adam; double-buffered pinned-host uploads on a copy stream"},
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
-#define HULC_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define HULC_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (++g_hulc_launches, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define HULC_DYN_SMEM(T, name)                              \
   extern __shared__ __align__(16) unsigned char _dyn_smem[]; \
   T* name = reinterpret_cast<T*>(_dyn_smem)
@@ -15,6 +16,9 @@
 
 #include <cfloat>
 #include <cmath>
+
+// number of kernel launches issued through this library since load (read by hulc_launch_count; bench.py reports it)
+extern unsigned long long g_hulc_launches;
 
 #define HULC_API extern "C" __attribute__((visibility("default")))
 

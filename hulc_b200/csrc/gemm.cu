@@ -313,6 +313,14 @@ __global__ void scale_vec_kernel(float* x, int n, float s) {
 
 }  // namespace
 
+unsigned long long g_hulc_launches = 0;
+
+HULC_API int hulc_launch_count(unsigned long long* out) {
+  if (!out) return (int)cudaErrorInvalidValue;
+  *out = g_hulc_launches;
+  return 0;
+}
+
 // See include/hulc_b200.h for the contract.
 HULC_API int hulc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA,
                        int transB, float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act,

@@ -51,19 +51,22 @@ class ParamStore:
         self.grad = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
-        self.p = {k: self._view(self.flat, k) for k in spec}
-        self.g = {k: self._view(self.grad, k) for k in spec}
         self.keys = list(spec)
         self.step_count = 0
-        # fused views over the head group
-        if head_w:
-            o, (n_out, n_in) = self.offsets[head_w[0]]
-            rows = sum(spec[k][0] for k in head_w)
+        self._head_w, self._head_b = head_w, head_b
+        self.rebuild_views()
+
+    def rebuild_views(self):
+        """(Re)create the named views after the flat buffers were allocated or moved to another device."""
+        self.p = {k: self._view(self.flat, k) for k in self.keys}
+        self.g = {k: self._view(self.grad, k) for k in self.keys}
+        if self._head_w:  # fused views over the decoder-head group
+            o, (_, n_in) = self.offsets[self._head_w[0]]
+            rows = sum(self.offsets[k][1][0] for k in self._head_w)
             self.heads_w = self.flat[o : o + rows * n_in].view(rows, n_in)
             self.heads_gw = self.grad[o : o + rows * n_in].view(rows, n_in)
-            ob, _ = self.offsets[head_b[0]]
-            self.heads_b = self.flat[ob : ob + rows]
-            self.heads_gb = self.grad[ob : ob + rows]
+            ob, _ = self.offsets[self._head_b[0]]
+            self.heads_b, self.heads_gb = self.flat[ob : ob + rows], self.grad[ob : ob + rows]
 
     def _view(self, flat, k):
         off, shape = self.offsets[k]

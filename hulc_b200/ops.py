@@ -100,6 +100,15 @@ def gemm(A, B, C=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=
     return C
 
 
+def launch_count() -> int:
+    """Kernel launches issued by libhulc_b200.so since it was loaded."""
+    import ctypes
+
+    n = ctypes.c_ulonglong(0)
+    _L().hulc_launch_count(ctypes.addressof(n))
+    return int(n.value)
+
+
 def colsum(X, out=None, beta=0.0):
     _chk(X, out)
     rows, cols = X.shape

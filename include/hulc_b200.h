@@ -35,6 +35,9 @@ int hulc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int
               const float* gate, int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site,
               const unsigned char* drop_keep, float* workspace, size_t workspace_bytes, void* stream);
 
+/* *out (HOST pointer) = number of kernel launches this library has issued since it was loaded (bench.py's gpu_launches). */
+int hulc_launch_count(unsigned long long* out);
+
 /* out[c] = beta*out[c] + sum_r X[r*ldx + c]  (bias gradients). */
 int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, void* stream);
 

@@ -18,4 +18,4 @@ def golden_dir():
     return ROOT / "tests" / "golden"
 
 sys.path.insert(0, str(ROOT / "tests"))
-from emu_fixture import emu, emu_lib_path  # noqa: E402,F401
+from emu_fixture import K, emu, emu_lib_path  # noqa: E402,F401

@@ -1,4 +1,4 @@
-"""SGEMM kernel source run on the host SIMT emulator vs torch (CPU).  Development aid; GPU parity is in test_gpu_*.py."""
+"""hulc_gemm / hulc_colsum against torch: on the host SIMT emulator (CPU suite) and on the B200 (`-m gpu`), via `K`."""
 import pytest
 import torch
 
@@ -38,55 +38,56 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("M,N,K,tA,tB", CASES)
-def test_gemm_plain(emu, M, N, K, tA, tB):
-    g = torch.Generator().manual_seed(M * 131 + N * 7 + K)
-    A = torch.randn((K, M) if tA else (M, K), generator=g)
-    B = torch.randn((N, K) if tB else (K, N), generator=g)
-    C = emu.gemm(A, B, transA=tA, transB=tB)
+@pytest.mark.parametrize("M,N,Kd,tA,tB", CASES)
+def test_gemm_plain(K, M, N, Kd, tA, tB):
+    g = torch.Generator().manual_seed(M * 131 + N * 7 + Kd)
+    A = torch.randn((Kd, M) if tA else (M, Kd), generator=g)
+    B = torch.randn((N, Kd) if tB else (Kd, N), generator=g)
+    C = K.gemm(A, B, transA=tA, transB=tB)
     ref = ref_gemm(A, B, tA, tB, 1.0, 0.0, None, None, None, 0, 0, None, None, 0)
-    torch.testing.assert_close(C, ref, rtol=1e-4, atol=1e-4 * K**0.5)
+    torch.testing.assert_close(C, ref, rtol=1e-4, atol=1e-4 * Kd**0.5)
 
 
-def test_gemm_epilogue_and_strides(emu):
+def test_gemm_epilogue_and_strides(K):
     g = torch.Generator().manual_seed(5)
-    M, N, K = 96, 72, 200
-    Abig = torch.randn(M, K + 24, generator=g)
-    A = Abig[:, 8 : 8 + K]  # unaligned-by-row view with a leading dimension
-    B = torch.randn(N, K, generator=g)
+    M, N, Kd = 96, 72, 200
+    Abig = torch.randn(M, Kd + 24, generator=g)
+    A = Abig[:, 8 : 8 + Kd]  # unaligned-by-row view with a leading dimension
+    B = torch.randn(N, Kd, generator=g)
     Cbig = torch.randn(M, N + 8, generator=g)
+    Cpad = Cbig.clone()
     C = Cbig[:, 4 : 4 + N]
     C0 = C.clone()
     bias = torch.randn(N, generator=g)
     addend = torch.randn(32, N, generator=g)
     gate = torch.randn(M, N, generator=g)
     keep = (torch.rand(M, N, generator=g) > 0.3).to(torch.uint8)
-    emu.gemm(A, B, C, transB=True, alpha=0.5, beta=2.0, bias=bias, addend=addend, add_mod=32, act=1, gate=gate,
-             drop=emu.Drop(0.3, keep=keep))
+    K.gemm(A, B, C, transB=True, alpha=0.5, beta=2.0, bias=bias, addend=addend, add_mod=32, act=1, gate=gate,
+             drop=K.Drop(0.3, keep=keep))
     ref = ref_gemm(A, B, False, True, 0.5, 2.0, C0, bias, addend, 32, 1, gate, keep, 0.3)
     torch.testing.assert_close(C, ref, rtol=1e-4, atol=1e-3)
     # padding columns of the strided output are untouched
-    assert torch.equal(Cbig[:, :4], Cbig[:, :4]) and Cbig.shape == (M, N + 8)
+    assert torch.equal(Cbig[:, :4], Cpad[:, :4]) and torch.equal(Cbig[:, 4 + N :], Cpad[:, 4 + N :])
 
 
-def test_gemm_philox_dropout_rate_and_determinism(emu):
+def test_gemm_philox_dropout_rate_and_determinism(K):
     A = torch.ones(128, 16)
     B = torch.ones(16, 256)
-    d = emu.Drop(0.25, seed=123, site=7)
-    C1 = emu.gemm(A, B, drop=d)
-    C2 = emu.gemm(A, B, drop=d)
+    d = K.Drop(0.25, seed=123, site=7)
+    C1 = K.gemm(A, B, drop=d)
+    C2 = K.gemm(A, B, drop=d)
     assert torch.equal(C1, C2)
     kept = (C1 != 0).float().mean().item()
     assert abs(kept - 0.75) < 0.02
     torch.testing.assert_close(C1[C1 != 0], torch.full_like(C1[C1 != 0], 16 / 0.75))
-    C3 = emu.gemm(A, B, drop=emu.Drop(0.25, seed=124, site=7))
+    C3 = K.gemm(A, B, drop=K.Drop(0.25, seed=124, site=7))
     assert not torch.equal(C1, C3)
 
 
-def test_colsum(emu):
+def test_colsum(K):
     X = torch.randn(5000, 70)
-    out = emu.colsum(X)
+    out = K.colsum(X)
     torch.testing.assert_close(out, X.sum(0), rtol=1e-4, atol=1e-3)
     out2 = torch.ones(70)
-    emu.colsum(X[:100], out2, beta=1.0)
+    K.colsum(X[:100], out2, beta=1.0)
     torch.testing.assert_close(out2, 1 + X[:100].sum(0), rtol=1e-4, atol=1e-4)

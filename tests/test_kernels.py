@@ -1,5 +1,6 @@
-"""Each kernel family of hulc_b200/csrc run on the host SIMT emulator against torch (CPU autograd for the backward
-kernels).  Development aid; the GPU parity tests are tests/test_gpu_*.py."""
+"""Each kernel family of hulc_b200/csrc against torch (CPU autograd for the backward kernels).  Every test body runs on both
+builds of the kernel sources through the `K` fixture: the host SIMT emulator (CPU suite) and the nvcc-built library on
+the B200 (`-m gpu`)."""
 import math
 
 import pytest
@@ -12,46 +13,46 @@ CONV_CASES = [(3, 32, 8, 4, 36, 2), (32, 64, 4, 2, 12, 3), (64, 64, 3, 1, 9, 2),
 
 
 @pytest.mark.parametrize("cin,cout,ks,st,hw,n", CONV_CASES)
-def test_conv_fwd_bwd(emu, cin, cout, ks, st, hw, n):
+def test_conv_fwd_bwd(K, cin, cout, ks, st, hw, n):
     g = torch.Generator().manual_seed(cin + hw)
     x = torch.randn(n, cin, hw, hw, generator=g).relu_()  # like a ReLU output: exercises the dgrad gate
     w = (torch.randn(cout, cin, ks, ks, generator=g) / math.sqrt(cin * ks * ks)).requires_grad_(True)
     b = torch.randn(cout, generator=g).requires_grad_(True)
     xr = x.clone().requires_grad_(True)
     ref = F.relu(F.conv2d(xr, w, b, stride=st))
-    y = emu.conv2d_fwd(x, w.detach(), b.detach(), st)
+    y = K.conv2d_fwd(x, w.detach(), b.detach(), st)
     torch.testing.assert_close(y, ref.detach(), rtol=1e-4, atol=1e-5)
     dy = torch.randn(ref.shape, generator=g) * (ref.detach() > 0)
     ref.backward(dy)
     dw = torch.zeros_like(w)
-    emu.conv2d_wgrad(x, dy, dw, st)
+    K.conv2d_wgrad(x, dy, dw, st)
     torch.testing.assert_close(dw, w.grad, rtol=1e-4, atol=1e-4)
-    emu.conv2d_wgrad(x, dy, dw, st, beta=1.0)
+    K.conv2d_wgrad(x, dy, dw, st, beta=1.0)
     torch.testing.assert_close(dw, 2 * w.grad, rtol=1e-4, atol=2e-4)
     db = torch.zeros(cout)
-    emu.nchw_channel_sum(dy, db)
+    K.nchw_channel_sum(dy, db)
     torch.testing.assert_close(db, b.grad, rtol=1e-4, atol=1e-4)
     if cin != 3:
-        dx = emu.conv2d_dgrad(dy, w.detach(), x.shape, st, gate=x)
+        dx = K.conv2d_dgrad(dy, w.detach(), x.shape, st, gate=x)
         torch.testing.assert_close(dx, xr.grad * (x > 0), rtol=1e-4, atol=1e-4)
-        dx2 = emu.conv2d_dgrad(dy, w.detach(), x.shape, st)
+        dx2 = K.conv2d_dgrad(dy, w.detach(), x.shape, st)
         torch.testing.assert_close(dx2, xr.grad, rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("h", [21, 5])
-def test_spatial_softmax(emu, h):
+def test_spatial_softmax(K, h):
     x = torch.randn(3, 4, h, h).relu_().requires_grad_(True)
     ref = O.spatial_softmax(x)
-    out = emu.spatial_softmax_fwd(x.detach())
+    out = K.spatial_softmax_fwd(x.detach())
     torch.testing.assert_close(out, ref.detach(), rtol=1e-5, atol=1e-6)
     dout = torch.randn_like(ref)
     ref.backward(dout)
-    dx = emu.spatial_softmax_bwd(x.detach(), dout, relu_gate=True)
+    dx = K.spatial_softmax_bwd(x.detach(), dout, relu_gate=True)
     torch.testing.assert_close(dx, x.grad * (x.detach() > 0), rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("D,rows", [(64, 37), (32, 5), (128, 70)])
-def test_layernorm_residual_dropout(emu, D, rows):
+def test_layernorm_residual_dropout(K, D, rows):
     g = torch.Generator().manual_seed(D)
     x = torch.randn(rows, D, generator=g, requires_grad=True)
     res = torch.randn(rows, D, generator=g, requires_grad=True)
@@ -60,25 +61,25 @@ def test_layernorm_residual_dropout(emu, D, rows):
     keep = (torch.rand(rows, D, generator=g) > 0.2)
     ref = F.layer_norm(res + x * keep / 0.8, (D,), w, b)
     y, z, st = torch.empty(rows, D), torch.empty(rows, D), torch.empty(rows, 2)
-    emu.layernorm_fwd(x.detach(), w.detach(), b.detach(), y, st, res=res.detach(), z=z, drop=emu.Drop(0.2, keep=keep.to(torch.uint8)))
+    K.layernorm_fwd(x.detach(), w.detach(), b.detach(), y, st, res=res.detach(), z=z, drop=K.Drop(0.2, keep=keep.to(torch.uint8)))
     torch.testing.assert_close(y, ref.detach(), rtol=1e-4, atol=1e-5)
     dy = torch.randn(rows, D, generator=g)
     ref.backward(dy)
     dz, dx, dw, db = torch.empty(rows, D), torch.empty(rows, D), torch.zeros(D), torch.zeros(D)
-    emu.layernorm_bwd(dy, z, st, w.detach(), dw, db, dz=dz, dx=dx, drop=emu.Drop(0.2, keep=keep.to(torch.uint8)))
+    K.layernorm_bwd(dy, z, st, w.detach(), dw, db, dz=dz, dx=dx, drop=K.Drop(0.2, keep=keep.to(torch.uint8)))
     torch.testing.assert_close(dz, res.grad, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(dx, x.grad, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(dw, w.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(db, b.grad, rtol=1e-4, atol=1e-4)
     # plain LN into a strided output view
     big = torch.zeros(rows, 2 * D)
-    emu.layernorm_fwd(x.detach(), w.detach(), b.detach(), big[:, D:], st)
+    K.layernorm_fwd(x.detach(), w.detach(), b.detach(), big[:, D:], st)
     torch.testing.assert_close(big[:, D:], F.layer_norm(x.detach(), (D,), w.detach(), b.detach()), rtol=1e-4, atol=1e-5)
     assert float(big[:, :D].abs().max()) == 0
 
 
 @pytest.mark.parametrize("B,S,H,dh,p", [(3, 8, 8, 16, 0.0), (2, 32, 8, 16, 0.1), (2, 5, 2, 4, 0.3)])
-def test_attention(emu, B, S, H, dh, p):
+def test_attention(K, B, S, H, dh, p):
     g = torch.Generator().manual_seed(S)
     D = H * dh
     qkv = torch.randn(B * S, 3 * D, generator=g, requires_grad=True)
@@ -86,52 +87,52 @@ def test_attention(emu, B, S, H, dh, p):
     q, k, v = [t.view(B, S, H, dh).transpose(1, 2) for t in qkv.split(D, -1)]
     a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1)
     ref = ((a * keep / (1 - p)) @ v).transpose(1, 2).reshape(B * S, D)
-    drop = emu.Drop(p, keep=keep.to(torch.uint8).contiguous()) if p > 0 else emu.NO_DROP
+    drop = K.Drop(p, keep=keep.to(torch.uint8).contiguous()) if p > 0 else K.NO_DROP
     out, probs = torch.empty(B * S, D), torch.empty(B, H, S, S)
-    emu.attention_fwd(qkv.detach(), out, probs, B, S, H, drop)
+    K.attention_fwd(qkv.detach(), out, probs, B, S, H, drop)
     torch.testing.assert_close(out, ref.detach(), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(probs, a.detach(), rtol=1e-4, atol=1e-6)
     dout = torch.randn(B * S, D, generator=g)
     ref.backward(dout)
     dqkv = torch.empty(B * S, 3 * D)
-    emu.attention_bwd(qkv.detach(), probs, dout, dqkv, B, S, H, drop)
+    K.attention_bwd(qkv.detach(), probs, dout, dqkv, B, S, H, drop)
     torch.testing.assert_close(dqkv, qkv.grad, rtol=1e-4, atol=1e-5)
 
 
-def test_posemb_strided_reduce(emu):
+def test_posemb_strided_reduce(K):
     x, pos = torch.randn(3, 5, 8), torch.randn(7, 8)
-    y = emu.add_posemb_fwd(x, pos, torch.empty(3, 5, 8))
+    y = K.add_posemb_fwd(x, pos, torch.empty(3, 5, 8))
     torch.testing.assert_close(y, x + pos[:5])
     dst = torch.zeros(5, 3, 4)
-    emu.strided_copy(dst, x[:, :, 4:].transpose(0, 1))
+    K.strided_copy(dst, x[:, :, 4:].transpose(0, 1))
     torch.testing.assert_close(dst, x[:, :, 4:].transpose(0, 1).contiguous())
-    emu.strided_copy(dst, x[:, :, 4:].transpose(0, 1), alpha=2.0, accumulate=True)
+    K.strided_copy(dst, x[:, :, 4:].transpose(0, 1), alpha=2.0, accumulate=True)
     torch.testing.assert_close(dst, 3 * x[:, :, 4:].transpose(0, 1))
     e = torch.empty(3, 5, 8)
-    emu.strided_copy(e, pos[0].view(1, 1, 8).expand(3, 5, 8), alpha=0.5)
+    K.strided_copy(e, pos[0].view(1, 1, 8).expand(3, 5, 8), alpha=0.5)
     torch.testing.assert_close(e, 0.5 * pos[0].expand(3, 5, 8))
-    torch.testing.assert_close(emu.reduce_mid(x, torch.empty(3, 8), 0.2), x.mean(1))
-    torch.testing.assert_close(emu.sum_to(x, torch.empty(1), 0.5), 0.5 * x.sum().view(1))
+    torch.testing.assert_close(K.reduce_mid(x, torch.empty(3, 8), 0.2), x.mean(1))
+    torch.testing.assert_close(K.sum_to(x, torch.empty(1), 0.5), 0.5 * x.sum().view(1))
     z = x.clone()
-    torch.testing.assert_close(emu.scale_(z, 3.0), 3 * x)
+    torch.testing.assert_close(K.scale_(z, 3.0), 3 * x)
 
 
-def test_world_to_tcp(emu):
+def test_world_to_tcp(K):
     from hulc_b200.utils import synthetic
     d = synthetic.make_modality("vis", 3, 7)
     ref = O.world_to_tcp_frame(d["actions"], d["state_info"]["robot_obs"])
     flag = torch.zeros(1, dtype=torch.int32)
-    out = emu.world_to_tcp(d["actions"], d["state_info"]["robot_obs"], torch.empty(3, 7, 7), flag)
+    out = K.world_to_tcp(d["actions"], d["state_info"]["robot_obs"], torch.empty(3, 7, 7), flag)
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)
     assert int(flag) == 0
     bad = d["actions"].clone()
     bad[0, 0, 0] = float("nan")
-    emu.world_to_tcp(bad, d["state_info"]["robot_obs"], torch.empty(3, 7, 7), flag)
+    K.world_to_tcp(bad, d["state_info"]["robot_obs"], torch.empty(3, 7, 7), flag)
     assert int(flag) == 1
 
 
 @pytest.mark.parametrize("time_major,n_dims,num_classes,has_grip", [(True, 6, 10, True), (False, 6, 10, True), (True, 7, 256, False)])
-def test_logistic_loss(emu, time_major, n_dims, num_classes, has_grip):
+def test_logistic_loss(K, time_major, n_dims, num_classes, has_grip):
     g = torch.Generator().manual_seed(3)
     B, S, b0, Bm, n_mix = 5, 6, 1, 3, 10
     nm = n_dims * n_mix
@@ -156,7 +157,7 @@ def test_logistic_loss(emu, time_major, n_dims, num_classes, has_grip):
     heads = heads_b.transpose(0, 1).contiguous().view(S * B, n) if time_major else heads_b.reshape(B * S, n)
     dheads = torch.zeros_like(heads)
     losses = torch.zeros(2)
-    emu.logistic_loss(heads, acts, dheads, losses, B, S, b0, Bm, time_major=time_major, n_dims=n_dims, n_mix=n_mix, num_classes=num_classes,
+    K.logistic_loss(heads, acts, dheads, losses, B, S, b0, Bm, time_major=time_major, n_dims=n_dims, n_mix=n_mix, num_classes=num_classes,
                       has_gripper=has_grip, grad_scale=0.5)
     torch.testing.assert_close(losses[0], nll.detach(), rtol=1e-5, atol=1e-5)
     if has_grip:
@@ -165,7 +166,7 @@ def test_logistic_loss(emu, time_major, n_dims, num_classes, has_grip):
     torch.testing.assert_close(d, hb.grad, rtol=1e-3, atol=1e-6)
 
 
-def test_plan_discrete(emu):
+def test_plan_discrete(K):
     g = torch.Generator().manual_seed(9)
     Bn = 5
     pr = torch.randn(Bn, 32, 32, generator=g, requires_grad=True)
@@ -177,25 +178,25 @@ def test_plan_discrete(emu):
     dplan = torch.randn(Bn, 1024, generator=g)
     ((plan_ref * dplan).sum() + kl).backward()
     plan, kl_rows, idx = torch.empty(Bn, 1024), torch.empty(Bn * 32), torch.empty(Bn * 32, dtype=torch.int32)
-    emu.plan_discrete_fwd(pr.detach(), pp.detach(), plan, kl_rows, u=u.view(-1), idx_out=idx)
+    K.plan_discrete_fwd(pr.detach(), pp.detach(), plan, kl_rows, u=u.view(-1), idx_out=idx)
     assert torch.equal(idx.long().view(Bn, 32), idx_ref)
     torch.testing.assert_close(plan, plan_ref.detach())
     torch.testing.assert_close(0.01 * kl_rows.sum() / Bn, kl.detach(), rtol=1e-5, atol=1e-7)
     d_pr, d_pp = torch.empty(Bn, 1024), torch.empty(Bn, 1024)
-    emu.plan_discrete_bwd(pr.detach(), pp.detach(), dplan, d_pr, d_pp, 0.01 * 0.8 / Bn, 0.01 * 0.2 / Bn)
+    K.plan_discrete_bwd(pr.detach(), pp.detach(), dplan, d_pr, d_pp, 0.01 * 0.8 / Bn, 0.01 * 0.2 / Bn)
     torch.testing.assert_close(d_pr.view(Bn, 32, 32), pr.grad, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(d_pp.view(Bn, 32, 32), pp.grad, rtol=1e-4, atol=1e-8)
     # injected indices; philox sampling is deterministic and in range
     plan2 = torch.empty(Bn, 1024)
-    emu.plan_discrete_fwd(pr.detach(), pp.detach(), plan2, kl_rows, idx_in=idx)
+    K.plan_discrete_fwd(pr.detach(), pp.detach(), plan2, kl_rows, idx_in=idx)
     assert torch.equal(plan2, plan)
     i1, i2 = torch.empty(Bn * 32, dtype=torch.int32), torch.empty(Bn * 32, dtype=torch.int32)
-    emu.plan_discrete_fwd(pr.detach(), pp.detach(), plan2, kl_rows, idx_out=i1, seed=5, site=1)
-    emu.plan_discrete_fwd(pr.detach(), pp.detach(), plan2, kl_rows, idx_out=i2, seed=5, site=1)
+    K.plan_discrete_fwd(pr.detach(), pp.detach(), plan2, kl_rows, idx_out=i1, seed=5, site=1)
+    K.plan_discrete_fwd(pr.detach(), pp.detach(), plan2, kl_rows, idx_out=i2, seed=5, site=1)
     assert torch.equal(i1, i2) and int(i1.min()) >= 0 and int(i1.max()) < 32 and plan2.sum() == Bn * 32
 
 
-def test_plan_continuous(emu):
+def test_plan_continuous(K):
     g = torch.Generator().manual_seed(4)
     Bn, Pn = 4, 256
     pr = torch.randn(Bn, 2 * Pn, generator=g, requires_grad=True)
@@ -207,17 +208,17 @@ def test_plan_continuous(emu):
     dplan = torch.randn(Bn, Pn, generator=g)
     ((plan_ref * dplan).sum() + kl).backward()
     plan, kl_el = torch.empty(Bn, Pn), torch.empty(Bn, Pn)
-    emu.plan_cont_fwd(pr.detach(), pp.detach(), plan, kl_el, eps=eps)
+    K.plan_cont_fwd(pr.detach(), pp.detach(), plan, kl_el, eps=eps)
     torch.testing.assert_close(plan, plan_ref.detach())
     torch.testing.assert_close(0.01 * kl_el.sum() / Bn, kl.detach(), rtol=1e-5, atol=1e-7)
     d_pr, d_pp = torch.empty(Bn, 2 * Pn), torch.empty(Bn, 2 * Pn)
-    emu.plan_cont_bwd(pr.detach(), pp.detach(), dplan, d_pr, d_pp, 0.01 * 0.8 / Bn, 0.01 * 0.2 / Bn, eps=eps)
+    K.plan_cont_bwd(pr.detach(), pp.detach(), dplan, d_pr, d_pp, 0.01 * 0.8 / Bn, 0.01 * 0.2 / Bn, eps=eps)
     torch.testing.assert_close(d_pr, pr.grad, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(d_pp, pp.grad, rtol=1e-4, atol=1e-7)
 
 
 @pytest.mark.parametrize("masked", [None, "some", "all"])
-def test_clip_loss(emu, masked):
+def test_clip_loss(K, masked):
     g = torch.Generator().manual_seed(2)
     n, D = 6, 32
     im = torch.randn(n, D, generator=g, requires_grad=True)
@@ -226,7 +227,7 @@ def test_clip_loss(emu, masked):
     mask = None if masked is None else (torch.tensor([1, 0, 1, 1, 0, 1], dtype=torch.bool) if masked == "some" else torch.zeros(n, dtype=torch.bool))
     sel = slice(None) if mask is None else mask
     loss, d_im, d_tx, d_ls = torch.empty(1), torch.empty(n, D), torch.empty(n, D), torch.empty(1)
-    emu.clip_loss(im.detach(), tx.detach(), ls.detach().view(1), None if mask is None else mask.to(torch.uint8), loss, d_im, d_tx, d_ls, grad_scale=3.0)
+    K.clip_loss(im.detach(), tx.detach(), ls.detach().view(1), None if mask is None else mask.to(torch.uint8), loss, d_im, d_tx, d_ls, grad_scale=3.0)
     if masked == "all":
         assert float(loss) == 0 and float(d_im.abs().max()) == 0 and float(d_ls) == 0
         return
@@ -243,7 +244,7 @@ def test_clip_loss(emu, masked):
     torch.testing.assert_close(d_ls[0], ls.grad, rtol=1e-4, atol=1e-6)
 
 
-def test_gru_gates(emu):
+def test_gru_gates(K):
     g = torch.Generator().manual_seed(8)
     B, H = 3, 40
     gi = torch.randn(B, 3 * H, generator=g, requires_grad=True)
@@ -256,23 +257,23 @@ def test_gru_gates(emu):
     d1, d2 = torch.randn(B, H, generator=g), torch.randn(B, H, generator=g)
     href.backward(d1 + d2)
     h, saved = torch.empty(B, H), torch.empty(B, 4 * H)
-    emu.gru_gates_fwd(gi.detach(), gh.detach(), hp.detach(), h, saved)
+    K.gru_gates_fwd(gi.detach(), gh.detach(), hp.detach(), h, saved)
     torch.testing.assert_close(h, href.detach())
     dgi, dgh, carry = torch.empty(B, 3 * H), torch.empty(B, 3 * H), torch.empty(B, H)
-    emu.gru_gates_bwd(d1, d2, saved, hp.detach(), dgi, dgh, carry)
+    K.gru_gates_bwd(d1, d2, saved, hp.detach(), dgi, dgh, carry)
     torch.testing.assert_close(dgi, gi.grad, rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(dgh, gh.grad, rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(carry, hp.grad, rtol=1e-4, atol=1e-6)
 
 
-def test_gemm_tanh_modes(emu):
+def test_gemm_tanh_modes(K):
     A, B = torch.randn(9, 20), torch.randn(20, 11)
-    torch.testing.assert_close(emu.gemm(A, B, act=2), torch.tanh(A @ B), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(K.gemm(A, B, act=2), torch.tanh(A @ B), rtol=1e-4, atol=1e-5)
     gate = torch.tanh(torch.randn(9, 11))
-    torch.testing.assert_close(emu.gemm(A, B, act=4, gate=gate), (A @ B) * (1 - gate * gate), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(K.gemm(A, B, act=4, gate=gate), (A @ B) * (1 - gate * gate), rtol=1e-4, atol=1e-5)
 
 
-def test_adam_matches_torch(emu):
+def test_adam_matches_torch(K):
     p = torch.randn(1000)
     ref = p.clone().requires_grad_(True)
     opt = torch.optim.Adam([ref], lr=2e-4)
@@ -281,5 +282,5 @@ def test_adam_matches_torch(emu):
         g = torch.randn(1000)
         ref.grad = g.clone()
         opt.step()
-        emu.adam_step(p, g * 4, m, v, lr=2e-4, step=step, grad_scale=0.25)
+        K.adam_step(p, g * 4, m, v, lr=2e-4, step=step, grad_scale=0.25)
     torch.testing.assert_close(p, ref.detach(), rtol=1e-6, atol=1e-7)
