@@ -164,8 +164,11 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     }
     res = {}
     for name, (fn, flops, per_step) in cands.items():
-        fn(); fn()
-        torch.cuda.synchronize()
+        try:
+            fn(); fn()
+            torch.cuda.synchronize()
+        except Exception as e:  # name the kernel before the context dies
+            raise RuntimeError(f"roofline candidate {name} failed: {e}") from e
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 5
         e0.record()

@@ -116,12 +116,16 @@ class HulcEngine:
         self.H = 2048
         self.gates = 3 if rnn_model == "gru_decoder" else 1
         self._bufs: Dict[str, torch.Tensor] = {}
+        self._step_shapes: Dict[str, tuple] = {}
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------------------------------
     def buf(self, name, *shape, zero=False):
         t = self._bufs.get(name)
+        seen = self._step_shapes.setdefault(name, tuple(shape))
+        if seen != tuple(shape):
+            raise RuntimeError(f"buffer name {name!r} requested with two shapes in one step: {seen} and {tuple(shape)}")
         if t is None or tuple(t.shape) != tuple(shape):
             t = (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device=self.device)
             if _POISON and not zero:
@@ -153,22 +157,22 @@ class HulcEngine:
         acts = [x]
         for i, n in enumerate(names):
             last = i == len(names) - 1
-            y = self.buf(f"{tag}.a{i}", x.shape[0], P[n + ".weight"].shape[0])
+            y = self.buf(f"{tag}.mlp{i}", x.shape[0], P[n + ".weight"].shape[0])
             gemm(acts[-1], P[n + ".weight"], y, transB=True, bias=P[n + ".bias"], act=0 if last else RELU)
             acts.append(y)
-        stats = self.buf(f"{tag}.stats", x.shape[0], 2)
+        stats = self.buf(f"{tag}.mlp_stats", x.shape[0], 2)
         ops.layernorm_fwd(acts[-1], P[ln + ".weight"], P[ln + ".bias"], out, stats)
         return acts, stats
 
     def _mlp_ln_bwd(self, tag, acts, stats, names, ln, dout, dx=None, dx_beta=0.0, need_dx=True):
         P, G = self.ps.p, self.ps.g
-        d = self.buf(f"{tag}.dz", *acts[-1].shape)
+        d = self.buf(f"{tag}.mlp_dz", *acts[-1].shape)
         ops.layernorm_bwd(dout, acts[-1], stats, P[ln + ".weight"], G[ln + ".weight"], G[ln + ".bias"], dz=d)
         for i in reversed(range(len(names))):
             first = i == 0
             if first:
                 return self._linear_bwd(names[i], acts[i], d, dx, dx_beta=dx_beta, need_dx=need_dx)
-            nd = self.buf(f"{tag}.d{i}", *acts[i].shape)
+            nd = self.buf(f"{tag}.mlp_d{i}", *acts[i].shape)
             self._linear_bwd(names[i], acts[i], d, nd, gate=acts[i])
             d = nd
 
@@ -214,10 +218,10 @@ class HulcEngine:
         else:
             # dgrad of the flatten-FC, gated by conv3's ReLU
             acts, names = ctx["acts"], ctx["names"]
-            d = self.buf(f"{which}.dz", *acts[-1].shape)
+            d = self.buf(f"{which}.mlp_dz", *acts[-1].shape)
             ops.layernorm_bwd(dout, acts[-1], ctx["stats"], P[f"{pre}.ln.weight"], G[f"{pre}.ln.weight"], G[f"{pre}.ln.bias"], dz=d)
             for i in (2, 1):
-                nd = self.buf(f"{which}.d{i}", *acts[i].shape)
+                nd = self.buf(f"{which}.mlp_d{i}", *acts[i].shape)
                 self._linear_bwd(names[i], acts[i], d, nd, gate=acts[i])
                 d = nd
             da3 = self.buf("gripper.da3", *a3.shape)
@@ -293,6 +297,7 @@ class HulcEngine:
         `dropout_masks` (dict site -> uint8 keep mask over the whole batch, modalities concatenated in batch order)
         inject it for parity runs; otherwise Philox streams keyed on `seed`."""
         P, G, ps = self.ps.p, self.ps.g, self.ps
+        self._step_shapes.clear()
         mods = list(batch.keys())
         n_mod = len(mods)
         Bs = [batch[m]["actions"].shape[0] for m in mods]
