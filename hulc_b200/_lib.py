@@ -59,7 +59,7 @@ class HulcError(RuntimeError):
 class Library:
     """Typed handle on the shared library; `lib.hulc_gemm(...)` raises HulcError on a non-zero return."""
 
-    def __init__(self, path: Path):
+    def __init__(self, path: Path, allow_missing: bool = False):
         if not Path(path).exists():
             raise HulcError(
                 f"{path} not found: the hulc_b200 CUDA library has not been built. Build it with "
@@ -68,11 +68,26 @@ class Library:
         self.path = Path(path)
         self.cdll = ctypes.CDLL(str(path))
         self.protos = parse_header()
+        self.missing = []
         for name, params in self.protos.items():
-            fn = getattr(self.cdll, name)  # AttributeError if the library does not export a declared symbol
+            try:
+                fn = getattr(self.cdll, name)  # AttributeError if the library does not export a declared symbol
+            except AttributeError:
+                if not allow_missing:
+                    raise
+                self.missing.append(name)
+                setattr(self, name, self._unavailable(name))
+                continue
             fn.restype = ctypes.c_int
             fn.argtypes = [_ctype(t) for t, _ in params]
             setattr(self, name, self._wrap(name, fn))
+
+    @staticmethod
+    def _unavailable(name):
+        def call(*args):
+            raise HulcError(f"{name} is not part of this build of the kernel sources (tcgen05 kernels only exist in the nvcc build)")
+
+        return call
 
     @staticmethod
     def _wrap(name, fn):

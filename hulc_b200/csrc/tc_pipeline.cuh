@@ -1,0 +1,260 @@
+// tc_pipeline.cuh — the warp-specialised tcgen05 main loop shared by the dense GEMM (gemm_tc.cu) and the implicit-GEMM
+// convolutions (conv_tc.cu).
+//
+//   D[128 x BN] (TMEM, fp32) (+)= A_tile[128 x BK] * B_tile[BN x BK]^T  over the k-blocks of a work item   (kind::tf32)
+//
+// One persistent CTA per SM walks the work items ("tiles").  Roles:
+//   warps 0-3        epilogue: tcgen05.ld the finished accumulator (warp w owns TMEM lanes 32w..32w+31 = tile rows), apply
+//                    the functor, store to global.  Two accumulator buffers in TMEM let the epilogue of item i overlap the
+//                    main loop of item i+1.
+//   warp  4          allocates TMEM; one lane issues every tcgen05.mma and the tcgen05.commit that recycles the stage.
+//   warps 5-12        producers: every producer thread owns a fixed set of 16-byte chunks of the stage tiles (so the im2col
+//                    row decode happens once per tile per thread) and fills them with cp.async straight into the swizzled
+//                    UMMA layout, no register staging.  Each thread keeps kLag+1 cp.async groups in flight; when the group
+//                    of k-block j-kLag has landed it fences (fence.proxy.async) and its warp arrives on that stage's
+//                    mbarrier (8 arrivals complete a stage).
+// Operands are gathered by cp.async rather than TMA because the A operands on this path are im2col views of NHWC / NCHW
+// activations (per-row base addresses, zero-filled halo taps) and the dense GEMMs reuse the same machinery.
+//
+// fp32 operands are consumed as tf32 (the tensor core ignores the low 13 mantissa bits).  The 3-pass mode (SPLIT) also
+// loads "lo" tiles from residual buffers x - tf32(x) prepared by split_lo_kernel and issues lo*hi + hi*lo + hi*hi.
+#pragma once
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int kEpiWarps = 4;
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kBM = 128;
+
+template <int BN, bool SPLIT, int BK = kBK>
+struct PipeCfg {
+  static constexpr int kATile = kBM * BK * 4;
+  static constexpr int kBTile = BN * BK * 4;
+  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kATile + kBTile);
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kLag = kStages - 1 < 3 ? kStages - 1 : 3;  // cp.async groups a producer thread leaves in flight
+  static constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // two accumulator buffers; the 3-pass mode keeps the small cross terms (lo*hi + hi*lo) in their own accumulator so the
+  // tensor core's truncating fp32 accumulation touches the main sum once per k-step instead of three times
+  static constexpr int kAccCols = (SPLIT ? 2 : 1) * BN;
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
+};
+
+struct PipeBarriers {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  // src-size 0 zero-fills the 16 bytes (out-of-range rows, k tails, halo taps)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Loader interface (called by all kProdThreads producer threads, ptid = 0..255):
+//   static constexpr bool kMNMajor;                          // tile layout / descriptor flavour
+//   void start_tile(int tile, int ptid);
+//   void issue(int kb, uint32_t dst, bool lo, int ptid);     // cp.async this thread's 16-byte chunks of the [rows x BK] tile
+// Epilogue interface (called by the 128 epilogue threads):  void operator()(int tile, int row, int col0, const float* v32)
+template <int BN, bool SPLIT, int BK, class ALoader, class BLoader, class Epilogue>
+__device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epilogue& ep, int num_tiles, int num_kb) {
+  using Cfg = PipeCfg<BN, SPLIT, BK>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + S * Cfg::kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&bars->full[s], kProdWarps);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], 1);
+      mbar_init(&bars->tmem_empty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp < kEpiWarps) {
+    // ================================ epilogue ================================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&bars->tmem_full[a], aphase);
+      tc_fence_after_sync();
+      const int row = warp * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * Cfg::kAccCols + c0), r);
+        if (SPLIT) {
+          uint32_t r2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * Cfg::kAccCols + BN + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        } else {
+          tmem_ld_wait();
+        }
+        ep(tile, row, c0, reinterpret_cast<const float*>(r));
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
+    }
+  } else if (warp == kEpiWarps) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, ALoader::kMNMajor, BLoader::kMNMajor);
+    int j = 0;  // k-block sequence number of this CTA
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&bars->tmem_empty[a], aphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * Cfg::kAccCols);
+      const uint32_t d_small = d_tmem + BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++j) {
+        const int stage = j % S;
+        const uint32_t phase = (j / S) & 1;
+        mbar_wait(&bars->full[stage], phase);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + Cfg::kATile;
+          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * Cfg::kATile;
+          const uint32_t b_lo = b_hi + Cfg::kBTile;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t da_hi = make_desc<ALoader::kMNMajor, kBM, BK>(a_hi, k), db_hi = make_desc<BLoader::kMNMajor, BN, BK>(b_hi, k);
+            if (SPLIT) {
+              const uint64_t da_lo = make_desc<ALoader::kMNMajor, kBM, BK>(a_lo, k), db_lo = make_desc<BLoader::kMNMajor, BN, BK>(b_lo, k);
+              umma_tf32(d_small, da_lo, db_hi, idesc, (kb | k) != 0);
+              umma_tf32(d_small, da_hi, db_lo, idesc, 1);
+              umma_tf32(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
+            } else {
+              umma_tf32(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(&bars->empty[stage]);                        // stage reusable once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&bars->tmem_full[a]);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ producers ================================
+    constexpr int L = Cfg::kLag;
+    const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;
+    int j = 0;  // k-block sequence number of this CTA
+    auto publish = [&](int jj) {  // the cp.async group of k-block jj has landed: hand this warp's share to the MMA warp
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->full[jj % S]);
+    };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      al.start_tile(tile, ptid);
+      bl.start_tile(tile, ptid);
+      for (int kb = 0; kb < num_kb; ++kb, ++j) {
+        const int stage = j % S;
+        mbar_wait(&bars->empty[stage], ((j / S) & 1) ^ 1);
+        const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t a_lo = a_hi + Cfg::kATile;
+        const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * Cfg::kATile;
+        const uint32_t b_lo = b_hi + Cfg::kBTile;
+        al.issue(kb, a_hi, false, ptid);
+        bl.issue(kb, b_hi, false, ptid);
+        if (SPLIT) {
+          al.issue(kb, a_lo, true, ptid);
+          bl.issue(kb, b_lo, true, ptid);
+        }
+        cp_async_commit();
+        if (j >= L) {
+          cp_async_wait<L>();
+          publish(j - L);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    for (int jj = j > L ? j - L : 0; jj < j; ++jj) publish(jj);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- dense operand loaders ----------------------------------------------------------------------------------------------
+// Logical operand: ROWS x K (rows = M or N index).  Requirements (checked by the host wrappers): 16-byte aligned base,
+// ld % 4 == 0, K % 4 == 0 (K-major) / rows % 4 == 0 (MN-major), so every 16-byte chunk is entirely valid or entirely zero.
+
+// stored rows x K row-major (K contiguous): K-major tile [ROWS][BK], 128-byte rows, SWIZZLE_128B
+template <int ROWS>
+struct KMajorLoader {
+  static constexpr bool kMNMajor = false;
+  const float* base;
+  const float* base_lo;
+  int rows, K, ld, ld_lo, tiles_other, is_n;  // tile -> (tm, tn): tm = tile / tiles_n, tn = tile % tiles_n
+  int row0;
+  __device__ __forceinline__ void start_tile(int tile, int) { row0 = (is_n ? tile % tiles_other : tile / tiles_other) * ROWS; }
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool lo, int ptid) const {
+    const float* b = lo ? base_lo : base;
+    const int ldx = lo ? ld_lo : ld;
+    const int k0 = kb * kBK;
+#pragma unroll
+    for (int q = ptid; q < ROWS * 8; q += kProdThreads) {
+      const int r = q >> 3, c = q & 7;
+      const int row = row0 + r, k = k0 + c * 4;
+      const bool ok = row < rows && k < K;
+      cp_async16(dst + swz(r, c), ok ? (const void*)(b + (size_t)row * ldx + k) : (const void*)b, ok);
+    }
+  }
+};
+
+// stored K x rows row-major (rows contiguous): MN-major tile [ROWS/32 groups][BK k-rows][32 elements], 128-byte rows,
+// SWIZZLE_128B_BASE32B over each 4 k-rows; groups BK*128 B apart
+template <int ROWS>
+struct MNMajorLoader {
+  static constexpr bool kMNMajor = true;
+  const float* base;
+  const float* base_lo;
+  int rows, K, ld, ld_lo, tiles_other, is_n;
+  int row0;
+  __device__ __forceinline__ void start_tile(int tile, int) { row0 = (is_n ? tile % tiles_other : tile / tiles_other) * ROWS; }
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool lo, int ptid) const {
+    const float* b = lo ? base_lo : base;
+    const int ldx = lo ? ld_lo : ld;
+    const int k0 = kb * kBK;
+    constexpr int RQ = ROWS / 4;
+#pragma unroll
+    for (int q = ptid; q < kBK * RQ; q += kProdThreads) {
+      const int kk = q / RQ, r = (q % RQ) * 4;
+      const int row = row0 + r, k = k0 + kk;
+      const bool ok = row < rows && k < K;
+      const uint32_t off = (uint32_t)(r >> 5) * (kBK * kRowBytes) + swz32(kk, (r & 31) >> 2);
+      cp_async16(dst + off, ok ? (const void*)(b + (size_t)k * ldx + row) : (const void*)b, ok);
+    }
+  }
+};
+
+}  // namespace tc

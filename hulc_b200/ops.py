@@ -81,9 +81,10 @@ def zeros(*shape, like: torch.Tensor) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------------------------------------------------
 def gemm(A, B, C=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, addend=None, add_mod=0, act=0,
-         gate=None, drop: Drop = NO_DROP):
+         gate=None, drop: Drop = NO_DROP, tc: int = 0):
     """C = epi(alpha * op(A) @ op(B)); see hulc_gemm in include/hulc_b200.h.  A, B, C, addend, gate are 2-D views with
-    contiguous rows (arbitrary leading dimension)."""
+    contiguous rows (arbitrary leading dimension).  tc = 0: exact-fp32 CUDA-core kernel; tc = 1 / 3: tensor cores
+    (hulc_gemm_tc) with tf32 operands / 3xTF32 split products."""
     _chk(A, B, C, bias, addend, gate)
     M, K = (A.shape[1], A.shape[0]) if transA else A.shape
     N = B.shape[0] if transB else B.shape[1]
@@ -91,6 +92,16 @@ def gemm(A, B, C=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=
     if C is None:
         C = empty(M, N, like=A)
     assert C.shape == (M, N)
+    if tc and not _tc_ok(A, B, M, N, K, transA, transB):
+        tc = 0  # shapes the 16-byte cp.async producers cannot take go to the CUDA-core kernel
+    if tc:
+        ws = workspace(A.device)
+        _L().hulc_gemm_tc(
+            _ptr(A), _ptr(B), _ptr(C), M, N, K, _rowmajor(A), _rowmajor(B), _rowmajor(C), int(transA), int(transB), float(alpha),
+            float(beta), _ptr(bias), _ptr(addend), _rowmajor(addend) if addend is not None else 0, int(add_mod), int(act), _ptr(gate),
+            _rowmajor(gate) if gate is not None else 0, *drop.args(), int(tc), _ptr(ws), ws.numel() * 4, _stream(),
+        )
+        return C
     ws = workspace(A.device)
     _L().hulc_gemm(
         _ptr(A), _ptr(B), _ptr(C), M, N, K, _rowmajor(A), _rowmajor(B), _rowmajor(C), int(transA), int(transB),
@@ -98,6 +109,12 @@ def gemm(A, B, C=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=
         int(act), _ptr(gate), _rowmajor(gate) if gate is not None else 0, *drop.args(), _ptr(ws), ws.numel() * 4, _stream(),
     )
     return C
+
+
+def _tc_ok(A, B, M, N, K, transA, transB) -> bool:
+    lda, ldb = _rowmajor(A), _rowmajor(B)
+    return (A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0
+            and (M if transA else K) % 4 == 0 and (K if transB else N) % 4 == 0)
 
 
 def launch_count() -> int:
@@ -175,6 +192,39 @@ def conv2d_wgrad(x, dy, dw, stride, beta=0.0):
     assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
     ws = workspace(x.device)
     _L().hulc_conv2d_wgrad(_ptr(x), _ptr(dy), _ptr(dw), float(beta), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
+    return dw
+
+
+# channels-last tensor-core variants: activations are NHWC [N,H,W,C]; the first layer reads the NCHW frames directly
+def conv2d_tc_fwd(x, w, b, stride, y, relu=True):
+    _chk(x, w, b, y)
+    assert x.is_contiguous() and w.is_contiguous() and y.is_contiguous()
+    COUT, CIN, KS, _ = w.shape
+    N, H, W = (x.shape[0], x.shape[2], x.shape[3]) if CIN == 3 else (x.shape[0], x.shape[1], x.shape[2])
+    assert tuple(y.shape) == (N, _conv_out(H, KS, stride), _conv_out(W, KS, stride), COUT), y.shape
+    ws = workspace(x.device)
+    _L().hulc_conv2d_tc_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, CIN, H, W, COUT, KS, stride, int(relu), _ptr(ws), ws.numel() * 4, _stream())
+    return y
+
+
+def conv2d_tc_dgrad(dy, w, dx, stride, gate=None):
+    _chk(dy, w, gate, dx)
+    COUT, CIN, KS, _ = w.shape
+    N, H, W, _ = dx.shape
+    assert dy.is_contiguous() and dx.is_contiguous() and (gate is None or (gate.is_contiguous() and gate.shape == dx.shape))
+    ws = workspace(dy.device)
+    _L().hulc_conv2d_tc_dgrad(_ptr(dy), _ptr(w), _ptr(gate), _ptr(dx), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
+    return dx
+
+
+def conv2d_tc_wgrad(x, dy, dw, stride, beta=0.0):
+    _chk(x, dy, dw)
+    COUT, CIN, KS, _ = dw.shape
+    nchw = CIN == 3
+    N, H, W = (x.shape[0], x.shape[2], x.shape[3]) if nchw else (x.shape[0], x.shape[1], x.shape[2])
+    assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
+    ws = workspace(x.device)
+    _L().hulc_conv2d_tc_wgrad(_ptr(x), _ptr(dy), _ptr(dw), float(beta), N, CIN, H, W, COUT, KS, stride, int(nchw), _ptr(ws), ws.numel() * 4, _stream())
     return dw
 
 

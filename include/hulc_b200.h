@@ -35,6 +35,14 @@ int hulc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int
               const float* gate, int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site,
               const unsigned char* drop_keep, float* workspace, size_t workspace_bytes, void* stream);
 
+/* hulc_gemm_tc: the same contract on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in TMEM).  passes = 1:
+ * operands consumed as tf32; passes = 3: 3xTF32 split products (fp32-level accuracy; needs workspace for (M+N)*K floats).
+ * Operands must be 16-byte aligned with lda, ldb and their contiguous extents multiples of 4, else cudaErrorInvalidValue. */
+int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                 float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act,
+                 const float* gate, int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site,
+                 const unsigned char* drop_keep, int passes, float* workspace, size_t workspace_bytes, void* stream);
+
 /* *out (HOST pointer) = number of kernel launches this library has issued since it was loaded (bench.py's gpu_launches). */
 int hulc_launch_count(unsigned long long* out);
 
@@ -66,6 +74,15 @@ int hulc_conv2d_dgrad(const float* dy, const float* w, const float* gate, float*
                       int S, float* workspace, size_t workspace_bytes, void* stream);
 int hulc_conv2d_wgrad(const float* x, const float* dy, float* dw, float beta, int N, int CIN, int H, int W, int COUT, int KS, int S,
                       float* workspace, size_t workspace_bytes, void* stream);
+/* The same three layers on the tensor cores (tcgen05.mma kind::tf32) with channels-last activations: x NHWC [N,H,W,CIN] (or,
+ * for the 3-channel first layer, the reference's NCHW frames: fwd reads them as they are, wgrad with x_nchw = 1);
+ * y / dy NHWC [N,HO,WO,COUT]; gate / dx NHWC; w / dw keep the reference layout [COUT,CIN,KS,KS]. */
+int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                       int relu, float* workspace, size_t workspace_bytes, void* stream);
+int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int KS,
+                         int S, float* workspace, size_t workspace_bytes, void* stream);
+int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, float beta, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                         int x_nchw, float* workspace, size_t workspace_bytes, void* stream);
 /* out[c] += sum_{n,p} x[n,c,p] (conv bias gradient; accumulates like the other parameter-gradient outputs) */
 int hulc_nchw_channel_sum(const float* x, float* out, int N, int C, int P, void* stream);
 

@@ -1,0 +1,64 @@
+"""Tensor-core (tcgen05, tf32) channels-last convolutions against torch fp32/fp64 on the B200: forward, data gradient
+(with the ReLU mask) and weight gradient for the three layer shapes of the perceptual encoders, ragged sizes included.
+Tolerances are those of tf32 operands (10-bit mantissa, truncated) with fp32 accumulation."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# cin, cout, ks, stride, hw, n
+CASES = [(3, 32, 8, 4, 200, 5), (3, 32, 8, 4, 84, 7), (32, 64, 4, 2, 49, 5), (32, 64, 4, 2, 20, 9), (64, 64, 3, 1, 23, 5), (64, 64, 3, 1, 9, 11),
+         (32, 64, 4, 2, 12, 1), (64, 64, 3, 1, 5, 2)]
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,ks,st,hw,n", CASES)
+def test_conv_tc(cin, cout, ks, st, hw, n):
+    from hulc_b200 import ops
+
+    g = torch.Generator().manual_seed(cin * 100 + hw)
+    x = torch.randn(n, cin, hw, hw, generator=g).cuda()
+    if cin != 3:
+        x = x.relu()
+    w = (torch.randn(cout, cin, ks, ks, generator=g) / math.sqrt(cin * ks * ks)).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    ref = F.relu(F.conv2d(xr, wr, b.double(), stride=st))
+    ho = ref.shape[-1]
+    xin = x if cin == 3 else nhwc(x)
+    y = ops.conv2d_tc_fwd(xin, w, b, st, torch.empty(n, ho, ho, cout, device="cuda"))
+    scale = float(ref.abs().max())
+    err = float((y.double() - nhwc(ref.detach())).abs().max())
+    assert err < 4e-3 * scale, f"fwd err {err:.3e} (scale {scale:.2f})"
+    dy = (torch.randn(ref.shape, generator=g).cuda() * (ref.detach() > 0)).float()
+    ref.backward(dy.double())
+    dw = torch.zeros_like(w)
+    ops.conv2d_tc_wgrad(xin, nhwc(dy), dw, st)
+    gs = float(wr.grad.abs().max())
+    err = float((dw.double() - wr.grad).abs().max())
+    assert err < 4e-3 * gs, f"wgrad err {err:.3e} (scale {gs:.2f})"
+    ops.conv2d_tc_wgrad(xin, nhwc(dy), dw, st, beta=1.0)
+    err = float((dw.double() - 2 * wr.grad).abs().max())
+    assert err < 8e-3 * gs
+    if cin != 3:
+        dx = ops.conv2d_tc_dgrad(nhwc(dy), w, torch.empty(n, hw, hw, cin, device="cuda"), st, gate=xin)
+        refdx = nhwc(xr.grad * (x > 0))
+        ds = float(refdx.abs().max())
+        err = float((dx.double() - refdx).abs().max())
+        assert err < 4e-3 * ds, f"dgrad err {err:.3e} (scale {ds:.2f})"
+        dx2 = ops.conv2d_tc_dgrad(nhwc(dy), w, torch.empty(n, hw, hw, cin, device="cuda"), st)
+        err = float((dx2.double() - nhwc(xr.grad)).abs().max())
+        assert err < 4e-3 * ds
