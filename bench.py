@@ -136,32 +136,54 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------------------------------
 def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
-    """Time the conv kernels of the static-camera encoder (the bulk of the step's FLOPs) one by one with CUDA events on
-    the launching stream and report the roofline of the one that takes the largest share of the step."""
+    """Time the heavy kernels of the step one by one (CUDA events on the launching stream) at the step's own shapes —
+    the conv layers of the static-camera encoder, the recurrent step GEMM and the large dense GEMMs — and report the
+    roofline of the one that takes the largest share of the step."""
     from hulc_b200 import ops
 
     P = eng.ps.p
     pre = "perceptual_encoder.rgb_static_encoder"
-    x = batch["vis"]["rgb_obs"]["rgb_static"].flatten(0, 1)  # one modality: 1024 frames
+    x = batch["vis"]["rgb_obs"]["rgb_static"].flatten(0, 1)  # one modality: 1024 frames (conv1 runs once per modality)
     n_mod = len(batch)
-    a1, a2, a3 = eng._bufs["static.a1"], eng._bufs["static.a2"], eng._bufs["static.a3"]
-    da1, da2, da3 = eng._bufs["static.da1"], eng._bufs["static.da2"], eng._bufs["static.da3"]
-    n1 = x.shape[0]
-    scratch = torch.empty_like(P[f"{pre}.conv_model.2.weight"])
-    scratch0 = torch.empty_like(P[f"{pre}.conv_model.0.weight"])
-    scratch4 = torch.empty_like(P[f"{pre}.conv_model.4.weight"])
-    mac = lambda n, co, ho, k: 2.0 * n * co * ho * ho * k  # flops
-    N = a1.shape[0]
-    cands = {
-        "conv1_fwd": (lambda: ops.conv2d_fwd(x, P[f"{pre}.conv_model.0.weight"], P[f"{pre}.conv_model.0.bias"], 4, a1[:n1]), mac(n1, 32, 49, 192), n_mod),
-        "conv2_fwd": (lambda: ops.conv2d_fwd(a1, P[f"{pre}.conv_model.2.weight"], P[f"{pre}.conv_model.2.bias"], 2, a2), mac(N, 64, 23, 512), 1),
-        "conv3_fwd": (lambda: ops.conv2d_fwd(a2, P[f"{pre}.conv_model.4.weight"], P[f"{pre}.conv_model.4.bias"], 1, a3), mac(N, 64, 21, 576), 1),
-        "conv3_dgrad": (lambda: ops.conv2d_dgrad(da3, P[f"{pre}.conv_model.4.weight"], a2.shape, 1, gate=a2, dx=da2), mac(N, 64, 21, 576), 1),
-        "conv2_dgrad": (lambda: ops.conv2d_dgrad(da2, P[f"{pre}.conv_model.2.weight"], a1.shape, 2, gate=a1, dx=da1), mac(N, 64, 23, 512), 1),
-        "conv3_wgrad": (lambda: ops.conv2d_wgrad(a2, da3, scratch4, 1), mac(N, 64, 21, 576), 1),
-        "conv2_wgrad": (lambda: ops.conv2d_wgrad(a1, da2, scratch, 2), mac(N, 64, 23, 512), 1),
-        "conv1_wgrad": (lambda: ops.conv2d_wgrad(x, da1[:n1], scratch0, 4), mac(n1, 32, 49, 192), n_mod),
-    }
+    B_ = eng._bufs
+    a1, a2, a3, da1, da2, da3 = (B_[f"static.{k}"] for k in ("a1", "a2", "a3", "da1", "da2", "da3"))
+    n1, N = x.shape[0], a1.shape[0]
+    w0, w2, w4 = (P[f"{pre}.conv_model.{i}.weight"] for i in (0, 2, 4))
+    b0, b2, b4 = (P[f"{pre}.conv_model.{i}.bias"] for i in (0, 2, 4))
+    s0, s2, s4 = torch.empty_like(w0), torch.empty_like(w2), torch.empty_like(w4)
+    fl = lambda n, co, ho, k: 2.0 * n * co * ho * ho * k
+    if eng.tc:
+        cands = {
+            "conv1_fwd": (lambda: ops.conv2d_tc_fwd(x, w0, b0, 4, a1[:n1]), fl(n1, 32, 49, 192), n_mod),
+            "conv2_fwd": (lambda: ops.conv2d_tc_fwd(a1, w2, b2, 2, a2), fl(N, 64, 23, 512), 1),
+            "conv3_fwd": (lambda: ops.conv2d_tc_fwd(a2, w4, b4, 1, a3), fl(N, 64, 21, 576), 1),
+            "conv3_dgrad": (lambda: ops.conv2d_tc_dgrad(da3, w4, da2, 1, gate=a2), fl(N, 64, 21, 576), 1),
+            "conv2_dgrad": (lambda: ops.conv2d_tc_dgrad(da2, w2, da1, 2, gate=a1), fl(N, 64, 23, 512), 1),
+            "conv3_wgrad": (lambda: ops.conv2d_tc_wgrad(a2, da3, s4, 1), fl(N, 64, 21, 576), 1),
+            "conv2_wgrad": (lambda: ops.conv2d_tc_wgrad(a1, da2, s2, 2), fl(N, 64, 23, 512), 1),
+            "conv1_wgrad": (lambda: ops.conv2d_tc_wgrad(x, da1[:n1], s0, 4), fl(n1, 32, 49, 192), n_mod),
+        }
+    else:
+        cands = {
+            "conv1_fwd": (lambda: ops.conv2d_fwd(x, w0, b0, 4, a1[:n1]), fl(n1, 32, 49, 192), n_mod),
+            "conv2_fwd": (lambda: ops.conv2d_fwd(a1, w2, b2, 2, a2), fl(N, 64, 23, 512), 1),
+            "conv3_fwd": (lambda: ops.conv2d_fwd(a2, w4, b4, 1, a3), fl(N, 64, 21, 576), 1),
+            "conv3_dgrad": (lambda: ops.conv2d_dgrad(da3, w4, a2.shape, 1, gate=a2, dx=da2), fl(N, 64, 21, 576), 1),
+            "conv2_dgrad": (lambda: ops.conv2d_dgrad(da2, w2, a1.shape, 2, gate=a1, dx=da1), fl(N, 64, 23, 512), 1),
+            "conv3_wgrad": (lambda: ops.conv2d_wgrad(a2, da3, s4, 1), fl(N, 64, 21, 576), 1),
+            "conv2_wgrad": (lambda: ops.conv2d_wgrad(a1, da2, s2, 2), fl(N, 64, 23, 512), 1),
+            "conv1_wgrad": (lambda: ops.conv2d_wgrad(x, da1[:n1], s0, 4), fl(n1, 32, 49, 192), n_mod),
+        }
+    # decoder: the recurrent step (64 sequences x 2048 hidden, 2 layers x 32 steps, forward + backward = 128 per step) and
+    # the large dense products (dW_hh x2, dW_ih1, dh0 as tf32; the layer-1 input projection as 3xTF32)
+    H, S, nB = eng.H, SEQ_LEN, 2 * B_PER_MODALITY
+    whh = P["action_decoder.rnn.weight_hh_l1"]
+    hb, pre1 = B_["dec.h1"], B_["dec.pre1"]
+    big_a, big_c = B_["dec.dh0"], torch.empty(H, H, device=x.device)
+    cands["rnn_step_gemm"] = (lambda: ops.gemm(hb[1], whh, hb[2], transB=True, addend=pre1[:nB], act=1), 2.0 * nB * H * H, 4 * S)
+    mode = 1 if eng.tc else 0
+    cands["dense_wgrad_2048^3"] = (lambda: ops.gemm(big_a, hb[1 : S + 1].view(S * nB, H), big_c, transA=True, tc=mode), 2.0 * H * H * S * nB, 4)
+    cands["dense_fwd_2048^3"] = (lambda: ops.gemm(big_a, whh, pre1, transB=True, tc=3 if eng.tc else 0), 2.0 * H * H * S * nB, 1)
     res = {}
     for name, (fn, flops, per_step) in cands.items():
         try:
@@ -183,9 +205,9 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     achieved = r["flops"] / (r["ms"] * 1e-3) / 1e12
     return {
         "bound": "tensor", "kernel": top, "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
-        "traffic": None, "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); this kernel is exact-fp32 on CUDA cores",
-        "ms_per_launch": r["ms"], "share_of_step": r["share"],
-        "kernels": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "share_of_step": round(v["share"], 4)} for k, v in res.items()},
+        "traffic": None, "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); tf32 tensor-core peak is half of it, fp32 CUDA-core kernels far below",
+        "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
+        "kernels": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "per_step": v["per_step"], "share_of_step": round(v["share"], 4)} for k, v in res.items()},
         "step": {"tensor_frac": None, "hbm_frac": None},
     }
 
@@ -338,7 +360,7 @@ def run_ours(args):
                    "sample": f"{Bs}+{Bs} sequences x {SEQ_LEN} frames, fwd+bwd+Adam fp32, 1 warm-up + {n} timed steps of the oracle (torch CPU, {cores} threads)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage/accumulate; tf32 tensor-core convs and backward GEMMs, 3xTF32 forward GEMMs, fp32 CUDA-core elsewhere" if eng.tc else "f32", "data": "synthetic",
             "config": {"workload": "HULC full model, batch=32 vis + 32 lang sequences per GPU, seq_len=32, 200x200 + 84x84 RGB fp32 frames, 384-d lang emb (BASELINE config 2), fwd+bwd+Adam",
                        "parallelism": f"dp{world}", "l2": "per-step inputs are 1.16 GB per GPU (> 126 MB L2); no explicit flush", "dropout_p": 0.1},
             "clocks": clk.summary(), "gpu_launches": launches, "launches_per_step": launches / args.steps, "loss": loss,

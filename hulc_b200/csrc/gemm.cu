@@ -342,8 +342,8 @@ HULC_API int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out
   if (cols <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int gy = 1, rpb = rows;
-  if (rows >= 4096) {  // long reductions: spread rows over CTAs, combine with atomics
-    gy = min(64, rows / 1024);
+  if (rows >= 4096) {  // long reductions: spread rows over CTAs (enough of them to fill the 148 SMs), combine with atomics
+    gy = max(1, min(rows / 512, (8 * kNumSMs) / hulc_cdiv(cols, 32)));
     rpb = hulc_cdiv(rows, gy);
     if (beta == 0.f) cudaMemsetAsync(out, 0, sizeof(float) * cols, st);
     else if (beta != 1.f) HULC_LAUNCH(scale_vec_kernel, dim3(hulc_cdiv(cols, 256)), dim3(256), 0, st, out, cols, beta);

@@ -180,6 +180,89 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spatial_softmax_bwd_kerne
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Spatial softmax on channels-last feature maps x [N, P = H*W, C] (the layout the tensor-core convolutions produce).
+// One CTA per frame, 4 position lanes x 64 channels: every global access is a contiguous 256-byte run of channels;
+// online softmax statistics per (position lane, channel), merged through shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSsPosLanes = 4;
+
+struct SsStat { float m, s, sx, sy; };
+
+__device__ __forceinline__ void ss_merge(SsStat& a, const SsStat& b) {
+  float m = fmaxf(a.m, b.m);
+  float fa = expf(a.m - m), fb = expf(b.m - m);
+  a.s = a.s * fa + b.s * fb; a.sx = a.sx * fa + b.sx * fb; a.sy = a.sy * fa + b.sy * fb; a.m = m;
+}
+
+// stats of channel c of frame n over positions pl, pl + kSsPosLanes, ...
+__device__ __forceinline__ SsStat ss_partial(const float* __restrict__ xf, int C, int H, int W, int c, int pl, float inv_temp, float gx, float gy, bool weighted) {
+  SsStat st{-FLT_MAX, 0.f, 0.f, 0.f};
+  const int P = H * W;
+  for (int p = pl; p < P; p += kSsPosLanes) {
+    float v = xf[(size_t)p * C + c] * inv_temp;
+    float m = fmaxf(st.m, v);
+    float f = expf(st.m - m), e = expf(v - m);
+    float cx = lin_coord(p / W, H), cy = lin_coord(p % W, W);
+    st.s = st.s * f + e;
+    if (weighted) { st.sx = st.sx * f + e * (gx * cx + gy * cy); }
+    else { st.sx = st.sx * f + e * cx; st.sy = st.sy * f + e * cy; }
+    st.m = m;
+  }
+  return st;
+}
+
+__global__ void __launch_bounds__(256) spatial_softmax_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int H, int W, float inv_temp) {
+  __shared__ SsStat sh[kSsPosLanes][64];
+  const int n = blockIdx.x, P = H * W;
+  const float* xf = x + (size_t)n * P * C;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
+    if (c < C) sh[pl][threadIdx.x & 63] = ss_partial(xf, C, H, W, c, pl, inv_temp, 0.f, 0.f, false);
+    __syncthreads();
+    if (pl == 0 && c < C) {
+      SsStat a = sh[0][threadIdx.x];
+#pragma unroll
+      for (int k = 1; k < kSsPosLanes; ++k) ss_merge(a, sh[k][threadIdx.x]);
+      out[(size_t)n * 2 * C + 2 * c] = a.sx / a.s;
+      out[(size_t)n * 2 * C + 2 * c + 1] = a.sy / a.s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) spatial_softmax_nhwc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, float* __restrict__ dx, int C,
+                                                                       int H, int W, float inv_temp, int relu_gate) {
+  __shared__ SsStat sh[kSsPosLanes][64];
+  const int n = blockIdx.x, P = H * W;
+  const float* xf = x + (size_t)n * P * C;
+  float* df = dx + (size_t)n * P * C;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int lc = threadIdx.x & 63, c = c0 + lc, pl = threadIdx.x >> 6;
+    float gx = 0.f, gy = 0.f;
+    if (c < C) {
+      gx = dout[(size_t)n * 2 * C + 2 * c]; gy = dout[(size_t)n * 2 * C + 2 * c + 1];
+      sh[pl][lc] = ss_partial(xf, C, H, W, c, pl, inv_temp, gx, gy, true);
+    }
+    __syncthreads();
+    if (c < C) {
+      SsStat a = sh[0][lc];
+#pragma unroll
+      for (int k = 1; k < kSsPosLanes; ++k) ss_merge(a, sh[k][lc]);
+      const float inv_s = 1.f / a.s, mean_c = a.sx * inv_s;  // sx holds sum e*(gx*xm + gy*ym)
+      for (int p = pl; p < P; p += kSsPosLanes) {
+        float xv = xf[(size_t)p * C + c];
+        float v = xv * inv_temp;
+        float cc = gx * lin_coord(p / W, H) + gy * lin_coord(p % W, W);
+        float g = expf(v - a.m) * inv_s * inv_temp * (cc - mean_c);
+        if (relu_gate && !(xv > 0.f)) g = 0.f;
+        df[(size_t)p * C + c] = g;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // y[b,s,:] = drop(x[b,s,:] + pos[s,:])   and the generic dropout re-application used by its backward
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void add_posemb_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ y, long long n, int S, int D,
@@ -292,6 +375,19 @@ HULC_API int hulc_spatial_softmax_bwd(const float* x, const float* dout, float* 
   if (H * W > 32 * 16) return (int)cudaErrorInvalidValue;
   HULC_LAUNCH(spatial_softmax_bwd_kernel<16>, dim3(hulc_cdiv(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, x, dout, dx,
               rows, H, W, inv_temp, relu_gate);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_spatial_softmax_nhwc_fwd(const float* x, float* out, int N, int C, int H, int W, float inv_temp, void* stream) {
+  if (N <= 0) return 0;
+  HULC_LAUNCH(spatial_softmax_nhwc_fwd_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, x, out, C, H, W, inv_temp);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_spatial_softmax_nhwc_bwd(const float* x, const float* dout, float* dx, int N, int C, int H, int W, float inv_temp, int relu_gate,
+                                           void* stream) {
+  if (N <= 0) return 0;
+  HULC_LAUNCH(spatial_softmax_nhwc_bwd_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, x, dout, dx, C, H, W, inv_temp, relu_gate);
   HULC_RETURN_LAST();
 }
 

@@ -98,8 +98,13 @@ class HulcEngine:
     """Owns the parameters and runs fused forward+backward steps.  `model` in {"hulc", "gcbc", "mcil"}."""
 
     def __init__(self, model="hulc", rnn_model="rnn_decoder", max_window=32, device="cuda", dropout_p=0.1, kl_beta=0.01,
-                 kl_balancing_mix=0.8, clip_beta=3.0, gripper_alpha=1.0, nhead=8, nlayers=2, lr=2e-4):
+                 kl_balancing_mix=0.8, clip_beta=3.0, gripper_alpha=1.0, nhead=8, nlayers=2, lr=2e-4, precision="tf32"):
+        """precision: "tf32" (default) runs the convolutions and the large backward GEMMs on the tensor cores with tf32
+        operands and the large forward GEMMs as 3xTF32 (fp32-level accuracy); "fp32" keeps every product on the exact-fp32
+        CUDA-core kernels (also the only mode of the host-emulated build used by the CPU tests)."""
         assert model in ("hulc", "gcbc", "mcil") and rnn_model in ("rnn_decoder", "gru_decoder")
+        assert precision in ("tf32", "fp32")
+        self.tc = precision == "tf32"
         self.model, self.rnn_model = model, rnn_model
         self.device = torch.device(device)
         self.spec = param_spec(model, rnn_model, max_window)
@@ -140,25 +145,48 @@ class HulcEngine:
         return self.ps.state_dict()
 
     # ------------------------------------------------------------------------------------------------------------------
+    # GEMM dispatch: which products go to the tensor cores
+    # ------------------------------------------------------------------------------------------------------------------
+    def _tc_mode(self, M, N, K, role):
+        """0 = exact fp32 on CUDA cores; 1 = tf32 (backward products: they only feed gradients); 3 = 3xTF32 (forward
+        products, whose outputs are held to the fp32 parity tolerance).  Small or skinny products stay on the CUDA-core
+        split-K kernel, which is faster for them."""
+        if not self.tc or M < 256 or N < 128 or K < 128 or 2.0 * M * N * K < 2e9:
+            return 0
+        return 3 if role == "fwd" else 1
+
+    def gemm_fwd(self, A, B, C=None, **kw):
+        M, K = (A.shape[1], A.shape[0]) if kw.get("transA") else A.shape
+        N = B.shape[0] if kw.get("transB") else B.shape[1]
+        return gemm(A, B, C, tc=self._tc_mode(M, N, K, "fwd"), **kw)
+
+    def gemm_bwd(self, A, B, C=None, **kw):
+        M, K = (A.shape[1], A.shape[0]) if kw.get("transA") else A.shape
+        N = B.shape[0] if kw.get("transB") else B.shape[1]
+        return gemm(A, B, C, tc=self._tc_mode(M, N, K, "bwd"), **kw)
+
+    # ------------------------------------------------------------------------------------------------------------------
     # small composites
     # ------------------------------------------------------------------------------------------------------------------
     def _linear_bwd(self, name, x, dy, dx=None, *, gate=None, dx_beta=0.0, need_dx=True, act=0, addend=None, drop=NO_DROP):
         """Gradients of y = x W^T + b: accumulates dW, db; returns dx = dy W (optionally gated by the producer's ReLU)."""
         P, G = self.ps.p, self.ps.g
-        gemm(dy, x, G[name + ".weight"], transA=True, beta=1.0)
+        self.gemm_bwd(dy, x, G[name + ".weight"], transA=True, beta=1.0)
         colsum(dy, G[name + ".bias"], beta=1.0)
         if not need_dx:
             return None
-        return gemm(dy, P[name + ".weight"], dx, beta=dx_beta, gate=gate, act=act, addend=addend, drop=drop)
+        return self.gemm_bwd(dy, P[name + ".weight"], dx, beta=dx_beta, gate=gate, act=act, addend=addend, drop=drop)
 
-    def _mlp_ln_fwd(self, tag, x, names, ln, out):
-        """x -> [Linear+ReLU]* -> Linear -> LayerNorm written into `out` (a 2-D view).  Saves activations under `tag`."""
+    def _mlp_ln_fwd(self, tag, x, names, ln, out, w0=None):
+        """x -> [Linear+ReLU]* -> Linear -> LayerNorm written into `out` (a 2-D view).  Saves activations under `tag`.
+        `w0` replaces the first layer's weight (a column-permuted copy, see _encoder_fwd_tc)."""
         P = self.ps.p
         acts = [x]
         for i, n in enumerate(names):
             last = i == len(names) - 1
             y = self.buf(f"{tag}.mlp{i}", x.shape[0], P[n + ".weight"].shape[0])
-            gemm(acts[-1], P[n + ".weight"], y, transB=True, bias=P[n + ".bias"], act=0 if last else RELU)
+            w = w0 if (i == 0 and w0 is not None) else P[n + ".weight"]
+            self.gemm_fwd(acts[-1], w, y, transB=True, bias=P[n + ".bias"], act=0 if last else RELU)
             acts.append(y)
         stats = self.buf(f"{tag}.mlp_stats", x.shape[0], 2)
         ops.layernorm_fwd(acts[-1], P[ln + ".weight"], P[ln + ".bias"], out, stats)
@@ -182,6 +210,8 @@ class HulcEngine:
     _CONVS = ((0, 4), (2, 2), (4, 1))
 
     def _encoder_fwd(self, which, frames: List[torch.Tensor], emb):
+        if self.tc:
+            return self._encoder_fwd_tc(which, frames, emb)
         P = self.ps.p
         pre = f"perceptual_encoder.rgb_{which}_encoder"
         N = sum(f.shape[0] for f in frames)
@@ -208,6 +238,8 @@ class HulcEngine:
         return dict(frames=frames, a1=a1, a2=a2, a3=a3, acts=acts, stats=stats, names=names, pre=pre)
 
     def _encoder_bwd(self, which, ctx, demb):
+        if self.tc:
+            return self._encoder_bwd_tc(which, ctx, demb)
         P, G = self.ps.p, self.ps.g
         pre, a1, a2, a3 = ctx["pre"], ctx["a1"], ctx["a2"], ctx["a3"]
         dout = demb[:, 0:64] if which == "static" else demb[:, 64:128]
@@ -238,6 +270,76 @@ class HulcEngine:
             ops.conv2d_wgrad(f, da1[n0 : n0 + f.shape[0]], G[f"{pre}.conv_model.0.weight"], 4, beta=1.0)
             n0 += f.shape[0]
 
+    # tensor-core variant: channels-last activations, tcgen05 implicit-GEMM convolutions (conv_tc.cu)
+    def _encoder_fwd_tc(self, which, frames: List[torch.Tensor], emb):
+        P = self.ps.p
+        pre = f"perceptual_encoder.rgb_{which}_encoder"
+        N = sum(f.shape[0] for f in frames)
+        sizes = [frames[0].shape[-1]]
+        for (_, s), k in zip(self._CONVS, (8, 4, 3)):
+            sizes.append((sizes[-1] - k) // s + 1)
+        a1 = self.buf(f"{which}.a1", N, sizes[1], sizes[1], 32)
+        n0 = 0
+        for f in frames:  # the first layer reads the reference's NCHW frames as they are
+            ops.conv2d_tc_fwd(f, P[f"{pre}.conv_model.0.weight"], P[f"{pre}.conv_model.0.bias"], 4, a1[n0 : n0 + f.shape[0]])
+            n0 += f.shape[0]
+        a2 = ops.conv2d_tc_fwd(a1, P[f"{pre}.conv_model.2.weight"], P[f"{pre}.conv_model.2.bias"], 2, self.buf(f"{which}.a2", N, sizes[2], sizes[2], 64))
+        a3 = ops.conv2d_tc_fwd(a2, P[f"{pre}.conv_model.4.weight"], P[f"{pre}.conv_model.4.bias"], 1, self.buf(f"{which}.a3", N, sizes[3], sizes[3], 64))
+        w0 = None
+        if which == "static":
+            feat = ops.spatial_softmax_nhwc_fwd(a3, self.buf("static.ss", N, 128))
+            names = [f"{pre}.fc1.0", f"{pre}.fc2"]
+            out = emb[:, 0:64]
+        else:
+            # nn.Flatten of the reference runs over (C, H, W); the channels-last map flattens as (H, W, C): permute the
+            # columns of the following Linear instead of the activation
+            feat = a3.view(N, -1)
+            PP = sizes[3] * sizes[3]
+            w7 = P[f"{pre}.conv_model.7.weight"]
+            w0 = self.buf("gripper.w7p", w7.shape[0], PP * 64)
+            ops.strided_copy(w0.view(-1, PP, 64), w7.view(-1, 64, PP).transpose(1, 2))
+            names = [f"{pre}.conv_model.7", f"{pre}.fc1.0", f"{pre}.fc2"]
+            out = emb[:, 64:128]
+        acts, stats = self._mlp_ln_fwd(which, feat, names, f"{pre}.ln", out, w0=w0)
+        return dict(frames=frames, a1=a1, a2=a2, a3=a3, acts=acts, stats=stats, names=names, pre=pre, w0=w0)
+
+    def _encoder_bwd_tc(self, which, ctx, demb):
+        P, G = self.ps.p, self.ps.g
+        pre, a1, a2, a3 = ctx["pre"], ctx["a1"], ctx["a2"], ctx["a3"]
+        dout = demb[:, 0:64] if which == "static" else demb[:, 64:128]
+        N = a3.shape[0]
+        if which == "static":
+            dss = self._mlp_ln_bwd(which, ctx["acts"], ctx["stats"], ctx["names"], f"{pre}.ln", dout, self.buf("static.dss", N, 128))
+            da3 = ops.spatial_softmax_nhwc_bwd(a3, dss, self.buf("static.da3", *a3.shape), relu_gate=True)
+        else:
+            acts, names, w0 = ctx["acts"], ctx["names"], ctx["w0"]
+            d = self.buf(f"{which}.mlp_dz", *acts[-1].shape)
+            ops.layernorm_bwd(dout, acts[-1], ctx["stats"], P[f"{pre}.ln.weight"], G[f"{pre}.ln.weight"], G[f"{pre}.ln.bias"], dz=d)
+            for i in (2, 1):
+                nd = self.buf(f"{which}.mlp_d{i}", *acts[i].shape)
+                self._linear_bwd(names[i], acts[i], d, nd, gate=acts[i])
+                d = nd
+            # flatten-FC in the permuted column order: weight gradient into a scratch, then back to the (C,H,W) order
+            da3 = self.buf("gripper.da3", *a3.shape)
+            PP = a3.shape[1] * a3.shape[2]
+            dw0 = self.buf("gripper.dw7p", *w0.shape)
+            self.gemm_bwd(d, acts[0], dw0, transA=True)
+            g7 = G[f"{pre}.conv_model.7.weight"]
+            ops.strided_copy(g7.view(-1, 64, PP).transpose(1, 2), dw0.view(-1, PP, 64), accumulate=True)
+            colsum(d, G[f"{pre}.conv_model.7.bias"], beta=1.0)
+            self.gemm_bwd(d, w0, da3.view(N, -1), gate=acts[0])
+        ops.conv2d_tc_wgrad(a2, da3, G[f"{pre}.conv_model.4.weight"], 1, beta=1.0)
+        colsum(da3.view(-1, 64), G[f"{pre}.conv_model.4.bias"], beta=1.0)
+        da2 = ops.conv2d_tc_dgrad(da3, P[f"{pre}.conv_model.4.weight"], self.buf(f"{which}.da2", *a2.shape), 1, gate=a2)
+        ops.conv2d_tc_wgrad(a1, da2, G[f"{pre}.conv_model.2.weight"], 2, beta=1.0)
+        colsum(da2.view(-1, 64), G[f"{pre}.conv_model.2.bias"], beta=1.0)
+        da1 = ops.conv2d_tc_dgrad(da2, P[f"{pre}.conv_model.2.weight"], self.buf(f"{which}.da1", *a1.shape), 2, gate=a1)
+        colsum(da1.view(-1, 32), G[f"{pre}.conv_model.0.bias"], beta=1.0)
+        n0 = 0
+        for f in ctx["frames"]:
+            ops.conv2d_tc_wgrad(f, da1[n0 : n0 + f.shape[0]], G[f"{pre}.conv_model.0.weight"], 4, beta=1.0)
+            n0 += f.shape[0]
+
     # ------------------------------------------------------------------------------------------------------------------
     # recurrent layers (torch.nn.RNN / nn.GRU semantics; decoders/utils/rnn.py:5-36, plan_recognition_net.py:27-34)
     # ------------------------------------------------------------------------------------------------------------------
@@ -252,10 +354,10 @@ class HulcEngine:
         for t in (range(S - 1, -1, -1) if reverse else range(S)):
             prev = h(t + 2) if reverse else h(t)
             if kind == "gru":
-                gemm(prev, w_hh, gh, transB=True, bias=b_hh)
+                self.gemm_fwd(prev, w_hh, gh, transB=True, bias=b_hh)
                 ops.gru_gates_fwd(pre3[t], gh, prev, h(t + 1), saved[t])
             else:
-                gemm(prev, w_hh, h(t + 1), transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH)
+                self.gemm_fwd(prev, w_hh, h(t + 1), transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH)
         return saved
 
     def _rnn_bwd(self, tag, dh_above, w_hh, hbuf, col0, S, B, *, kind, saved=None, reverse=False):
@@ -274,7 +376,7 @@ class HulcEngine:
             for t in (range(S) if reverse else range(S - 1, -1, -1)):
                 prev = h(t + 2) if reverse else h(t)
                 ops.gru_gates_bwd(ab(t), None if first else rec, saved[t], prev, dgi[t], dgh[t], carry)
-                gemm(dgh[t], w_hh, rec, addend=carry)
+                self.gemm_bwd(dgh[t], w_hh, rec, addend=carry)
                 first = False
             return dgi.view(S * B, 3 * H), dgh.view(S * B, 3 * H)
         # Elman: dpre_t = (dh_above_t + dpre_{t+1} W_hh) * act'(h_t); slot S (or slot 0 for reverse) of dbuf stays zero
@@ -282,7 +384,7 @@ class HulcEngine:
         act = GATE_TANH if kind == "tanh" else 0
         for t in (range(S) if reverse else range(S - 1, -1, -1)):
             nxt, cur = (dbuf[t], dbuf[t + 1]) if reverse else (dbuf[t + 1], dbuf[t])
-            gemm(nxt, w_hh, cur, addend=ab(t), gate=h(t + 1), act=act)
+            self.gemm_bwd(nxt, w_hh, cur, addend=ab(t), gate=h(t + 1), act=act)
         d = (dbuf[1:] if reverse else dbuf[:S]).reshape(S * B, H)
         return d, d
 
@@ -344,14 +446,14 @@ class HulcEngine:
         if self.model != "gcbc":
             w0 = P["plan_proposal.fc_model.0.weight"]
             pp = [None, self.buf("pp.a1", nB, H)]
-            gemm(emb3[:, 0, :], w0[:, :128], pp[1], transB=True, bias=P["plan_proposal.fc_model.0.bias"])
-            gemm(goal, w0[:, 128:], pp[1], transB=True, beta=1.0, act=RELU)
+            self.gemm_fwd(emb3[:, 0, :], w0[:, :128], pp[1], transB=True, bias=P["plan_proposal.fc_model.0.bias"])
+            self.gemm_fwd(goal, w0[:, 128:], pp[1], transB=True, beta=1.0, act=RELU)
             for j, i in enumerate((2, 4, 6)):
                 y = self.buf(f"pp.a{j + 2}", nB, H)
-                gemm(pp[-1], P[f"plan_proposal.fc_model.{i}.weight"], y, transB=True, bias=P[f"plan_proposal.fc_model.{i}.bias"], act=RELU)
+                self.gemm_fwd(pp[-1], P[f"plan_proposal.fc_model.{i}.weight"], y, transB=True, bias=P[f"plan_proposal.fc_model.{i}.bias"], act=RELU)
                 pp.append(y)
             state_dim = P["plan_proposal.fc_state.0.weight"].shape[0]
-            pp_state = gemm(pp[-1], P["plan_proposal.fc_state.0.weight"], self.buf("pp.state", nB, state_dim), transB=True,
+            pp_state = self.gemm_fwd(pp[-1], P["plan_proposal.fc_state.0.weight"], self.buf("pp.state", nB, state_dim), transB=True,
                             bias=P["plan_proposal.fc_state.0.bias"])
             out["pp_state"] = pp_state
 
@@ -363,7 +465,7 @@ class HulcEngine:
             post = self._transformer_fwd(emb3, S, nB, drop)
             seq_feat = post["seq_feat"]
         state_dim = P["plan_recognition.fc_state.0.weight"].shape[0]
-        pr_state = gemm(seq_feat, P["plan_recognition.fc_state.0.weight"], self.buf("pr.state", nB, state_dim), transB=True,
+        pr_state = self.gemm_fwd(seq_feat, P["plan_recognition.fc_state.0.weight"], self.buf("pr.state", nB, state_dim), transB=True,
                         bias=P["plan_recognition.fc_state.0.bias"])
         out["pr_state"], out["seq_feat"] = pr_state, seq_feat
 
@@ -404,22 +506,22 @@ class HulcEngine:
         percep_tm = self.buf("dec.percep", S, nB, C)
         ops.strided_copy(percep_tm, emb3[:, :, self.percep_lo :].transpose(0, 1))
         const = self.buf("dec.const", nB, Gn * H)
-        gemm(goal, w_goal, const, transB=True, bias=P[f"{rp}.bias_ih_l0"])
+        self.gemm_fwd(goal, w_goal, const, transB=True, bias=P[f"{rp}.bias_ih_l0"])
         if PF:
-            gemm(plan, w_plan, const, transB=True, beta=1.0)
+            self.gemm_fwd(plan, w_plan, const, transB=True, beta=1.0)
         hb = [self.buf(f"dec.h{l}", S + 2, nB, H, zero=True) for l in range(2)]
         pre0 = self.buf("dec.pre0", S * nB, Gn * H)
-        gemm(percep_tm.view(S * nB, C), w_pc, pre0, transB=True, addend=const, add_mod=nB,
+        self.gemm_fwd(percep_tm.view(S * nB, C), w_pc, pre0, transB=True, addend=const, add_mod=nB,
              bias=None if kind == "gru" else P[f"{rp}.bias_hh_l0"])
         sv0 = self._rnn_fwd("dec.l0", pre0, P[f"{rp}.weight_hh_l0"], P[f"{rp}.bias_hh_l0"], hb[0], 0, S, nB, kind=kind)
         h0_all = hb[0][1 : S + 1].view(S * nB, H)
         pre1 = self.buf("dec.pre1", S * nB, Gn * H)
-        gemm(h0_all, P[f"{rp}.weight_ih_l1"], pre1, transB=True, bias=P[f"{rp}.bias_ih_l1"],
+        self.gemm_fwd(h0_all, P[f"{rp}.weight_ih_l1"], pre1, transB=True, bias=P[f"{rp}.bias_ih_l1"],
              addend=None if kind == "gru" else P[f"{rp}.bias_hh_l1"].view(1, -1), add_mod=1)
         sv1 = self._rnn_fwd("dec.l1", pre1, P[f"{rp}.weight_hh_l1"], P[f"{rp}.bias_hh_l1"], hb[1], 0, S, nB, kind=kind)
         h1_all = hb[1][1 : S + 1].view(S * nB, H)
         n_heads = ps.heads_w.shape[0]
-        heads = gemm(h1_all, ps.heads_w, self.buf("dec.heads", S * nB, n_heads), transB=True, bias=ps.heads_b)
+        heads = self.gemm_fwd(h1_all, ps.heads_w, self.buf("dec.heads", S * nB, n_heads), transB=True, bias=ps.heads_b)
         out["heads_tm"] = heads.view(S, nB, n_heads)
 
         # ---- losses (logistic_decoder_rnn.py:121-155,184-231; gripper_control.py:16-36) ----------------------------------------
@@ -444,10 +546,10 @@ class HulcEngine:
                 if "lang" not in m:
                     continue
                 sf, gl = seq_feat[b0 : b0 + Bm], goal[b0 : b0 + Bm]
-                im1 = gemm(sf, P["proj_vis_lang.mlp_im.0.weight"], self.buf("clip.im1", Bm, 128), transB=True, bias=P["proj_vis_lang.mlp_im.0.bias"], act=RELU)
-                im2 = gemm(im1, P["proj_vis_lang.mlp_im.2.weight"], self.buf("clip.im2", Bm, 32), transB=True, bias=P["proj_vis_lang.mlp_im.2.bias"])
-                tx1 = gemm(gl, P["proj_vis_lang.mlp_lang.0.weight"], self.buf("clip.tx1", Bm, 128), transB=True, bias=P["proj_vis_lang.mlp_lang.0.bias"], act=RELU)
-                tx2 = gemm(tx1, P["proj_vis_lang.mlp_lang.2.weight"], self.buf("clip.tx2", Bm, 32), transB=True, bias=P["proj_vis_lang.mlp_lang.2.bias"])
+                im1 = self.gemm_fwd(sf, P["proj_vis_lang.mlp_im.0.weight"], self.buf("clip.im1", Bm, 128), transB=True, bias=P["proj_vis_lang.mlp_im.0.bias"], act=RELU)
+                im2 = self.gemm_fwd(im1, P["proj_vis_lang.mlp_im.2.weight"], self.buf("clip.im2", Bm, 32), transB=True, bias=P["proj_vis_lang.mlp_im.2.bias"])
+                tx1 = self.gemm_fwd(gl, P["proj_vis_lang.mlp_lang.0.weight"], self.buf("clip.tx1", Bm, 128), transB=True, bias=P["proj_vis_lang.mlp_lang.0.bias"], act=RELU)
+                tx2 = self.gemm_fwd(tx1, P["proj_vis_lang.mlp_lang.2.weight"], self.buf("clip.tx2", Bm, 32), transB=True, bias=P["proj_vis_lang.mlp_lang.2.bias"])
                 mask = batch[m].get("use_for_aux_lang_loss")
                 mask8 = mask.to(torch.uint8) if mask is not None else None
                 d_im2, d_tx2 = self.buf("clip.dim2", Bm, 32), self.buf("clip.dtx2", Bm, 32)
@@ -476,32 +578,32 @@ class HulcEngine:
         dgoal = self.buf("dgoal", nB, 32)
 
         # heads
-        gemm(dheads, h1_all, ps.heads_gw, transA=True, beta=1.0)
+        self.gemm_bwd(dheads, h1_all, ps.heads_gw, transA=True, beta=1.0)
         colsum(dheads, ps.heads_gb, beta=1.0)
-        dh1 = gemm(dheads, ps.heads_w, self.buf("dec.dh1", S * nB, H))
+        dh1 = self.gemm_bwd(dheads, ps.heads_w, self.buf("dec.dh1", S * nB, H))
         # layer 1
         dpre1, dgh1 = self._rnn_bwd("dec.l1", dh1, P[f"{rp}.weight_hh_l1"], hb[1], 0, S, nB, kind=kind, saved=sv1)
-        gemm(dgh1, hb[1][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l1"], transA=True, beta=1.0)
-        gemm(dpre1, h0_all, G[f"{rp}.weight_ih_l1"], transA=True, beta=1.0)
+        self.gemm_bwd(dgh1, hb[1][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l1"], transA=True, beta=1.0)
+        self.gemm_bwd(dpre1, h0_all, G[f"{rp}.weight_ih_l1"], transA=True, beta=1.0)
         colsum(dpre1, G[f"{rp}.bias_ih_l1"], beta=1.0)
         colsum(dgh1, G[f"{rp}.bias_hh_l1"], beta=1.0)
-        dh0 = gemm(dpre1, P[f"{rp}.weight_ih_l1"], self.buf("dec.dh0", S * nB, H))
+        dh0 = self.gemm_bwd(dpre1, P[f"{rp}.weight_ih_l1"], self.buf("dec.dh0", S * nB, H))
         # layer 0
         dpre0, dgh0 = self._rnn_bwd("dec.l0", dh0, P[f"{rp}.weight_hh_l0"], hb[0], 0, S, nB, kind=kind, saved=sv0)
-        gemm(dgh0, hb[0][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l0"], transA=True, beta=1.0)
+        self.gemm_bwd(dgh0, hb[0][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l0"], transA=True, beta=1.0)
         colsum(dgh0, G[f"{rp}.bias_hh_l0"], beta=1.0)
         g_ih0 = G[f"{rp}.weight_ih_l0"]
-        gemm(dpre0, percep_tm.view(S * nB, C), g_ih0[:, PF : PF + C], transA=True, beta=1.0)
+        self.gemm_bwd(dpre0, percep_tm.view(S * nB, C), g_ih0[:, PF : PF + C], transA=True, beta=1.0)
         dconst = self.buf("dec.dconst", nB, Gn * H)
         colsum(dpre0.view(S, nB * Gn * H), dconst.view(-1))
         colsum(dconst, G[f"{rp}.bias_ih_l0"], beta=1.0)
-        gemm(dconst, goal, g_ih0[:, PF + C :], transA=True, beta=1.0)
-        gemm(dconst, w_goal, dgoal)
+        self.gemm_bwd(dconst, goal, g_ih0[:, PF + C :], transA=True, beta=1.0)
+        self.gemm_bwd(dconst, w_goal, dgoal)
         dplan = None
         if PF:
-            gemm(dconst, plan, g_ih0[:, :PF], transA=True, beta=1.0)
-            dplan = gemm(dconst, w_plan, self.buf("dplan", nB, PF))
-        dpercep = gemm(dpre0, w_pc, self.buf("dec.dpercep", S * nB, C))
+            self.gemm_bwd(dconst, plan, g_ih0[:, :PF], transA=True, beta=1.0)
+            dplan = self.gemm_bwd(dconst, w_plan, self.buf("dplan", nB, PF))
+        dpercep = self.gemm_bwd(dpre0, w_pc, self.buf("dec.dpercep", S * nB, C))
         ops.strided_copy(demb3[:, :, self.percep_lo :].transpose(0, 1), dpercep.view(S, nB, C), accumulate=True)
 
         # CLIP head
@@ -546,11 +648,11 @@ class HulcEngine:
                 self._linear_bwd(n, x, d, nd, gate=x)
                 d = nd
             g0 = G["plan_proposal.fc_model.0.weight"]
-            gemm(d, emb3[:, 0, :], g0[:, :128], transA=True, beta=1.0)
-            gemm(d, goal, g0[:, 128:], transA=True, beta=1.0)
+            self.gemm_bwd(d, emb3[:, 0, :], g0[:, :128], transA=True, beta=1.0)
+            self.gemm_bwd(d, goal, g0[:, 128:], transA=True, beta=1.0)
             colsum(d, G["plan_proposal.fc_model.0.bias"], beta=1.0)
-            gemm(d, w0[:, :128], demb3[:, 0, :], beta=1.0)
-            gemm(d, w0[:, 128:], dgoal, beta=1.0)
+            self.gemm_bwd(d, w0[:, :128], demb3[:, 0, :], beta=1.0)
+            self.gemm_bwd(d, w0[:, 128:], dgoal, beta=1.0)
 
         # goal encoders
         for (m, b0, Bm), (acts, stats, names, ln) in zip(zip(mods, b0s, Bs), goal_ctx):
@@ -575,22 +677,22 @@ class HulcEngine:
         for l in range(self.nlayers):
             pre = f"plan_recognition.transformer_encoder.layers.{l}"
             c = dict(x=x, pre=pre)
-            c["qkv"] = gemm(x, P[f"{pre}.self_attn.in_proj_weight"], self.buf(f"tr{l}.qkv", T, 3 * D), transB=True, bias=P[f"{pre}.self_attn.in_proj_bias"])
+            c["qkv"] = self.gemm_fwd(x, P[f"{pre}.self_attn.in_proj_weight"], self.buf(f"tr{l}.qkv", T, 3 * D), transB=True, bias=P[f"{pre}.self_attn.in_proj_bias"])
             c["probs"] = self.buf(f"tr{l}.probs", nB, Hh, S, S)
             c["ctx"] = ops.attention_fwd(c["qkv"], self.buf(f"tr{l}.ctx", T, D), c["probs"], nB, S, Hh, drop(f"l{l}.attn", 1 + 4 * l))
-            o = gemm(c["ctx"], P[f"{pre}.self_attn.out_proj.weight"], self.buf(f"tr{l}.o", T, D), transB=True, bias=P[f"{pre}.self_attn.out_proj.bias"])
+            o = self.gemm_fwd(c["ctx"], P[f"{pre}.self_attn.out_proj.weight"], self.buf(f"tr{l}.o", T, D), transB=True, bias=P[f"{pre}.self_attn.out_proj.bias"])
             c["z1"], c["st1"], c["y1"] = self.buf(f"tr{l}.z1", T, D), self.buf(f"tr{l}.st1", T, 2), self.buf(f"tr{l}.y1", T, D)
             ops.layernorm_fwd(o, P[f"{pre}.norm1.weight"], P[f"{pre}.norm1.bias"], c["y1"], c["st1"], res=x, z=c["z1"], drop=drop(f"l{l}.drop1", 2 + 4 * l))
-            c["h"] = gemm(c["y1"], P[f"{pre}.linear1.weight"], self.buf(f"tr{l}.h", T, P[f"{pre}.linear1.weight"].shape[0]), transB=True,
+            c["h"] = self.gemm_fwd(c["y1"], P[f"{pre}.linear1.weight"], self.buf(f"tr{l}.h", T, P[f"{pre}.linear1.weight"].shape[0]), transB=True,
                           bias=P[f"{pre}.linear1.bias"], act=RELU, drop=drop(f"l{l}.ffn", 3 + 4 * l))
-            f = gemm(c["h"], P[f"{pre}.linear2.weight"], self.buf(f"tr{l}.f", T, D), transB=True, bias=P[f"{pre}.linear2.bias"])
+            f = self.gemm_fwd(c["h"], P[f"{pre}.linear2.weight"], self.buf(f"tr{l}.f", T, D), transB=True, bias=P[f"{pre}.linear2.bias"])
             c["z2"], c["st2"], c["y2"] = self.buf(f"tr{l}.z2", T, D), self.buf(f"tr{l}.st2", T, 2), self.buf(f"tr{l}.y2", T, D)
             ops.layernorm_fwd(f, P[f"{pre}.norm2.weight"], P[f"{pre}.norm2.bias"], c["y2"], c["st2"], res=c["y1"], z=c["z2"], drop=drop(f"l{l}.drop2", 4 + 4 * l))
             x = c["y2"]
             layers.append(c)
         # fc then mean over time == mean over time then fc (both linear): only the (B,128) mean goes through the 4096-wide GEMM
         ybar = ops.reduce_mid(x.view(nB, S, D), self.buf("tr.ybar", nB, D), 1.0 / S)
-        seq_feat = gemm(ybar, P["plan_recognition.fc.weight"], self.buf("tr.seq_feat", nB, P["plan_recognition.fc.weight"].shape[0]), transB=True,
+        seq_feat = self.gemm_fwd(ybar, P["plan_recognition.fc.weight"], self.buf("tr.seq_feat", nB, P["plan_recognition.fc.weight"].shape[0]), transB=True,
                         bias=P["plan_recognition.fc.bias"])
         return dict(layers=layers, ybar=ybar, seq_feat=seq_feat)
 
@@ -614,9 +716,9 @@ class HulcEngine:
                               drop=drop(f"l{l}.drop1", 2 + 4 * l))
             dctx = self._linear_bwd(f"{pre}.self_attn.out_proj", c["ctx"], do, self.buf(f"tr{l}.dctx", T, D))
             dqkv = ops.attention_bwd(c["qkv"], c["probs"], dctx, self.buf(f"tr{l}.dqkv", T, 3 * D), nB, S, Hh, drop(f"l{l}.attn", 1 + 4 * l))
-            gemm(dqkv, c["x"], G[f"{pre}.self_attn.in_proj_weight"], transA=True, beta=1.0)
+            self.gemm_bwd(dqkv, c["x"], G[f"{pre}.self_attn.in_proj_weight"], transA=True, beta=1.0)
             colsum(dqkv, G[f"{pre}.self_attn.in_proj_bias"], beta=1.0)
-            dy = gemm(dqkv, P[f"{pre}.self_attn.in_proj_weight"], self.buf(f"tr{l}.dx", T, D), addend=dz1)
+            dy = self.gemm_bwd(dqkv, P[f"{pre}.self_attn.in_proj_weight"], self.buf(f"tr{l}.dx", T, D), addend=dz1)
         dx0 = dy
         d = drop("in", 0)
         if d.p > 0:
@@ -639,7 +741,7 @@ class HulcEngine:
             hb = self.buf(f"bi.h{l}", S + 2, nB, 2 * H, zero=True)
             for d, sfx in enumerate(("", "_reverse")):
                 pre = self.buf(f"bi.pre{l}{d}", S * nB, H)
-                gemm(inp, P[f"{rp}.weight_ih_l{l}{sfx}"], pre, transB=True, bias=P[f"{rp}.bias_ih_l{l}{sfx}"],
+                self.gemm_fwd(inp, P[f"{rp}.weight_ih_l{l}{sfx}"], pre, transB=True, bias=P[f"{rp}.bias_ih_l{l}{sfx}"],
                      addend=P[f"{rp}.bias_hh_l{l}{sfx}"].view(1, -1), add_mod=1)
                 self._rnn_fwd(f"bi.l{l}{d}", pre, P[f"{rp}.weight_hh_l{l}{sfx}"], None, hb, d * H, S, nB, kind="tanh", reverse=bool(d))
             outs.append(hb)
@@ -663,11 +765,11 @@ class HulcEngine:
                 dpre, _ = self._rnn_bwd(f"bi.l{l}{d}", dabove[:, d * H : (d + 1) * H], P[f"{rp}.weight_hh_l{l}{sfx}"], hb, d * H, S, nB,
                                         kind="tanh", reverse=bool(d))
                 hprev = (hb[2 : S + 2] if d else hb[0:S])[:, :, d * H : (d + 1) * H].reshape(S * nB, H)
-                gemm(dpre, hprev, G[f"{rp}.weight_hh_l{l}{sfx}"], transA=True, beta=1.0)
-                gemm(dpre, inp, G[f"{rp}.weight_ih_l{l}{sfx}"], transA=True, beta=1.0)
+                self.gemm_bwd(dpre, hprev, G[f"{rp}.weight_hh_l{l}{sfx}"], transA=True, beta=1.0)
+                self.gemm_bwd(dpre, inp, G[f"{rp}.weight_ih_l{l}{sfx}"], transA=True, beta=1.0)
                 colsum(dpre, G[f"{rp}.bias_ih_l{l}{sfx}"], beta=1.0)
                 colsum(dpre, G[f"{rp}.bias_hh_l{l}{sfx}"], beta=1.0)
-                gemm(dpre, P[f"{rp}.weight_ih_l{l}{sfx}"], dinp, beta=float(d))
+                self.gemm_bwd(dpre, P[f"{rp}.weight_ih_l{l}{sfx}"], dinp, beta=float(d))
             dabove = dinp
         ops.strided_copy(demb3.transpose(0, 1), dabove.view(S, nB, 128), accumulate=True)
 

@@ -138,6 +138,7 @@ class Hulc(_Base):
         mia_lang_discriminator=None,
         proj_vis_lang=None,
         device: Optional[str] = None,
+        precision: str = "tf32",
     ):
         super().__init__()
         if state_recons or use_bc_z_auxiliary_loss or use_mia_auxiliary_loss:
@@ -161,7 +162,7 @@ class Hulc(_Base):
             model, rnn_model, max_window=max_window, device=dev, dropout_p=float(_get(plan_recognition, "dropout_p", 0.0) or 0.0),
             kl_beta=kl_beta, kl_balancing_mix=kl_balancing_mix, clip_beta=clip_auxiliary_loss_beta,
             gripper_alpha=float(_get(action_decoder, "gripper_alpha", 1.0)), nhead=int(_get(plan_recognition, "num_heads", 8)),
-            nlayers=int(_get(plan_recognition, "num_layers", 2)), lr=float(_get(optimizer, "lr", 2e-4)),
+            nlayers=int(_get(plan_recognition, "num_layers", 2)), lr=float(_get(optimizer, "lr", 2e-4)), precision=precision,
         )
         self._param_by_key: Dict[str, nn.Parameter] = {}
         for k in self.engine.ps.keys:

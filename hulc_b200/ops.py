@@ -257,6 +257,26 @@ def spatial_softmax_bwd(x, dout, dx=None, temperature=1.0, relu_gate=True):
     return dx
 
 
+def spatial_softmax_nhwc_fwd(x, out=None, temperature=1.0):
+    _chk(x, out)
+    N, H, W, C = x.shape
+    if out is None:
+        out = empty(N, 2 * C, like=x)
+    assert x.is_contiguous() and out.is_contiguous()
+    _L().hulc_spatial_softmax_nhwc_fwd(_ptr(x), _ptr(out), N, C, H, W, 1.0 / float(temperature), _stream())
+    return out
+
+
+def spatial_softmax_nhwc_bwd(x, dout, dx=None, temperature=1.0, relu_gate=True):
+    _chk(x, dout, dx)
+    N, H, W, C = x.shape
+    if dx is None:
+        dx = empty(N, H, W, C, like=x)
+    assert x.is_contiguous() and dout.is_contiguous() and dx.is_contiguous()
+    _L().hulc_spatial_softmax_nhwc_bwd(_ptr(x), _ptr(dout), _ptr(dx), N, C, H, W, 1.0 / float(temperature), int(relu_gate), _stream())
+    return dx
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # LayerNorm / transformer pieces
 # ----------------------------------------------------------------------------------------------------------------------

@@ -93,6 +93,11 @@ int hulc_spatial_softmax_fwd(const float* x, float* out, int rows, int H, int W,
 int hulc_spatial_softmax_bwd(const float* x, const float* dout, float* dx, int rows, int H, int W, float inv_temp, int relu_gate,
                              void* stream);
 
+/* the same on channels-last maps x [N, H*W, C] (the layout of the tensor-core convolutions); out [N, 2C] as above */
+int hulc_spatial_softmax_nhwc_fwd(const float* x, float* out, int N, int C, int H, int W, float inv_temp, void* stream);
+int hulc_spatial_softmax_nhwc_bwd(const float* x, const float* dout, float* dx, int N, int C, int H, int W, float inv_temp, int relu_gate,
+                                  void* stream);
+
 /* ---- LayerNorm (+ residual + dropout) ----------------------------------------------------------------------------------
  * nn.LayerNorm at vision_network.py:53, goal_encoders.py:29, and the post-norm residual blocks of
  * nn.TransformerEncoderLayer (plan_recognition_net.py:83-85): z = res + dropout(x) (z = x when res == NULL),

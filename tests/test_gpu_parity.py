@@ -32,16 +32,28 @@ VARIANTS = [
 ]
 
 
+# precision "fp32": every product on the exact-fp32 CUDA-core kernels, the latent plan sampled from injected uniforms (so
+# even the sampled classes must agree).  precision "tf32" (the default engine mode): tensor-core convolutions with tf32
+# operands + 3xTF32 forward GEMMs; losses and action logits are held to the SAME rtol 1e-3 / atol 1e-4, the sampled plan
+# classes are injected (a categorical sample is discontinuous in its logits), intermediates and gradients get the
+# tolerance of a 10-bit mantissa.  Gradients: a tf32 forward flips the ReLU gate of the ~1e-3 of conv pre-activations that sit
+# within rounding distance of zero; each flip is a 100 % error of that element's gradient, so the L2 error of the conv
+# gradients is ~sqrt(1e-3) = 3 % (measured 3.4 %), unbiased — the same holds for the reference under cuDNN's default tf32.
+TF32 = dict(inter_rtol=1e-2, inter_atol=5e-3, grad_rtol=8e-2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
 @pytest.mark.parametrize("model,rnn_model,p,B,S", VARIANTS)
-def test_step_matches_oracle(model, rnn_model, p, B, S):
-    res = run_pair(model, rnn_model, B=B, S=S, p=p, device="cuda")
-    rep = compare(res, rtol=RTOL, atol=ATOL)
-    assert rep["worst_grad"][1] < 2e-3, rep
+def test_step_matches_oracle(model, rnn_model, p, B, S, precision):
+    res = run_pair(model, rnn_model, B=B, S=S, p=p, device="cuda", precision=precision, use_idx=precision == "tf32")
+    rep = compare(res, rtol=RTOL, atol=ATOL, **(TF32 if precision == "tf32" else {}))
+    print(precision, rep)
+    assert rep["worst_grad"][1] < (8e-2 if precision == "tf32" else 2e-3), rep
 
 
 def test_gcbc_seq64_gru():
     """BASELINE config 5: GCBC, S=64 (needs max_position_embeddings=64), GRU decoder."""
-    res = run_pair("gcbc", "gru_decoder", B=2, S=64, p=0.0, device="cuda", max_window=64)
+    res = run_pair("gcbc", "gru_decoder", B=2, S=64, p=0.0, device="cuda", max_window=64, precision="fp32")
     # 64-step GRU chain: the conv bias gradients are sums with heavy cancellation over 600k pixels, so give the relative
     # gradient check a little more room than at S=8/32
     compare(res, rtol=RTOL, atol=ATOL, grad_rtol=5e-3)
@@ -58,20 +70,25 @@ GOLDEN = {
 }
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
 @pytest.mark.parametrize("name", list(GOLDEN))
-def test_step_matches_reference_fixture(name, golden_dir):
+def test_step_matches_reference_fixture(name, golden_dir, precision):
     from hulc_b200.engine import HulcEngine
 
     model, rnn_model, B, S, p = GOLDEN[name]
+    tf32 = precision == "tf32"
     fx = np.load(golden_dir / f"{name}.npz")
-    eng = HulcEngine(model, rnn_model, device="cuda", dropout_p=p)
+    eng = HulcEngine(model, rnn_model, device="cuda", dropout_p=p, precision=precision)
     eng.load_state_dict(synthetic.make_state_dict(model, rnn_model))
     batch = synthetic.make_batch(B, S, seed=1, device="cuda")
     mods = list(batch)
     noise = {m: synthetic.plan_noise(B, S, m) for m in mods}
     kw = {}
     if model == "hulc":
-        kw["plan_u"] = {m: noise[m]["u"].cuda() for m in mods}
+        if tf32:  # inject the classes the reference sampled (see the note above test_step_matches_oracle)
+            kw["plan_idx"] = {m: torch.from_numpy(fx[f"plan_idx_{m}"]).cuda() for m in mods}
+        else:
+            kw["plan_u"] = {m: noise[m]["u"].cuda() for m in mods}
     if model == "mcil":
         kw["plan_eps"] = {m: noise[m]["eps"].cuda() for m in mods}
     if p > 0:
@@ -106,9 +123,14 @@ def test_step_matches_reference_fixture(name, golden_dir):
         if gn < 0:
             assert float(g.abs().max()) == 0.0, k
             continue
-        np.testing.assert_allclose(float(g.norm()), gn, rtol=2e-3, atol=1e-8, err_msg=f"|grad {k}|")
+        np.testing.assert_allclose(float(g.norm()), gn, rtol=3e-2 if tf32 else 2e-3, atol=1e-8, err_msg=f"|grad {k}|")
         head = fx[f"gradhead/{k}"]
-        np.testing.assert_allclose(g.reshape(-1)[: head.size].numpy(), head, rtol=5e-3, atol=1e-6 + 1e-3 * gn, err_msg=f"grad {k}")
+        if tf32:  # L2 criterion (see the note on ReLU-gate flips above): 8 % of the larger of the slice norm and its expected share
+            ghead = g.reshape(-1)[: head.size].numpy()
+            bound = 8e-2 * max(float(np.linalg.norm(head)), gn * (head.size / g.numel()) ** 0.5) + 1e-7
+            assert float(np.linalg.norm(ghead - head)) <= bound, f"grad {k}: {np.linalg.norm(ghead - head):.3e} > {bound:.3e}"
+        else:
+            np.testing.assert_allclose(g.reshape(-1)[: head.size].numpy(), head, rtol=5e-3, atol=1e-6 + 1e-3 * gn, err_msg=f"grad {k}")
         checked += 1
     assert checked > 50
 

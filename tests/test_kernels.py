@@ -51,6 +51,19 @@ def test_spatial_softmax(K, h):
     torch.testing.assert_close(dx, x.grad * (x.detach() > 0), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("h,c", [(21, 64), (5, 8), (7, 100)])
+def test_spatial_softmax_channels_last(K, h, c):
+    x = torch.randn(3, c, h, h).relu_().requires_grad_(True)
+    ref = O.spatial_softmax(x)
+    xh = x.detach().permute(0, 2, 3, 1).contiguous()
+    out = K.spatial_softmax_nhwc_fwd(xh)
+    torch.testing.assert_close(out, ref.detach(), rtol=1e-5, atol=1e-6)
+    dout = torch.randn_like(ref)
+    ref.backward(dout)
+    dx = K.spatial_softmax_nhwc_bwd(xh, dout, relu_gate=True)
+    torch.testing.assert_close(dx.permute(0, 3, 1, 2), x.grad * (x.detach() > 0), rtol=1e-4, atol=1e-6)
+
+
 @pytest.mark.parametrize("D,rows", [(64, 37), (32, 5), (128, 70)])
 def test_layernorm_residual_dropout(K, D, rows):
     g = torch.Generator().manual_seed(D)
