@@ -214,13 +214,18 @@ struct KMajorLoader {
   static constexpr bool kMNMajor = false;
   const float* base;
   const float* base_lo;
-  int rows, K, ld, ld_lo, tiles_other, is_n;  // tile -> (tm, tn): tm = tile / tiles_n, tn = tile % tiles_n
-  int row0;
-  __device__ __forceinline__ void start_tile(int tile, int) { row0 = (is_n ? tile % tiles_other : tile / tiles_other) * ROWS; }
+  int rows, K, ld, ld_lo, tiles_other, is_n;  // tile -> ((tm, tn), k-split): tm = t2 / tiles_n, tn = t2 % tiles_n
+  int splits, kb_per_split;
+  int row0, kb0;
+  __device__ __forceinline__ void start_tile(int tile, int) {
+    const int t2 = tile / splits;
+    kb0 = (tile - t2 * splits) * kb_per_split;
+    row0 = (is_n ? t2 % tiles_other : t2 / tiles_other) * ROWS;
+  }
   __device__ __forceinline__ void issue(int kb, uint32_t dst, bool lo, int ptid) const {
     const float* b = lo ? base_lo : base;
     const int ldx = lo ? ld_lo : ld;
-    const int k0 = kb * kBK;
+    const int k0 = (kb0 + kb) * kBK;
 #pragma unroll
     for (int q = ptid; q < ROWS * 8; q += kProdThreads) {
       const int r = q >> 3, c = q & 7;
@@ -239,12 +244,17 @@ struct MNMajorLoader {
   const float* base;
   const float* base_lo;
   int rows, K, ld, ld_lo, tiles_other, is_n;
-  int row0;
-  __device__ __forceinline__ void start_tile(int tile, int) { row0 = (is_n ? tile % tiles_other : tile / tiles_other) * ROWS; }
+  int splits, kb_per_split;
+  int row0, kb0;
+  __device__ __forceinline__ void start_tile(int tile, int) {
+    const int t2 = tile / splits;
+    kb0 = (tile - t2 * splits) * kb_per_split;
+    row0 = (is_n ? t2 % tiles_other : t2 / tiles_other) * ROWS;
+  }
   __device__ __forceinline__ void issue(int kb, uint32_t dst, bool lo, int ptid) const {
     const float* b = lo ? base_lo : base;
     const int ldx = lo ? ld_lo : ld;
-    const int k0 = kb * kBK;
+    const int k0 = (kb0 + kb) * kBK;
     constexpr int RQ = ROWS / 4;
 #pragma unroll
     for (int q = ptid; q < kBK * RQ; q += kProdThreads) {

@@ -151,7 +151,11 @@ class HulcEngine:
         """0 = exact fp32 on CUDA cores; 1 = tf32 (backward products: they only feed gradients); 3 = 3xTF32 (forward
         products, whose outputs are held to the fp32 parity tolerance).  Small or skinny products stay on the CUDA-core
         split-K kernel, which is faster for them."""
-        if not self.tc or M < 256 or N < 128 or K < 128 or 2.0 * M * N * K < 2e9:
+        if not self.tc:
+            return 0
+        big = M >= 256 and N >= 128 and K >= 128 and 2.0 * M * N * K >= 2e9
+        skinny = M >= 32 and N >= 1024 and K >= 1024  # weight-streaming products (prior / goal MLPs): split-K on the tensor cores
+        if not (big or skinny):
             return 0
         return 3 if role == "fwd" else 1
 
@@ -345,19 +349,31 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     def _rnn_fwd(self, tag, pre, w_hh, b_hh, hbuf, col0, S, B, *, kind, reverse=False):
         """Run one direction of one layer.  pre [S*B, G*H] holds x W_ih^T + b_ih (+ b_hh for Elman cells); hbuf has S+2
-        time slots of [B, ld] (slot 0 and S+1 stay zero), h_t is written to slot t+1, columns col0:col0+H."""
+        time slots of [B, ld] (slot 0 and S+1 stay zero), h_t is written to slot t+1, columns col0:col0+H.
+        Tensor-core mode: every step is a split-K 3xTF32 product; the residual of W_hh is computed once per layer and the
+        residual of each h_t is written by the step that produces it."""
         H = self.H
         h = lambda slot: hbuf[slot, :, col0 : col0 + H]
         pre3 = pre.view(S, B, -1)
         saved = self.buf(f"{tag}.saved", S, B, 4 * H) if kind == "gru" else None
         gh = self.buf(f"{tag}.gh", B, 3 * H) if kind == "gru" else None
+        tc = 3 if self.tc else 0
+        w_lo = hlo = None
+        if tc:
+            w_lo = ops.split_lo(w_hh, self.buf(f"{tag}.w_lo", *w_hh.shape))
+            hlo = self.buf(f"{tag}.h_lo", S + 2, B, H, zero=True)
+        lo = lambda slot: hlo[slot] if tc else None
         for t in (range(S - 1, -1, -1) if reverse else range(S)):
-            prev = h(t + 2) if reverse else h(t)
+            ps = t + 2 if reverse else t
+            prev = h(ps)
             if kind == "gru":
-                self.gemm_fwd(prev, w_hh, gh, transB=True, bias=b_hh)
+                gemm(prev, w_hh, gh, transB=True, bias=b_hh, tc=tc, A_lo=lo(ps), B_lo=w_lo)
                 ops.gru_gates_fwd(pre3[t], gh, prev, h(t + 1), saved[t])
+                if tc:
+                    ops.split_lo(h(t + 1), hlo[t + 1])
             else:
-                self.gemm_fwd(prev, w_hh, h(t + 1), transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH)
+                gemm(prev, w_hh, h(t + 1), transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH, tc=tc, A_lo=lo(ps), B_lo=w_lo,
+                     C_lo=lo(t + 1))
         return saved
 
     def _rnn_bwd(self, tag, dh_above, w_hh, hbuf, col0, S, B, *, kind, saved=None, reverse=False):
@@ -376,7 +392,7 @@ class HulcEngine:
             for t in (range(S) if reverse else range(S - 1, -1, -1)):
                 prev = h(t + 2) if reverse else h(t)
                 ops.gru_gates_bwd(ab(t), None if first else rec, saved[t], prev, dgi[t], dgh[t], carry)
-                self.gemm_bwd(dgh[t], w_hh, rec, addend=carry)
+                gemm(dgh[t], w_hh, rec, addend=carry, tc=1 if self.tc else 0)
                 first = False
             return dgi.view(S * B, 3 * H), dgh.view(S * B, 3 * H)
         # Elman: dpre_t = (dh_above_t + dpre_{t+1} W_hh) * act'(h_t); slot S (or slot 0 for reverse) of dbuf stays zero
@@ -384,7 +400,7 @@ class HulcEngine:
         act = GATE_TANH if kind == "tanh" else 0
         for t in (range(S) if reverse else range(S - 1, -1, -1)):
             nxt, cur = (dbuf[t], dbuf[t + 1]) if reverse else (dbuf[t + 1], dbuf[t])
-            self.gemm_bwd(nxt, w_hh, cur, addend=ab(t), gate=h(t + 1), act=act)
+            gemm(nxt, w_hh, cur, addend=ab(t), gate=h(t + 1), act=act, tc=1 if self.tc else 0)
         d = (dbuf[1:] if reverse else dbuf[:S]).reshape(S * B, H)
         return d, d
 

