@@ -180,7 +180,12 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     whh = P["action_decoder.rnn.weight_hh_l1"]
     hb, pre1 = B_["dec.h1"], B_["dec.pre1"]
     big_a, big_c = B_["dec.dh0"], torch.empty(H, H, device=x.device)
-    cands["rnn_step_gemm"] = (lambda: ops.gemm(hb[1], whh, hb[2], transB=True, addend=pre1[:nB], act=1), 2.0 * nB * H * H, 4 * S)
+    if eng.tc:
+        cands["rnn_step_fwd_3xtf32"] = (lambda: ops.gemm(hb[1], whh, hb[2], transB=True, addend=pre1[:nB], act=1, tc=3), 2.0 * nB * H * H, 2 * S)
+        dbuf = B_["dec.l1.dpre"]
+        cands["rnn_step_bwd_tf32"] = (lambda: ops.gemm(dbuf[2], whh, dbuf[1], addend=big_a[:nB], gate=hb[2], tc=1), 2.0 * nB * H * H, 2 * S)
+    else:
+        cands["rnn_step_gemm"] = (lambda: ops.gemm(hb[1], whh, hb[2], transB=True, addend=pre1[:nB], act=1), 2.0 * nB * H * H, 4 * S)
     mode = 1 if eng.tc else 0
     cands["dense_wgrad_2048^3"] = (lambda: ops.gemm(big_a, hb[1 : S + 1].view(S * nB, H), big_c, transA=True, tc=mode), 2.0 * H * H * S * nB, 4)
     cands["dense_fwd_2048^3"] = (lambda: ops.gemm(big_a, whh, pre1, transB=True, tc=3 if eng.tc else 0), 2.0 * H * H * S * nB, 1)

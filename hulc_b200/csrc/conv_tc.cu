@@ -55,7 +55,7 @@ struct FwdNhwcLoader {
       rowoff[i] = off;
     }
   }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool, int ptid) const {
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
     constexpr int KB_PER_TAP = CIN / 32;
     const int c = ptid & 7;
     const int tap = kb / KB_PER_TAP, ci0 = (kb % KB_PER_TAP) * 32;
@@ -92,7 +92,7 @@ struct FwdNchw3Loader {
       rowoff[i] = off;
     }
   }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool, int ptid) const {
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
     static_assert(KS == 8, "k-block = 4 (ci, ky) pairs of 8 kx");
     const int c = ptid & 7;
     const int pair = kb * 4 + (c >> 1);
@@ -114,7 +114,7 @@ struct WeightLoader {
   const float* w;
   int K;
   __device__ __forceinline__ void start_tile(int, int) {}
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool, int ptid) const {
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
 #pragma unroll
     for (int q = ptid; q < ROWS * 8; q += kProdThreads) {
       const int r = q >> 3, c = q & 7;
@@ -169,7 +169,7 @@ struct DgradLoader {
       rowoff[i] = off; rowyx[i] = yx;
     }
   }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool, int ptid) const {
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
     constexpr int KB_PER_TAP = COUT / 32;
     const int c = ptid & 7;
     const int tap = kb / KB_PER_TAP, co0 = (kb % KB_PER_TAP) * 32;
@@ -233,7 +233,7 @@ struct WgradXLoader {
   WgradTiling t;
   int tm, pix0, pix_end;
   __device__ __forceinline__ void start_tile(int tile, int) { t.decode(tile, tm, pix0, pix_end); }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool, int ptid) const {
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
     const int c4 = ptid & 7, p = ptid >> 3;  // this thread: pixel p of the k-block, chunk c4 of each of the 4 k-groups
     const int pix = pix0 + kb * tc::kBK + p;
     const bool pv = pix < pix_end;
@@ -270,7 +270,7 @@ struct WgradDyLoader {
   WgradTiling t;
   int tm, pix0, pix_end;
   __device__ __forceinline__ void start_tile(int tile, int) { t.decode(tile, tm, pix0, pix_end); }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool, int ptid) const {
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
 #pragma unroll
     for (int q = ptid; q < COUT * 8; q += kProdThreads) {
       const int c4 = q & 7, p = (q >> 3) & 31, grp = q >> 8;

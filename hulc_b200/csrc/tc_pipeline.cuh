@@ -16,9 +16,13 @@
 // Operands are gathered by cp.async rather than TMA because the A operands on this path are im2col views of NHWC / NCHW
 // activations (per-row base addresses, zero-filled halo taps) and the dense GEMMs reuse the same machinery.
 //
-// fp32 operands are consumed as tf32 (the tensor core ignores the low 13 mantissa bits).  The 3-pass mode (SPLIT) also
-// loads "lo" tiles from residual buffers x - tf32(x) prepared by split_lo_kernel and issues lo*hi + hi*lo + hi*hi.
+// fp32 operands are consumed as tf32 (the tensor core ignores the low 13 mantissa bits).  In the 3-pass mode (SPLIT) each
+// producer thread, once its copies of a k-block have landed, reads its own chunks back from shared memory and writes the
+// residual x - tf32(x) into a second ("lo") tile; the MMA warp then issues lo*hi + hi*lo (into a side accumulator) and
+// hi*hi: 3xTF32, fp32-level accuracy without any extra global traffic.
 #pragma once
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace tc {
@@ -50,20 +54,36 @@ struct PipeBarriers {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  uint32_t flag;  // scratch for epilogue hooks (split-K "last CTA" election)
 };
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+
+template <class E, class = void>
+struct has_finish : std::false_type {};
+template <class E>
+struct has_finish<E, std::void_t<decltype(&E::finish)>> : std::true_type {};
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   // src-size 0 zero-fills the 16 bytes (out-of-range rows, k tails, halo taps)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// lo[off] = x - tf32(x) for one 16-byte chunk already resident at hi[off] (shared-memory addresses)
+__device__ __forceinline__ void lo_chunk(uint32_t hi, uint32_t lo) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi));
+  auto res = [](float f) { return f - __uint_as_float(__float_as_uint(f) & 0xFFFFE000u); };
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo), "f"(res(v.x)), "f"(res(v.y)), "f"(res(v.z)), "f"(res(v.w)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Loader interface (called by all kProdThreads producer threads, ptid = 0..255):
 //   static constexpr bool kMNMajor;                          // tile layout / descriptor flavour
 //   void start_tile(int tile, int ptid);
-//   void issue(int kb, uint32_t dst, bool lo, int ptid);     // cp.async this thread's 16-byte chunks of the [rows x BK] tile
+//   void issue(int kb, uint32_t dst, int ptid);              // cp.async this thread's 16-byte chunks of the [rows x BK] tile
+//   void split(uint32_t hi, uint32_t lo, int ptid);          // (3-pass) residuals of the same chunks, smem -> smem
 // Epilogue interface (called by the 128 epilogue threads):  void operator()(int tile, int row, int col0, const float* v32)
 template <int BN, bool SPLIT, int BK, class ALoader, class BLoader, class Epilogue>
 __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epilogue& ep, int num_tiles, int num_kb) {
@@ -118,6 +138,7 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
+      if constexpr (has_finish<Epilogue>::value) ep.finish(tile, warp, lane, &bars->flag);
     }
   } else if (warp == kEpiWarps) {
     // ================================ MMA issuer ================================
@@ -165,6 +186,11 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
     const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;
     int j = 0;  // k-block sequence number of this CTA
     auto publish = [&](int jj) {  // the cp.async group of k-block jj has landed: hand this warp's share to the MMA warp
+      if constexpr (SPLIT) {
+        const uint32_t hi = smem_u32(smem + (jj % S) * Cfg::kStageBytes);
+        al.split(hi, hi + Cfg::kATile, ptid);
+        bl.split(hi + 2 * Cfg::kATile, hi + 2 * Cfg::kATile + Cfg::kBTile, ptid);
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->full[jj % S]);
@@ -176,15 +202,9 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
         const int stage = j % S;
         mbar_wait(&bars->empty[stage], ((j / S) & 1) ^ 1);
         const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t a_lo = a_hi + Cfg::kATile;
         const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * Cfg::kATile;
-        const uint32_t b_lo = b_hi + Cfg::kBTile;
-        al.issue(kb, a_hi, false, ptid);
-        bl.issue(kb, b_hi, false, ptid);
-        if (SPLIT) {
-          al.issue(kb, a_lo, true, ptid);
-          bl.issue(kb, b_lo, true, ptid);
-        }
+        al.issue(kb, a_hi, ptid);
+        bl.issue(kb, b_hi, ptid);
         cp_async_commit();
         if (j >= L) {
           cp_async_wait<L>();
@@ -207,32 +227,33 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
 // ---- dense operand loaders ----------------------------------------------------------------------------------------------
 // Logical operand: ROWS x K (rows = M or N index).  Requirements (checked by the host wrappers): 16-byte aligned base,
 // ld % 4 == 0, K % 4 == 0 (K-major) / rows % 4 == 0 (MN-major), so every 16-byte chunk is entirely valid or entirely zero.
+// Work items: tile -> ((tm, tn), k-split).
 
 // stored rows x K row-major (K contiguous): K-major tile [ROWS][BK], 128-byte rows, SWIZZLE_128B
 template <int ROWS>
 struct KMajorLoader {
   static constexpr bool kMNMajor = false;
   const float* base;
-  const float* base_lo;
-  int rows, K, ld, ld_lo, tiles_other, is_n;  // tile -> ((tm, tn), k-split): tm = t2 / tiles_n, tn = t2 % tiles_n
-  int splits, kb_per_split;
+  int rows, K, ld, tiles_n, is_n, splits, kb_per_split;
   int row0, kb0;
   __device__ __forceinline__ void start_tile(int tile, int) {
     const int t2 = tile / splits;
     kb0 = (tile - t2 * splits) * kb_per_split;
-    row0 = (is_n ? t2 % tiles_other : t2 / tiles_other) * ROWS;
+    row0 = (is_n ? t2 % tiles_n : t2 / tiles_n) * ROWS;
   }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool lo, int ptid) const {
-    const float* b = lo ? base_lo : base;
-    const int ldx = lo ? ld_lo : ld;
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
     const int k0 = (kb0 + kb) * kBK;
 #pragma unroll
     for (int q = ptid; q < ROWS * 8; q += kProdThreads) {
       const int r = q >> 3, c = q & 7;
       const int row = row0 + r, k = k0 + c * 4;
       const bool ok = row < rows && k < K;
-      cp_async16(dst + swz(r, c), ok ? (const void*)(b + (size_t)row * ldx + k) : (const void*)b, ok);
+      cp_async16(dst + swz(r, c), ok ? (const void*)(base + (size_t)row * ld + k) : (const void*)base, ok);
     }
+  }
+  __device__ __forceinline__ void split(uint32_t hi, uint32_t lo, int ptid) const {
+#pragma unroll
+    for (int q = ptid; q < ROWS * 8; q += kProdThreads) lo_chunk(hi + swz(q >> 3, q & 7), lo + swz(q >> 3, q & 7));
   }
 };
 
@@ -242,18 +263,19 @@ template <int ROWS>
 struct MNMajorLoader {
   static constexpr bool kMNMajor = true;
   const float* base;
-  const float* base_lo;
-  int rows, K, ld, ld_lo, tiles_other, is_n;
-  int splits, kb_per_split;
+  int rows, K, ld, tiles_n, is_n, splits, kb_per_split;
   int row0, kb0;
   __device__ __forceinline__ void start_tile(int tile, int) {
     const int t2 = tile / splits;
     kb0 = (tile - t2 * splits) * kb_per_split;
-    row0 = (is_n ? t2 % tiles_other : t2 / tiles_other) * ROWS;
+    row0 = (is_n ? t2 % tiles_n : t2 / tiles_n) * ROWS;
   }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, bool lo, int ptid) const {
-    const float* b = lo ? base_lo : base;
-    const int ldx = lo ? ld_lo : ld;
+  static __device__ __forceinline__ uint32_t offset(int q) {
+    constexpr int RQ = ROWS / 4;
+    const int kk = q / RQ, r = (q % RQ) * 4;
+    return (uint32_t)(r >> 5) * (kBK * kRowBytes) + swz32(kk, (r & 31) >> 2);
+  }
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
     const int k0 = (kb0 + kb) * kBK;
     constexpr int RQ = ROWS / 4;
 #pragma unroll
@@ -261,9 +283,12 @@ struct MNMajorLoader {
       const int kk = q / RQ, r = (q % RQ) * 4;
       const int row = row0 + r, k = k0 + kk;
       const bool ok = row < rows && k < K;
-      const uint32_t off = (uint32_t)(r >> 5) * (kBK * kRowBytes) + swz32(kk, (r & 31) >> 2);
-      cp_async16(dst + off, ok ? (const void*)(b + (size_t)k * ldx + row) : (const void*)b, ok);
+      cp_async16(dst + offset(q), ok ? (const void*)(base + (size_t)k * ld + row) : (const void*)base, ok);
     }
+  }
+  __device__ __forceinline__ void split(uint32_t hi, uint32_t lo, int ptid) const {
+#pragma unroll
+    for (int q = ptid; q < kBK * (ROWS / 4); q += kProdThreads) lo_chunk(hi + offset(q), lo + offset(q));
   }
 };
 

@@ -350,30 +350,20 @@ class HulcEngine:
     def _rnn_fwd(self, tag, pre, w_hh, b_hh, hbuf, col0, S, B, *, kind, reverse=False):
         """Run one direction of one layer.  pre [S*B, G*H] holds x W_ih^T + b_ih (+ b_hh for Elman cells); hbuf has S+2
         time slots of [B, ld] (slot 0 and S+1 stay zero), h_t is written to slot t+1, columns col0:col0+H.
-        Tensor-core mode: every step is a split-K 3xTF32 product; the residual of W_hh is computed once per layer and the
-        residual of each h_t is written by the step that produces it."""
+        Tensor-core mode: every step is a split-K 3xTF32 product (fp32-level accuracy on the 32-step chain)."""
         H = self.H
         h = lambda slot: hbuf[slot, :, col0 : col0 + H]
         pre3 = pre.view(S, B, -1)
         saved = self.buf(f"{tag}.saved", S, B, 4 * H) if kind == "gru" else None
         gh = self.buf(f"{tag}.gh", B, 3 * H) if kind == "gru" else None
         tc = 3 if self.tc else 0
-        w_lo = hlo = None
-        if tc:
-            w_lo = ops.split_lo(w_hh, self.buf(f"{tag}.w_lo", *w_hh.shape))
-            hlo = self.buf(f"{tag}.h_lo", S + 2, B, H, zero=True)
-        lo = lambda slot: hlo[slot] if tc else None
         for t in (range(S - 1, -1, -1) if reverse else range(S)):
-            ps = t + 2 if reverse else t
-            prev = h(ps)
+            prev = h(t + 2) if reverse else h(t)
             if kind == "gru":
-                gemm(prev, w_hh, gh, transB=True, bias=b_hh, tc=tc, A_lo=lo(ps), B_lo=w_lo)
+                gemm(prev, w_hh, gh, transB=True, bias=b_hh, tc=tc)
                 ops.gru_gates_fwd(pre3[t], gh, prev, h(t + 1), saved[t])
-                if tc:
-                    ops.split_lo(h(t + 1), hlo[t + 1])
             else:
-                gemm(prev, w_hh, h(t + 1), transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH, tc=tc, A_lo=lo(ps), B_lo=w_lo,
-                     C_lo=lo(t + 1))
+                gemm(prev, w_hh, h(t + 1), transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH, tc=tc)
         return saved
 
     def _rnn_bwd(self, tag, dh_above, w_hh, hbuf, col0, S, B, *, kind, saved=None, reverse=False):

@@ -81,7 +81,7 @@ def zeros(*shape, like: torch.Tensor) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------------------------------------------------
 def gemm(A, B, C=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, addend=None, add_mod=0, act=0,
-         gate=None, drop: Drop = NO_DROP, tc: int = 0, A_lo=None, B_lo=None, C_lo=None):
+         gate=None, drop: Drop = NO_DROP, tc: int = 0):
     """C = epi(alpha * op(A) @ op(B)); see hulc_gemm in include/hulc_b200.h.  A, B, C, addend, gate are 2-D views with
     contiguous rows (arbitrary leading dimension).  tc = 0: exact-fp32 CUDA-core kernel; tc = 1 / 3: tensor cores
     (hulc_gemm_tc) with tf32 operands / 3xTF32 split products."""
@@ -99,8 +99,7 @@ def gemm(A, B, C=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=
         _L().hulc_gemm_tc(
             _ptr(A), _ptr(B), _ptr(C), M, N, K, _rowmajor(A), _rowmajor(B), _rowmajor(C), int(transA), int(transB), float(alpha),
             float(beta), _ptr(bias), _ptr(addend), _rowmajor(addend) if addend is not None else 0, int(add_mod), int(act), _ptr(gate),
-            _rowmajor(gate) if gate is not None else 0, *drop.args(), int(tc), _ptr(A_lo), _ptr(B_lo), _ptr(C_lo),
-            _rowmajor(C_lo) if C_lo is not None else 0, _ptr(ws), ws.numel() * 4, _stream(),
+            _rowmajor(gate) if gate is not None else 0, *drop.args(), int(tc), _ptr(ws), ws.numel() * 4, _stream(),
         )
         return C
     ws = workspace(A.device)
@@ -116,15 +115,6 @@ def _tc_ok(A, B, M, N, K, transA, transB) -> bool:
     lda, ldb = _rowmajor(A), _rowmajor(B)
     return (A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0
             and (M if transA else K) % 4 == 0 and (K if transB else N) % 4 == 0)
-
-
-def split_lo(x, lo):
-    """lo = x - tf32(x): the residual operand of the 3xTF32 products (compact copy)."""
-    _chk(x, lo)
-    rows, cols = x.shape
-    assert lo.is_contiguous() and lo.shape == x.shape
-    _L().hulc_split_lo(_ptr(x), _rowmajor(x), _ptr(lo), rows, cols, _stream())
-    return lo
 
 
 def launch_count() -> int:

@@ -36,18 +36,14 @@ int hulc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int
               const unsigned char* drop_keep, float* workspace, size_t workspace_bytes, void* stream);
 
 /* hulc_gemm_tc: the same contract on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in TMEM).  passes = 1:
- * operands consumed as tf32; passes = 3: 3xTF32 split products (fp32-level accuracy) using residual operands x - tf32(x):
- * A_lo / B_lo (compact copies from hulc_split_lo; NULL = computed into the workspace); C_lo (optional, leading dimension
- * ldc_lo) receives the residual of the result for a following product.  Skinny products are split along K (partials in the
- * workspace, fixed-order reduction).  Operands must be 16-byte aligned with lda, ldb and their contiguous extents multiples
- * of 4, else cudaErrorInvalidValue. */
+ * operands consumed as tf32; passes = 3: 3xTF32 split products (fp32-level accuracy; the residuals x - tf32(x) are formed
+ * in shared memory).  Skinny products are split along K (partials and tickets in the workspace, fixed-order reduction by
+ * the last CTA of each tile).  Operands must be 16-byte aligned with lda, ldb and their contiguous extents multiples of 4,
+ * else cudaErrorInvalidValue. */
 int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                  float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act,
                  const float* gate, int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site,
-                 const unsigned char* drop_keep, int passes, const float* A_lo, const float* B_lo, float* C_lo, int ldc_lo,
-                 float* workspace, size_t workspace_bytes, void* stream);
-/* lo[r][c] = x[r*ld + c] - tf32(x[r*ld + c]) as a compact rows x cols matrix */
-int hulc_split_lo(const float* x, int ld, float* lo, int rows, int cols, void* stream);
+                 const unsigned char* drop_keep, int passes, float* workspace, size_t workspace_bytes, void* stream);
 
 /* *out (HOST pointer) = number of kernel launches this library has issued since it was loaded (bench.py's gpu_launches). */
 int hulc_launch_count(unsigned long long* out);
