@@ -100,16 +100,23 @@ struct DropSpec {
   float p;
   float scale;  // 1/(1-p)
   unsigned long long seed;
+  const unsigned long long* seed_ptr;  // optional device-resident offset added to `seed` (see hulc_set_rng_offset_ptr)
   unsigned site;
   const unsigned char* keep;
 };
+// effective Philox seed: the by-value seed plus the device-resident offset.  Keeping the per-step part of the seed in device
+// memory lets a captured CUDA graph of the whole training step draw fresh dropout masks / plan samples on every replay.
+__device__ __forceinline__ unsigned long long rng_seed(unsigned long long seed, const unsigned long long* seed_ptr) {
+  return seed + (seed_ptr ? *seed_ptr : 0ull);
+}
 __device__ __forceinline__ float drop_factor(const DropSpec& d, unsigned long long idx) {
   if (d.p <= 0.f) return 1.f;
-  bool k = d.keep ? (d.keep[idx] != 0) : (philox_uniform(d.seed, d.site, idx) >= d.p);
+  bool k = d.keep ? (d.keep[idx] != 0) : (philox_uniform(rng_seed(d.seed, d.seed_ptr), d.site, idx) >= d.p);
   return k ? d.scale : 0.f;
 }
+extern const unsigned long long* g_hulc_rng_offset_ptr;  // device pointer or null; set by hulc_set_rng_offset_ptr
 static inline DropSpec make_drop(float p, unsigned long long seed, unsigned site, const unsigned char* keep) {
   DropSpec d;
-  d.p = p; d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f; d.seed = seed; d.site = site; d.keep = keep;
+  d.p = p; d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f; d.seed = seed; d.seed_ptr = g_hulc_rng_offset_ptr; d.site = site; d.keep = keep;
   return d;
 }

@@ -314,6 +314,12 @@ __global__ void scale_vec_kernel(float* x, int n, float s) {
 }  // namespace
 
 unsigned long long g_hulc_launches = 0;
+const unsigned long long* g_hulc_rng_offset_ptr = nullptr;
+
+HULC_API int hulc_set_rng_offset_ptr(const unsigned long long* device_ptr) {
+  g_hulc_rng_offset_ptr = device_ptr;
+  return 0;
+}
 
 HULC_API int hulc_launch_count(unsigned long long* out) {
   if (!out) return (int)cudaErrorInvalidValue;

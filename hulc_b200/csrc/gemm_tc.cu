@@ -88,25 +88,46 @@ struct TcEpilogue {
     if (*flag) {
       __threadfence();
       const int tm = t2 / tiles_n, tn = t2 % tiles_n;
-      for (int r = warp; r < tc::kBM; r += tc::kEpiWarps) {
-        const int m = tm * tc::kBM + r;
-        if (m >= M) break;
+      const bool vec = (N & 3) == 0 && (ldc & 3) == 0 && (reinterpret_cast<size_t>(C) & 15) == 0;
+      constexpr int RG = 4;  // rows per round: RG x 4 independent 16-byte loads in flight per thread hide the L2 latency
+      for (int rb = warp * RG; rb < tc::kBM; rb += tc::kEpiWarps * RG) {
+        const int m0 = tm * tc::kBM + rb;
+        if (m0 >= M) break;
         for (int c = lane * 4; c < BN; c += 128) {
           const int n = tn * BN + c;
           if (n >= N) break;
-          if ((N & 3) == 0 && (ldc & 3) == 0 && (reinterpret_cast<size_t>(C) & 15) == 0) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int k = 0; k < splits; ++k) {
-              const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)k * M + m) * N + n));
-              s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+          if (vec) {
+            float4 acc[RG];
+#pragma unroll
+            for (int i = 0; i < RG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k0 = 0; k0 < splits; k0 += 4) {
+              float4 p[RG][4];
+#pragma unroll
+              for (int i = 0; i < RG; ++i)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const bool ok = m0 + i < M && k0 + kk < splits;
+                  p[i][kk] = ok ? __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)(k0 + kk) * M + m0 + i) * N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+              for (int i = 0; i < RG; ++i)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) { acc[i].x += p[i][kk].x; acc[i].y += p[i][kk].y; acc[i].z += p[i][kk].z; acc[i].w += p[i][kk].w; }
             }
-            *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = make_float4(one(s.x, m, n), one(s.y, m, n + 1), one(s.z, m, n + 2), one(s.w, m, n + 3));
+#pragma unroll
+            for (int i = 0; i < RG; ++i) {
+              const int m = m0 + i;
+              if (m < M)
+                *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) =
+                    make_float4(one(acc[i].x, m, n), one(acc[i].y, m, n + 1), one(acc[i].z, m, n + 2), one(acc[i].w, m, n + 3));
+            }
           } else {
-            for (int e = 0; e < 4 && n + e < N; ++e) {
-              float s = 0.f;
-              for (int k = 0; k < splits; ++k) s += __ldcg(partial + ((size_t)k * M + m) * N + n + e);
-              C[(size_t)m * ldc + n + e] = one(s, m, n + e);
-            }
+            for (int i = 0; i < RG && m0 + i < M; ++i)
+              for (int e = 0; e < 4 && n + e < N; ++e) {
+                float s = 0.f;
+                for (int k = 0; k < splits; ++k) s += __ldcg(partial + ((size_t)k * M + m0 + i) * N + n + e);
+                C[(size_t)(m0 + i) * ldc + n + e] = one(s, m0 + i, n + e);
+              }
           }
         }
       }

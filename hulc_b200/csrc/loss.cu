@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) logistic_loss_kernel(const float* __restr
 __global__ void __launch_bounds__(256) plan_discrete_fwd_kernel(const float* __restrict__ pr_logit, const float* __restrict__ pp_logit,
                                                                 const float* __restrict__ u_in, const int* __restrict__ idx_in,
                                                                 float* __restrict__ plan, int* __restrict__ idx_out, float* __restrict__ kl_rows,
-                                                                int rows, unsigned long long seed, unsigned site) {
+                                                                int rows, unsigned long long seed, const unsigned long long* seed_ptr, unsigned site) {
   int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   float lq = pr_logit[(size_t)row * 32 + lane];
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) plan_discrete_fwd_kernel(const float* __r
   int idx;
   if (idx_in) idx = idx_in[row];
   else {
-    float u = u_in ? u_in[row] : philox_uniform(seed, site, (unsigned long long)row);
+    float u = u_in ? u_in[row] : philox_uniform(rng_seed(seed, seed_ptr), site, (unsigned long long)row);
     // sequential inclusive prefix sum (same association as torch.cumsum) -> #{j : c_j <= u}
     float c = 0.f;
     int cnt = 0;
@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(256) plan_discrete_bwd_kernel(const float* __r
 // plan = mean + std * eps, KL(N_q || N_p) summed over dims.  One thread per (sequence, dim).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void plan_cont_fwd_kernel(const float* __restrict__ pr, const float* __restrict__ pp, const float* __restrict__ eps_in,
-                                     float* __restrict__ plan, float* __restrict__ kl_elem, int Bn, int P, unsigned long long seed, unsigned site) {
+                                     float* __restrict__ plan, float* __restrict__ kl_elem, int Bn, int P, unsigned long long seed0,
+                                     const unsigned long long* seed_ptr, unsigned site) {
+  const unsigned long long seed = rng_seed(seed0, seed_ptr);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * P) return;
   int b = i / P, d = i % P;
@@ -264,7 +266,9 @@ __global__ void plan_cont_fwd_kernel(const float* __restrict__ pr, const float* 
 }
 __global__ void plan_cont_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ pp, const float* __restrict__ eps_in,
                                      const float* __restrict__ dplan, const float* __restrict__ dkl, float coef_lhs, float coef_rhs,
-                                     float* __restrict__ d_pr, float* __restrict__ d_pp, int Bn, int P, unsigned long long seed, unsigned site) {
+                                     float* __restrict__ d_pr, float* __restrict__ d_pp, int Bn, int P, unsigned long long seed0,
+                                     const unsigned long long* seed_ptr, unsigned site) {
+  const unsigned long long seed = rng_seed(seed0, seed_ptr);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * P) return;
   int b = i / P, d = i % P;
@@ -425,7 +429,7 @@ HULC_API int hulc_plan_discrete_fwd(const float* pr_logit, const float* pp_logit
   if (rows <= 0) return 0;
   if (class_size != 32) return (int)cudaErrorInvalidValue;
   HULC_LAUNCH(plan_discrete_fwd_kernel, dim3(hulc_cdiv(rows, 8)), dim3(256), 0, (cudaStream_t)stream, pr_logit, pp_logit, u, idx_in, plan, idx_out,
-              kl_rows, rows, seed, site);
+              kl_rows, rows, seed, g_hulc_rng_offset_ptr, site);
   HULC_RETURN_LAST();
 }
 
@@ -443,7 +447,7 @@ HULC_API int hulc_plan_cont_fwd(const float* pr_state, const float* pp_state, co
   int n = batch * plan_features;
   if (n <= 0) return 0;
   HULC_LAUNCH(plan_cont_fwd_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, pr_state, pp_state, eps, plan, kl_elem, batch,
-              plan_features, seed, site);
+              plan_features, seed, g_hulc_rng_offset_ptr, site);
   HULC_RETURN_LAST();
 }
 
@@ -453,7 +457,7 @@ HULC_API int hulc_plan_cont_bwd(const float* pr_state, const float* pp_state, co
   int n = batch * plan_features;
   if (n <= 0) return 0;
   HULC_LAUNCH(plan_cont_bwd_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, pr_state, pp_state, eps, dplan, dkl, coef_lhs,
-              coef_rhs, d_pr, d_pp, batch, plan_features, seed, site);
+              coef_rhs, d_pr, d_pp, batch, plan_features, seed, g_hulc_rng_offset_ptr, site);
   HULC_RETURN_LAST();
 }
 

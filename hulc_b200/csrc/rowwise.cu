@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(256) nchw_channel_sum_kernel(const float* __re
 
 // torch.optim.Adam (no weight decay, no amsgrad): one launch over the flat parameter buffer
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
-                            float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+                            float b1, float b2, float eps, int step, const int* __restrict__ step_ptr, float grad_scale) {
+  if (step_ptr) step = *step_ptr;  // device-resident step count: the launch can live in a replayed CUDA graph
+  const float bc1 = 1.f - powf(b1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -434,12 +437,10 @@ HULC_API int hulc_nchw_channel_sum(const float* x, float* out, int N, int C, int
 }
 
 HULC_API int hulc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, int step,
-                            float grad_scale, void* stream) {
+                            const int* step_ptr, float grad_scale, void* stream) {
   if (n <= 0) return 0;
-  float bc1 = 1.f - powf(beta1, (float)step);
-  float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   int blocks = (int)min((long long)kNumSMs * 8, (n + 255) / 256);
-  HULC_LAUNCH(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+  HULC_LAUNCH(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, step, step_ptr, grad_scale);
   HULC_RETURN_LAST();
 }
 

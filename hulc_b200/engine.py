@@ -53,6 +53,7 @@ class ParamStore:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.keys = list(spec)
         self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)  # device copy of step_count (read by the Adam kernel)
         self._head_w, self._head_b = head_w, head_b
         self.rebuild_views()
 
@@ -89,9 +90,26 @@ class ParamStore:
         self.grad.zero_()
 
     def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        """torch.optim.Adam update of the whole flat buffer in one launch.  The step count lives on the device so that the
+        launch can be captured in (and replayed from) a CUDA graph."""
         self.step_count += 1
+        self.step_dev.add_(1)
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
-                      step=self.step_count, grad_scale=grad_scale)
+                      step=0, step_dev=self.step_dev, grad_scale=grad_scale)
+
+
+class StepGraph:
+    """A captured training step (see HulcEngine.capture)."""
+
+    def __init__(self, engine, graph, out, optimizer, launches):
+        self.engine, self.graph, self.out, self.optimizer = engine, graph, out, optimizer
+        self.launches = launches  # kernels of libhulc_b200.so inside one replay
+
+    def replay(self) -> Dict[str, torch.Tensor]:
+        self.graph.replay()
+        if self.optimizer:
+            self.engine.ps.step_count += 1
+        return self.out
 
 
 class HulcEngine:
@@ -123,7 +141,8 @@ class HulcEngine:
         self._bufs: Dict[str, torch.Tensor] = {}
         self._step_shapes: Dict[str, tuple] = {}
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
-        self.launches = 0
+        # per-step Philox seed, device resident: advanced on the device so a captured step draws fresh randomness per replay
+        self.rng_dev = torch.zeros(1, dtype=torch.int64, device=device)
 
     # ------------------------------------------------------------------------------------------------------------------
     def buf(self, name, *shape, zero=False):
@@ -398,14 +417,21 @@ class HulcEngine:
     # the step
     # ------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_u=None, plan_eps=None, dropout_masks=None, seed: int = 0,
+    def step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_u=None, plan_eps=None, dropout_masks=None, seed: Optional[int] = None,
              backward: bool = True) -> Dict[str, torch.Tensor]:
         """One fused forward(+backward) over `batch` (the reference's {"vis": ..., "lang": ...} contract).  Gradients of
         total_loss land in `self.ps.grad` (zeroed first).  Randomness: `plan_idx[m]` / `plan_u[m]` / `plan_eps[m]` and
         `dropout_masks` (dict site -> uint8 keep mask over the whole batch, modalities concatenated in batch order)
-        inject it for parity runs; otherwise Philox streams keyed on `seed`."""
+        inject it for parity runs; otherwise Philox streams keyed on `seed` (None: the previous seed + 1)."""
         P, G, ps = self.ps.p, self.ps.g, self.ps
         self._step_shapes.clear()
+        if seed is not None:
+            self.rng_dev.fill_(int(seed))
+        else:
+            self.rng_dev.add_(1)
+        if self.device.type == "cuda":
+            ops.set_rng_offset(self.rng_dev)
+        seed = 0 if self.device.type == "cuda" else int(self.rng_dev.item())  # by-value part of the seed (all of it on the emulator)
         mods = list(batch.keys())
         n_mod = len(mods)
         Bs = [batch[m]["actions"].shape[0] for m in mods]
@@ -782,6 +808,23 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     def optimizer_step(self, grad_scale=1.0):
         self.ps.adam_step(lr=self.lr, grad_scale=grad_scale)
+
+    def capture(self, batch, *, optimizer: bool = True, grad_scale: float = 1.0) -> "StepGraph":
+        """Capture forward + backward (+ Adam) over `batch` into a CUDA graph: ~500 kernel launches become one
+        cudaGraphLaunch, which removes the host launch cost that otherwise bounds the 128 dependent recurrent steps.  The
+        tensors of `batch` are the graph's static inputs (copy new data into them before each replay); the per-step RNG
+        seed and the Adam step count advance on the device."""
+        self.step(batch)  # eager warm-up: allocates every activation buffer the step needs
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g):
+            out = self.step(batch)
+            if optimizer:
+                self.ps.adam_step(lr=self.lr, grad_scale=grad_scale)
+        if optimizer:
+            self.ps.step_count -= 1  # the capture itself did not execute the update
+        return StepGraph(self, g, out, optimizer, ops.launch_count() - n0)
 
     def check_nan_flag(self):
         """The reference asserts on NaNs inside world_to_tcp_frame every step (gripper_control.py:35), which stalls the

@@ -57,6 +57,14 @@ def _get(cfg, key, default=None):
         return getattr(cfg, key, default)
 
 
+def _tensors(d):
+    for v in d.values():
+        if isinstance(v, dict):
+            yield from _tensors(v)
+        elif torch.is_tensor(v):
+            yield v
+
+
 class _Block(nn.Module):
     """Name-space node so that `state_dict()` reproduces the reference's dotted keys."""
 
@@ -175,7 +183,7 @@ class Hulc(_Base):
         self.optimizer_config, self.lr_scheduler = optimizer, lr_scheduler
         self.replan_freq = replan_freq
         self.val_instructions = val_instructions
-        self._seed = 0
+        self._graphs = None
         self.save_hyperparameters()
 
     # ---- parameter plumbing ---------------------------------------------------------------------------------------------
@@ -272,11 +280,20 @@ class Hulc(_Base):
         self.kl_beta = kl_beta
         self.engine.kl_beta = float(kl_beta)
 
+    def enable_cuda_graphs(self, flag: bool = True):
+        """Replay the training step from a CUDA graph captured per distinct set of input buffers (the batch tensors are the
+        graph's static inputs: a loader that re-uses its device staging buffers hits the same graph every step)."""
+        self._graphs = {} if flag else None
+
     def fused_step(self, batch, **inject) -> Dict[str, torch.Tensor]:
         """Forward + backward in the kernels; gradients land in the flat gradient buffer.  No autograd graph."""
-        self._seed += 1
-        out = self.engine.step(batch, seed=inject.pop("seed", self._seed), **inject)
-        return out
+        if self._graphs is not None and not inject:
+            key = tuple((t.data_ptr(), tuple(t.shape)) for t in _tensors(batch))
+            sg = self._graphs.get(key)
+            if sg is None:
+                sg = self._graphs[key] = self.engine.capture(batch, optimizer=False)
+            return sg.replay()
+        return self.engine.step(batch, **inject)
 
     def training_step(self, batch: Dict[str, Dict], batch_idx: int = 0, **inject) -> torch.Tensor:
         """hulc.py:390-537.  Returns total_loss with an autograd edge to every parameter, so Lightning's

@@ -62,8 +62,9 @@ def _rowmajor(t: torch.Tensor) -> int:
 
 
 def workspace(device) -> torch.Tensor:
-    """Zero-initialised scratch for split-K partials and counters, one per (device, stream)."""
-    key = (str(device), _stream())
+    """Zero-initialised scratch for split-K partials and tickets, one per device (calls are issued on one stream at a time;
+    keying it by stream would re-allocate — and re-zero on every replay — inside a CUDA-graph capture)."""
+    key = str(device)
     ws = _workspaces.get(key)
     if ws is None:
         ws = torch.zeros(_WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
@@ -424,8 +425,16 @@ def clip_loss(im, tx, logit_scale, mask, loss, d_im, d_tx, d_logit_scale, grad_s
                         float(grad_scale), _stream())
 
 
-def adam_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, grad_scale=1.0):
+def set_rng_offset(t: Optional[torch.Tensor]):
+    """Point the library's device-resident RNG offset at a 1-element int64 tensor (None clears it)."""
+    if t is not None:
+        _chk(t, dtype=torch.int64)
+    _L().hulc_set_rng_offset_ptr(_ptr(t))
+
+
+def adam_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, grad_scale=1.0, step_dev=None):
     _chk(p, g, m, v)
+    _chk(step_dev, dtype=torch.int32)
     assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
     _L().hulc_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
-                        float(grad_scale), _stream())
+                        _ptr(step_dev), float(grad_scale), _stream())

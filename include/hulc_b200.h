@@ -45,6 +45,11 @@ int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, 
                  const float* gate, int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site,
                  const unsigned char* drop_keep, int passes, float* workspace, size_t workspace_bytes, void* stream);
 
+/* Device-resident RNG offset: when set (non-NULL device pointer), every Philox-drawn quantity (dropout keep decisions, latent
+ * plan samples) uses seed + *ptr.  Advancing *ptr on the device between steps gives a captured CUDA graph of the whole
+ * training step fresh randomness on every replay. */
+int hulc_set_rng_offset_ptr(const unsigned long long* device_ptr);
+
 /* *out (HOST pointer) = number of kernel launches this library has issued since it was loaded (bench.py's gpu_launches). */
 int hulc_launch_count(unsigned long long* out);
 
@@ -169,9 +174,10 @@ int hulc_clip_loss(const float* im, const float* tx, const float* logit_scale, c
                    float* d_tx, float* d_logit_scale, int n, int D, float grad_scale, void* stream);
 
 /* ---- optimizer: torch.optim.Adam(lr, betas, eps), no weight decay (hulc/models/hulc.py:239-252) over a flat buffer ---------
- * g is multiplied by grad_scale first (1/world after the all-reduce); `step` is the 1-based step count. */
+ * g is multiplied by grad_scale first (1/world after the all-reduce); `step` is the 1-based step count, read from the device
+ * integer *step_ptr instead when step_ptr != NULL (so the launch can be replayed from a CUDA graph). */
 int hulc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, int step,
-                   float grad_scale, void* stream);
+                   const int* step_ptr, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from hulc_b200 import ops
 
-def t(fn, n=10):
+def t(fn, n=20):
     fn(); fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -13,7 +13,7 @@ def t(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-for (M, N, K, tA, tB) in [(2048, 2048, 1120, 0, 1), (2048, 2048, 2048, 0, 1), (2048, 2048, 2048, 0, 0), (2048, 2048, 2048, 1, 0), (8192, 8192, 4096, 0, 1), (2048, 182, 2048, 0, 1), (2048, 4096, 128, 0, 1)]:
+for (M, N, K, tA, tB) in [(64, 2048, 2048, 0, 1), (64, 2048, 2048, 0, 0), (64, 6144, 2048, 0, 1), (64, 2048, 160, 0, 1), (2048, 2048, 1120, 0, 1), (2048, 2048, 2048, 0, 1), (2048, 2048, 2048, 0, 0), (2048, 2048, 2048, 1, 0), (8192, 8192, 4096, 0, 1), (2048, 182, 2048, 0, 1), (2048, 4096, 128, 0, 1)]:
     A = torch.randn((K, M) if tA else (M, K), device="cuda"); B = torch.randn((N, K) if tB else (K, N), device="cuda"); C = torch.empty(M, N, device="cuda")
     fl = 2.0 * M * N * K
     r = {}
