@@ -334,7 +334,7 @@ __global__ void prep_dgrad_weights_kernel(const float* __restrict__ w, float* __
 
 template <int BN, class AL, class BL, class EP>
 __global__ void __launch_bounds__(tc::PipeCfg<BN, false>::kThreads, 1) conv_tc_kernel(AL al, BL bl, EP ep, int num_tiles, int num_kb) {
-  tc::run_pipeline<BN, false, tc::kBK>(al, bl, ep, num_tiles, num_kb);
+  tc::run_pipeline<BN, false, tc::kBK, 1>(al, bl, ep, num_tiles, num_kb);
 }
 
 template <int BN, class AL, class BL, class EP>

@@ -27,19 +27,44 @@ struct GemmParams {
   unsigned* counters;           // [tiles], zero on entry, zero on exit
 };
 
-__device__ __forceinline__ float epilogue(const GemmParams& p, float acc, int m, int n) {
-  float v = p.alpha * acc;
-  if (p.bias) v += p.bias[n];
-  if (p.addend) v += p.addend[(size_t)(p.add_mod ? m % p.add_mod : m) * p.ldadd + n];
-  if (p.beta != 0.f) v += p.beta * p.C[(size_t)m * p.ldc + n];
-  if ((p.act & 3) == 1) v = fmaxf(v, 0.f);
-  else if ((p.act & 3) == 2) v = tanhf(v);
-  if (p.gate) {
-    float g = p.gate[(size_t)m * p.ldg + n];
-    v = (p.act & 4) ? v * (1.f - g * g) : (g > 0.f ? v : 0.f);
+// Epilogue stages as short vector passes over W contiguous columns of one row: the branches are uniform, hoisting them
+// out of the element loop keeps the fully unrolled thread-tile epilogue small (it is instruction-fetch bound otherwise).
+// Dropout is applied afterwards by drop_rows_kernel.
+template <int W>
+__device__ __forceinline__ void epilogue_vec(const GemmParams& p, float* o, int m, int n0) {
+#pragma unroll
+  for (int j = 0; j < W; ++j) o[j] *= p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] += p.bias[n0 + j];
   }
-  v *= drop_factor(p.drop, (unsigned long long)m * p.N + n);
-  return v;
+  if (p.addend) {
+    const float* a = p.addend + (size_t)(p.add_mod ? m % p.add_mod : m) * p.ldadd + n0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] += a[j];
+  }
+  if (p.beta != 0.f) {
+    const float* c = p.C + (size_t)m * p.ldc + n0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] += p.beta * c[j];
+  }
+  if ((p.act & 3) == 1) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] = fmaxf(o[j], 0.f);
+  } else if ((p.act & 3) == 2) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] = tanhf(o[j]);
+  }
+  if (p.gate) {
+    const float* g = p.gate + (size_t)m * p.ldg + n0;
+    if (p.act & 4) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) o[j] *= 1.f - g[j] * g[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) o[j] = g[j] > 0.f ? o[j] : 0.f;
+    }
+  }
 }
 
 template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
@@ -246,9 +271,23 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmParams
     int m = m0 + (i / 4) * SM_STRIDE + tm * 4 + (i % 4);
     if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      int n = n0 + (j / 4) * SN_STRIDE + tn * 4 + (j % 4);
-      if (n < p.N) p.C[(size_t)m * p.ldc + n] = epilogue(p, acc[i][j], m, n);
+    for (int g = 0; g < GN; ++g) {
+      const int n = n0 + g * SN_STRIDE + tn * 4;
+      float* dst = p.C + (size_t)m * p.ldc + n;
+      if (n + 3 < p.N) {
+        float o[4] = {acc[i][g * 4], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]};
+        epilogue_vec<4>(p, o, m, n);
+        if ((reinterpret_cast<size_t>(dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        else { dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < p.N) {
+            float o[1] = {acc[i][g * 4 + j]};
+            epilogue_vec<1>(p, o, m, n + j);
+            dst[j] = o[0];
+          }
+      }
     }
   }
 }
@@ -287,6 +326,14 @@ int launch_cfg(GemmParams p, int transA, int transB, float* workspace, size_t wo
   HULC_RETURN_LAST();
 }
 
+// C[m][n] *= dropout factor of element m*N + n  (the `drop` stage of the GEMM epilogue contract)
+__global__ void drop_rows_kernel(float* __restrict__ C, int M, int N, int ldc, DropSpec drop) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+  C[(size_t)m * ldc + n] *= drop_factor(drop, (unsigned long long)i);
+}
+
 // out[c] = beta*out[c] + sum_r X[r*ldx + c]
 __global__ void colsum_kernel(const float* __restrict__ X, int rows, int cols, int ldx, float* __restrict__ out, float beta, int rows_per_block) {
   __shared__ float red[8][33];
@@ -312,6 +359,13 @@ __global__ void scale_vec_kernel(float* x, int n, float s) {
 }
 
 }  // namespace
+
+// shared with gemm_tc.cu
+int hulc_apply_dropout_rows(float* C, int M, int N, int ldc, DropSpec drop, cudaStream_t st) {
+  if (drop.p <= 0.f) return 0;
+  HULC_LAUNCH(drop_rows_kernel, dim3(hulc_cdiv((long long)M * N, 256)), dim3(256), 0, st, C, M, N, ldc, drop);
+  HULC_RETURN_LAST();
+}
 
 unsigned long long g_hulc_launches = 0;
 const unsigned long long* g_hulc_rng_offset_ptr = nullptr;
@@ -340,8 +394,9 @@ HULC_API int hulc_gemm(const float* A, const float* B, float* C, int M, int N, i
   p.act = act; p.gate = gate; p.ldg = ldg; p.drop = make_drop(drop_p, drop_seed, drop_site, drop_keep);
   p.splits = 1; p.k_per_split = K; p.partial = nullptr; p.counters = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  if (M >= 256 && N >= 96) return launch_cfg<128, 128, 8, 8>(p, transA, transB, workspace, workspace_bytes, st);
-  return launch_cfg<64, 64, 4, 4>(p, transA, transB, workspace, workspace_bytes, st);
+  if (M >= 256 && N >= 96) HULC_TRY((launch_cfg<128, 128, 8, 8>(p, transA, transB, workspace, workspace_bytes, st)));
+  else HULC_TRY((launch_cfg<64, 64, 4, 4>(p, transA, transB, workspace, workspace_bytes, st)));
+  return hulc_apply_dropout_rows(C, M, N, ldc, p.drop, st);
 }
 
 HULC_API int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, void* stream) {

@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "tc_pipeline.cuh"
 
+int hulc_apply_dropout_rows(float* C, int M, int N, int ldc, DropSpec drop, cudaStream_t st);  // gemm.cu
+
 namespace {
 
 struct TcEpilogue {
@@ -20,51 +22,72 @@ struct TcEpilogue {
   int act;
   const float* gate;
   int ldg;
-  DropSpec drop;
   int BN, tiles_n;
-  int splits;          // > 1: split-K: every CTA stores raw partial sums, the last one to finish a tile reduces them
-  float* partial;      // [splits][M][N]
-  unsigned* counters;  // one ticket per output tile, zero on entry and on exit
+  int splits;  // > 1: split-K over a thread-block cluster of that size (tile index = output tile * splits + k-slice)
 
-  __device__ __forceinline__ float one(float acc, int m, int n) const {
-    float v = alpha * acc;
-    if (bias) v += bias[n];
-    if (addend) v += addend[(size_t)(add_mod ? m % add_mod : m) * ldadd + n];
-    if (beta != 0.f) v += beta * C[(size_t)m * ldc + n];
-    if ((act & 3) == 1) v = fmaxf(v, 0.f);
-    else if ((act & 3) == 2) v = tanhf(v);
-    if (gate) {
-      float g = gate[(size_t)m * ldg + n];
-      v = (act & 4) ? v * (1.f - g * g) : (g > 0.f ? v : 0.f);
+  // The epilogue stages are applied as short vector passes over W contiguous columns of one row (uniform branches hoisted
+  // out of the element loops keeps the unrolled code small — it is instruction-fetch bound otherwise).  Dropout is applied
+  // by a separate elementwise pass (hulc_apply_dropout_rows).
+  template <int W>
+  __device__ __forceinline__ void apply(float* o, int m, int n0) const {  // all W columns valid
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] *= alpha;
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) o[j] += bias[n0 + j];
     }
-    v *= drop_factor(drop, (unsigned long long)m * N + n);
-    return v;
+    if (addend) {
+      const float* a = addend + (size_t)(add_mod ? m % add_mod : m) * ldadd + n0;
+#pragma unroll
+      for (int j = 0; j < W; ++j) o[j] += a[j];
+    }
+    if (beta != 0.f) {
+      const float* c = C + (size_t)m * ldc + n0;
+#pragma unroll
+      for (int j = 0; j < W; ++j) o[j] += beta * c[j];
+    }
+    if ((act & 3) == 1) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) o[j] = fmaxf(o[j], 0.f);
+    } else if ((act & 3) == 2) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) o[j] = tanhf(o[j]);
+    }
+    if (gate) {
+      const float* g = gate + (size_t)m * ldg + n0;
+      if (act & 4) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) o[j] *= 1.f - g[j] * g[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) o[j] = g[j] > 0.f ? o[j] : 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ float one(float acc, int m, int n) const {  // single element (ragged edges)
+    float o[1] = {acc};
+    apply<1>(o, m, n);
+    return o[0];
   }
   __device__ __forceinline__ void operator()(int tile, int row, int col0, const float* v) const {
-    const int t2 = tile / splits, ks = tile - t2 * splits;
+    const int t2 = tile / splits;
     const int tm = t2 / tiles_n, tn = t2 % tiles_n;
     const int m = tm * tc::kBM + row;
     if (m >= M) return;
     const int n0 = tn * BN + col0;
     if (n0 >= N) return;
-    if (splits > 1) {
-      float* dst = partial + ((size_t)ks * M + m) * N + n0;
-      if (n0 + 32 <= N && (N & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < N) dst[j] = v[j];
-      }
-      return;
-    }
     float* dst = C + (size_t)m * ldc + n0;
-    const bool vec = ((reinterpret_cast<size_t>(dst) & 15) == 0) && n0 + 32 <= N;
-    if (vec) {
+    if (n0 + 32 <= N) {
+      float o[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(one(v[j], m, n0 + j), one(v[j + 1], m, n0 + j + 1), one(v[j + 2], m, n0 + j + 2), one(v[j + 3], m, n0 + j + 3));
-        *reinterpret_cast<float4*>(dst + j) = o;
+      for (int j = 0; j < 32; ++j) o[j] = v[j];
+      apply<32>(o, m, n0);
+      if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = o[j];
       }
     } else {
 #pragma unroll
@@ -72,100 +95,76 @@ struct TcEpilogue {
         if (n0 + j < N) dst[j] = one(v[j], m, n0 + j);
     }
   }
-  // split-K: the CTA that delivers the last partial of an output tile sums all of them in a fixed order (bit-reproducible)
-  // and applies the epilogue.  Called by the 128 epilogue threads after their partial stores.
-  __device__ __forceinline__ void finish(int tile, int warp, int lane, uint32_t* flag) const {
-    if (splits <= 1) return;
+  // cluster split-K hooks (see tc_pipeline.cuh)
+  __device__ __forceinline__ int rows_valid(int tile) const { return min(tc::kBM, M - ((tile / splits) / tiles_n) * tc::kBM); }
+  __device__ __forceinline__ void store4(int tile, int row, int col, float4 v) const {
     const int t2 = tile / splits;
-    __threadfence();
-    tc::epi_bar_sync();
-    if (warp == 0 && lane == 0) {
-      const unsigned t = atomicAdd(&counters[t2], 1u);
-      *flag = (t == (unsigned)(splits - 1));
-      if (*flag) counters[t2] = 0u;
+    const int m = (t2 / tiles_n) * tc::kBM + row, n = (t2 % tiles_n) * BN + col;
+    if (n >= N) return;
+    float* dst = C + (size_t)m * ldc + n;
+    if (n + 3 < N && (reinterpret_cast<size_t>(dst) & 15) == 0) {
+      float o[4] = {v.x, v.y, v.z, v.w};
+      apply<4>(o, m, n);
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < N) dst[e] = one(a[e], m, n + e);
     }
-    tc::epi_bar_sync();
-    if (*flag) {
-      __threadfence();
-      const int tm = t2 / tiles_n, tn = t2 % tiles_n;
-      const bool vec = (N & 3) == 0 && (ldc & 3) == 0 && (reinterpret_cast<size_t>(C) & 15) == 0;
-      constexpr int RG = 4;  // rows per round: RG x 4 independent 16-byte loads in flight per thread hide the L2 latency
-      for (int rb = warp * RG; rb < tc::kBM; rb += tc::kEpiWarps * RG) {
-        const int m0 = tm * tc::kBM + rb;
-        if (m0 >= M) break;
-        for (int c = lane * 4; c < BN; c += 128) {
-          const int n = tn * BN + c;
-          if (n >= N) break;
-          if (vec) {
-            float4 acc[RG];
-#pragma unroll
-            for (int i = 0; i < RG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int k0 = 0; k0 < splits; k0 += 4) {
-              float4 p[RG][4];
-#pragma unroll
-              for (int i = 0; i < RG; ++i)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const bool ok = m0 + i < M && k0 + kk < splits;
-                  p[i][kk] = ok ? __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)(k0 + kk) * M + m0 + i) * N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-              for (int i = 0; i < RG; ++i)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) { acc[i].x += p[i][kk].x; acc[i].y += p[i][kk].y; acc[i].z += p[i][kk].z; acc[i].w += p[i][kk].w; }
-            }
-#pragma unroll
-            for (int i = 0; i < RG; ++i) {
-              const int m = m0 + i;
-              if (m < M)
-                *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) =
-                    make_float4(one(acc[i].x, m, n), one(acc[i].y, m, n + 1), one(acc[i].z, m, n + 2), one(acc[i].w, m, n + 3));
-            }
-          } else {
-            for (int i = 0; i < RG && m0 + i < M; ++i)
-              for (int e = 0; e < 4 && n + e < N; ++e) {
-                float s = 0.f;
-                for (int k = 0; k < splits; ++k) s += __ldcg(partial + ((size_t)k * M + m0 + i) * N + n + e);
-                C[(size_t)(m0 + i) * ldc + n + e] = one(s, m0 + i, n + e);
-              }
-          }
-        }
-      }
-    }
-    tc::epi_bar_sync();
   }
 };
 
-template <int BN, bool SPLIT, class AL, class BL>
+template <int BN, bool SPLIT, int CLUSTER, class AL, class BL>
 __global__ void __launch_bounds__(tc::PipeCfg<BN, SPLIT>::kThreads, 1) gemm_tc_kernel(AL al, BL bl, TcEpilogue ep, int num_tiles, int num_kb) {
-  tc::run_pipeline<BN, SPLIT, tc::kBK>(al, bl, ep, num_tiles, num_kb);
+  tc::run_pipeline<BN, SPLIT, tc::kBK, CLUSTER>(al, bl, ep, num_tiles, num_kb);
 }
 
-// how many k-splits a skinny product gets so that its tiles cover the 148 SMs
+// k-slices (= cluster size) for a skinny product: the largest of 8 / 4 / 2 whose tiles still fit one wave of the 148 SMs
 inline int choose_splits(int tiles, int num_kb) {
-  if (tiles * 2 > kNumSMs || num_kb < 16) return 1;
-  int s = min(kNumSMs / tiles, num_kb / 4);
-  return max(1, s);
+  for (int s = 8; s >= 2; s >>= 1)
+    if (tiles * s <= kNumSMs && num_kb >= 4 * s) return s;
+  return 1;
+}
+
+template <int BN, bool SPLIT, int CLUSTER, class AL, class BL>
+int launch_one(AL al, BL bl, TcEpilogue ep, int tiles, int kbps, cudaStream_t st) {
+  using Cfg = tc::PipeCfg<BN, SPLIT>;
+  auto kfn = gemm_tc_kernel<BN, SPLIT, CLUSTER, AL, BL>;
+  HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  if (CLUSTER == 1) {
+    HULC_LAUNCH(kfn, dim3(min(kNumSMs, tiles)), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, al, bl, ep, tiles, kbps);
+    HULC_RETURN_LAST();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles);  // one work item per CTA; consecutive CTAs = the k-slices of one output tile = one cluster
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  ++g_hulc_launches;
+  HULC_TRY(cudaLaunchKernelEx(&cfg, kfn, al, bl, ep, tiles, kbps));
+  HULC_RETURN_LAST();
 }
 
 template <int BN, bool SPLIT, class AL, class BL>
 int launch(AL al, BL bl, TcEpilogue ep, int M, int N, int K, cudaStream_t st) {
-  using Cfg = tc::PipeCfg<BN, SPLIT>;
-  auto kfn = gemm_tc_kernel<BN, SPLIT, AL, BL>;
-  HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   int tiles_m = hulc_cdiv(M, tc::kBM), tiles_n = hulc_cdiv(N, BN);
   const int num_kb = hulc_cdiv(K, tc::kBK);
-  int kbps = num_kb;
-  if (ep.splits > 1) {
-    kbps = hulc_cdiv(num_kb, ep.splits);
-    ep.splits = hulc_cdiv(num_kb, kbps);
-  }
+  const int kbps = hulc_cdiv(num_kb, ep.splits);
   const int tiles = tiles_m * tiles_n * ep.splits;
   ep.BN = BN; ep.tiles_n = tiles_n;
   al.tiles_n = tiles_n; al.is_n = 0; al.splits = ep.splits; al.kb_per_split = kbps;
   bl.tiles_n = tiles_n; bl.is_n = 1; bl.splits = ep.splits; bl.kb_per_split = kbps;
-  HULC_LAUNCH(kfn, dim3(min(kNumSMs, tiles)), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, al, bl, ep, tiles, kbps);
-  HULC_RETURN_LAST();
+  switch (ep.splits) {
+    case 8: return launch_one<BN, SPLIT, 8>(al, bl, ep, tiles, kbps, st);
+    case 4: return launch_one<BN, SPLIT, 4>(al, bl, ep, tiles, kbps, st);
+    case 2: return launch_one<BN, SPLIT, 2>(al, bl, ep, tiles, kbps, st);
+    default: return launch_one<BN, SPLIT, 1>(al, bl, ep, tiles, kbps, st);
+  }
 }
 
 template <int BN, bool SPLIT>
@@ -184,11 +183,18 @@ int dispatch_layout(const float* A, const float* B, int M, int N, int K, int lda
 
 }  // namespace
 
+#ifdef HULC_TC_TRACE
+HULC_API int hulc_tc_trace_read(unsigned long long* host_out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_out, tc::g_tc_trace, sizeof(unsigned long long) * 64);
+}
+#endif
+
 // Same contract as hulc_gemm (include/hulc_b200.h) plus `passes` (1 = tf32, 3 = 3xTF32).  Operand requirements: 16-byte
 // aligned A and B, lda % 4 == ldb % 4 == 0, and the contiguous extent of each operand a multiple of 4 (K for K-contiguous
 // storage, M / N for the transposed storage); otherwise cudaErrorInvalidValue (callers use hulc_gemm for such shapes).
-// Skinny products (few output tiles, long K — the recurrent steps, the prior / goal MLPs) are split along K; the partial
-// sums and tickets live in the workspace (zero-initialised head, as for hulc_gemm).
+// Skinny products (few output tiles, long K — the recurrent steps, the prior / goal MLPs, the decoder heads) are split along
+// K over a thread-block cluster and reduced through distributed shared memory; the workspace is not used.
 HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                           float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate,
                           int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, int passes,
@@ -199,21 +205,17 @@ HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N
   if (((transA ? M : K) & 3) || ((transB ? K : N) & 3)) return (int)cudaErrorInvalidValue;
   TcEpilogue ep;
   ep.C = C; ep.M = M; ep.N = N; ep.ldc = ldc; ep.alpha = alpha; ep.beta = beta; ep.bias = bias; ep.addend = addend; ep.ldadd = ldadd;
-  ep.add_mod = add_mod; ep.act = act; ep.gate = gate; ep.ldg = ldg; ep.drop = make_drop(drop_p, drop_seed, drop_site, drop_keep);
-  ep.BN = 0; ep.tiles_n = 0; ep.splits = 1; ep.partial = nullptr; ep.counters = nullptr;
+  ep.add_mod = add_mod; ep.act = act; ep.gate = gate; ep.ldg = ldg;
+  ep.BN = 0; ep.tiles_n = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool wide = N > 64;
-  const size_t ws_floats = workspace && workspace_bytes > 4096 ? (workspace_bytes - 4096) / sizeof(float) : 0;
-  const int tiles = hulc_cdiv(M, tc::kBM) * hulc_cdiv(N, wide ? 128 : 64);
-  int splits = choose_splits(tiles, hulc_cdiv(K, tc::kBK));
-  while (splits > 1 && (size_t)splits * M * N > ws_floats) --splits;
-  if (splits > 1) {
-    ep.splits = splits; ep.partial = workspace + 1024; ep.counters = reinterpret_cast<unsigned*>(workspace);
-  }
+  ep.splits = choose_splits(hulc_cdiv(M, tc::kBM) * hulc_cdiv(N, wide ? 128 : 64), hulc_cdiv(K, tc::kBK));
   if (passes == 3) {
-    if (wide) return dispatch_layout<128, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
-    return dispatch_layout<64, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
+    if (wide) HULC_TRY((dispatch_layout<128, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st)));
+    else HULC_TRY((dispatch_layout<64, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st)));
+  } else {
+    if (wide) HULC_TRY((dispatch_layout<128, false>(A, B, M, N, K, lda, ldb, transA, transB, ep, st)));
+    else HULC_TRY((dispatch_layout<64, false>(A, B, M, N, K, lda, ldb, transA, transB, ep, st)));
   }
-  if (wide) return dispatch_layout<128, false>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
-  return dispatch_layout<64, false>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
+  return hulc_apply_dropout_rows(C, M, N, ldc, make_drop(drop_p, drop_seed, drop_site, drop_keep), st);
 }

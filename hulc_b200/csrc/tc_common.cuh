@@ -147,6 +147,20 @@ __device__ __forceinline__ void st_chunk_split(unsigned char* hi, unsigned char*
   }
 }
 
+// Optional device-side timeline (development aid, compiled in with -DHULC_TC_TRACE): globaltimer stamps of CTA 0.
+#ifdef HULC_TC_TRACE
+__device__ unsigned long long g_tc_trace[64];
+__device__ __forceinline__ void trace(int slot) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_tc_trace[slot] = t;
+  }
+}
+#else
+__device__ __forceinline__ void trace(int) {}
+#endif
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -21,8 +21,6 @@
 // residual x - tf32(x) into a second ("lo") tile; the MMA warp then issues lo*hi + hi*lo (into a side accumulator) and
 // hi*hi: 3xTF32, fp32-level accuracy without any extra global traffic.
 #pragma once
-#include <type_traits>
-
 #include "tc_common.cuh"
 
 namespace tc {
@@ -54,15 +52,26 @@ struct PipeBarriers {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  uint32_t flag;  // scratch for epilogue hooks (split-K "last CTA" election)
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
-
-template <class E, class = void>
-struct has_finish : std::false_type {};
-template <class E>
-struct has_finish<E, std::void_t<decltype(&E::finish)>> : std::true_type {};
+// ---- thread-block cluster helpers (split-K over a cluster, reduced through distributed shared memory) ------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 bytes from the shared memory of CTA `rank` of this cluster, at the same offset as local address `addr`
+__device__ __forceinline__ float4 ld_dsmem16(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   // src-size 0 zero-fills the 16 bytes (out-of-range rows, k tails, halo taps)
@@ -85,7 +94,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   void issue(int kb, uint32_t dst, int ptid);              // cp.async this thread's 16-byte chunks of the [rows x BK] tile
 //   void split(uint32_t hi, uint32_t lo, int ptid);          // (3-pass) residuals of the same chunks, smem -> smem
 // Epilogue interface (called by the 128 epilogue threads):  void operator()(int tile, int row, int col0, const float* v32)
-template <int BN, bool SPLIT, int BK, class ALoader, class BLoader, class Epilogue>
+//
+// CLUSTER > 1 (split-K): the CLUSTER consecutive CTAs of a thread-block cluster hold the k-slices of ONE output tile (tile
+// index = output tile * CLUSTER + k-slice = blockIdx.x, exactly one work item per CTA).  Each CTA parks its partial
+// accumulator in its own shared memory; after a cluster barrier CTA r sums rows r, r+CLUSTER, ... of all the partials
+// through distributed shared memory in a fixed order and hands them to the epilogue
+//   int rows_valid(int tile) const;  void store4(int tile, int row, int col, float4 v) const;
+// — no partials in global memory, no second launch, bit-reproducible.
+template <int BN, bool SPLIT, int BK, int CLUSTER, class ALoader, class BLoader, class Epilogue>
 __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epilogue& ep, int num_tiles, int num_kb) {
   using Cfg = PipeCfg<BN, SPLIT, BK>;
   constexpr int S = Cfg::kStages;
@@ -93,6 +109,7 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + S * Cfg::kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) trace(0);  // kernel entry
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -110,6 +127,7 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  if (warp == 0) trace(1);  // barriers initialised, TMEM allocated
 
   if (warp < kEpiWarps) {
     // ================================ epilogue ================================
@@ -119,6 +137,7 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&bars->tmem_full[a], aphase);
       tc_fence_after_sync();
+      if (warp == 0) trace(4);  // accumulator ready
       const int row = warp * 32 + lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -133,12 +152,20 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
         } else {
           tmem_ld_wait();
         }
-        ep(tile, row, c0, reinterpret_cast<const float*>(r));
+        if constexpr (CLUSTER > 1) {
+          // park the partial tile in shared memory (the stage buffers are idle: every MMA of this CTA has completed);
+          // rows are padded by 4 floats so the per-row 16-byte stores of a warp spread over all banks
+          float* prow = reinterpret_cast<float*>(smem) + (size_t)row * (BN + 4) + c0;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            *reinterpret_cast<float4*>(prow + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+        } else {
+          ep(tile, row, c0, reinterpret_cast<const float*>(r));
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
-      if constexpr (has_finish<Epilogue>::value) ep.finish(tile, warp, lane, &bars->flag);
     }
   } else if (warp == kEpiWarps) {
     // ================================ MMA issuer ================================
@@ -157,6 +184,8 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
         const uint32_t phase = (j / S) & 1;
         mbar_wait(&bars->full[stage], phase);
         tc_fence_after_sync();
+        if (kb == 0) trace(2);  // first stage landed
+        if (kb == num_kb - 1) trace(3);  // last stage landed
         if (lane == 0) {
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t a_lo = a_hi + Cfg::kATile;
@@ -216,8 +245,38 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
     for (int jj = j > L ? j - L : 0; jj < j; ++jj) publish(jj);
   }
 
+  if (warp == 0) trace(5);  // epilogue warp 0 done with its role loop
+  if constexpr (CLUSTER > 1) {
+    static_assert(kBM * (BN + 4) * 4 <= Cfg::kStages * Cfg::kStageBytes, "partial tile must fit in the stage buffers");
+    cluster_sync_all();  // all partial tiles of the cluster are in place
+    if (warp == 0) trace(6);
+    if (warp < kEpiWarps && (int)blockIdx.x < num_tiles) {
+      const int tile = blockIdx.x;
+      const uint32_t rank = cluster_ctarank();
+      const int rows = ep.rows_valid(tile);
+      constexpr int CQ = BN / 4;  // 16-byte column chunks per row
+      const int e = threadIdx.x;  // 0..127
+      const uint32_t base = smem_u32(smem);
+      for (int idx = e; idx < kBM * CQ; idx += kEpiWarps * 32) {
+        const int rr = idx / CQ, cq = idx - rr * CQ;
+        const int row = rr * CLUSTER + (int)rank;  // this CTA's share of the tile's rows
+        if (row >= rows) break;
+        const uint32_t off = base + (uint32_t)(row * (BN + 4) + cq * 4) * 4u;
+        float4 p[CLUSTER];
+#pragma unroll
+        for (int q = 0; q < CLUSTER; ++q) p[q] = ld_dsmem16(off, (uint32_t)q);
+        float4 s = p[0];
+#pragma unroll
+        for (int q = 1; q < CLUSTER; ++q) { s.x += p[q].x; s.y += p[q].y; s.z += p[q].z; s.w += p[q].w; }
+        ep.store4(tile, row, cq * 4, s);
+      }
+    }
+    if (warp == 0) trace(7);
+    cluster_sync_all();  // nobody leaves (and releases its shared memory) while a peer may still read it
+  }
   tc_fence_before_sync();
   __syncthreads();
+  if (warp == 0) trace(8);
   if (warp == kEpiWarps) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
