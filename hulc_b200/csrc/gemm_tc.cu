@@ -120,11 +120,23 @@ __global__ void __launch_bounds__(tc::PipeCfg<BN, SPLIT>::kThreads, 1) gemm_tc_k
   tc::run_pipeline<BN, SPLIT, tc::kBK, CLUSTER>(al, bl, ep, num_tiles, num_kb);
 }
 
-// k-slices (= cluster size) for a skinny product: the largest of 8 / 4 / 2 whose tiles still fit one wave of the 148 SMs
-inline int choose_splits(int tiles, int num_kb) {
-  for (int s = 8; s >= 2; s >>= 1)
-    if (tiles * s <= kNumSMs && num_kb >= 4 * s) return s;
-  return 1;
+// Tile width and k-slices (= cluster size) of a product.  Clusters of 8 / 4 / 2 CTAs of this kernel (one CTA per SM, ~200 KB
+// of shared memory) fit 15 / 33 / 74 at a time on the 148 SMs (cudaOccupancyMaxActiveClusters); a skinny product takes the
+// combination that puts the most CTAs to work in ONE wave.
+inline void choose_config(int M, int N, int K, int& bn, int& splits) {
+  const int num_kb = hulc_cdiv(K, tc::kBK), tiles_m = hulc_cdiv(M, tc::kBM);
+  static const int kClusters[3] = {8, 4, 2}, kCap[3] = {15, 33, 74};
+  bn = N > 64 ? 128 : 64; splits = 1;
+  if (tiles_m * hulc_cdiv(N, bn) * 2 > kNumSMs) return;  // enough tiles to fill the machine without splitting
+  int best = tiles_m * hulc_cdiv(N, bn);
+  for (int b = 128; b >= 64; b >>= 1) {
+    if (b == 128 && N <= 64) continue;
+    const int tiles = tiles_m * hulc_cdiv(N, b);
+    for (int i = 0; i < 3; ++i) {
+      const int c = kClusters[i];
+      if (tiles <= kCap[i] && num_kb >= 4 * c && tiles * c > best) { best = tiles * c; bn = b; splits = c; }
+    }
+  }
 }
 
 template <int BN, bool SPLIT, int CLUSTER, class AL, class BL>
@@ -183,6 +195,39 @@ int dispatch_layout(const float* A, const float* B, int M, int N, int K, int lda
 
 }  // namespace
 
+// development aid: how many clusters of the skinny-product kernel can be resident at once
+HULC_API int hulc_debug_max_clusters(int cluster, int split, int* out) {
+  using AL = tc::KMajorLoader<tc::kBM>;
+  using BL = tc::KMajorLoader<128>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(128);
+  int n = -1;
+  cudaError_t e;
+  if (split) {
+    using Cfg = tc::PipeCfg<128, true>;
+    cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    auto k8 = gemm_tc_kernel<128, true, 8, AL, BL>; auto k4 = gemm_tc_kernel<128, true, 4, AL, BL>; auto k2 = gemm_tc_kernel<128, true, 2, AL, BL>;
+    cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    e = cluster == 8 ? cudaOccupancyMaxActiveClusters(&n, k8, &cfg) : cluster == 4 ? cudaOccupancyMaxActiveClusters(&n, k4, &cfg) : cudaOccupancyMaxActiveClusters(&n, k2, &cfg);
+  } else {
+    using Cfg = tc::PipeCfg<128, false>;
+    cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    auto k8 = gemm_tc_kernel<128, false, 8, AL, BL>; auto k4 = gemm_tc_kernel<128, false, 4, AL, BL>; auto k2 = gemm_tc_kernel<128, false, 2, AL, BL>;
+    cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    e = cluster == 8 ? cudaOccupancyMaxActiveClusters(&n, k8, &cfg) : cluster == 4 ? cudaOccupancyMaxActiveClusters(&n, k4, &cfg) : cudaOccupancyMaxActiveClusters(&n, k2, &cfg);
+  }
+  *out = n;
+  return (int)e;
+}
+
 #ifdef HULC_TC_TRACE
 HULC_API int hulc_tc_trace_read(unsigned long long* host_out) {
   cudaDeviceSynchronize();
@@ -208,8 +253,9 @@ HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N
   ep.add_mod = add_mod; ep.act = act; ep.gate = gate; ep.ldg = ldg;
   ep.BN = 0; ep.tiles_n = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool wide = N > 64;
-  ep.splits = choose_splits(hulc_cdiv(M, tc::kBM) * hulc_cdiv(N, wide ? 128 : 64), hulc_cdiv(K, tc::kBK));
+  int bn;
+  choose_config(M, N, K, bn, ep.splits);
+  const bool wide = bn == 128;
   if (passes == 3) {
     if (wide) HULC_TRY((dispatch_layout<128, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st)));
     else HULC_TRY((dispatch_layout<64, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st)));
