@@ -335,23 +335,89 @@ __global__ void drop_rows_kernel(float* __restrict__ C, int M, int N, int ldc, D
 }
 
 // out[c] = beta*out[c] + sum_r X[r*ldx + c]
-__global__ void colsum_kernel(const float* __restrict__ X, int rows, int cols, int ldx, float* __restrict__ out, float beta, int rows_per_block) {
-  __shared__ float red[8][33];
-  int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  int ry = threadIdx.x >> 5;  // 8 row lanes
-  int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  float s = 0.f;
-  if (c < cols)
-    for (int r = r0 + ry; r < r1; r += 8) s += X[(size_t)r * ldx + c];
-  red[ry][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (ry == 0 && c < cols) {
-    float t = 0.f;
+// Column sums out[c] = beta*out[c] + sum_r X[r][c].  A block of 256 threads = CL column lanes (VEC columns each) x 256/CL row
+// lanes; the rows are split over gridDim.y blocks whose partial sums meet in `partial` and are added in a fixed order by the
+// last block to arrive (ticket) -> bit-reproducible, no atomics on the data.
+template <int VEC>
+__global__ void colsum_kernel(const float* __restrict__ X, int rows, int cols, int ldx, float* __restrict__ out, float beta, int rows_per_block,
+                              int CL, float* __restrict__ partial, unsigned* __restrict__ counters) {
+  __shared__ float red[256 * VEC];
+  __shared__ unsigned s_ticket;
+  const int tid = threadIdx.x;
+  const int cl = tid % CL, rl = tid / CL, RL = 256 / CL;
+  const int c = (blockIdx.x * CL + cl) * VEC;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s[4][VEC];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    if (gridDim.y == 1) out[c] = (beta != 0.f ? beta * out[c] : 0.f) + t;
-    else atomicAdd(&out[c], t);
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) s[u][v] = 0.f;
+  if (c < cols) {
+    int r = r0 + rl;
+    for (; r + 3 * RL < r1; r += 4 * RL) {  // four independent loads in flight per thread
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* src = X + (size_t)(r + u * RL) * ldx + c;
+        if (VEC == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(src);
+          s[u][0] += t.x; s[u][VEC > 1 ? 1 : 0] += t.y; s[u][VEC > 2 ? 2 : 0] += t.z; s[u][VEC > 3 ? 3 : 0] += t.w;
+        } else {
+          s[u][0] += src[0];
+        }
+      }
+    }
+    for (; r < r1; r += RL) {
+      const float* src = X + (size_t)r * ldx + c;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s[0][v] += src[v];
+    }
   }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[tid * VEC + v] = (s[0][v] + s[1][v]) + (s[2][v] + s[3][v]);
+  __syncthreads();
+  float t[VEC];
+  if (rl == 0 && c < cols) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) t[v] = 0.f;
+    for (int i = 0; i < RL; ++i)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) t[v] += red[(i * CL + cl) * VEC + v];
+    if (gridDim.y == 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) out[c + v] = (beta != 0.f ? beta * out[c + v] : 0.f) + t[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) partial[(size_t)blockIdx.y * cols + c + v] = t[v];
+    }
+  }
+  if (gridDim.y == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(&counters[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
+  // last block of this column group: every row lane adds its share of the partial rows, then the lanes meet in shared
+  // memory in lane order (fixed summation order for a given grid)
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) t[v] = 0.f;
+  if (c < cols)
+    for (int y = rl; y < (int)gridDim.y; y += RL)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) t[v] += __ldcg(&partial[(size_t)y * cols + c + v]);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[tid * VEC + v] = t[v];
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) t[v] = 0.f;
+    for (int i = 0; i < RL; ++i)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) t[v] += red[(i * CL + cl) * VEC + v];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) out[c + v] = (beta != 0.f ? beta * out[c + v] : 0.f) + t[v];
+  }
+  if (tid == 0) counters[blockIdx.x] = 0u;
 }
 __global__ void scale_vec_kernel(float* x, int n, float s) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,16 +465,27 @@ HULC_API int hulc_gemm(const float* A, const float* B, float* C, int M, int N, i
   return hulc_apply_dropout_rows(C, M, N, ldc, p.drop, st);
 }
 
-HULC_API int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, void* stream) {
+HULC_API int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, float* workspace, size_t workspace_bytes,
+                        void* stream) {
   if (cols <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int gy = 1, rpb = rows;
-  if (rows >= 4096) {  // long reductions: spread rows over CTAs (enough of them to fill the 148 SMs), combine with atomics
-    gy = max(1, min(rows / 512, (8 * kNumSMs) / hulc_cdiv(cols, 32)));
-    rpb = hulc_cdiv(rows, gy);
-    if (beta == 0.f) cudaMemsetAsync(out, 0, sizeof(float) * cols, st);
-    else if (beta != 1.f) HULC_LAUNCH(scale_vec_kernel, dim3(hulc_cdiv(cols, 256)), dim3(256), 0, st, out, cols, beta);
+  const bool vec = (cols % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<size_t>(X) & 15) == 0);
+  const int V = vec ? 4 : 1;
+  int CL = 32;
+  while (CL > 8 && (CL / 2) * V >= cols) CL /= 2;  // narrow matrices: more row lanes per block
+  const int gx = hulc_cdiv(cols, CL * V);
+  // split the rows over blocks until ~4 blocks per SM are in flight (each row lane keeps >= 8 rows); the partial sums go
+  // through the workspace (tickets in its first 1024 words, shared with the split-K GEMM: zero on entry, zero on exit)
+  int gy = 1;
+  if (workspace && gx <= 1024) {
+    gy = max(1, min(rows / (8 * (256 / CL)), (4 * kNumSMs) / gx));
+    while (gy > 1 && (1024 + (size_t)gy * cols) * sizeof(float) > workspace_bytes) --gy;
   }
-  HULC_LAUNCH(colsum_kernel, dim3(hulc_cdiv(cols, 32), gy), dim3(256), 0, st, X, rows, cols, ldx, out, beta, rpb);
+  const int rpb = hulc_cdiv(rows, gy);
+  gy = hulc_cdiv(rows, rpb);
+  unsigned* counters = reinterpret_cast<unsigned*>(workspace);
+  float* partial = workspace ? workspace + 1024 : nullptr;
+  if (vec) HULC_LAUNCH(colsum_kernel<4>, dim3(gx, gy), dim3(256), 0, st, X, rows, cols, ldx, out, beta, rpb, CL, partial, counters);
+  else HULC_LAUNCH(colsum_kernel<1>, dim3(gx, gy), dim3(256), 0, st, X, rows, cols, ldx, out, beta, rpb, CL, partial, counters);
   HULC_RETURN_LAST();
 }

@@ -262,6 +262,76 @@ __global__ void __launch_bounds__(256) spatial_softmax_nhwc_bwd_kernel(const flo
   }
 }
 
+// Register-resident variant for maps of up to PL*MAXV positions (the 21x21 map of the static camera: 16 x 28): a CTA of
+// PL x 32 threads per (frame, 32 channels), thread (pl, c) keeps positions pl, pl+PL, ... of channel c in registers, so every load of the
+// frame is issued before the first use (the serial online-softmax chain above is latency bound) and the backward pass reads
+// x once.  Statistics of the PL position lanes meet in shared memory and are added in lane order.
+template <int PL, int MAXV, bool BWD>
+__global__ void __launch_bounds__(PL * 32, 2) spatial_softmax_nhwc_reg_kernel(const float* __restrict__ x, const float* __restrict__ dout, float* __restrict__ out,
+                                                                           float* __restrict__ dx, int C, int H, int W, float inv_temp, int relu_gate) {
+  static_assert(MAXV <= 32, "the ReLU signs of a thread's values are kept in one 32-bit mask");
+  __shared__ float sh_m[PL][32], sh_s[PL][32], sh_a[PL][32], sh_b[PL][32];
+  __shared__ float cxs[PL * MAXV], cys[PL * MAXV];  // coordinate maps of the flattened positions (no per-element divisions)
+  const int n = blockIdx.x, P = H * W;
+  const int lc = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const float* xf = x + (size_t)n * P * C;
+  for (int p = threadIdx.x; p < P; p += PL * 32) { cxs[p] = lin_coord(p / W, H); cys[p] = lin_coord(p % W, W); }
+  const int c = blockIdx.y * 32 + lc;  // one CTA per (frame, group of 32 channels): two CTAs share an SM
+  const bool cv = c < C;
+  float v[MAXV];
+  float mx = -FLT_MAX;
+  unsigned pos_mask = 0u;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int p = pl + PL * i;
+    v[i] = (cv && p < P) ? xf[(size_t)p * C + c] * inv_temp : -FLT_MAX;
+    mx = fmaxf(mx, v[i]);
+    pos_mask |= (v[i] > 0.f ? 1u : 0u) << i;  // inv_temp > 0: sign(v) == sign(x)
+  }
+  sh_m[pl][lc] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < PL; ++k) mx = fmaxf(mx, sh_m[k][lc]);
+  float gx = 0.f, gy = 0.f;
+  if (BWD && cv) { gx = dout[(size_t)n * 2 * C + 2 * c]; gy = dout[(size_t)n * 2 * C + 2 * c + 1]; }
+  float s = 0.f, a = 0.f, b = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int p = pl + PL * i;
+    if (p < P) {
+      const float e = expf(v[i] - mx);
+      v[i] = e;  // the values are only needed as exponentials from here on
+      s += e;
+      if (BWD) { a += e * (gx * cxs[p] + gy * cys[p]); }
+      else { a += e * cxs[p]; b += e * cys[p]; }
+    }
+  }
+  sh_s[pl][lc] = s; sh_a[pl][lc] = a;
+  if (!BWD) sh_b[pl][lc] = b;
+  __syncthreads();
+  s = 0.f; a = 0.f; b = 0.f;
+#pragma unroll
+  for (int k = 0; k < PL; ++k) { s += sh_s[k][lc]; a += sh_a[k][lc]; if (!BWD) b += sh_b[k][lc]; }
+  if (!BWD) {
+    if (pl == 0 && cv) {
+      out[(size_t)n * 2 * C + 2 * c] = a / s;
+      out[(size_t)n * 2 * C + 2 * c + 1] = b / s;
+    }
+  } else if (cv) {
+    const float scale = inv_temp / s, mean_c = a / s;
+    float* df = dx + (size_t)n * P * C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int p = pl + PL * i;
+      if (p < P) {
+        float g = v[i] * scale * (gx * cxs[p] + gy * cys[p] - mean_c);
+        if (relu_gate && !((pos_mask >> i) & 1u)) g = 0.f;
+        df[(size_t)p * C + c] = g;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // y[b,s,:] = drop(x[b,s,:] + pos[s,:])   and the generic dropout re-application used by its backward
 // ---------------------------------------------------------------------------------------------------------------------
@@ -383,6 +453,11 @@ HULC_API int hulc_spatial_softmax_bwd(const float* x, const float* dout, float* 
 
 HULC_API int hulc_spatial_softmax_nhwc_fwd(const float* x, float* out, int N, int C, int H, int W, float inv_temp, void* stream) {
   if (N <= 0) return 0;
+  if (H * W <= 16 * 28 && inv_temp > 0.f) {
+    HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, false>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, x, (const float*)nullptr, out,
+                (float*)nullptr, C, H, W, inv_temp, 0);
+    HULC_RETURN_LAST();
+  }
   HULC_LAUNCH(spatial_softmax_nhwc_fwd_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, x, out, C, H, W, inv_temp);
   HULC_RETURN_LAST();
 }
@@ -390,6 +465,11 @@ HULC_API int hulc_spatial_softmax_nhwc_fwd(const float* x, float* out, int N, in
 HULC_API int hulc_spatial_softmax_nhwc_bwd(const float* x, const float* dout, float* dx, int N, int C, int H, int W, float inv_temp, int relu_gate,
                                            void* stream) {
   if (N <= 0) return 0;
+  if (H * W <= 16 * 28 && inv_temp > 0.f) {
+    HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, true>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, x, dout, (float*)nullptr, dx, C, H, W,
+                inv_temp, relu_gate);
+    HULC_RETURN_LAST();
+  }
   HULC_LAUNCH(spatial_softmax_nhwc_bwd_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, x, dout, dx, C, H, W, inv_temp, relu_gate);
   HULC_RETURN_LAST();
 }

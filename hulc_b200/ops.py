@@ -132,7 +132,8 @@ def colsum(X, out=None, beta=0.0):
     rows, cols = X.shape
     if out is None:
         out = empty(cols, like=X)
-    _L().hulc_colsum(_ptr(X), rows, cols, _rowmajor(X), _ptr(out), float(beta), _stream())
+    ws = workspace(X.device)
+    _L().hulc_colsum(_ptr(X), rows, cols, _rowmajor(X), _ptr(out), float(beta), _ptr(ws), ws.numel() * 4, _stream())
     return out
 
 

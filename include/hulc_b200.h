@@ -53,8 +53,10 @@ int hulc_set_rng_offset_ptr(const unsigned long long* device_ptr);
 /* *out (HOST pointer) = number of kernel launches this library has issued since it was loaded (bench.py's gpu_launches). */
 int hulc_launch_count(unsigned long long* out);
 
-/* out[c] = beta*out[c] + sum_r X[r*ldx + c]  (bias gradients). */
-int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, void* stream);
+/* out[c] = beta*out[c] + sum_r X[r*ldx + c]  (bias gradients).  Long reductions are split over CTAs through the workspace
+ * and combined in a fixed order (bit-reproducible). */
+int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, float* workspace, size_t workspace_bytes,
+                void* stream);
 
 /* activation / gate selectors for hulc_gemm's `act` argument */
 #define HULC_ACT_NONE 0

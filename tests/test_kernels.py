@@ -51,7 +51,7 @@ def test_spatial_softmax(K, h):
     torch.testing.assert_close(dx, x.grad * (x.detach() > 0), rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize("h,c", [(21, 64), (5, 8), (7, 100)])
+@pytest.mark.parametrize("h,c", [(21, 64), (5, 8), (7, 100), (22, 8)])
 def test_spatial_softmax_channels_last(K, h, c):
     x = torch.randn(3, c, h, h).relu_().requires_grad_(True)
     ref = O.spatial_softmax(x)
