@@ -115,9 +115,14 @@ struct TcEpilogue {
   }
 };
 
+// 32-wide k-blocks per pipeline stage: two for the 1-pass products (8 MMAs per barrier round of the issuing thread); the
+// 3-pass products already issue 12 MMAs per k-block and their stages are twice as large
+template <bool SPLIT>
+constexpr int kps() { return SPLIT ? 1 : 2; }
+
 template <int BN, bool SPLIT, int CLUSTER, class AL, class BL>
-__global__ void __launch_bounds__(tc::PipeCfg<BN, SPLIT>::kThreads, 1) gemm_tc_kernel(AL al, BL bl, TcEpilogue ep, int num_tiles, int num_kb) {
-  tc::run_pipeline<BN, SPLIT, tc::kBK, CLUSTER>(al, bl, ep, num_tiles, num_kb);
+__global__ void __launch_bounds__(tc::PipeCfg<BN, SPLIT, tc::kBK, kps<SPLIT>()>::kThreads, 1) gemm_tc_kernel(AL al, BL bl, TcEpilogue ep, int num_tiles, int num_kb) {
+  tc::run_pipeline<BN, SPLIT, tc::kBK, CLUSTER, AL, BL, TcEpilogue, kps<SPLIT>()>(al, bl, ep, num_tiles, num_kb);
 }
 
 // Tile width and k-slices (= cluster size) of a product.  Clusters of 8 / 4 / 2 CTAs of this kernel (one CTA per SM, ~200 KB
@@ -141,7 +146,7 @@ inline void choose_config(int M, int N, int K, int& bn, int& splits) {
 
 template <int BN, bool SPLIT, int CLUSTER, class AL, class BL>
 int launch_one(AL al, BL bl, TcEpilogue ep, int tiles, int kbps, cudaStream_t st) {
-  using Cfg = tc::PipeCfg<BN, SPLIT>;
+  using Cfg = tc::PipeCfg<BN, SPLIT, tc::kBK, kps<SPLIT>()>;
   auto kfn = gemm_tc_kernel<BN, SPLIT, CLUSTER, AL, BL>;
   HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   if (CLUSTER == 1) {
@@ -166,7 +171,8 @@ template <int BN, bool SPLIT, class AL, class BL>
 int launch(AL al, BL bl, TcEpilogue ep, int M, int N, int K, cudaStream_t st) {
   int tiles_m = hulc_cdiv(M, tc::kBM), tiles_n = hulc_cdiv(N, BN);
   const int num_kb = hulc_cdiv(K, tc::kBK);
-  const int kbps = hulc_cdiv(num_kb, ep.splits);
+  // k-blocks per k-slice, a whole number of stage rounds (a slice must not read into its neighbour's range; past K the loaders zero-fill)
+  const int kbps = hulc_cdiv(hulc_cdiv(num_kb, ep.splits), kps<SPLIT>()) * kps<SPLIT>();
   const int tiles = tiles_m * tiles_n * ep.splits;
   ep.BN = BN; ep.tiles_n = tiles_n;
   al.tiles_n = tiles_n; al.is_n = 0; al.splits = ep.splits; al.kb_per_split = kbps;
@@ -208,7 +214,7 @@ HULC_API int hulc_debug_max_clusters(int cluster, int split, int* out) {
   int n = -1;
   cudaError_t e;
   if (split) {
-    using Cfg = tc::PipeCfg<128, true>;
+    using Cfg = tc::PipeCfg<128, true, tc::kBK, 1>;
     cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     auto k8 = gemm_tc_kernel<128, true, 8, AL, BL>; auto k4 = gemm_tc_kernel<128, true, 4, AL, BL>; auto k2 = gemm_tc_kernel<128, true, 2, AL, BL>;
     cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -216,7 +222,7 @@ HULC_API int hulc_debug_max_clusters(int cluster, int split, int* out) {
     cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     e = cluster == 8 ? cudaOccupancyMaxActiveClusters(&n, k8, &cfg) : cluster == 4 ? cudaOccupancyMaxActiveClusters(&n, k4, &cfg) : cudaOccupancyMaxActiveClusters(&n, k2, &cfg);
   } else {
-    using Cfg = tc::PipeCfg<128, false>;
+    using Cfg = tc::PipeCfg<128, false, tc::kBK, 2>;
     cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     auto k8 = gemm_tc_kernel<128, false, 8, AL, BL>; auto k4 = gemm_tc_kernel<128, false, 4, AL, BL>; auto k2 = gemm_tc_kernel<128, false, 2, AL, BL>;
     cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);

@@ -30,11 +30,14 @@ constexpr int kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kBM = 128;
 
-template <int BN, bool SPLIT, int BK = kBK>
+template <int BN, bool SPLIT, int BK = kBK, int KPS = 1>
 struct PipeCfg {
   static constexpr int kATile = kBM * BK * 4;
   static constexpr int kBTile = BN * BK * 4;
-  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kATile + kBTile);
+  static constexpr int kSubBytes = (SPLIT ? 2 : 1) * (kATile + kBTile);  // one BK-wide k-block: [A hi][A lo][B hi][B lo]
+  // KPS k-blocks share one stage (one full/empty barrier round trip, one wait and one commit of the MMA thread per KPS*4 MMAs):
+  // the per-round cost of the issuing thread (~200 cycles: try_wait + commit) is what bounds small-N products
+  static constexpr int kStageBytes = KPS * kSubBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kLag = kStages - 1 < 3 ? kStages - 1 : 3;  // cp.async groups a producer thread leaves in flight
@@ -44,6 +47,7 @@ struct PipeCfg {
   // tensor core's truncating fp32 accumulation touches the main sum once per k-step instead of three times
   static constexpr int kAccCols = (SPLIT ? 2 : 1) * BN;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
+  static_assert(kStages >= 2, "at least two stages");
 };
 
 struct PipeBarriers {
@@ -101,9 +105,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // through distributed shared memory in a fixed order and hands them to the epilogue
 //   int rows_valid(int tile) const;  void store4(int tile, int row, int col, float4 v) const;
 // — no partials in global memory, no second launch, bit-reproducible.
-template <int BN, bool SPLIT, int BK, int CLUSTER, class ALoader, class BLoader, class Epilogue>
+template <int BN, bool SPLIT, int BK, int CLUSTER, class ALoader, class BLoader, class Epilogue, int KPS = 1>
 __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epilogue& ep, int num_tiles, int num_kb) {
-  using Cfg = PipeCfg<BN, SPLIT, BK>;
+  using Cfg = PipeCfg<BN, SPLIT, BK, KPS>;
+  const int num_rounds = (num_kb + KPS - 1) / KPS;  // a ragged last round reads k-blocks past num_kb: loaders zero-fill them
   constexpr int S = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -169,44 +174,51 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
     }
   } else if (warp == kEpiWarps) {
     // ================================ MMA issuer ================================
-    constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, ALoader::kMNMajor, BLoader::kMNMajor);
-    int j = 0;  // k-block sequence number of this CTA
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int a = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&bars->tmem_empty[a], aphase ^ 1);
-      tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(a * Cfg::kAccCols);
-      const uint32_t d_small = d_tmem + BN;
-      for (int kb = 0; kb < num_kb; ++kb, ++j) {
-        const int stage = j % S;
-        const uint32_t phase = (j / S) & 1;
-        mbar_wait(&bars->full[stage], phase);
+    // One thread runs the whole loop.  Descriptors are formed once (for stage 0, k-step 0) and advanced by adding the
+    // byte offset >> 4 to the start-address field: every tcgen05.mma costs its thread a handful of integer instructions.
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, ALoader::kMNMajor, BLoader::kMNMajor);
+      constexpr uint32_t kAStep = (ALoader::kMNMajor ? 1024u : 32u) >> 4, kBStep = (BLoader::kMNMajor ? 1024u : 32u) >> 4;  // per k-step of 8
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t a_hi0 = make_desc<ALoader::kMNMajor, kBM, BK>(s0, 0);
+      const uint64_t b_hi0 = make_desc<BLoader::kMNMajor, BN, BK>(s0 + (SPLIT ? 2 : 1) * Cfg::kATile, 0);
+      int j = 0;  // stage-round sequence number of this CTA
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[a], aphase ^ 1);
         tc_fence_after_sync();
-        if (kb == 0) trace(2);  // first stage landed
-        if (kb == num_kb - 1) trace(3);  // last stage landed
-        if (lane == 0) {
-          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t a_lo = a_hi + Cfg::kATile;
-          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * Cfg::kATile;
-          const uint32_t b_lo = b_hi + Cfg::kBTile;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * Cfg::kAccCols);
+        const uint32_t d_small = d_tmem + BN;
+        for (int r = 0; r < num_rounds; ++r, ++j) {
+          const int stage = j % S;
+          const uint32_t phase = (j / S) & 1;
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after_sync();
+          if (r == 0) trace(2);  // first stage landed
+          if (r == num_rounds - 1) trace(3);  // last stage landed
+          const uint32_t soff = (uint32_t)(stage * Cfg::kStageBytes) >> 4;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t da_hi = make_desc<ALoader::kMNMajor, kBM, BK>(a_hi, k), db_hi = make_desc<BLoader::kMNMajor, BN, BK>(b_hi, k);
-            if (SPLIT) {
-              const uint64_t da_lo = make_desc<ALoader::kMNMajor, kBM, BK>(a_lo, k), db_lo = make_desc<BLoader::kMNMajor, BN, BK>(b_lo, k);
-              umma_tf32(d_small, da_lo, db_hi, idesc, (kb | k) != 0);
-              umma_tf32(d_small, da_hi, db_lo, idesc, 1);
-              umma_tf32(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
-            } else {
-              umma_tf32(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
+          for (int u = 0; u < KPS; ++u) {
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint32_t first = (uint32_t)((r | u | k) != 0);
+              const uint64_t da_hi = a_hi0 + (soff + ((uint32_t)(u * Cfg::kSubBytes) >> 4) + k * kAStep);
+              const uint64_t db_hi = b_hi0 + (soff + ((uint32_t)(u * Cfg::kSubBytes) >> 4) + k * kBStep);
+              if (SPLIT) {
+                const uint64_t da_lo = da_hi + ((uint32_t)Cfg::kATile >> 4), db_lo = db_hi + ((uint32_t)Cfg::kBTile >> 4);
+                umma_tf32(d_small, da_lo, db_hi, idesc, first);
+                umma_tf32(d_small, da_hi, db_lo, idesc, 1);
+                umma_tf32(d_tmem, da_hi, db_hi, idesc, first);
+              } else {
+                umma_tf32(d_tmem, da_hi, db_hi, idesc, first);
+              }
             }
           }
-          umma_commit(&bars->empty[stage]);                        // stage reusable once these MMAs have read it
-          if (kb == num_kb - 1) umma_commit(&bars->tmem_full[a]);  // accumulator complete
+          umma_commit(&bars->empty[stage]);                             // stage reusable once these MMAs have read it
+          if (r == num_rounds - 1) umma_commit(&bars->tmem_full[a]);  // accumulator complete
         }
-        __syncwarp();
       }
     }
   } else {
@@ -214,11 +226,14 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
     constexpr int L = Cfg::kLag;
     const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;
     int j = 0;  // k-block sequence number of this CTA
-    auto publish = [&](int jj) {  // the cp.async group of k-block jj has landed: hand this warp's share to the MMA warp
+    auto publish = [&](int jj) {  // the cp.async group of stage-round jj has landed: hand this warp's share to the MMA warp
       if constexpr (SPLIT) {
-        const uint32_t hi = smem_u32(smem + (jj % S) * Cfg::kStageBytes);
-        al.split(hi, hi + Cfg::kATile, ptid);
-        bl.split(hi + 2 * Cfg::kATile, hi + 2 * Cfg::kATile + Cfg::kBTile, ptid);
+#pragma unroll
+        for (int u = 0; u < KPS; ++u) {
+          const uint32_t hi = smem_u32(smem + (jj % S) * Cfg::kStageBytes + u * Cfg::kSubBytes);
+          al.split(hi, hi + Cfg::kATile, ptid);
+          bl.split(hi + 2 * Cfg::kATile, hi + 2 * Cfg::kATile + Cfg::kBTile, ptid);
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -227,13 +242,16 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       al.start_tile(tile, ptid);
       bl.start_tile(tile, ptid);
-      for (int kb = 0; kb < num_kb; ++kb, ++j) {
+      for (int r = 0; r < num_rounds; ++r, ++j) {
         const int stage = j % S;
         mbar_wait(&bars->empty[stage], ((j / S) & 1) ^ 1);
-        const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * Cfg::kATile;
-        al.issue(kb, a_hi, ptid);
-        bl.issue(kb, b_hi, ptid);
+#pragma unroll
+        for (int u = 0; u < KPS; ++u) {
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes + u * Cfg::kSubBytes);
+          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * Cfg::kATile;
+          al.issue(r * KPS + u, a_hi, ptid);
+          bl.issue(r * KPS + u, b_hi, ptid);
+        }
         cp_async_commit();
         if (j >= L) {
           cp_async_wait<L>();

@@ -123,6 +123,7 @@ class HulcEngine:
         assert model in ("hulc", "gcbc", "mcil") and rnn_model in ("rnn_decoder", "gru_decoder")
         assert precision in ("tf32", "fp32")
         self.tc = precision == "tf32"
+        self.persistent_rnn = os.environ.get("HULC_B200_PERSISTENT_RNN", "1") != "0"  # whole recurrence in one launch (csrc/rnn_tc.cu)
         self.model, self.rnn_model = model, rnn_model
         self.device = torch.device(device)
         self.spec = param_spec(model, rnn_model, max_window)
@@ -371,6 +372,14 @@ class HulcEngine:
         saved = self.buf(f"{tag}.saved", S, B, 4 * H) if kind == "gru" else None
         gh = self.buf(f"{tag}.gh", B, 3 * H) if kind == "gru" else None
         tc = 3 if self.tc else 0
+        if self.tc and self.persistent_rnn and kind != "gru" and ops.rnn_tc_seq_ok(B, H):
+            # one persistent launch for the whole chain (W_hh resident in shared memory, csrc/rnn_tc.cu)
+            st, sp = hbuf.stride(0), pre3.stride(0)
+            if reverse:
+                ops.rnn_tc_seq(w_hh, h(S + 1), h(S), pre3[S - 1], S, prev_step=-st, out_step=-st, add_step=-sp, act=TANH if kind == "tanh" else RELU)
+            else:
+                ops.rnn_tc_seq(w_hh, h(0), h(1), pre3[0], S, prev_step=st, out_step=st, add_step=sp, act=TANH if kind == "tanh" else RELU)
+            return saved
         for t in (range(S - 1, -1, -1) if reverse else range(S)):
             prev = h(t + 2) if reverse else h(t)
             if kind == "gru":
@@ -402,6 +411,15 @@ class HulcEngine:
         # Elman: dpre_t = (dh_above_t + dpre_{t+1} W_hh) * act'(h_t); slot S (or slot 0 for reverse) of dbuf stays zero
         dbuf = self.buf(f"{tag}.dpre", S + 1, B, H, zero=True)
         act = GATE_TANH if kind == "tanh" else 0
+        if self.tc and self.persistent_rnn and ops.rnn_tc_seq_ok(B, H):
+            sd, sh, sa = dbuf.stride(0), hbuf.stride(0), B * dh_above.stride(0)
+            if reverse:
+                ops.rnn_tc_seq(w_hh, dbuf[0], dbuf[1], ab(0), S, prev_step=sd, out_step=sd, add_step=sa, gate0=h(1), gate_step=sh, act=act, transW=True)
+            else:
+                ops.rnn_tc_seq(w_hh, dbuf[S], dbuf[S - 1], ab(S - 1), S, prev_step=-sd, out_step=-sd, add_step=-sa, gate0=h(S), gate_step=-sh, act=act,
+                               transW=True)
+            d = (dbuf[1:] if reverse else dbuf[:S]).reshape(S * B, H)
+            return d, d
         for t in (range(S) if reverse else range(S - 1, -1, -1)):
             nxt, cur = (dbuf[t], dbuf[t + 1]) if reverse else (dbuf[t + 1], dbuf[t])
             gemm(nxt, w_hh, cur, addend=ab(t), gate=h(t + 1), act=act, tc=1 if self.tc else 0)

@@ -155,6 +155,23 @@ def gru_gates_bwd(dh_above, dh_rec, saved, hprev, dgi, dgh, dh_carry):
                             _ptr(dgh), ld(dgh), _ptr(dh_carry), ld(dh_carry), B, H, _stream())
 
 
+def rnn_tc_seq_ok(B: int, H: int) -> bool:
+    """Shapes the persistent recurrence kernel takes (hulc_rnn_tc_seq): hidden size 2048, at most 64 sequences."""
+    return _DEVICE_TYPE == "cuda" and H == 2048 and B <= 64
+
+
+def rnn_tc_seq(W, prev0, out0, add0, S: int, *, prev_step: int, out_step: int, add_step: int, gate0=None, gate_step: int = 0, act: int = 0,
+               transW: bool = False):
+    """All S dependent steps of one Elman layer / direction in one launch (see hulc_rnn_tc_seq in include/hulc_b200.h).
+    prev0 / out0 / add0 / gate0 are the [B, H] views of step 0; *_step the element strides from one step to the next."""
+    _chk(W, prev0, out0, add0, gate0)
+    B, H = out0.shape
+    ws = workspace(W.device)
+    _L().hulc_rnn_tc_seq(_ptr(W), _rowmajor(W), int(transW), _ptr(prev0), int(prev_step), _rowmajor(prev0), _ptr(out0), int(out_step),
+                         _rowmajor(out0), _ptr(add0), int(add_step), _rowmajor(add0), _ptr(gate0), int(gate_step),
+                         _rowmajor(gate0) if gate0 is not None else 0, int(act), B, H, int(S), _ptr(ws), ws.numel() * 4, _stream())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # convolutions
 # ----------------------------------------------------------------------------------------------------------------------

@@ -73,6 +73,19 @@ int hulc_gru_gates_fwd(const float* gi, int ldgi, const float* gh, int ldgh, con
 int hulc_gru_gates_bwd(const float* dh_above, int lda, const float* dh_rec, int ldr, const float* saved, const float* hprev,
                        int ldhp, float* dgi, int ldgi, float* dgh, int ldgh, float* dh_carry, int ldc, int B, int H, void* stream);
 
+/* ---- a whole Elman recurrence in one persistent launch (tensor cores, W_hh resident in shared memory) ----------------------
+ * torch.nn.RNN as built at decoders/utils/rnn.py:5-14 (ReLU) and plan_encoders/plan_recognition_net.py:27-34 (tanh,
+ * bidirectional), one layer and direction per call, all S dependent steps:
+ *   transW = 0 (forward):  out_s = act(add_s + prev_s W^T)            W [H,H] = weight_hh (out x in)
+ *   transW = 1 (BPTT):     out_s = (add_s + prev_s W) * act'(gate_s)   gate_s = h_t; act & HULC_GATE_TANH selects 1 - g^2
+ * for s = 0..S-1 with X_s = X0 + s * X_step (element strides, may be negative: reverse direction / backward in time);
+ * every operand is a [B, H] view with its own leading dimension.  out_s of one step is prev_{s+1} of the next (the caller
+ * lays the slots out so).  H must be 2048 and B <= 64, else cudaErrorInvalidValue (callers fall back to per-step
+ * hulc_gemm_tc).  Operands are rounded to tf32 (nearest), accumulation and epilogue are fp32. */
+int hulc_rnn_tc_seq(const float* W, int ldw, int transW, const float* prev0, long long prev_step, int ldp, float* out0, long long out_step,
+                    int ldo, const float* add0, long long add_step, int ldadd, const float* gate0, long long gate_step, int ldg, int act,
+                    int B, int H, int S, float* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- convolutions of the perceptual encoders -------------------------------------------------------------------------
  * perceptual_encoders/vision_network.py:36-47 and vision_network_gripper.py:11-17: nn.Conv2d (valid, NCHW) + ReLU for
  * the three layer shapes (3->32 k8 s4, 32->64 k4 s2, 64->64 k3 s1).  x [N,CIN,H,W], w [COUT,CIN,KS,KS], y [N,COUT,HO,WO].
