@@ -180,7 +180,18 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     whh = P["action_decoder.rnn.weight_hh_l1"]
     hb, pre1 = B_["dec.h1"], B_["dec.pre1"]
     big_a, big_c = B_["dec.dh0"], torch.empty(H, H, device=x.device)
-    if eng.tc:
+    if eng.tc and eng.persistent_rnn:
+        # the whole 32-step chain of one layer is one persistent launch (csrc/rnn_tc.cu); 2 layers forward + 2 backward per step
+        st, sp = hb.stride(0), pre1.view(S, nB, -1).stride(0)
+        pre3 = pre1.view(S, nB, -1)
+        cands["rnn_seq_fwd_32steps"] = (lambda: ops.rnn_tc_seq(whh, hb[0], hb[1], pre3[0], S, prev_step=st, out_step=st, add_step=sp, act=1),
+                                        2.0 * nB * H * H * S, 2)
+        dbuf = B_["dec.l1.dpre"]
+        sd = dbuf.stride(0)
+        dh = big_a.view(S, nB, H)
+        cands["rnn_seq_bwd_32steps"] = (lambda: ops.rnn_tc_seq(whh, dbuf[S], dbuf[S - 1], dh[S - 1], S, prev_step=-sd, out_step=-sd, add_step=-dh.stride(0),
+                                                               gate0=hb[S], gate_step=-st, act=0, transW=True), 2.0 * nB * H * H * S, 2)
+    elif eng.tc:
         cands["rnn_step_fwd_3xtf32"] = (lambda: ops.gemm(hb[1], whh, hb[2], transB=True, addend=pre1[:nB], act=1, tc=3), 2.0 * nB * H * H, 2 * S)
         dbuf = B_["dec.l1.dpre"]
         cands["rnn_step_bwd_tf32"] = (lambda: ops.gemm(dbuf[2], whh, dbuf[1], addend=big_a[:nB], gate=hb[2], tc=1), 2.0 * nB * H * H, 2 * S)
@@ -205,16 +216,34 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         res[name] = dict(ms=ms, flops=flops, per_step=per_step, share=ms * per_step / step_ms)
+    # algorithmic HBM bytes per launch: operands read once + result written once, fp32
+    fr = lambda n, c, hw: 4.0 * n * c * hw * hw
+    abytes = {
+        "conv1_fwd": fr(n1, 3, 200) + fr(n1, 32, 49), "conv1_wgrad": fr(n1, 3, 200) + fr(n1, 32, 49),
+        "conv2_fwd": fr(N, 32, 49) + fr(N, 64, 23), "conv2_wgrad": fr(N, 32, 49) + fr(N, 64, 23), "conv2_dgrad": fr(N, 64, 23) + 2 * fr(N, 32, 49),
+        "conv3_fwd": fr(N, 64, 23) + fr(N, 64, 21), "conv3_wgrad": fr(N, 64, 23) + fr(N, 64, 21), "conv3_dgrad": fr(N, 64, 21) + 2 * fr(N, 64, 23),
+        "rnn_seq_fwd_32steps": 4.0 * (H * H + 3 * S * nB * H), "rnn_seq_bwd_32steps": 4.0 * (H * H + 4 * S * nB * H),
+        "rnn_step_fwd_3xtf32": 4.0 * (H * H + 3 * nB * H), "rnn_step_bwd_tf32": 4.0 * (H * H + 4 * nB * H), "rnn_step_gemm": 4.0 * (H * H + 3 * nB * H),
+        "dense_wgrad_2048^3": 4.0 * (2 * S * nB * H + H * H), "dense_fwd_2048^3": 4.0 * (2 * S * nB * H + H * H),
+    }
     top = max(res, key=lambda k: res[k]["ms"] * res[k]["per_step"])
     r = res[top]
-    achieved = r["flops"] / (r["ms"] * 1e-3) / 1e12
-    return {
-        "bound": "tensor", "kernel": top, "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
-        "traffic": None, "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); tf32 tensor-core peak is half of it, fp32 CUDA-core kernels far below",
-        "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
-        "kernels": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "per_step": v["per_step"], "share_of_step": round(v["share"], 4)} for k, v in res.items()},
-        "step": {"tensor_frac": None, "hbm_frac": None},
-    }
+    tflops = r["flops"] / (r["ms"] * 1e-3) / 1e12
+    gbs = abytes[top] / (r["ms"] * 1e-3) / 1e9
+    # the kernel runs tf32 operands: its tensor ceiling is half the measured bf16 rate; it is HBM-bound when its arithmetic
+    # intensity is below that ridge
+    tf32_peak = peaks["tf_burst"] / 2.0
+    hbm_bound = (r["flops"] / abytes[top]) < (tf32_peak * 1e12) / (peaks["hbm"] * 1e9)
+    kern = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "gbs": round(abytes[k] / (v["ms"] * 1e-3) / 1e9, 1),
+                "per_step": v["per_step"], "share_of_step": round(v["share"], 4)} for k, v in res.items()}
+    common = {"kernel": top, "traffic": None, "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
+              "algorithmic_bytes_per_launch": abytes[top], "algorithmic_flops_per_launch": r["flops"], "kernels": kern,
+              "step": {"tensor_frac": None, "hbm_frac": None}}
+    if hbm_bound:
+        return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                "peak_source": f"{peaks['src']} HBM copy bandwidth (MEASURED_PEAKS.json hbm_gbs)", **common}
+    return {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tflops / peaks["tf_burst"],
+            "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); the kernel runs tf32 operands, whose tensor-core peak is half of it", **common}
 
 
 def run_ours(args):
@@ -247,10 +276,14 @@ def run_ours(args):
     host = synthetic.make_batch(B_PER_MODALITY, SEQ_LEN, seed=1 + rank)  # per-rank data (weak scaling)
     batch = synthetic._to(host, dev)
 
+    from hulc_b200.ddp import FlatGradientSync
+
+    sync = FlatGradientSync(eng)
+    sync.broadcast_parameters(0)
+
     def allreduce_and_adam():
-        if world > 1:
-            dist.all_reduce(eng.ps.grad)  # the one per-step collective: 188 MB fp32 gradient over NVLink
-        eng.ps.adam_step(lr=eng.lr, grad_scale=1.0 / world)
+        sync.sync()  # the one per-step collective: 188 MB fp32 gradient over NVLink; no-op on one GPU
+        sync.step()  # fused Adam with grad_scale = 1 / world
 
     # the whole step (forward, backward and — on one GPU — Adam) is replayed from one CUDA graph; with several ranks the
     # gradient all-reduce and Adam follow the graph

@@ -332,17 +332,21 @@ __global__ void prep_dgrad_weights_kernel(const float* __restrict__ w, float* __
   wd[i] = w[(((size_t)co * CIN + ci) * KS + (py + S * jy)) * KS + (px + S * jx)];
 }
 
-constexpr int kKPS = 2;  // 32-wide k-blocks per pipeline stage (tc_pipeline.cuh); every K of these layers is a multiple of 64
+// 32-wide k-blocks per pipeline stage (tc_pipeline.cuh).  Measured on the B200: the narrow tiles (BN = 32: the first layer and
+// the data gradient of the second) gain from two k-blocks per barrier round; with BN = 64 the halved stage count costs more
+// than the saved barrier traffic.  Every K of these layers is a multiple of 64.
+template <int BN>
+constexpr int kps() { return BN == 32 ? 2 : 1; }
 
 template <int BN, class AL, class BL, class EP>
-__global__ void __launch_bounds__(tc::PipeCfg<BN, false, tc::kBK, kKPS>::kThreads, 1) conv_tc_kernel(AL al, BL bl, EP ep, int num_tiles, int num_kb) {
-  tc::run_pipeline<BN, false, tc::kBK, 1, AL, BL, EP, kKPS>(al, bl, ep, num_tiles, num_kb);
+__global__ void __launch_bounds__(tc::PipeCfg<BN, false, tc::kBK, kps<BN>()>::kThreads, 1) conv_tc_kernel(AL al, BL bl, EP ep, int num_tiles, int num_kb) {
+  tc::run_pipeline<BN, false, tc::kBK, 1, AL, BL, EP, kps<BN>()>(al, bl, ep, num_tiles, num_kb);
 }
 
 template <int BN, class AL, class BL, class EP>
 int launch(AL al, BL bl, EP ep, int num_tiles, int num_kb, cudaStream_t st) {
-  using Cfg = tc::PipeCfg<BN, false, tc::kBK, kKPS>;
-  if (num_kb % kKPS) return (int)cudaErrorInvalidValue;
+  using Cfg = tc::PipeCfg<BN, false, tc::kBK, kps<BN>()>;
+  if (num_kb % kps<BN>()) return (int)cudaErrorInvalidValue;
   auto kfn = conv_tc_kernel<BN, AL, BL, EP>;
   HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   HULC_LAUNCH(kfn, dim3(min(kNumSMs, num_tiles)), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, al, bl, ep, num_tiles, num_kb);
@@ -391,7 +395,7 @@ int wgrad(const Geom& g, const float* x, const float* dy, float* dw, float beta,
   int splits = max(1, min((2 * kNumSMs) / mt, hulc_cdiv(M, 8 * tc::kBK)));
   while (splits > 1 && (size_t)splits * KTOT * COUT * sizeof(float) > ws_bytes) --splits;
   if ((size_t)splits * KTOT * COUT * sizeof(float) > ws_bytes) return (int)cudaErrorInvalidValue;
-  const int pps = hulc_cdiv(hulc_cdiv(M, splits), kKPS * tc::kBK) * (kKPS * tc::kBK);
+  const int pps = hulc_cdiv(hulc_cdiv(M, splits), 2 * tc::kBK) * (2 * tc::kBK);
   splits = hulc_cdiv(M, pps);
   WgradTiling t{splits, pps, M};
   WgradXLoader<CIN, KS, S, NCHW3> al{x, g, t, 0, 0, 0};

@@ -115,10 +115,9 @@ struct TcEpilogue {
   }
 };
 
-// 32-wide k-blocks per pipeline stage: two for the 1-pass products (8 MMAs per barrier round of the issuing thread); the
-// 3-pass products already issue 12 MMAs per k-block and their stages are twice as large
+// 32-wide k-blocks per pipeline stage (tc_pipeline.cuh)
 template <bool SPLIT>
-constexpr int kps() { return SPLIT ? 1 : 2; }
+constexpr int kps() { return 1; }  // measured: two k-blocks per stage (half the stages) is slower for BN = 64 / 128
 
 template <int BN, bool SPLIT, int CLUSTER, class AL, class BL>
 __global__ void __launch_bounds__(tc::PipeCfg<BN, SPLIT, tc::kBK, kps<SPLIT>()>::kThreads, 1) gemm_tc_kernel(AL al, BL bl, TcEpilogue ep, int num_tiles, int num_kb) {
@@ -222,7 +221,7 @@ HULC_API int hulc_debug_max_clusters(int cluster, int split, int* out) {
     cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     e = cluster == 8 ? cudaOccupancyMaxActiveClusters(&n, k8, &cfg) : cluster == 4 ? cudaOccupancyMaxActiveClusters(&n, k4, &cfg) : cudaOccupancyMaxActiveClusters(&n, k2, &cfg);
   } else {
-    using Cfg = tc::PipeCfg<128, false, tc::kBK, 2>;
+    using Cfg = tc::PipeCfg<128, false, tc::kBK, 1>;
     cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     auto k8 = gemm_tc_kernel<128, false, 8, AL, BL>; auto k4 = gemm_tc_kernel<128, false, 4, AL, BL>; auto k2 = gemm_tc_kernel<128, false, 2, AL, BL>;
     cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
