@@ -14,8 +14,16 @@
 //             in a fixed order and written back in the reference's [COUT][CIN][KS][KS] layout.
 // Operands are consumed as tf32 (10-bit mantissa), as cuDNN does by default for the reference's convolutions on
 // Ampere-or-newer GPUs; the effect on the parity metrics is quantified in DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_pipeline.cuh"
+
+// conv_tma.cu: the same layers with the A operand delivered by TMA (cudaErrorNotSupported -> use the gather kernels below)
+int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S, int relu,
+                      cudaStream_t st);
+int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
+                              int R, int S, int py, int px, cudaStream_t st);
 
 namespace {
 
@@ -25,6 +33,8 @@ using tc::swz;
 using tc::swz32;
 
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+// HULC_B200_CONV_TMA=0 keeps the cp.async gather kernels (A/B comparison, fallback)
+const bool g_use_tma = [] { const char* e = getenv("HULC_B200_CONV_TMA"); return !(e && e[0] == '0'); }();
 constexpr size_t kCounterFloats = 1024;  // head of the shared workspace reserved for the split-K / loss tickets
 
 struct Geom {
@@ -364,6 +374,10 @@ template <int CIN, int KS, int S, int COUT>
 int fwd_nhwc(const Geom& g, const float* x, const float* w, const float* b, float* y, int relu, float* ws, cudaStream_t st) {
   const int K = CIN * KS * KS, M = g.N * g.HO * g.WO;
   HULC_LAUNCH(prep_fwd_weights_kernel, dim3(hulc_cdiv(COUT * K, 256)), dim3(256), 0, st, w, ws, COUT, CIN, KS);
+  if (g_use_tma) {
+    const int rc = hulc_conv_tma_fwd(x, ws, b, y, g.N, CIN, g.H, g.W, COUT, KS, S, relu, st);
+    if (rc != (int)cudaErrorNotSupported) return rc;
+  }
   FwdNhwcLoader<CIN, KS, S> al{x, g, M, {0, 0, 0, 0}};
   WeightLoader<COUT> bl{ws, K};
   FwdEpilogue ep{y, b, M, COUT, relu};
@@ -379,6 +393,11 @@ int dgrad_nhwc(const Geom& g, const float* dy, const float* w, const float* gate
     const int HP = (g.H - py + S - 1) / S, WP = (g.W - px + S - 1) / S;
     const int M = g.N * HP * WP;
     if (M <= 0) continue;
+    if (g_use_tma) {
+      const int rc = hulc_conv_tma_dgrad_phase(dy, ws + (size_t)ph * CIN * Kp, gate, dx, g.N, CIN, g.H, g.W, COUT, g.HO, g.WO, R, S, py, px, st);
+      if (rc == 0) continue;
+      if (rc != (int)cudaErrorNotSupported) return rc;
+    }
     DgradLoader<COUT, KS, S> al{dy, g, M, HP, WP, {0, 0, 0, 0}, {0, 0, 0, 0}};
     WeightLoader<CIN> bl{ws + (size_t)ph * CIN * Kp, Kp};
     DgradEpilogue<S> ep{dx, gate, g, M, HP, WP, py, px};

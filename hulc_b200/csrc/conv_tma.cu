@@ -1,0 +1,258 @@
+// conv_tma.cu — the channels-last convolutions of the perceptual encoders (layers 2 and 3: 32 -> 64, k4, s2 and 64 -> 64,
+// k3, s1; vision_network.py:39-43, vision_network_gripper.py:14-16), forward and data gradient, as implicit GEMMs whose A
+// operand is delivered by TMA.
+//
+// With NHWC activations the im2col block of one kernel tap and 32 channels is a BOX of the activation tensor: output
+// pixels (n, y0.., 0..OW-1) read input pixels (n, S*y + ky, S*x + kx), i.e. a 4-d box (32 ch, OW, RT, NB) walked with element
+// strides (1, S, S, 1) from the corner (c0, kx, S*y0 + ky, n0).  One cp.async.bulk.tensor lands it in shared memory as
+// [pixel][128 B] rows with the 128-byte swizzle — the K-major UMMA operand tile — and the halo of the data gradient is the
+// TMA's out-of-bounds zero fill.  One thread issues the copies, one thread issues tcgen05.mma (kind::tf32), the prepared
+// weights [BN x K] stay resident in shared memory for the whole kernel, four warps run the epilogue.  Compared with the
+// cp.async gather of conv_tc.cu there is no per-thread address arithmetic at all (that kernel is bound by the latency of
+// the ~150 instructions per warp per k-block its producers execute).
+//
+//   forward      : source = x,  output grid = (HO, WO), taps (+ky, +kx), B = w as [COUT][(ky, kx, ci)], epilogue bias + ReLU
+//   data gradient: source = dY, output grid = the input pixels of one stride phase (py, px), taps (-jy, -jx),
+//                  B = w as [CIN][(jy, jx, co)] for that phase, epilogue = ReLU mask of the activation that fed the layer
+#include "common.cuh"
+#include "tc_pipeline.cuh"
+#include "tma.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kATileB = kBM * kRowBytes;  // 16 KB: one k-block of the A operand (128 pixels x 32 channels)
+constexpr int kThr = (kEpiWarps + 2) * 32;
+constexpr int kSmemBudget = 224 * 1024;
+
+struct TcParams {
+  int N, OH, OW;       // output grid of this launch
+  int NB, RT, TPF;     // frames / rows per tile, tiles per frame (NB == 1) — GEMM rows per tile = NB * RT * OW <= 128
+  int S;               // element stride of the source walk (the layer's stride forward, 1 for the data gradient)
+  int taps_x, cblocks, sign;  // k-block kb -> tap = kb / cblocks (ty = tap / taps_x, tx = tap % taps_x), channel block kb % cblocks
+  const float* wprep;  // [BN][num_kb * 32] K-major
+  float* out;          // NHWC, [N][out_H][out_W][BN]
+  int out_H, out_W, o_mul, oy_add, ox_add;  // output pixel of grid point (y, x): (o_mul * y + oy_add, o_mul * x + ox_add)
+  const float* bias;
+  const float* gate;   // same geometry as out (data gradient), or null
+  int relu;
+};
+
+struct TcBars {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void st_shared16(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int BN, int NKB, int STAGES>
+__global__ void __launch_bounds__(kThr, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap smap, TcParams p, int num_tiles) {
+  constexpr int kWTileB = BN * kRowBytes;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* w_smem = smem;
+  unsigned char* a_smem = smem + NKB * kWTileB;
+  TcBars* bars = reinterpret_cast<TcBars*>(a_smem + STAGES * kATileB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], 1);
+      mbar_init(&bars->tmem_empty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 2 * BN);
+  // rows of the A stages beyond the pixels of a tile are never written by the TMA box: keep them finite
+  for (int i = threadIdx.x; i < STAGES * kATileB / 16; i += kThr) reinterpret_cast<float4*>(a_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // resident weights: NKB K-major swizzled tiles [BN rows x 128 B]
+  for (int q = threadIdx.x; q < NKB * BN * 8; q += kThr) {
+    const int kb = q / (BN * 8), qq = q - kb * (BN * 8);
+    const int n = qq >> 3, c = qq & 7;
+    st_shared16(smem_u32(w_smem) + kb * kWTileB + swz(n, c), __ldg(reinterpret_cast<const float4*>(p.wprep + (size_t)n * (NKB * kBK) + kb * kBK + c * 4)));
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int frame_px = p.RT * p.OW;
+
+  if (warp < kEpiWarps) {
+    // ================================ epilogue ================================
+    const int r = warp * 32 + lane;
+    const int nl = r / frame_px, rem = r - nl * frame_px;
+    const int yl = rem / p.OW, xx = rem - yl * p.OW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int n0 = p.NB > 1 ? tile * p.NB : tile / p.TPF;
+      const int y0 = p.NB > 1 ? 0 : (tile - n0 * p.TPF) * p.RT;
+      const bool valid = nl < p.NB && n0 + nl < p.N && y0 + yl < p.OH;
+      const size_t off = (((size_t)(n0 + nl) * p.out_H + (p.o_mul * (y0 + yl) + p.oy_add)) * p.out_W + (p.o_mul * xx + p.ox_add)) * BN;
+      mbar_wait(&bars->tmem_full[a], (it >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN + c0), v);
+        tmem_ld_wait();
+        if (c0 + 32 == BN) {  // the accumulator is in registers: hand it back before the stores
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.gate) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + off + c0 + j));
+              o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(p.out + off + c0 + j) = o;
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, false, false);
+      const uint64_t a0 = make_desc<false, kBM, kBK>(smem_u32(a_smem), 0), b0 = make_desc<false, BN, kBK>(smem_u32(w_smem), 0);
+      int j = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        mbar_wait(&bars->tmem_empty[a], ((it >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < NKB; ++kb, ++j) {
+          const int stage = j % STAGES;
+          mbar_wait(&bars->full[stage], (j / STAGES) & 1);
+          tc_fence_after_sync();
+          const uint64_t da = a0 + (uint32_t)(stage * (kATileB >> 4)), db = b0 + (uint32_t)(kb * (kWTileB >> 4));
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&bars->empty[stage]);
+        }
+        umma_commit(&bars->tmem_full[a]);
+      }
+    }
+  } else {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      tma::prefetch_map(&smap);
+      const uint32_t box_bytes = (uint32_t)(p.NB * frame_px * kRowBytes);
+      int j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = p.NB > 1 ? tile * p.NB : tile / p.TPF;
+        const int y0 = p.NB > 1 ? 0 : (tile - n0 * p.TPF) * p.RT;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < NKB; ++kb, ++j) {
+          const int stage = j % STAGES;
+          mbar_wait(&bars->empty[stage], ((j / STAGES) & 1) ^ 1);
+          const int ty = tap / p.taps_x, tx = tap - ty * p.taps_x;
+          tma::expect_tx(&bars->full[stage], box_bytes);
+          tma::load_4d(smem_u32(a_smem) + stage * kATileB, &smap, &bars->full[stage], cb * kBK, p.sign * tx, p.S * y0 + p.sign * ty, n0);
+          if (++cb == p.cblocks) { cb = 0; ++tap; }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <int BN, int NKB>
+int launch(const CUtensorMap& smap, const TcParams& p, int num_tiles, cudaStream_t st) {
+  constexpr int kW = NKB * BN * kRowBytes;
+  constexpr int kStagesRaw = (kSmemBudget - kW - 1280) / kATileB;
+  constexpr int STAGES = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static_assert(STAGES >= 2, "weights too large to stay resident");
+  constexpr int smem = kW + STAGES * kATileB + 256 + 1024;
+  auto kfn = conv_tma_kernel<BN, NKB, STAGES>;
+  HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  HULC_LAUNCH(kfn, dim3(min(kNumSMs, num_tiles)), dim3(kThr), smem, st, smap, p, num_tiles);
+  HULC_RETURN_LAST();
+}
+
+// tiling of an (OH, OW) output grid: whole rows; several frames per tile when a frame is small
+bool tiling(int N, int OH, int OW, TcParams& p, int& num_tiles) {
+  if (OW > kBM || OW <= 0 || OH <= 0) return false;
+  p.RT = min(OH, kBM / OW);
+  if (p.RT == OH) { p.NB = max(1, min(kBM / (OH * OW), 256)); p.TPF = 1; num_tiles = hulc_cdiv(N, p.NB); }
+  else { p.NB = 1; p.TPF = hulc_cdiv(OH, p.RT); num_tiles = N * p.TPF; }
+  return true;
+}
+
+// source tensor map: NHWC [N][H][W][C], box = 32 channels x OW x RT x NB grid points walked with element stride S
+int source_map(CUtensorMap* m, const float* src, int N, int H, int W, int C, const TcParams& p) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+  const uint32_t box[4] = {32, (uint32_t)(p.OW * p.S), (uint32_t)(p.RT * p.S), (uint32_t)p.NB};
+  const uint32_t es[4] = {1, (uint32_t)p.S, (uint32_t)p.S, 1};
+  if (box[1] > 256 || box[2] > 256) return (int)cudaErrorNotSupported;
+  return tma::make_map(m, src, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
+}
+
+}  // namespace
+
+// y (NHWC) = relu?(conv(x NHWC, w) + b); wprep = w as [COUT][(ky, kx, ci)] (prep_fwd_weights_kernel).  cudaErrorNotSupported
+// when the geometry does not fit: the caller falls back to the gather kernel.
+int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S, int relu,
+                      cudaStream_t st) {
+  if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(wprep) | reinterpret_cast<size_t>(y)) & 15) return (int)cudaErrorNotSupported;
+  TcParams p{};
+  p.N = N; p.OH = (H - KS) / S + 1; p.OW = (W - KS) / S + 1; p.S = S;
+  int num_tiles;
+  if (!tiling(N, p.OH, p.OW, p, num_tiles)) return (int)cudaErrorNotSupported;
+  p.taps_x = KS; p.cblocks = CIN / 32; p.sign = 1; p.wprep = wprep; p.out = y; p.out_H = p.OH; p.out_W = p.OW; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0;
+  p.bias = b; p.gate = nullptr; p.relu = relu;
+  CUtensorMap m;
+  const int rc = source_map(&m, x, N, H, W, CIN, p);
+  if (rc != 0) return (int)cudaErrorNotSupported;
+  if (CIN == 32 && COUT == 64 && KS == 4) return launch<64, 16>(m, p, num_tiles, st);
+  if (CIN == 64 && COUT == 64 && KS == 3) return launch<64, 18>(m, p, num_tiles, st);
+  return (int)cudaErrorNotSupported;
+}
+
+// One stride phase (py, px) of dx (NHWC [N][H][W][CIN]) = conv_transpose(dy NHWC [N][HO][WO][COUT], w), masked by gate > 0.
+// wphase = w as [CIN][(jy, jx, co)] for this phase (prep_dgrad_weights_kernel), R = KS / S taps per axis.
+int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
+                              int R, int S, int py, int px, cudaStream_t st) {
+  if ((reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(wphase) | reinterpret_cast<size_t>(dx) | reinterpret_cast<size_t>(gate)) & 15)
+    return (int)cudaErrorNotSupported;
+  TcParams p{};
+  p.N = N; p.OH = (H - py + S - 1) / S; p.OW = (W - px + S - 1) / S; p.S = 1;
+  int num_tiles;
+  if (p.OH <= 0 || p.OW <= 0) return 0;
+  if (!tiling(N, p.OH, p.OW, p, num_tiles)) return (int)cudaErrorNotSupported;
+  p.taps_x = R; p.cblocks = COUT / 32; p.sign = -1; p.wprep = wphase; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = S; p.oy_add = py; p.ox_add = px;
+  p.bias = nullptr; p.gate = gate; p.relu = 0;
+  CUtensorMap m;
+  const int rc = source_map(&m, dy, N, HO, WO, COUT, p);
+  if (rc != 0) return (int)cudaErrorNotSupported;
+  if (CIN == 32 && COUT == 64 && R == 2) return launch<32, 8>(m, p, num_tiles, st);
+  if (CIN == 64 && COUT == 64 && R == 3) return launch<64, 18>(m, p, num_tiles, st);
+  return (int)cudaErrorNotSupported;
+}

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 # cin, cout, ks, stride, hw, n
-CASES = [(3, 32, 8, 4, 200, 5), (3, 32, 8, 4, 84, 7), (32, 64, 4, 2, 49, 5), (32, 64, 4, 2, 20, 9), (64, 64, 3, 1, 23, 5), (64, 64, 3, 1, 9, 11),
+CASES = [(3, 32, 8, 4, 200, 5), (3, 32, 8, 4, 84, 7), (3, 32, 8, 4, 36, 3), (3, 32, 8, 4, 100, 2), (32, 64, 4, 2, 49, 300), (64, 64, 3, 1, 7, 37), (32, 64, 4, 2, 49, 5), (32, 64, 4, 2, 20, 9), (64, 64, 3, 1, 23, 5), (64, 64, 3, 1, 9, 11),
          (32, 64, 4, 2, 12, 1), (64, 64, 3, 1, 5, 2)]
 
 
