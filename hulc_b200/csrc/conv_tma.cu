@@ -6,8 +6,11 @@
 // pixels (n, y0.., 0..OW-1) read input pixels (n, S*y + ky, S*x + kx), i.e. a 4-d box (32 ch, OW, RT, NB) walked with element
 // strides (1, S, S, 1) from the corner (c0, kx, S*y0 + ky, n0).  One cp.async.bulk.tensor lands it in shared memory as
 // [pixel][128 B] rows with the 128-byte swizzle — the K-major UMMA operand tile — and the halo of the data gradient is the
-// TMA's out-of-bounds zero fill.  One thread issues the copies, one thread issues tcgen05.mma (kind::tf32), the prepared
-// weights [BN x K] stay resident in shared memory for the whole kernel, four warps run the epilogue.  Compared with the
+// TMA's out-of-bounds zero fill.  One thread issues the copies, the prepared weights [BN x K] stay resident in shared memory
+// for the whole kernel, four warps run the epilogue.  tcgen05.mma (kind::tf32) is issued by FOUR threads, each taking every
+// fourth k-block into its own TMEM accumulator (summed by the epilogue): a k-block of 4 MMAs costs its issuing thread ~600
+// cycles (barrier wait, descriptor setup, commit) but the tensor pipe only ~256, so one issuer leaves the pipe idle half the
+// time (scripts/micro/mma_rate.cu: 640 cycles per k-block with one issuer, 330 with two).  Compared with the
 // cp.async gather of conv_tc.cu there is no per-thread address arithmetic at all (that kernel is bound by the latency of
 // the ~150 instructions per warp per k-block its producers execute).
 //
@@ -23,7 +26,8 @@ namespace {
 using namespace tc;
 
 constexpr int kATileB = kBM * kRowBytes;  // 16 KB: one k-block of the A operand (128 pixels x 32 channels)
-constexpr int kThr = (kEpiWarps + 2) * 32;
+constexpr int kNI = 4;  // MMA-issuing threads (one warp each): every 4th k-block each, into an accumulator of its own
+constexpr int kThr = (kEpiWarps + kNI + 1) * 32;
 constexpr int kSmemBudget = 224 * 1024;
 
 struct TcParams {
@@ -67,12 +71,13 @@ __global__ void __launch_bounds__(kThr, 1) conv_tma_kernel(const __grid_constant
       mbar_init(&bars->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&bars->tmem_full[a], 1);
+      mbar_init(&bars->tmem_full[a], kNI);
       mbar_init(&bars->tmem_empty[a], kEpiWarps);
     }
     fence_barrier_init();
   }
-  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 2 * BN);
+  static_assert(2 * kNI * BN <= 512, "TMEM columns");
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 2 * kNI * BN);
   // rows of the A stages beyond the pixels of a tile are never written by the TMA box: keep them finite
   for (int i = threadIdx.x; i < STAGES * kATileB / 16; i += kThr) reinterpret_cast<float4*>(a_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   // resident weights: NKB K-major swizzled tiles [BN rows x 128 B]
@@ -105,8 +110,16 @@ __global__ void __launch_bounds__(kThr, 1) conv_tma_kernel(const __grid_constant
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kNI * BN + c0), v);
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 1; i < kNI; ++i) {  // partial sums of the other issuers
+          uint32_t u[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((a * kNI + i) * BN + c0), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
+        }
         if (c0 + 32 == BN) {  // the accumulator is in registers: hand it back before the stores
           tc_fence_before_sync();
           __syncwarp();
@@ -130,24 +143,30 @@ __global__ void __launch_bounds__(kThr, 1) conv_tma_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp == kEpiWarps) {
-    // ================================ MMA issuer ================================
+  } else if (warp < kEpiWarps + kNI) {
+    // ================================ MMA issuers ================================
     if (lane == 0) {
+      const int me = warp - kEpiWarps;
       constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, false, false);
       const uint64_t a0 = make_desc<false, kBM, kBK>(smem_u32(a_smem), 0), b0 = make_desc<false, BN, kBK>(smem_u32(w_smem), 0);
-      int j = 0, it = 0;
+      int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int a = it & 1;
         mbar_wait(&bars->tmem_empty[a], ((it >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t d = tmem_base + (uint32_t)(a * BN);
-        for (int kb = 0; kb < NKB; ++kb, ++j) {
+        const uint32_t d = tmem_base + (uint32_t)((a * kNI + me) * BN);
+        // k-block j of the CTA's stage sequence belongs to issuer j % kNI; STAGES is a multiple of kNI, so every stage has ONE
+        // consumer that sees each of its uses in order (a consumer that skipped uses could mistake an older phase of the
+        // stage's barrier for the one it waits for)
+        const int kb0 = ((me - it * NKB) % kNI + kNI) % kNI;
+        for (int kb = kb0; kb < NKB; kb += kNI) {
+          const int j = it * NKB + kb;
           const int stage = j % STAGES;
           mbar_wait(&bars->full[stage], (j / STAGES) & 1);
           tc_fence_after_sync();
           const uint64_t da = a0 + (uint32_t)(stage * (kATileB >> 4)), db = b0 + (uint32_t)(kb * (kWTileB >> 4));
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (uint32_t)(kb != kb0 || k != 0));
           umma_commit(&bars->empty[stage]);
         }
         umma_commit(&bars->tmem_full[a]);
@@ -179,7 +198,7 @@ __global__ void __launch_bounds__(kThr, 1) conv_tma_kernel(const __grid_constant
   __syncthreads();
   if (warp == kEpiWarps) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, 2 * kNI * BN);
   }
 }
 
@@ -187,8 +206,8 @@ template <int BN, int NKB>
 int launch(const CUtensorMap& smap, const TcParams& p, int num_tiles, cudaStream_t st) {
   constexpr int kW = NKB * BN * kRowBytes;
   constexpr int kStagesRaw = (kSmemBudget - kW - 1280) / kATileB;
-  constexpr int STAGES = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static_assert(STAGES >= 2, "weights too large to stay resident");
+  constexpr int STAGES = kStagesRaw >= 8 ? 8 : (kStagesRaw / kNI) * kNI;  // a multiple of the issuer count (see the MMA issuers)
+  static_assert(STAGES >= kNI && NKB >= kNI, "weights too large to stay resident");
   constexpr int smem = kW + STAGES * kATileB + 256 + 1024;
   auto kfn = conv_tma_kernel<BN, NKB, STAGES>;
   HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -147,7 +147,69 @@ void runp(const char* name) {
   cudaFree(d);
 }
 
+// Two MMA-issuing threads (warps 1 and 2) take alternate k-blocks of the same stage ring into separate accumulators: do their
+// per-k-block overheads (barrier wait, commit) overlap?  Producers are null (8 warps arriving on full[] as empty[] allows).
+template <int N, int STAGES>
+__global__ void __launch_bounds__(32 * 11, 1) dual(long long* out, int iters) {
+  extern __shared__ unsigned char raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[8], empty[8];
+  __shared__ uint32_t tbase;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) ((float*)smem)[i] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 8); mbar_init(&empty[i], 1); } fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tbase, 512);
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 1 || warp == 2) {
+    const int me = warp - 1;
+    const uint32_t a = smem_u32(smem), b = a + 64 * 1024;
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint64_t a0 = make_desc<false, 128, 32>(a, 0), b0 = make_desc<false, 128, 32>(b, 0);
+    long long t0 = clock64();
+    if (lane == 0) {
+      for (int it = me; it < iters; it += 2) {
+        const int st = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[st], ph);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_tf32(tbase + me * 256, a0 + (uint32_t)(st * 1024 + kk * 2), b0 + (uint32_t)((st & 1) * 2048 + kk * 2), idesc, 1);
+        umma_commit(&empty[st]);
+      }
+    }
+    long long t1 = clock64();
+    if (lane == 0 && me == 0) { out[0] = t1 - t0; }
+  } else if (warp >= 3) {
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&empty[st], ph ^ 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tbase, 512); }
+}
+template <int N, int STAGES>
+void rund(const char* name) {
+  long long* d; cudaMalloc(&d, 64);
+  auto fn = dual<N, STAGES>;
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 512;
+  for (int rep = 0; rep < 2; ++rep) fn<<<1, 352, 200 * 1024>>>(d, iters);
+  long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("%-40s %.0f cyc per k-block (%s)\n", name, (double)h[0] / iters, cudaGetErrorString(e));
+  cudaFree(d);
+}
+
 int main() {
+  rund<64, 8>("dual issue N64 8 stages");
+  rund<64, 4>("dual issue N64 4 stages");
+  rund<128, 4>("dual issue N128 4 stages");
   runp<64, 8, 0>("protocol N64 8 stages try_wait");
   runp<64, 4, 0>("protocol N64 4 stages try_wait");
   runp<64, 8, 1>("protocol N64 8 stages test_wait spin");
