@@ -25,6 +25,8 @@ int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float*
 int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
                               int R, int S, int py, int px, cudaStream_t st);
 
+int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int relu, cudaStream_t st);  // conv1_tc.cu
+
 namespace {
 
 using tc::cp_async16;
@@ -439,6 +441,10 @@ HULC_API int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, 
   if ((long long)N * H * W * CIN >= (1ll << 32) / 4) return (int)cudaErrorInvalidValue;  // 32-bit element offsets
   switch (conv_kind(CIN, COUT, KS, S)) {
     case 1: {
+      if (g_use_tma) {  // band-staged kernel (conv1_tc.cu) when the geometry fits; otherwise the im2col gather below
+        const int rc = hulc_conv1_band_fwd(x, w, b, y, N, H, W, relu, st);
+        if (rc != (int)cudaErrorNotSupported) return rc;
+      }
       const int M = g.N * g.HO * g.WO;
       FwdNchw3Loader<8, 4> al{x, g, M, {0, 0, 0, 0}};
       WeightLoader<32> bl{w, 192};  // the reference layout [co][ci][ky][kx] already is K-major in (ci, ky, kx) order

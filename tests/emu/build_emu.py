@@ -13,7 +13,7 @@ OUT = HERE / "_build"
 
 def build(verbose=False) -> Path:
     OUT.mkdir(exist_ok=True)
-    srcs = sorted(p for p in CSRC.glob("*.cu") if "_tc" not in p.stem) + [HERE / "cuda_emu.cc"]
+    srcs = sorted(p for p in CSRC.glob("*.cu") if "_tc" not in p.stem and "_tma" not in p.stem) + [HERE / "cuda_emu.cc"]  # tcgen05 / TMA kernels are not emulated
     deps = srcs + sorted(CSRC.glob("*.cuh")) + [HERE / "cuda_emu.h"]
     hdr_hash = hashlib.sha1(b"".join(p.read_bytes() for p in deps if p.suffix in (".cuh", ".h"))).hexdigest()[:12]
     objs = []
