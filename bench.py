@@ -236,7 +236,11 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     hbm_bound = (r["flops"] / abytes[top]) < (tf32_peak * 1e12) / (peaks["hbm"] * 1e9)
     kern = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "gbs": round(abytes[k] / (v["ms"] * 1e-3) / 1e9, 1),
                 "per_step": v["per_step"], "share_of_step": round(v["share"], 4)} for k, v in res.items()}
-    common = {"kernel": top, "traffic": None, "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
+    traffic = None
+    tp = ROOT / "profiles" / "r01_traffic.json"  # dram bytes per launch from the committed ncu --set full capture of the same kernels
+    if tp.exists():
+        traffic = json.loads(tp.read_text())["kernels"].get(top, {}).get("dram_bytes_per_launch")
+    common = {"kernel": top, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram read+write bytes per launch)" if traffic else None, "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
               "algorithmic_bytes_per_launch": abytes[top], "algorithmic_flops_per_launch": r["flops"], "kernels": kern,
               "step": {"tensor_frac": None, "hbm_frac": None}}
     if hbm_bound:

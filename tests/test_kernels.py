@@ -91,7 +91,7 @@ def test_layernorm_residual_dropout(K, D, rows):
     assert float(big[:, :D].abs().max()) == 0
 
 
-@pytest.mark.parametrize("B,S,H,dh,p", [(3, 8, 8, 16, 0.0), (2, 32, 8, 16, 0.1), (2, 5, 2, 4, 0.3)])
+@pytest.mark.parametrize("B,S,H,dh,p", [(3, 8, 8, 16, 0.0), (2, 32, 8, 16, 0.1), (2, 5, 2, 4, 0.3), (2, 64, 8, 16, 0.1), (2, 4, 2, 8, 0.0)])
 def test_attention(K, B, S, H, dh, p):
     g = torch.Generator().manual_seed(S)
     D = H * dh
