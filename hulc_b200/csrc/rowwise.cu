@@ -524,6 +524,39 @@ HULC_API int hulc_adam_step(float* p, const float* g, float* m, float* v, long l
   HULC_RETURN_LAST();
 }
 
+namespace {
+// uint8 camera frames -> the normalised fp32 the encoders take: ((x / 255) - mean) / std, evaluated in that order with IEEE
+// fp32 operations so it matches the reference's CPU transforms bit for bit.  16 pixels per thread (one 16-byte load).
+__global__ void frames_u8_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, long long n16, float mean, float stdv) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 v = src[i];
+  const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) o[b] = (((float)((w[q] >> (8 * b)) & 0xFFu) / 255.0f) - mean) / stdv;
+    dst[i * 4 + q] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+__global__ void frames_u8_tail_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, long long n0, long long n, float mean, float stdv) {
+  long long i = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (((float)src[i] / 255.0f) - mean) / stdv;
+}
+
+}  // namespace
+
+HULC_API int hulc_frames_u8_to_f32(const unsigned char* src, float* dst, long long n, float mean, float stdv, void* stream) {
+  if (n <= 0) return 0;
+  if (!src || !dst || stdv == 0.f) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long n16 = ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(dst)) & 15) ? 0 : n / 16;
+  if (n16 > 0) HULC_LAUNCH(frames_u8_kernel, dim3(hulc_cdiv(n16, 256)), dim3(256), 0, st, reinterpret_cast<const uint4*>(src), reinterpret_cast<float4*>(dst), n16, mean, stdv);
+  if (n16 * 16 < n) HULC_LAUNCH(frames_u8_tail_kernel, dim3(hulc_cdiv(n - n16 * 16, 256)), dim3(256), 0, st, src, dst, n16 * 16, n, mean, stdv);
+  HULC_RETURN_LAST();
+}
+
 HULC_API int hulc_scale(float* x, long long n, float alpha, void* stream) {
   if (n <= 0) return 0;
   HULC_LAUNCH(scale_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, n, alpha);

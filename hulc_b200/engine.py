@@ -228,7 +228,19 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     _CONVS = ((0, 4), (2, 2), (4, 1))
 
+    def _normalised_frames(self, which, frames: List[torch.Tensor]) -> List[torch.Tensor]:
+        """uint8 frames (as read from disk) are scaled / normalised on the device into a persistent fp32 buffer — the
+        deterministic part of the reference's image transforms (conf/datamodule/transforms/rand_shift.yaml:3-22); fp32
+        frames (the reference's batch contract) pass through untouched."""
+        out = []
+        for i, f in enumerate(frames):
+            if f.dtype == torch.uint8:
+                f = ops.frames_u8_to_f32(f.contiguous(), self.buf(f"{which}.frames{i}", *f.shape))
+            out.append(f)
+        return out
+
     def _encoder_fwd(self, which, frames: List[torch.Tensor], emb):
+        frames = self._normalised_frames(which, frames)
         if self.tc:
             return self._encoder_fwd_tc(which, frames, emb)
         P = self.ps.p

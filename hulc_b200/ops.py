@@ -378,6 +378,15 @@ def sum_to(x, out, scale=1.0):
     return out
 
 
+def frames_u8_to_f32(src, dst, mean=0.5, std=0.5):
+    """dst = ((src / 255) - mean) / std for uint8 camera frames (hulc_frames_u8_to_f32)."""
+    _chk(src, dtype=torch.uint8)
+    _chk(dst)
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    _L().hulc_frames_u8_to_f32(_ptr(src), _ptr(dst), src.numel(), float(mean), float(std), _stream())
+    return dst
+
+
 def scale_(x, alpha):
     _chk(x)
     assert x.is_contiguous()

@@ -153,6 +153,12 @@ int hulc_reduce_mid(const float* x, float* out, int B, int S, int D, float scale
 int hulc_sum(const float* x, int n, float* out, float scale, void* stream);
 int hulc_scale(float* x, long long n, float alpha, void* stream);
 
+/* ---- uint8 camera frames -> normalised fp32 (the input pipeline on the device) ---------------------------
+ * dst[i] = ((src[i] / 255) - mean) / std in fp32, the deterministic part of the reference's image transforms (ScaleImageTensor +
+ * Normalize(0.5, 0.5), conf/datamodule/transforms/rand_shift.yaml:3-22; hulc/utils/transforms.py:8-29) — lets the host hand over the
+ * uint8 frames it read from disk (4x fewer PCIe bytes).  The random-shift augmentation stays with the data pipeline. */
+int hulc_frames_u8_to_f32(const unsigned char* src, float* dst, long long n, float mean, float stdv, void* stream);
+
 /* ---- world_to_tcp_frame (decoders/utils/gripper_control.py:16-36) ----------------------------------------------------------
  * actions [n,7], robot_obs [n,obs_dim] (euler XYZ at 3:6) -> out [n,7].  *nan_flag is OR-ed with 1 if any output is NaN
  * (the reference asserts on the host, :35; the flag is checked without stalling the stream). */

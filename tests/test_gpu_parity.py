@@ -198,3 +198,30 @@ def test_no_cpu_fallback(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", _lib.PKG / "lib" / "missing.so")
     with pytest.raises(_lib.HulcError):
         _lib.lib()
+
+
+def test_uint8_frames_match_normalised_fp32():
+    """uint8 frames normalised on the device give the same step as the reference's fp32 contract."""
+    from hulc_b200.engine import HulcEngine
+
+    B, S = 2, 8
+    g = torch.Generator().manual_seed(3)
+    batch = synthetic.make_batch(B, S, seed=1)
+    u8 = {}
+    for m in batch:
+        for k in ("rgb_static", "rgb_gripper"):
+            raw = torch.randint(0, 256, batch[m]["rgb_obs"][k].shape, generator=g, dtype=torch.uint8)
+            u8[(m, k)] = raw
+            batch[m]["rgb_obs"][k] = (raw.float() / 255 - 0.5) / 0.5
+    outs = []
+    for use_u8 in (False, True):
+        eng = HulcEngine("hulc", "rnn_decoder", device="cuda", dropout_p=0.0)
+        eng.load_state_dict(synthetic.make_state_dict("hulc"))
+        b = synthetic._to(batch, "cuda")
+        if use_u8:
+            for (m, k), raw in u8.items():
+                b[m]["rgb_obs"][k] = raw.cuda()
+        out = eng.step(b, seed=5)
+        outs.append((float(out["total_loss"]), eng.ps.grad.clone()))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[0][0])
+    assert float((outs[0][1] - outs[1][1]).norm()) <= 1e-4 * float(outs[0][1].norm())  # same bound as the repeatability test

@@ -297,3 +297,14 @@ def test_adam_matches_torch(K):
         opt.step()
         K.adam_step(p, g * 4, m, v, lr=2e-4, step=step, grad_scale=0.25)
     torch.testing.assert_close(p, ref.detach(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n", [16 * 7, 1003])
+def test_frames_u8_to_f32(K, n):
+    """uint8 frames -> normalised fp32: bit-identical to the reference's CPU transforms (x / 255 - 0.5) / 0.5."""
+    g = torch.Generator().manual_seed(n)
+    src = torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8)
+    dst = torch.empty(n)
+    K.frames_u8_to_f32(src, dst)
+    ref = (src.float() / 255 - 0.5) / 0.5
+    assert torch.equal(dst, ref)
