@@ -17,6 +17,8 @@
 //   forward      : source = x,  output grid = (HO, WO), taps (+ky, +kx), B = w as [COUT][(ky, kx, ci)], epilogue bias + ReLU
 //   data gradient: source = dY, output grid = the input pixels of one stride phase (py, px), taps (-jy, -jx),
 //                  B = w as [CIN][(jy, jx, co)] for that phase, epilogue = ReLU mask of the activation that fed the layer
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_pipeline.cuh"
 #include "tma.cuh"
@@ -29,6 +31,8 @@ constexpr int kATileB = kBM * kRowBytes;  // 16 KB: one k-block of the A operand
 constexpr int kNI = 4;  // MMA-issuing threads (one warp each): every 4th k-block each, into an accumulator of its own
 constexpr int kThr = (kEpiWarps + kNI + 1) * 32;
 constexpr int kSmemBudget = 224 * 1024;
+// HULC_B200_CONV_BAND=0 keeps the box-per-tap kernel for the stride-1 layer (A/B comparison)
+const bool g_use_band = [] { const char* e = getenv("HULC_B200_CONV_BAND"); return !(e && e[0] == '0'); }();
 
 struct TcParams {
   int N, OH, OW;       // output grid of this launch
@@ -202,6 +206,209 @@ __global__ void __launch_bounds__(kThr, 1) conv_tma_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Stride-1 layers: shifted views of ONE staged band.
+// For a stride-1 convolution the A tile of tap (ty, tx) is the A tile of tap (0, 0) moved by ty * PW + tx pixels along the
+// flattened band, so a tile loads its band of PH = RT + KS - 1 source rows x PW columns x 32 channels ONCE ([pixel][128 B]
+// rows, 128-byte swizzle keyed on the absolute shared-memory address) and every tap reads it through a descriptor whose
+// start address is shifted by whole rows (verified on the B200, scripts/micro/desc_shift_probe.cu: arbitrary row shifts work
+// with the descriptor's base-offset field left at zero).  GEMM rows are positions of the band's PW-wide grid (the KS - 1
+// extra columns per row are computed and dropped): 9x less L2 -> SM traffic than fetching a box per tap, which is what bounds
+// conv_tma_kernel.  Forward: band origin (0, y0), shift = ty PW + tx.  Data gradient: the band starts KS - 1 rows / columns
+// before the output pixel (out-of-bounds zero fill = the halo), shift = (KS-1-ty) PW + (KS-1-tx).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBandNI = 3;                 // MMA-issuing threads: taps me, me + 3, me + 6 of every channel block
+constexpr int kBandRows = 184;             // 127 + largest shift (2 * 25 + 2) + 1, rounded up to a multiple of 8
+constexpr int kBandB = kBandRows * kRowBytes;
+constexpr int kBandSlots = 3;
+constexpr int kBandThr = (kEpiWarps + kBandNI + 1) * 32;
+
+struct BandParams {
+  int N, OH, OWv;      // output rows; valid output columns (< PW)
+  int PW, PH, RT, TPF; // band pitch / rows, output rows per tile, tiles per frame
+  int x0, yoff, flip;  // band origin = (x0, y0 + yoff); flip = 1 for the data gradient
+  const float* wprep;  // [BN][KS*KS*CB*32] K-major, k-block (tap, cb) at (tap * CB + cb) * 32
+  float* out;          // NHWC [N][OH][OWv][BN]
+  const float* bias;
+  const float* gate;
+  int relu;
+};
+
+struct BandBars {
+  uint64_t full[kBandSlots];
+  uint64_t empty[kBandSlots];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int BN, int KS, int CB>
+__global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_constant__ CUtensorMap smap, BandParams p, int num_tiles) {
+  constexpr int kWTileB = BN * kRowBytes, NKB = KS * KS * CB, kTaps = KS * KS;
+  static_assert(kTaps % kBandNI == 0 && 2 * kBandNI * BN <= 512, "issuer split / TMEM columns");
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* w_smem = smem;
+  unsigned char* band_smem = smem + NKB * kWTileB;
+  BandBars* bars = reinterpret_cast<BandBars*>(band_smem + kBandSlots * kBandB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBandSlots; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], kBandNI);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], kBandNI);
+      mbar_init(&bars->tmem_empty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 512);
+  for (int i = threadIdx.x; i < kBandSlots * kBandB / 16; i += kBandThr) reinterpret_cast<float4*>(band_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = threadIdx.x; q < NKB * BN * 8; q += kBandThr) {
+    const int kb = q / (BN * 8), qq = q - kb * (BN * 8);
+    const int n = qq >> 3, c = qq & 7;
+    st_shared16(smem_u32(w_smem) + kb * kWTileB + swz(n, c), __ldg(reinterpret_cast<const float4*>(p.wprep + (size_t)n * (NKB * kBK) + kb * kBK + c * 4)));
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp < kEpiWarps) {
+    // ================================ epilogue ================================
+    const int r = warp * 32 + lane;
+    const int yl = r / p.PW, xx = r - yl * p.PW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int n = tile / p.TPF, y0 = (tile - n * p.TPF) * p.RT;
+      const bool valid = yl < p.RT && xx < p.OWv && y0 + yl < p.OH;
+      const size_t off = (((size_t)n * p.OH + y0 + yl) * p.OWv + xx) * BN;
+      mbar_wait(&bars->tmem_full[a], (it >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kBandNI * BN + c0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 1; i < kBandNI; ++i) {
+          uint32_t u[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((a * kBandNI + i) * BN + c0), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
+        }
+        if (c0 + 32 == BN) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.gate) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + off + c0 + j));
+              o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(p.out + off + c0 + j) = o;
+          }
+        }
+      }
+    }
+  } else if (warp < kEpiWarps + kBandNI) {
+    // ================================ MMA issuers ================================
+    if (lane == 0) {
+      const int me = warp - kEpiWarps;
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, false, false);
+      const uint64_t a0 = make_desc<false, kBM, kBK>(smem_u32(band_smem), 0), b0 = make_desc<false, BN, kBK>(smem_u32(w_smem), 0);
+      int it = 0, u = 0;  // u: band sequence number of this CTA
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        mbar_wait(&bars->tmem_empty[a], ((it >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)((a * kBandNI + me) * BN);
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb, ++u) {
+          const int slot = u % kBandSlots;
+          mbar_wait(&bars->full[slot], (u / kBandSlots) & 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int tap = me; tap < kTaps; tap += kBandNI) {
+            const int ty = tap / KS, tx = tap - ty * KS;
+            const int shift = p.flip ? (KS - 1 - ty) * p.PW + (KS - 1 - tx) : ty * p.PW + tx;  // rows of 128 B
+            const uint64_t da = a0 + (uint32_t)((slot * kBandB + shift * kRowBytes) >> 4), db = b0 + (uint32_t)(((tap * CB + cb) * kWTileB) >> 4);
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (uint32_t)(cb != 0 || tap != me || k != 0));
+          }
+          umma_commit(&bars->empty[slot]);
+        }
+        umma_commit(&bars->tmem_full[a]);
+      }
+    }
+  } else {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      tma::prefetch_map(&smap);
+      const uint32_t box_bytes = (uint32_t)(p.PW * p.PH * kRowBytes);
+      int u = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n = tile / p.TPF, y0 = (tile - n * p.TPF) * p.RT;
+        for (int cb = 0; cb < CB; ++cb, ++u) {
+          const int slot = u % kBandSlots;
+          mbar_wait(&bars->empty[slot], ((u / kBandSlots) & 1) ^ 1);
+          tma::expect_tx(&bars->full[slot], box_bytes);
+          tma::load_4d(smem_u32(band_smem) + slot * kBandB, &smap, &bars->full[slot], cb * kBK, p.x0, y0 + p.yoff, n);
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// out (NHWC [N][OH][OWv][64]) = stride-1 3x3 convolution / its data gradient of src (NHWC [N][SH][SW][64]) on the band scheme
+int launch_s1_band(const float* src, int N, int SH, int SW, int OH, int OWv, int flip, const float* wprep, const float* bias, const float* gate, int relu,
+                   float* out, cudaStream_t st) {
+  constexpr int BN = 64, KS = 3, CB = 2;
+  BandParams p{};
+  p.N = N; p.OH = OH; p.OWv = OWv; p.flip = flip;
+  p.PW = flip ? OWv + KS - 1 : SW;  // forward: the source width; gradient: output width + halo
+  if (p.PW > kBM) return (int)cudaErrorNotSupported;
+  p.RT = min(OH, kBM / p.PW);
+  p.PH = p.RT + KS - 1;
+  p.TPF = hulc_cdiv(OH, p.RT);
+  if (p.PW * p.PH > kBandRows || 127 + (KS - 1) * p.PW + KS - 1 >= kBandRows) return (int)cudaErrorNotSupported;
+  p.x0 = flip ? -(KS - 1) : 0; p.yoff = flip ? -(KS - 1) : 0;
+  p.wprep = wprep; p.out = out; p.bias = bias; p.gate = gate; p.relu = relu;
+  CUtensorMap m;
+  const uint64_t dims[4] = {(uint64_t)(32 * CB), (uint64_t)SW, (uint64_t)SH, (uint64_t)N};
+  const uint64_t strides[3] = {(uint64_t)32 * CB * 4, (uint64_t)SW * 32 * CB * 4, (uint64_t)SH * SW * 32 * CB * 4};
+  const uint32_t box[4] = {32, (uint32_t)p.PW, (uint32_t)p.PH, 1};
+  if (tma::make_map(&m, src, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return (int)cudaErrorNotSupported;
+  const long long tiles = (long long)N * p.TPF;
+  if (tiles >= (1ll << 31)) return (int)cudaErrorNotSupported;
+  constexpr int smem = KS * KS * CB * BN * kRowBytes + kBandSlots * kBandB + 256 + 1024;
+  auto kfn = conv_s1_band_kernel<BN, KS, CB>;
+  HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  HULC_LAUNCH(kfn, dim3((unsigned)min((long long)kNumSMs, tiles)), dim3(kBandThr), smem, st, m, p, (int)tiles);
+  HULC_RETURN_LAST();
+}
+
 template <int BN, int NKB>
 int launch(const CUtensorMap& smap, const TcParams& p, int num_tiles, cudaStream_t st) {
   constexpr int kW = NKB * BN * kRowBytes;
@@ -251,7 +458,13 @@ int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float*
   const int rc = source_map(&m, x, N, H, W, CIN, p);
   if (rc != 0) return (int)cudaErrorNotSupported;
   if (CIN == 32 && COUT == 64 && KS == 4) return launch<64, 16>(m, p, num_tiles, st);
-  if (CIN == 64 && COUT == 64 && KS == 3) return launch<64, 18>(m, p, num_tiles, st);
+  if (CIN == 64 && COUT == 64 && KS == 3) {
+    if (S == 1 && g_use_band) {
+      const int rb = launch_s1_band(x, N, H, W, p.OH, p.OW, 0, wprep, b, nullptr, relu, y, st);
+      if (rb != (int)cudaErrorNotSupported) return rb;
+    }
+    return launch<64, 18>(m, p, num_tiles, st);
+  }
   return (int)cudaErrorNotSupported;
 }
 
@@ -272,6 +485,12 @@ int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float*
   const int rc = source_map(&m, dy, N, HO, WO, COUT, p);
   if (rc != 0) return (int)cudaErrorNotSupported;
   if (CIN == 32 && COUT == 64 && R == 2) return launch<32, 8>(m, p, num_tiles, st);
-  if (CIN == 64 && COUT == 64 && R == 3) return launch<64, 18>(m, p, num_tiles, st);
+  if (CIN == 64 && COUT == 64 && R == 3) {
+    if (S == 1 && g_use_band) {
+      const int rb = launch_s1_band(dy, N, HO, WO, H, W, 1, wphase, nullptr, gate, 0, dx, st);
+      if (rb != (int)cudaErrorNotSupported) return rb;
+    }
+    return launch<64, 18>(m, p, num_tiles, st);
+  }
   return (int)cudaErrorNotSupported;
 }
