@@ -22,6 +22,8 @@
 // conv_tma.cu: the same layers with the A operand delivered by TMA (cudaErrorNotSupported -> use the gather kernels below)
 int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S, int relu,
                       cudaStream_t st);
+int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
+                               cudaStream_t st);
 int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
                               int R, int S, int py, int px, cudaStream_t st);
 
@@ -390,6 +392,10 @@ template <int CIN, int KS, int S, int COUT>
 int dgrad_nhwc(const Geom& g, const float* dy, const float* w, const float* gate, float* dx, float* ws, cudaStream_t st) {
   constexpr int R = KS / S, Kp = R * R * COUT;
   HULC_LAUNCH(prep_dgrad_weights_kernel, dim3(hulc_cdiv(S * S * CIN * Kp, 256)), dim3(256), 0, st, w, ws, COUT, CIN, KS, S);
+  if (g_use_tma && S == 2 && KS == 4) {  // all four stride phases in one launch
+    const int rc = hulc_conv_tma_dgrad_s2_all(dy, ws, gate, dx, g.N, CIN, g.H, g.W, COUT, g.HO, g.WO, st);
+    if (rc != (int)cudaErrorNotSupported) return rc;
+  }
   for (int ph = 0; ph < S * S; ++ph) {
     const int py = ph / S, px = ph % S;
     const int HP = (g.H - py + S - 1) / S, WP = (g.W - px + S - 1) / S;

@@ -207,28 +207,38 @@ __global__ void __launch_bounds__(kThr, 1) conv_tma_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Stride-1 layers: shifted views of ONE staged band.
+// Shifted views of staged bands.
 // For a stride-1 convolution the A tile of tap (ty, tx) is the A tile of tap (0, 0) moved by ty * PW + tx pixels along the
-// flattened band, so a tile loads its band of PH = RT + KS - 1 source rows x PW columns x 32 channels ONCE ([pixel][128 B]
-// rows, 128-byte swizzle keyed on the absolute shared-memory address) and every tap reads it through a descriptor whose
-// start address is shifted by whole rows (verified on the B200, scripts/micro/desc_shift_probe.cu: arbitrary row shifts work
-// with the descriptor's base-offset field left at zero).  GEMM rows are positions of the band's PW-wide grid (the KS - 1
-// extra columns per row are computed and dropped): 9x less L2 -> SM traffic than fetching a box per tap, which is what bounds
-// conv_tma_kernel.  Forward: band origin (0, y0), shift = ty PW + tx.  Data gradient: the band starts KS - 1 rows / columns
-// before the output pixel (out-of-bounds zero fill = the halo), shift = (KS-1-ty) PW + (KS-1-tx).
+// flattened band, so a tile loads a band of PH source rows x PW columns x 32 channels ONCE ([pixel][128 B] rows, 128-byte
+// swizzle keyed on the absolute shared-memory address) and every tap reads it through a descriptor whose start address is
+// shifted by whole rows (verified on the B200, scripts/micro/desc_shift_probe.cu: arbitrary row shifts work with the
+// descriptor's base-offset field left at zero).  GEMM rows are positions of the band's PW-wide grid (the extra columns per
+// row are computed and dropped).  This removes the per-tap re-fetch (4x / 9x the activation through L2 -> SM) that bounds
+// conv_tma_kernel.
+//   3x3 stride 1 forward : one band per 32-channel block, origin (0, y0), 9 taps, shift = ty PW + tx
+//   4x4 stride 2 forward : one band per input phase (py, px) — the TMA walks the activation with element stride 2 from
+//                          (px, 2 y0 + py), which de-interleaves the phase plane for free — 2 x 2 taps (ky, kx) = (2 ty + py, 2 tx + px)
+//   data gradients       : the band starts R - 1 rows / columns before the output pixel (out-of-bounds zero fill = the halo),
+//                          shift = (R-1-ty) PW + (R-1-tx); for stride 2 one launch per output phase (R = 2), stride 1 R = 3
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBandNI = 3;                 // MMA-issuing threads: taps me, me + 3, me + 6 of every channel block
 constexpr int kBandRows = 184;             // 127 + largest shift (2 * 25 + 2) + 1, rounded up to a multiple of 8
 constexpr int kBandB = kBandRows * kRowBytes;
 constexpr int kBandSlots = 3;
-constexpr int kBandThr = (kEpiWarps + kBandNI + 1) * 32;
+constexpr int kMaxBands = 4, kMaxTaps = 9;
+// (An epilogue that transposes each warp's 32 x 32 chunk through shared memory so that global accesses are whole 128-byte rows
+// was measured SLOWER than the row-owner stores used here — conv2 forward 0.22 -> 0.24 ms, the fused stride-2 gradient
+// 0.56 -> 1.97 ms — and was dropped.)
 
 struct BandParams {
-  int N, OH, OWv;      // output rows; valid output columns (< PW)
-  int PW, PH, RT, TPF; // band pitch / rows, output rows per tile, tiles per frame
-  int x0, yoff, flip;  // band origin = (x0, y0 + yoff); flip = 1 for the data gradient
-  const float* wprep;  // [BN][KS*KS*CB*32] K-major, k-block (tap, cb) at (tap * CB + cb) * 32
-  float* out;          // NHWC [N][OH][OWv][BN]
+  int N, OH, OWv;        // output grid rows; valid output columns (< PW)
+  int PW, PH, RT, TPF;   // band pitch / rows, output rows per tile, tiles per frame
+  int nbands, es, flip;  // bands per tile; element stride of the source walk; flip = 1 for a data gradient
+  int bc[kMaxBands], bx[kMaxBands], by[kMaxBands];  // TMA corner of band b: (bc, bx, es * y0 + by, n)
+  int wkb[kMaxBands * kMaxTaps];                    // weight k-block of (band, local tap)
+  const float* wprep;    // [BN][NKB * 32] K-major
+  float* out;            // NHWC [N][out_H][out_W][BN]; grid point (y, x) -> pixel (o_mul y + oy_add, o_mul x + ox_add)
+  int out_H, out_W, o_mul, oy_add, ox_add;
+  int scatter;           // 1: the BN = 128 columns are 4 stride phases x 32 channels; chunk ph goes to pixel (2 y + ph / 2, 2 x + ph % 2)
   const float* bias;
   const float* gate;
   int relu;
@@ -242,10 +252,11 @@ struct BandBars {
   uint32_t tmem_base;
 };
 
-template <int BN, int KS, int CB>
-__global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_constant__ CUtensorMap smap, BandParams p, int num_tiles) {
-  constexpr int kWTileB = BN * kRowBytes, NKB = KS * KS * CB, kTaps = KS * KS;
-  static_assert(kTaps % kBandNI == 0 && 2 * kBandNI * BN <= 512, "issuer split / TMEM columns");
+// R = local taps per axis of one band (3 or 2); NI = MMA-issuing threads (local taps me, me + NI, ... of every band)
+template <int BN, int NKB, int R, int NI>
+__global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel(const __grid_constant__ CUtensorMap smap, BandParams p, int num_tiles) {
+  constexpr int kWTileB = BN * kRowBytes, kTaps = R * R, kThreadsB = (kEpiWarps + NI + 1) * 32;
+  static_assert(kTaps % NI == 0 && 2 * NI * BN <= 512, "issuer split / TMEM columns");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* w_smem = smem;
@@ -256,17 +267,17 @@ __global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBandSlots; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], kBandNI);
+      mbar_init(&bars->empty[s], NI);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&bars->tmem_full[a], kBandNI);
+      mbar_init(&bars->tmem_full[a], NI);
       mbar_init(&bars->tmem_empty[a], kEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 512);
-  for (int i = threadIdx.x; i < kBandSlots * kBandB / 16; i += kBandThr) reinterpret_cast<float4*>(band_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int q = threadIdx.x; q < NKB * BN * 8; q += kBandThr) {
+  for (int i = threadIdx.x; i < kBandSlots * kBandB / 16; i += kThreadsB) reinterpret_cast<float4*>(band_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = threadIdx.x; q < NKB * BN * 8; q += kThreadsB) {
     const int kb = q / (BN * 8), qq = q - kb * (BN * 8);
     const int n = qq >> 3, c = qq & 7;
     st_shared16(smem_u32(w_smem) + kb * kWTileB + swz(n, c), __ldg(reinterpret_cast<const float4*>(p.wprep + (size_t)n * (NKB * kBK) + kb * kBK + c * 4)));
@@ -285,19 +296,32 @@ __global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
       const int n = tile / p.TPF, y0 = (tile - n * p.TPF) * p.RT;
-      const bool valid = yl < p.RT && xx < p.OWv && y0 + yl < p.OH;
-      const size_t off = (((size_t)n * p.OH + y0 + yl) * p.OWv + xx) * BN;
+      const bool valid0 = yl < p.RT && xx < p.OWv && y0 + yl < p.OH;
+      const size_t off0 = (((size_t)n * p.out_H + (p.o_mul * (y0 + yl) + p.oy_add)) * p.out_W + (p.o_mul * xx + p.ox_add)) * BN;
+      if (p.gate && valid0) {
+        // the ReLU masks this thread will need come from DRAM: pull their lines into L2 while the tile's MMAs are still running
+        // (four epilogue warps cannot hide one DRAM latency per 32-column chunk)
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          size_t off = off0 + c0;
+          if (p.scatter) {
+            const int oy = min(2 * (y0 + yl) + (c0 >> 6), p.out_H - 1), ox = min(2 * xx + ((c0 >> 5) & 1), p.out_W - 1);
+            off = (((size_t)n * p.out_H + oy) * p.out_W + ox) * 32;
+          }
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gate + off));
+        }
+      }
       mbar_wait(&bars->tmem_full[a], (it >> 1) & 1);
       tc_fence_after_sync();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kBandNI * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NI * BN + c0), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 1; i < kBandNI; ++i) {
+        for (int i = 1; i < NI; ++i) {
           uint32_t u[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((a * kBandNI + i) * BN + c0), u);
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((a * NI + i) * BN + c0), u);
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
@@ -306,6 +330,13 @@ __global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
+        }
+        bool valid = valid0;
+        size_t off = off0 + c0;
+        if (p.scatter) {  // chunk c0 / 32 = stride phase (py, px): 32 channels of pixel (2 y + py, 2 x + px)
+          const int oy = 2 * (y0 + yl) + (c0 >> 6), ox = 2 * xx + ((c0 >> 5) & 1);
+          valid = valid0 && oy < p.out_H && ox < p.out_W;
+          off = (((size_t)n * p.out_H + oy) * p.out_W + ox) * 32;
         }
         if (valid) {
 #pragma unroll
@@ -317,15 +348,15 @@ __global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_
             }
             if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             if (p.gate) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + off + c0 + j));
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + off + j));
               o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
             }
-            *reinterpret_cast<float4*>(p.out + off + c0 + j) = o;
+            *reinterpret_cast<float4*>(p.out + off + j) = o;
           }
         }
       }
     }
-  } else if (warp < kEpiWarps + kBandNI) {
+  } else if (warp < kEpiWarps + NI) {
     // ================================ MMA issuers ================================
     if (lane == 0) {
       const int me = warp - kEpiWarps;
@@ -336,19 +367,18 @@ __global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_
         const int a = it & 1;
         mbar_wait(&bars->tmem_empty[a], ((it >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t d = tmem_base + (uint32_t)((a * kBandNI + me) * BN);
-#pragma unroll
-        for (int cb = 0; cb < CB; ++cb, ++u) {
+        const uint32_t d = tmem_base + (uint32_t)((a * NI + me) * BN);
+        for (int b = 0; b < p.nbands; ++b, ++u) {
           const int slot = u % kBandSlots;
           mbar_wait(&bars->full[slot], (u / kBandSlots) & 1);
           tc_fence_after_sync();
 #pragma unroll
-          for (int tap = me; tap < kTaps; tap += kBandNI) {
-            const int ty = tap / KS, tx = tap - ty * KS;
-            const int shift = p.flip ? (KS - 1 - ty) * p.PW + (KS - 1 - tx) : ty * p.PW + tx;  // rows of 128 B
-            const uint64_t da = a0 + (uint32_t)((slot * kBandB + shift * kRowBytes) >> 4), db = b0 + (uint32_t)(((tap * CB + cb) * kWTileB) >> 4);
+          for (int tap = me; tap < kTaps; tap += NI) {
+            const int ty = tap / R, tx = tap - ty * R;
+            const int shift = p.flip ? (R - 1 - ty) * p.PW + (R - 1 - tx) : ty * p.PW + tx;  // rows of 128 B
+            const uint64_t da = a0 + (uint32_t)((slot * kBandB + shift * kRowBytes) >> 4), db = b0 + (uint32_t)((p.wkb[b * kMaxTaps + tap] * kWTileB) >> 4);
 #pragma unroll
-            for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (uint32_t)(cb != 0 || tap != me || k != 0));
+            for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (uint32_t)(b != 0 || tap != me || k != 0));
           }
           umma_commit(&bars->empty[slot]);
         }
@@ -363,11 +393,11 @@ __global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_
       int u = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile / p.TPF, y0 = (tile - n * p.TPF) * p.RT;
-        for (int cb = 0; cb < CB; ++cb, ++u) {
+        for (int b = 0; b < p.nbands; ++b, ++u) {
           const int slot = u % kBandSlots;
           mbar_wait(&bars->empty[slot], ((u / kBandSlots) & 1) ^ 1);
           tma::expect_tx(&bars->full[slot], box_bytes);
-          tma::load_4d(smem_u32(band_smem) + slot * kBandB, &smap, &bars->full[slot], cb * kBK, p.x0, y0 + p.yoff, n);
+          tma::load_4d(smem_u32(band_smem) + slot * kBandB, &smap, &bars->full[slot], p.bc[b], p.bx[b], p.es * y0 + p.by[b], n);
         }
       }
     }
@@ -381,32 +411,81 @@ __global__ void __launch_bounds__(kBandThr, 1) conv_s1_band_kernel(const __grid_
   }
 }
 
-// out (NHWC [N][OH][OWv][64]) = stride-1 3x3 convolution / its data gradient of src (NHWC [N][SH][SW][64]) on the band scheme
-int launch_s1_band(const float* src, int N, int SH, int SW, int OH, int OWv, int flip, const float* wprep, const float* bias, const float* gate, int relu,
-                   float* out, cudaStream_t st) {
-  constexpr int BN = 64, KS = 3, CB = 2;
-  BandParams p{};
-  p.N = N; p.OH = OH; p.OWv = OWv; p.flip = flip;
-  p.PW = flip ? OWv + KS - 1 : SW;  // forward: the source width; gradient: output width + halo
-  if (p.PW > kBM) return (int)cudaErrorNotSupported;
-  p.RT = min(OH, kBM / p.PW);
-  p.PH = p.RT + KS - 1;
-  p.TPF = hulc_cdiv(OH, p.RT);
-  if (p.PW * p.PH > kBandRows || 127 + (KS - 1) * p.PW + KS - 1 >= kBandRows) return (int)cudaErrorNotSupported;
-  p.x0 = flip ? -(KS - 1) : 0; p.yoff = flip ? -(KS - 1) : 0;
-  p.wprep = wprep; p.out = out; p.bias = bias; p.gate = gate; p.relu = relu;
+template <int BN, int NKB, int R, int NI>
+int launch_band(const float* src, int N, int SH, int SW, int SC, BandParams& p, cudaStream_t st) {
+  if (p.PW > kBM || p.PW * p.es > 256 || p.PH * p.es > 256) return (int)cudaErrorNotSupported;
+  if (p.PW * p.PH > kBandRows || 127 + (R - 1) * p.PW + R - 1 >= kBandRows) return (int)cudaErrorNotSupported;
   CUtensorMap m;
-  const uint64_t dims[4] = {(uint64_t)(32 * CB), (uint64_t)SW, (uint64_t)SH, (uint64_t)N};
-  const uint64_t strides[3] = {(uint64_t)32 * CB * 4, (uint64_t)SW * 32 * CB * 4, (uint64_t)SH * SW * 32 * CB * 4};
-  const uint32_t box[4] = {32, (uint32_t)p.PW, (uint32_t)p.PH, 1};
-  if (tma::make_map(&m, src, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return (int)cudaErrorNotSupported;
+  const uint64_t dims[4] = {(uint64_t)SC, (uint64_t)SW, (uint64_t)SH, (uint64_t)N};
+  const uint64_t strides[3] = {(uint64_t)SC * 4, (uint64_t)SW * SC * 4, (uint64_t)SH * SW * SC * 4};
+  const uint32_t box[4] = {32, (uint32_t)(p.PW * p.es), (uint32_t)(p.PH * p.es), 1};
+  const uint32_t es[4] = {1, (uint32_t)p.es, (uint32_t)p.es, 1};
+  if (tma::make_map(&m, src, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, es) != 0) return (int)cudaErrorNotSupported;
   const long long tiles = (long long)N * p.TPF;
   if (tiles >= (1ll << 31)) return (int)cudaErrorNotSupported;
-  constexpr int smem = KS * KS * CB * BN * kRowBytes + kBandSlots * kBandB + 256 + 1024;
-  auto kfn = conv_s1_band_kernel<BN, KS, CB>;
+  constexpr int smem = NKB * BN * kRowBytes + kBandSlots * kBandB + 256 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kfn = conv_band_kernel<BN, NKB, R, NI>;
   HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  HULC_LAUNCH(kfn, dim3((unsigned)min((long long)kNumSMs, tiles)), dim3(kBandThr), smem, st, m, p, (int)tiles);
+  HULC_LAUNCH(kfn, dim3((unsigned)min((long long)kNumSMs, tiles)), dim3((kEpiWarps + NI + 1) * 32), smem, st, m, p, (int)tiles);
   HULC_RETURN_LAST();
+}
+
+// forward of the two channels-last layers on the band scheme (cudaErrorNotSupported: geometry does not fit)
+int band_fwd(const float* x, const float* wprep, const float* b, float* y, int N, int CIN, int H, int W, int KS, int S, int OH, int OW, int relu, cudaStream_t st) {
+  BandParams p{};
+  p.N = N; p.OH = OH; p.OWv = OW; p.flip = 0; p.es = S;
+  p.wprep = wprep; p.out = y; p.out_H = OH; p.out_W = OW; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = b; p.gate = nullptr; p.relu = relu;
+  if (KS == 3 && S == 1 && CIN == 64) {  // bands = channel blocks
+    p.PW = W; p.RT = min(OH, kBM / p.PW); p.PH = p.RT + 2; p.TPF = hulc_cdiv(OH, p.RT); p.nbands = 2;
+    for (int cb = 0; cb < 2; ++cb) {
+      p.bc[cb] = cb * 32; p.bx[cb] = 0; p.by[cb] = 0;
+      for (int tap = 0; tap < 9; ++tap) p.wkb[cb * kMaxTaps + tap] = tap * 2 + cb;
+    }
+    return launch_band<64, 18, 3, 3>(x, N, H, W, 64, p, st);
+  }
+  if (KS == 4 && S == 2 && CIN == 32) {  // bands = input phases (py, px); local tap (ty, tx) is kernel tap (2 ty + py, 2 tx + px)
+    p.PW = (W + 1) / 2; p.RT = min(OH, kBM / p.PW); p.PH = p.RT + 1; p.TPF = hulc_cdiv(OH, p.RT); p.nbands = 4;
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      p.bc[ph] = 0; p.bx[ph] = px; p.by[ph] = py;
+      for (int tap = 0; tap < 4; ++tap) p.wkb[ph * kMaxTaps + tap] = (2 * (tap >> 1) + py) * 4 + 2 * (tap & 1) + px;
+    }
+    return launch_band<64, 16, 2, 2>(x, N, H, W, 32, p, st);
+  }
+  return (int)cudaErrorNotSupported;
+}
+
+// ALL four stride phases of the 4x4 stride-2 data gradient in one launch: the phases read the same shifted views of dY and differ
+// only in their weights, so they are stacked along N (4 phases x 32 input channels = 128 columns: one tcgen05.mma does the work of
+// four N = 32 ones) and the epilogue scatters column chunk ph to pixel (2 y + ph / 2, 2 x + ph % 2).  wall = [4][CIN][(jy, jx, co)].
+int band_dgrad_s2_all(const float* dy, const float* wall, const float* gate, float* dx, int N, int H, int W, int HO, int WO, cudaStream_t st) {
+  constexpr int R = 2;
+  BandParams p{};
+  p.N = N; p.OH = (H + 1) / 2; p.OWv = (W + 1) / 2; p.flip = 1; p.es = 1; p.scatter = 1;
+  p.wprep = wall; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = nullptr; p.gate = gate; p.relu = 0;
+  p.PW = p.OWv + R - 1; p.RT = min(p.OH, kBM / p.PW); p.PH = p.RT + R - 1; p.TPF = hulc_cdiv(p.OH, p.RT); p.nbands = 2;
+  for (int cb = 0; cb < 2; ++cb) {
+    p.bc[cb] = cb * 32; p.bx[cb] = -(R - 1); p.by[cb] = -(R - 1);
+    for (int tap = 0; tap < R * R; ++tap) p.wkb[cb * kMaxTaps + tap] = tap * 2 + cb;
+  }
+  return launch_band<128, 8, 2, 2>(dy, N, HO, WO, 64, p, st);
+}
+
+// one stride phase of a data gradient on the band scheme: output grid (OH, OW) = the phase's input pixels
+int band_dgrad(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int HO, int WO, int R, int S, int py, int px,
+               int OH, int OW, cudaStream_t st) {
+  BandParams p{};
+  p.N = N; p.OH = OH; p.OWv = OW; p.flip = 1; p.es = 1;
+  p.wprep = wphase; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = S; p.oy_add = py; p.ox_add = px; p.bias = nullptr; p.gate = gate; p.relu = 0;
+  p.PW = OW + R - 1; p.RT = min(OH, kBM / p.PW); p.PH = p.RT + R - 1; p.TPF = hulc_cdiv(OH, p.RT); p.nbands = 2;
+  for (int cb = 0; cb < 2; ++cb) {
+    p.bc[cb] = cb * 32; p.bx[cb] = -(R - 1); p.by[cb] = -(R - 1);
+    for (int tap = 0; tap < R * R; ++tap) p.wkb[cb * kMaxTaps + tap] = tap * 2 + cb;
+  }
+  if (CIN == 64 && R == 3) return launch_band<64, 18, 3, 3>(dy, N, HO, WO, 64, p, st);
+  if (CIN == 32 && R == 2) return launch_band<32, 8, 2, 2>(dy, N, HO, WO, 64, p, st);
+  return (int)cudaErrorNotSupported;
 }
 
 template <int BN, int NKB>
@@ -457,15 +536,23 @@ int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float*
   CUtensorMap m;
   const int rc = source_map(&m, x, N, H, W, CIN, p);
   if (rc != 0) return (int)cudaErrorNotSupported;
-  if (CIN == 32 && COUT == 64 && KS == 4) return launch<64, 16>(m, p, num_tiles, st);
-  if (CIN == 64 && COUT == 64 && KS == 3) {
-    if (S == 1 && g_use_band) {
-      const int rb = launch_s1_band(x, N, H, W, p.OH, p.OW, 0, wprep, b, nullptr, relu, y, st);
-      if (rb != (int)cudaErrorNotSupported) return rb;
-    }
-    return launch<64, 18>(m, p, num_tiles, st);
+  if (g_use_band && COUT == 64) {
+    const int rb = band_fwd(x, wprep, b, y, N, CIN, H, W, KS, S, p.OH, p.OW, relu, st);
+    if (rb != (int)cudaErrorNotSupported) return rb;
   }
+  if (CIN == 32 && COUT == 64 && KS == 4) return launch<64, 16>(m, p, num_tiles, st);
+  if (CIN == 64 && COUT == 64 && KS == 3) return launch<64, 18>(m, p, num_tiles, st);
   return (int)cudaErrorNotSupported;
+}
+
+// dx (NHWC [N][H][W][32]) = data gradient of the 32 -> 64, 4x4, stride-2 layer, all stride phases in one launch; wall = the four
+// prepared phase weight matrices, contiguous.  cudaErrorNotSupported -> per-phase launches.
+int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
+                               cudaStream_t st) {
+  if (!g_use_band || CIN != 32 || COUT != 64) return (int)cudaErrorNotSupported;
+  if ((reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(wall) | reinterpret_cast<size_t>(dx) | reinterpret_cast<size_t>(gate)) & 15)
+    return (int)cudaErrorNotSupported;
+  return band_dgrad_s2_all(dy, wall, gate, dx, N, H, W, HO, WO, st);
 }
 
 // One stride phase (py, px) of dx (NHWC [N][H][W][CIN]) = conv_transpose(dy NHWC [N][HO][WO][COUT], w), masked by gate > 0.
@@ -484,13 +571,11 @@ int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float*
   CUtensorMap m;
   const int rc = source_map(&m, dy, N, HO, WO, COUT, p);
   if (rc != 0) return (int)cudaErrorNotSupported;
-  if (CIN == 32 && COUT == 64 && R == 2) return launch<32, 8>(m, p, num_tiles, st);
-  if (CIN == 64 && COUT == 64 && R == 3) {
-    if (S == 1 && g_use_band) {
-      const int rb = launch_s1_band(dy, N, HO, WO, H, W, 1, wphase, nullptr, gate, 0, dx, st);
-      if (rb != (int)cudaErrorNotSupported) return rb;
-    }
-    return launch<64, 18>(m, p, num_tiles, st);
+  if (g_use_band && COUT == 64) {
+    const int rb = band_dgrad(dy, wphase, gate, dx, N, CIN, H, W, HO, WO, R, S, py, px, p.OH, p.OW, st);
+    if (rb != (int)cudaErrorNotSupported) return rb;
   }
+  if (CIN == 32 && COUT == 64 && R == 2) return launch<32, 8>(m, p, num_tiles, st);
+  if (CIN == 64 && COUT == 64 && R == 3) return launch<64, 18>(m, p, num_tiles, st);
   return (int)cudaErrorNotSupported;
 }
