@@ -154,11 +154,11 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     fl = lambda n, co, ho, k: 2.0 * n * co * ho * ho * k
     if eng.tc:
         cands = {
-            "conv1_fwd": (lambda: ops.conv2d_tc_fwd(x, w0, b0, 4, a1[:n1]), fl(n1, 32, 49, 192), n_mod),
-            "conv2_fwd": (lambda: ops.conv2d_tc_fwd(a1, w2, b2, 2, a2), fl(N, 64, 23, 512), 1),
+            "conv1_fwd": (lambda: ops.conv2d_tc_fwd(x, w0, b0, 4, a1[:n1], relu_bits=B_["static.a1_bits"][:n1]), fl(n1, 32, 49, 192), n_mod),
+            "conv2_fwd": (lambda: ops.conv2d_tc_fwd(a1, w2, b2, 2, a2, relu_bits=B_["static.a2_bits"]), fl(N, 64, 23, 512), 1),
             "conv3_fwd": (lambda: ops.conv2d_tc_fwd(a2, w4, b4, 1, a3), fl(N, 64, 21, 576), 1),
-            "conv3_dgrad": (lambda: ops.conv2d_tc_dgrad(da3, w4, da2, 1, gate=a2), fl(N, 64, 21, 576), 1),
-            "conv2_dgrad": (lambda: ops.conv2d_tc_dgrad(da2, w2, da1, 2, gate=a1), fl(N, 64, 23, 512), 1),
+            "conv3_dgrad": (lambda: ops.conv2d_tc_dgrad(da3, w4, da2, 1, gate=a2, gate_bits=B_["static.a2_bits"]), fl(N, 64, 21, 576), 1),
+            "conv2_dgrad": (lambda: ops.conv2d_tc_dgrad(da2, w2, da1, 2, gate=a1, gate_bits=B_["static.a1_bits"]), fl(N, 64, 23, 512), 1),
             "conv3_wgrad": (lambda: ops.conv2d_tc_wgrad(a2, da3, s4, 1), fl(N, 64, 21, 576), 1),
             "conv2_wgrad": (lambda: ops.conv2d_tc_wgrad(a1, da2, s2, 2), fl(N, 64, 23, 512), 1),
             "conv1_wgrad": (lambda: ops.conv2d_tc_wgrad(x, da1[:n1], s0, 4), fl(n1, 32, 49, 192), n_mod),
@@ -220,8 +220,9 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     fr = lambda n, c, hw: 4.0 * n * c * hw * hw
     abytes = {
         "conv1_fwd": fr(n1, 3, 200) + fr(n1, 32, 49), "conv1_wgrad": fr(n1, 3, 200) + fr(n1, 32, 49),
-        "conv2_fwd": fr(N, 32, 49) + fr(N, 64, 23), "conv2_wgrad": fr(N, 32, 49) + fr(N, 64, 23), "conv2_dgrad": fr(N, 64, 23) + 2 * fr(N, 32, 49),
-        "conv3_fwd": fr(N, 64, 23) + fr(N, 64, 21), "conv3_wgrad": fr(N, 64, 23) + fr(N, 64, 21), "conv3_dgrad": fr(N, 64, 21) + 2 * fr(N, 64, 23),
+        # data gradients: dY in, dX out, + the ReLU sign mask of the gating activation (1 bit per element)
+        "conv2_fwd": fr(N, 32, 49) + fr(N, 64, 23), "conv2_wgrad": fr(N, 32, 49) + fr(N, 64, 23), "conv2_dgrad": fr(N, 64, 23) + (1 + 1 / 32) * fr(N, 32, 49),
+        "conv3_fwd": fr(N, 64, 23) + fr(N, 64, 21), "conv3_wgrad": fr(N, 64, 23) + fr(N, 64, 21), "conv3_dgrad": fr(N, 64, 21) + (1 + 1 / 32) * fr(N, 64, 23),
         "rnn_seq_fwd_32steps": 4.0 * (H * H + 3 * S * nB * H), "rnn_seq_bwd_32steps": 4.0 * (H * H + 4 * S * nB * H),
         "rnn_step_fwd_3xtf32": 4.0 * (H * H + 3 * nB * H), "rnn_step_bwd_tf32": 4.0 * (H * H + 4 * nB * H), "rnn_step_gemm": 4.0 * (H * H + 3 * nB * H),
         "dense_wgrad_2048^3": 4.0 * (2 * S * nB * H + H * H), "dense_fwd_2048^3": 4.0 * (2 * S * nB * H + H * H),

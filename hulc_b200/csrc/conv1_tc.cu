@@ -42,6 +42,7 @@ struct C1Params {
   const float* w;   // [32, 3, 8, 8] = [32][192], K-major in (ci, ky, kx) order
   const float* b;
   float* y;         // [N, HO, WO, 32]
+  unsigned* bits;   // optional: sign mask of y, one word per pixel
   int N, H, W, HO, WO;
   int RT, TPF, BR;  // output rows per tile, tiles per frame, band rows = 4 RT + 4
   int relu;
@@ -134,14 +135,21 @@ __global__ void __launch_bounds__(kThr, 1) conv1_band_fwd_kernel(C1Params p, int
       if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);  // the values are in registers: the accumulators may be reused
       const int n = tile / p.TPF, y0 = (tile - n * p.TPF) * p.RT;
       if (r < tile_px && y0 + yl < p.HO) {
-        float* dst = p.y + ((size_t)(n * p.HO + y0 + yl) * p.WO + xx) * kCout;
+        const size_t pix = (size_t)(n * p.HO + y0 + yl) * p.WO + xx;
+        float* dst = p.y + pix * kCout;
+        unsigned om = 0u;
 #pragma unroll
         for (int j = 0; j < kCout; j += 4) {
           float4 o = make_float4(__uint_as_float(v[j]) + __uint_as_float(u[j]) + bias[j], __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]) + bias[j + 1],
                                  __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]) + bias[j + 2], __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]) + bias[j + 3]);
           if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (o.x > 0.f) om |= 1u << j;
+            if (o.y > 0.f) om |= 1u << (j + 1);
+            if (o.z > 0.f) om |= 1u << (j + 2);
+            if (o.w > 0.f) om |= 1u << (j + 3);
           *reinterpret_cast<float4*>(dst + j) = o;
         }
+        if (p.bits) p.bits[pix] = om;
       }
     }
   } else if (warp < kLoaderWarp) {
@@ -236,12 +244,12 @@ __global__ void __launch_bounds__(kThr, 1) conv1_band_fwd_kernel(C1Params p, int
 }  // namespace
 
 // Returns cudaErrorNotSupported when the geometry does not fit the band scheme (the caller then uses the gather kernel).
-int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int relu, cudaStream_t st) {
+int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st) {
   const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
   if (HO <= 0 || WO <= 0 || WO > kBM || (W & 3) || (reinterpret_cast<size_t>(x) & 15) || (reinterpret_cast<size_t>(w) & 15) || (reinterpret_cast<size_t>(y) & 15))
     return (int)cudaErrorNotSupported;
   C1Params p;
-  p.x = x; p.w = w; p.b = b; p.y = y; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.relu = relu;
+  p.x = x; p.w = w; p.b = b; p.y = y; p.bits = relu_bits; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.relu = relu;
   p.RT = min(HO, kBM / WO);
   p.TPF = hulc_cdiv(HO, p.RT);
   p.BR = 4 * p.RT + 4;

@@ -20,14 +20,14 @@
 #include "tc_pipeline.cuh"
 
 // conv_tma.cu: the same layers with the A operand delivered by TMA (cudaErrorNotSupported -> use the gather kernels below)
-int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S, int relu,
-                      cudaStream_t st);
-int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
-                               cudaStream_t st);
-int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
-                              int R, int S, int py, int px, cudaStream_t st);
+int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float* y, unsigned* relu_bits, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                      int relu, cudaStream_t st);
+int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int COUT,
+                               int HO, int WO, cudaStream_t st);
+int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int COUT,
+                              int HO, int WO, int R, int S, int py, int px, cudaStream_t st);
 
-int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int relu, cudaStream_t st);  // conv1_tc.cu
+int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st);  // conv1_tc.cu
 
 namespace {
 
@@ -141,17 +141,24 @@ struct FwdEpilogue {
   float* y;
   const float* bias;
   int M, COUT, relu;
+  unsigned* bits;  // optional sign mask of the output: word [pixel][channel / 32]
   __device__ __forceinline__ void operator()(int tile, int row, int col0, const float* v) const {
     const int m = tile * tc::kBM + row;
     if (m >= M) return;
     float* dst = y + (size_t)m * COUT + col0;
+    unsigned om = 0u;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       float4 o;
       o.x = v[j] + bias[col0 + j]; o.y = v[j + 1] + bias[col0 + j + 1]; o.z = v[j + 2] + bias[col0 + j + 2]; o.w = v[j + 3] + bias[col0 + j + 3];
       if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (o.x > 0.f) om |= 1u << j;
+            if (o.y > 0.f) om |= 1u << (j + 1);
+            if (o.z > 0.f) om |= 1u << (j + 2);
+            if (o.w > 0.f) om |= 1u << (j + 3);
       *reinterpret_cast<float4*>(dst + j) = o;
     }
+    if (bits) bits[((size_t)m * COUT + col0) >> 5] = om;
   }
 };
 
@@ -375,25 +382,25 @@ int conv_kind(int CIN, int COUT, int KS, int S) {
 }
 
 template <int CIN, int KS, int S, int COUT>
-int fwd_nhwc(const Geom& g, const float* x, const float* w, const float* b, float* y, int relu, float* ws, cudaStream_t st) {
+int fwd_nhwc(const Geom& g, const float* x, const float* w, const float* b, float* y, unsigned* bits, int relu, float* ws, cudaStream_t st) {
   const int K = CIN * KS * KS, M = g.N * g.HO * g.WO;
   HULC_LAUNCH(prep_fwd_weights_kernel, dim3(hulc_cdiv(COUT * K, 256)), dim3(256), 0, st, w, ws, COUT, CIN, KS);
   if (g_use_tma) {
-    const int rc = hulc_conv_tma_fwd(x, ws, b, y, g.N, CIN, g.H, g.W, COUT, KS, S, relu, st);
+    const int rc = hulc_conv_tma_fwd(x, ws, b, y, bits, g.N, CIN, g.H, g.W, COUT, KS, S, relu, st);
     if (rc != (int)cudaErrorNotSupported) return rc;
   }
   FwdNhwcLoader<CIN, KS, S> al{x, g, M, {0, 0, 0, 0}};
   WeightLoader<COUT> bl{ws, K};
-  FwdEpilogue ep{y, b, M, COUT, relu};
+  FwdEpilogue ep{y, b, M, COUT, relu, bits};
   return launch<COUT>(al, bl, ep, hulc_cdiv(M, tc::kBM), K / tc::kBK, st);
 }
 
 template <int CIN, int KS, int S, int COUT>
-int dgrad_nhwc(const Geom& g, const float* dy, const float* w, const float* gate, float* dx, float* ws, cudaStream_t st) {
+int dgrad_nhwc(const Geom& g, const float* dy, const float* w, const float* gate, const unsigned* gate_bits, float* dx, float* ws, cudaStream_t st) {
   constexpr int R = KS / S, Kp = R * R * COUT;
   HULC_LAUNCH(prep_dgrad_weights_kernel, dim3(hulc_cdiv(S * S * CIN * Kp, 256)), dim3(256), 0, st, w, ws, COUT, CIN, KS, S);
   if (g_use_tma && S == 2 && KS == 4) {  // all four stride phases in one launch
-    const int rc = hulc_conv_tma_dgrad_s2_all(dy, ws, gate, dx, g.N, CIN, g.H, g.W, COUT, g.HO, g.WO, st);
+    const int rc = hulc_conv_tma_dgrad_s2_all(dy, ws, gate, gate_bits, dx, g.N, CIN, g.H, g.W, COUT, g.HO, g.WO, st);
     if (rc != (int)cudaErrorNotSupported) return rc;
   }
   for (int ph = 0; ph < S * S; ++ph) {
@@ -402,7 +409,7 @@ int dgrad_nhwc(const Geom& g, const float* dy, const float* w, const float* gate
     const int M = g.N * HP * WP;
     if (M <= 0) continue;
     if (g_use_tma) {
-      const int rc = hulc_conv_tma_dgrad_phase(dy, ws + (size_t)ph * CIN * Kp, gate, dx, g.N, CIN, g.H, g.W, COUT, g.HO, g.WO, R, S, py, px, st);
+      const int rc = hulc_conv_tma_dgrad_phase(dy, ws + (size_t)ph * CIN * Kp, gate, gate_bits, dx, g.N, CIN, g.H, g.W, COUT, g.HO, g.WO, R, S, py, px, st);
       if (rc == 0) continue;
       if (rc != (int)cudaErrorNotSupported) return rc;
     }
@@ -438,7 +445,7 @@ int wgrad(const Geom& g, const float* x, const float* dy, float* dw, float beta,
 // Channels-last convolutions on the tensor cores.  x is NHWC [N,H,W,CIN] (or, for the 3-channel first layer, the
 // reference's NCHW [N,3,H,W]); y / dy are NHWC [N,HO,WO,COUT]; w, dw keep the reference layout [COUT,CIN,KS,KS].
 HULC_API int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S,
-                                int relu, float* workspace, size_t workspace_bytes, void* stream) {
+                                int relu, unsigned* relu_bits, float* workspace, size_t workspace_bytes, void* stream) {
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (workspace_bytes < (kCounterFloats + (size_t)COUT * CIN * KS * KS) * sizeof(float)) return (int)cudaErrorInvalidValue;
@@ -448,24 +455,24 @@ HULC_API int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, 
   switch (conv_kind(CIN, COUT, KS, S)) {
     case 1: {
       if (g_use_tma) {  // band-staged kernel (conv1_tc.cu) when the geometry fits; otherwise the im2col gather below
-        const int rc = hulc_conv1_band_fwd(x, w, b, y, N, H, W, relu, st);
+        const int rc = hulc_conv1_band_fwd(x, w, b, y, relu_bits, N, H, W, relu, st);
         if (rc != (int)cudaErrorNotSupported) return rc;
       }
       const int M = g.N * g.HO * g.WO;
       FwdNchw3Loader<8, 4> al{x, g, M, {0, 0, 0, 0}};
       WeightLoader<32> bl{w, 192};  // the reference layout [co][ci][ky][kx] already is K-major in (ci, ky, kx) order
-      FwdEpilogue ep{y, b, M, 32, relu};
+      FwdEpilogue ep{y, b, M, 32, relu, relu_bits};
       return launch<32>(al, bl, ep, hulc_cdiv(M, tc::kBM), 192 / tc::kBK, st);
     }
-    case 2: return fwd_nhwc<32, 4, 2, 64>(g, x, w, b, y, relu, ws, st);
-    case 3: return fwd_nhwc<64, 3, 1, 64>(g, x, w, b, y, relu, ws, st);
+    case 2: return fwd_nhwc<32, 4, 2, 64>(g, x, w, b, y, relu_bits, relu, ws, st);
+    case 3: return fwd_nhwc<64, 3, 1, 64>(g, x, w, b, y, relu_bits, relu, ws, st);
   }
   return (int)cudaErrorInvalidValue;
 }
 
 // dx (NHWC) = conv_transpose(dy, w), masked by (gate > 0) when gate != NULL (gate: the NHWC activation that fed the conv)
-HULC_API int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int KS,
-                                  int S, float* workspace, size_t workspace_bytes, void* stream) {
+HULC_API int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int COUT,
+                                  int KS, int S, float* workspace, size_t workspace_bytes, void* stream) {
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (workspace_bytes < (kCounterFloats + (size_t)COUT * CIN * KS * KS) * sizeof(float) || KS % S != 0) return (int)cudaErrorInvalidValue;
@@ -473,8 +480,8 @@ HULC_API int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* 
   Geom g{N, H, W, CIN, (H - KS) / S + 1, (W - KS) / S + 1, COUT};
   if ((long long)N * g.HO * g.WO * COUT >= (1ll << 31)) return (int)cudaErrorInvalidValue;
   switch (conv_kind(CIN, COUT, KS, S)) {
-    case 2: return dgrad_nhwc<32, 4, 2, 64>(g, dy, w, gate, dx, ws, st);
-    case 3: return dgrad_nhwc<64, 3, 1, 64>(g, dy, w, gate, dx, ws, st);
+    case 2: return dgrad_nhwc<32, 4, 2, 64>(g, dy, w, gate, gate_bits, dx, ws, st);
+    case 3: return dgrad_nhwc<64, 3, 1, 64>(g, dy, w, gate, gate_bits, dx, ws, st);
   }
   return (int)cudaErrorInvalidValue;  // the first layer needs no data gradient: its input is the image
 }

@@ -241,6 +241,8 @@ struct BandParams {
   int scatter;           // 1: the BN = 128 columns are 4 stride phases x 32 channels; chunk ph goes to pixel (2 y + ph / 2, 2 x + ph % 2)
   const float* bias;
   const float* gate;
+  const unsigned* gate_bits;  // ReLU sign mask of the gating activation, one word per (pixel, 32 channels); preferred over `gate`
+  unsigned* relu_bits;        // forward: sign mask of the output, written next to it (lets the data gradient skip re-reading the activation)
   int relu;
 };
 
@@ -292,13 +294,16 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
     // ================================ epilogue ================================
     const int r = warp * 32 + lane;
     const int yl = r / p.PW, xx = r - yl * p.PW;
+    float bias[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) bias[j] = p.bias ? __ldg(p.bias + j) : 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
       const int n = tile / p.TPF, y0 = (tile - n * p.TPF) * p.RT;
       const bool valid0 = yl < p.RT && xx < p.OWv && y0 + yl < p.OH;
       const size_t off0 = (((size_t)n * p.out_H + (p.o_mul * (y0 + yl) + p.oy_add)) * p.out_W + (p.o_mul * xx + p.ox_add)) * BN;
-      if (p.gate && valid0) {
+      if (p.gate && !p.gate_bits && valid0) {
         // the ReLU masks this thread will need come from DRAM: pull their lines into L2 while the tile's MMAs are still running
         // (four epilogue warps cannot hide one DRAM latency per 32-column chunk)
 #pragma unroll
@@ -315,17 +320,15 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
       tc_fence_after_sync();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
+        uint32_t v[32], u[NI > 1 ? NI - 1 : 1][32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NI * BN + c0), v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 1; i < NI; ++i) {
-          uint32_t u[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((a * NI + i) * BN + c0), u);
-          tmem_ld_wait();
+        for (int i = 1; i < NI; ++i) tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((a * NI + i) * BN + c0), u[i - 1]);
+        tmem_ld_wait();  // one wait for the partial sums of all issuers
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
-        }
+        for (int i = 1; i < NI; ++i)
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[i - 1][q]));
         if (c0 + 32 == BN) {
           tc_fence_before_sync();
           __syncwarp();
@@ -339,20 +342,30 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
           off = (((size_t)n * p.out_H + oy) * p.out_W + ox) * 32;
         }
         if (valid) {
+          // word of the sign masks for this (pixel, 32-channel chunk): `off` is the element offset of the chunk's first channel
+          const size_t word = off >> 5;
+          unsigned gm = 0xFFFFFFFFu, om = 0u;
+          if (p.gate_bits) gm = __ldg(p.gate_bits + word);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            if (p.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
+            o.x += bias[c0 + j]; o.y += bias[c0 + j + 1]; o.z += bias[c0 + j + 2]; o.w += bias[c0 + j + 3];
             if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (p.gate) {
+            if (p.gate_bits) {
+              o.x = (gm >> j) & 1u ? o.x : 0.f; o.y = (gm >> (j + 1)) & 1u ? o.y : 0.f; o.z = (gm >> (j + 2)) & 1u ? o.z : 0.f; o.w = (gm >> (j + 3)) & 1u ? o.w : 0.f;
+            } else if (p.gate) {
               const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + off + j));
               o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
             }
+            if (p.relu_bits) {
+              if (o.x > 0.f) om |= 1u << j;
+              if (o.y > 0.f) om |= 1u << (j + 1);
+              if (o.z > 0.f) om |= 1u << (j + 2);
+              if (o.w > 0.f) om |= 1u << (j + 3);
+            }
             *reinterpret_cast<float4*>(p.out + off + j) = o;
           }
+          if (p.relu_bits) p.relu_bits[word] = om;
         }
       }
     }
@@ -432,10 +445,11 @@ int launch_band(const float* src, int N, int SH, int SW, int SC, BandParams& p, 
 }
 
 // forward of the two channels-last layers on the band scheme (cudaErrorNotSupported: geometry does not fit)
-int band_fwd(const float* x, const float* wprep, const float* b, float* y, int N, int CIN, int H, int W, int KS, int S, int OH, int OW, int relu, cudaStream_t st) {
+int band_fwd(const float* x, const float* wprep, const float* b, float* y, unsigned* relu_bits, int N, int CIN, int H, int W, int KS, int S, int OH, int OW, int relu,
+             cudaStream_t st) {
   BandParams p{};
   p.N = N; p.OH = OH; p.OWv = OW; p.flip = 0; p.es = S;
-  p.wprep = wprep; p.out = y; p.out_H = OH; p.out_W = OW; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = b; p.gate = nullptr; p.relu = relu;
+  p.wprep = wprep; p.out = y; p.out_H = OH; p.out_W = OW; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = b; p.gate = nullptr; p.gate_bits = nullptr; p.relu_bits = relu_bits; p.relu = relu;
   if (KS == 3 && S == 1 && CIN == 64) {  // bands = channel blocks
     p.PW = W; p.RT = min(OH, kBM / p.PW); p.PH = p.RT + 2; p.TPF = hulc_cdiv(OH, p.RT); p.nbands = 2;
     for (int cb = 0; cb < 2; ++cb) {
@@ -459,11 +473,12 @@ int band_fwd(const float* x, const float* wprep, const float* b, float* y, int N
 // ALL four stride phases of the 4x4 stride-2 data gradient in one launch: the phases read the same shifted views of dY and differ
 // only in their weights, so they are stacked along N (4 phases x 32 input channels = 128 columns: one tcgen05.mma does the work of
 // four N = 32 ones) and the epilogue scatters column chunk ph to pixel (2 y + ph / 2, 2 x + ph % 2).  wall = [4][CIN][(jy, jx, co)].
-int band_dgrad_s2_all(const float* dy, const float* wall, const float* gate, float* dx, int N, int H, int W, int HO, int WO, cudaStream_t st) {
+int band_dgrad_s2_all(const float* dy, const float* wall, const float* gate, const unsigned* gate_bits, float* dx, int N, int H, int W, int HO, int WO,
+                      cudaStream_t st) {
   constexpr int R = 2;
   BandParams p{};
   p.N = N; p.OH = (H + 1) / 2; p.OWv = (W + 1) / 2; p.flip = 1; p.es = 1; p.scatter = 1;
-  p.wprep = wall; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = nullptr; p.gate = gate; p.relu = 0;
+  p.wprep = wall; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = nullptr; p.gate = gate; p.gate_bits = gate_bits; p.relu_bits = nullptr; p.relu = 0;
   p.PW = p.OWv + R - 1; p.RT = min(p.OH, kBM / p.PW); p.PH = p.RT + R - 1; p.TPF = hulc_cdiv(p.OH, p.RT); p.nbands = 2;
   for (int cb = 0; cb < 2; ++cb) {
     p.bc[cb] = cb * 32; p.bx[cb] = -(R - 1); p.by[cb] = -(R - 1);
@@ -473,11 +488,11 @@ int band_dgrad_s2_all(const float* dy, const float* wall, const float* gate, flo
 }
 
 // one stride phase of a data gradient on the band scheme: output grid (OH, OW) = the phase's input pixels
-int band_dgrad(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int HO, int WO, int R, int S, int py, int px,
-               int OH, int OW, cudaStream_t st) {
+int band_dgrad(const float* dy, const float* wphase, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int HO, int WO, int R,
+               int S, int py, int px, int OH, int OW, cudaStream_t st) {
   BandParams p{};
   p.N = N; p.OH = OH; p.OWv = OW; p.flip = 1; p.es = 1;
-  p.wprep = wphase; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = S; p.oy_add = py; p.ox_add = px; p.bias = nullptr; p.gate = gate; p.relu = 0;
+  p.wprep = wphase; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = S; p.oy_add = py; p.ox_add = px; p.bias = nullptr; p.gate = gate; p.gate_bits = gate_bits; p.relu_bits = nullptr; p.relu = 0;
   p.PW = OW + R - 1; p.RT = min(OH, kBM / p.PW); p.PH = p.RT + R - 1; p.TPF = hulc_cdiv(OH, p.RT); p.nbands = 2;
   for (int cb = 0; cb < 2; ++cb) {
     p.bc[cb] = cb * 32; p.bx[cb] = -(R - 1); p.by[cb] = -(R - 1);
@@ -524,8 +539,8 @@ int source_map(CUtensorMap* m, const float* src, int N, int H, int W, int C, con
 
 // y (NHWC) = relu?(conv(x NHWC, w) + b); wprep = w as [COUT][(ky, kx, ci)] (prep_fwd_weights_kernel).  cudaErrorNotSupported
 // when the geometry does not fit: the caller falls back to the gather kernel.
-int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S, int relu,
-                      cudaStream_t st) {
+int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float* y, unsigned* relu_bits, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                      int relu, cudaStream_t st) {
   if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(wprep) | reinterpret_cast<size_t>(y)) & 15) return (int)cudaErrorNotSupported;
   TcParams p{};
   p.N = N; p.OH = (H - KS) / S + 1; p.OW = (W - KS) / S + 1; p.S = S;
@@ -537,9 +552,10 @@ int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float*
   const int rc = source_map(&m, x, N, H, W, CIN, p);
   if (rc != 0) return (int)cudaErrorNotSupported;
   if (g_use_band && COUT == 64) {
-    const int rb = band_fwd(x, wprep, b, y, N, CIN, H, W, KS, S, p.OH, p.OW, relu, st);
+    const int rb = band_fwd(x, wprep, b, y, relu_bits, N, CIN, H, W, KS, S, p.OH, p.OW, relu, st);
     if (rb != (int)cudaErrorNotSupported) return rb;
   }
+  if (relu_bits) return (int)cudaErrorNotSupported;  // only the band kernels (and the gather fallback) write the sign mask
   if (CIN == 32 && COUT == 64 && KS == 4) return launch<64, 16>(m, p, num_tiles, st);
   if (CIN == 64 && COUT == 64 && KS == 3) return launch<64, 18>(m, p, num_tiles, st);
   return (int)cudaErrorNotSupported;
@@ -547,18 +563,18 @@ int hulc_conv_tma_fwd(const float* x, const float* wprep, const float* b, float*
 
 // dx (NHWC [N][H][W][32]) = data gradient of the 32 -> 64, 4x4, stride-2 layer, all stride phases in one launch; wall = the four
 // prepared phase weight matrices, contiguous.  cudaErrorNotSupported -> per-phase launches.
-int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
-                               cudaStream_t st) {
+int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int COUT,
+                               int HO, int WO, cudaStream_t st) {
   if (!g_use_band || CIN != 32 || COUT != 64) return (int)cudaErrorNotSupported;
   if ((reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(wall) | reinterpret_cast<size_t>(dx) | reinterpret_cast<size_t>(gate)) & 15)
     return (int)cudaErrorNotSupported;
-  return band_dgrad_s2_all(dy, wall, gate, dx, N, H, W, HO, WO, st);
+  return band_dgrad_s2_all(dy, wall, gate, gate_bits, dx, N, H, W, HO, WO, st);
 }
 
 // One stride phase (py, px) of dx (NHWC [N][H][W][CIN]) = conv_transpose(dy NHWC [N][HO][WO][COUT], w), masked by gate > 0.
 // wphase = w as [CIN][(jy, jx, co)] for this phase (prep_dgrad_weights_kernel), R = KS / S taps per axis.
-int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO,
-                              int R, int S, int py, int px, cudaStream_t st) {
+int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int COUT,
+                              int HO, int WO, int R, int S, int py, int px, cudaStream_t st) {
   if ((reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(wphase) | reinterpret_cast<size_t>(dx) | reinterpret_cast<size_t>(gate)) & 15)
     return (int)cudaErrorNotSupported;
   TcParams p{};
@@ -572,7 +588,7 @@ int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float*
   const int rc = source_map(&m, dy, N, HO, WO, COUT, p);
   if (rc != 0) return (int)cudaErrorNotSupported;
   if (g_use_band && COUT == 64) {
-    const int rb = band_dgrad(dy, wphase, gate, dx, N, CIN, H, W, HO, WO, R, S, py, px, p.OH, p.OW, st);
+    const int rb = band_dgrad(dy, wphase, gate, gate_bits, dx, N, CIN, H, W, HO, WO, R, S, py, px, p.OH, p.OW, st);
     if (rb != (int)cudaErrorNotSupported) return rb;
   }
   if (CIN == 32 && COUT == 64 && R == 2) return launch<32, 8>(m, p, num_tiles, st);

@@ -158,6 +158,13 @@ class HulcEngine:
             self._bufs[name] = t
         return t
 
+    def ibuf(self, name, *shape):
+        """persistent int32 buffer (ReLU sign masks: one word per pixel and 32 channels)"""
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self._bufs[name] = torch.zeros(*shape, dtype=torch.int32, device=self.device)
+        return t
+
     def load_state_dict(self, sd, strict=True):
         self.ps.load_state_dict(sd, strict)
 
@@ -310,11 +317,17 @@ class HulcEngine:
         for (_, s), k in zip(self._CONVS, (8, 4, 3)):
             sizes.append((sizes[-1] - k) // s + 1)
         a1 = self.buf(f"{which}.a1", N, sizes[1], sizes[1], 32)
+        # sign masks of the two hidden activations, written by the forward epilogues: the data gradients gate on 4 bytes per
+        # (pixel, 32 channels) instead of re-reading the fp32 activation
+        a1_bits = self.ibuf(f"{which}.a1_bits", N, sizes[1], sizes[1], 1)
+        a2_bits = self.ibuf(f"{which}.a2_bits", N, sizes[2], sizes[2], 2)
         n0 = 0
         for f in frames:  # the first layer reads the reference's NCHW frames as they are
-            ops.conv2d_tc_fwd(f, P[f"{pre}.conv_model.0.weight"], P[f"{pre}.conv_model.0.bias"], 4, a1[n0 : n0 + f.shape[0]])
+            ops.conv2d_tc_fwd(f, P[f"{pre}.conv_model.0.weight"], P[f"{pre}.conv_model.0.bias"], 4, a1[n0 : n0 + f.shape[0]],
+                              relu_bits=a1_bits[n0 : n0 + f.shape[0]])
             n0 += f.shape[0]
-        a2 = ops.conv2d_tc_fwd(a1, P[f"{pre}.conv_model.2.weight"], P[f"{pre}.conv_model.2.bias"], 2, self.buf(f"{which}.a2", N, sizes[2], sizes[2], 64))
+        a2 = ops.conv2d_tc_fwd(a1, P[f"{pre}.conv_model.2.weight"], P[f"{pre}.conv_model.2.bias"], 2, self.buf(f"{which}.a2", N, sizes[2], sizes[2], 64),
+                               relu_bits=a2_bits)
         a3 = ops.conv2d_tc_fwd(a2, P[f"{pre}.conv_model.4.weight"], P[f"{pre}.conv_model.4.bias"], 1, self.buf(f"{which}.a3", N, sizes[3], sizes[3], 64))
         w0 = None
         if which == "static":
@@ -332,7 +345,7 @@ class HulcEngine:
             names = [f"{pre}.conv_model.7", f"{pre}.fc1.0", f"{pre}.fc2"]
             out = emb[:, 64:128]
         acts, stats = self._mlp_ln_fwd(which, feat, names, f"{pre}.ln", out, w0=w0)
-        return dict(frames=frames, a1=a1, a2=a2, a3=a3, acts=acts, stats=stats, names=names, pre=pre, w0=w0)
+        return dict(frames=frames, a1=a1, a2=a2, a3=a3, acts=acts, stats=stats, names=names, pre=pre, w0=w0, a1_bits=a1_bits, a2_bits=a2_bits)
 
     def _encoder_bwd_tc(self, which, ctx, demb):
         P, G = self.ps.p, self.ps.g
@@ -361,10 +374,10 @@ class HulcEngine:
             self.gemm_bwd(d, w0, da3.view(N, -1), gate=acts[0])
         ops.conv2d_tc_wgrad(a2, da3, G[f"{pre}.conv_model.4.weight"], 1, beta=1.0)
         colsum(da3.view(-1, 64), G[f"{pre}.conv_model.4.bias"], beta=1.0)
-        da2 = ops.conv2d_tc_dgrad(da3, P[f"{pre}.conv_model.4.weight"], self.buf(f"{which}.da2", *a2.shape), 1, gate=a2)
+        da2 = ops.conv2d_tc_dgrad(da3, P[f"{pre}.conv_model.4.weight"], self.buf(f"{which}.da2", *a2.shape), 1, gate=a2, gate_bits=ctx["a2_bits"])
         ops.conv2d_tc_wgrad(a1, da2, G[f"{pre}.conv_model.2.weight"], 2, beta=1.0)
         colsum(da2.view(-1, 64), G[f"{pre}.conv_model.2.bias"], beta=1.0)
-        da1 = ops.conv2d_tc_dgrad(da2, P[f"{pre}.conv_model.2.weight"], self.buf(f"{which}.da1", *a1.shape), 2, gate=a1)
+        da1 = ops.conv2d_tc_dgrad(da2, P[f"{pre}.conv_model.2.weight"], self.buf(f"{which}.da1", *a1.shape), 2, gate=a1, gate_bits=ctx["a1_bits"])
         colsum(da1.view(-1, 32), G[f"{pre}.conv_model.0.bias"], beta=1.0)
         n0 = 0
         for f in ctx["frames"]:

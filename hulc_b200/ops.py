@@ -215,24 +215,27 @@ def conv2d_wgrad(x, dy, dw, stride, beta=0.0):
 
 
 # channels-last tensor-core variants: activations are NHWC [N,H,W,C]; the first layer reads the NCHW frames directly
-def conv2d_tc_fwd(x, w, b, stride, y, relu=True):
+def conv2d_tc_fwd(x, w, b, stride, y, relu=True, relu_bits=None):
     _chk(x, w, b, y)
     assert x.is_contiguous() and w.is_contiguous() and y.is_contiguous()
     COUT, CIN, KS, _ = w.shape
     N, H, W = (x.shape[0], x.shape[2], x.shape[3]) if CIN == 3 else (x.shape[0], x.shape[1], x.shape[2])
     assert tuple(y.shape) == (N, _conv_out(H, KS, stride), _conv_out(W, KS, stride), COUT), y.shape
     ws = workspace(x.device)
-    _L().hulc_conv2d_tc_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, CIN, H, W, COUT, KS, stride, int(relu), _ptr(ws), ws.numel() * 4, _stream())
+    _chk(relu_bits, dtype=torch.int32)
+    _L().hulc_conv2d_tc_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, CIN, H, W, COUT, KS, stride, int(relu), _ptr(relu_bits), _ptr(ws), ws.numel() * 4, _stream())
     return y
 
 
-def conv2d_tc_dgrad(dy, w, dx, stride, gate=None):
+def conv2d_tc_dgrad(dy, w, dx, stride, gate=None, gate_bits=None):
     _chk(dy, w, gate, dx)
     COUT, CIN, KS, _ = w.shape
     N, H, W, _ = dx.shape
     assert dy.is_contiguous() and dx.is_contiguous() and (gate is None or (gate.is_contiguous() and gate.shape == dx.shape))
     ws = workspace(dy.device)
-    _L().hulc_conv2d_tc_dgrad(_ptr(dy), _ptr(w), _ptr(gate), _ptr(dx), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
+    _chk(gate_bits, dtype=torch.int32)
+    assert gate_bits is None or gate is not None
+    _L().hulc_conv2d_tc_dgrad(_ptr(dy), _ptr(w), _ptr(gate), _ptr(gate_bits), _ptr(dx), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
     return dx
 
 

@@ -99,10 +99,13 @@ int hulc_conv2d_wgrad(const float* x, const float* dy, float* dw, float beta, in
 /* The same three layers on the tensor cores (tcgen05.mma kind::tf32) with channels-last activations: x NHWC [N,H,W,CIN] (or,
  * for the 3-channel first layer, the reference's NCHW frames: fwd reads them as they are, wgrad with x_nchw = 1);
  * y / dy NHWC [N,HO,WO,COUT]; gate / dx NHWC; w / dw keep the reference layout [COUT,CIN,KS,KS]. */
+/* relu_bits (optional, fwd): the sign mask of y, bit c % 32 of word [pixel][c / 32] = (y > 0), written next to y; gate_bits (optional,
+ * dgrad): the same mask of the gating activation — the data gradient then reads 4 bytes instead of 128 per (pixel, 32 channels); `gate`
+ * must still be given (kernels that do not take the mask use it). */
 int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S,
-                       int relu, float* workspace, size_t workspace_bytes, void* stream);
-int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* gate, float* dx, int N, int CIN, int H, int W, int COUT, int KS,
-                         int S, float* workspace, size_t workspace_bytes, void* stream);
+                       int relu, unsigned* relu_bits, float* workspace, size_t workspace_bytes, void* stream);
+int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W,
+                         int COUT, int KS, int S, float* workspace, size_t workspace_bytes, void* stream);
 int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, float beta, int N, int CIN, int H, int W, int COUT, int KS, int S,
                          int x_nchw, float* workspace, size_t workspace_bytes, void* stream);
 /* out[c] += sum_{n,p} x[n,c,p] (conv bias gradient; accumulates like the other parameter-gradient outputs) */

@@ -39,7 +39,11 @@ def test_conv_tc(cin, cout, ks, st, hw, n):
     ref = F.relu(F.conv2d(xr, wr, b.double(), stride=st))
     ho = ref.shape[-1]
     xin = x if cin == 3 else nhwc(x)
-    y = ops.conv2d_tc_fwd(xin, w, b, st, torch.empty(n, ho, ho, cout, device="cuda"))
+    bits = torch.zeros(n, ho, ho, cout // 32, dtype=torch.int32, device="cuda")
+    y = ops.conv2d_tc_fwd(xin, w, b, st, torch.empty(n, ho, ho, cout, device="cuda"), relu_bits=bits)
+    # the sign mask written next to the output: bit c % 32 of word [pixel][c / 32] = (y > 0)
+    want = ((y > 0).view(n, ho, ho, cout // 32, 32).to(torch.int64) << torch.arange(32, device="cuda")).sum(-1)
+    assert torch.equal(bits.to(torch.int64) & 0xFFFFFFFF, want)
     scale = float(ref.abs().max())
     err = float((y.double() - nhwc(ref.detach())).abs().max())
     assert err < 4e-3 * scale, f"fwd err {err:.3e} (scale {scale:.2f})"
@@ -55,6 +59,10 @@ def test_conv_tc(cin, cout, ks, st, hw, n):
     assert err < 8e-3 * gs
     if cin != 3:
         dx = ops.conv2d_tc_dgrad(nhwc(dy), w, torch.empty(n, hw, hw, cin, device="cuda"), st, gate=xin)
+        gbits = ((xin > 0).view(n, hw, hw, cin // 32, 32).to(torch.int64) << torch.arange(32, device="cuda")).sum(-1)
+        gbits = torch.where(gbits >= 2 ** 31, gbits - 2 ** 32, gbits).to(torch.int32)
+        dxb = ops.conv2d_tc_dgrad(nhwc(dy), w, torch.empty(n, hw, hw, cin, device="cuda"), st, gate=xin, gate_bits=gbits)
+        assert torch.equal(dxb, dx), "gating on the sign mask must equal gating on the activation"
         refdx = nhwc(xr.grad * (x > 0))
         ds = float(refdx.abs().max())
         err = float((dx.double() - refdx).abs().max())
