@@ -241,6 +241,183 @@ __global__ void __launch_bounds__(kThr, 1) conv1_band_fwd_kernel(C1Params p, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the same layer: dW[k = (ci, ky, kx)][co] = sum over pixels of Xcol[pixel][k] * dY[pixel][co].
+// GEMM-K = pixels, so both operands are MN-major tiles ([32 elements of M or N][pixel k-rows][128 B], 32-byte-atom swizzle):
+//   A = Xcol^T: six groups of 32 k's (group g = (ci, ky) pairs 4g .. 4g+3 x 8 kx), built from the SAME staged input band as the
+//       forward kernel — a pixel's 32 k's of a group are four 32-byte pieces of four band rows;
+//   B = dY^T  : one group of 32 channels, copied from the contiguous channels-last rows of dY.
+// A tile is ONE output row of one frame (WO <= 56 pixels, padded to a multiple of 8 k-rows with zero rows); seven builder warps
+// (six A groups + dY) fill a 3-deep ring of tile slots; two threads issue tcgen05.mma — k 0..127 into accumulator 0 and
+// k 128..191 into accumulator 1 — and the accumulators stay in TMEM across ALL tiles of the CTA: each CTA writes one partial
+// [192 x 32] at the end, which the existing reduction sums over CTAs in a fixed order.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kWgKR = 56;                       // k-rows (pixels) per tile, multiple of 8
+constexpr int kWgGroupB = kWgKR * kRowBytes;    // one 32-element group of a tile: 7 KB
+constexpr int kWgGroups = 7;                    // 6 groups of Xcol^T + 1 group of dY^T
+constexpr int kWgSlotB = kWgGroups * kWgGroupB; // 49 KB
+constexpr int kWgSlots = 3;
+constexpr int kWgBandB = 20 * 1024;             // 8 input rows x 3 channels x W floats (W <= 212)
+constexpr int kWgBands = 3;
+constexpr int kWgSmem = kWgSlots * kWgSlotB + kWgBands * kWgBandB + 2 * kWgGroupB /*phantom groups of the second MMA*/ + 256 + 1024;
+// warps: 0-3 epilogue (end of kernel only) | 4-5 MMA issuers | 6 band loader | 7-13 builders
+constexpr int kWgLoader = kEpiWarps + 2, kWgBuilder0 = kWgLoader + 1;
+constexpr int kWgThr = (kWgBuilder0 + kWgGroups) * 32;
+
+struct C1WgParams {
+  const float* x;    // [N, 3, H, W]
+  const float* dy;   // [N, HO, WO, 32]
+  float* partial;    // [gridDim.x][192][32]
+  int N, H, W, HO, WO, KR;  // KR = WO rounded up to 8
+};
+
+struct C1WgBars {
+  uint64_t full[kWgSlots];
+  uint64_t empty[kWgSlots];
+  uint64_t band_full[kWgBands];
+  uint64_t band_empty[kWgBands];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams p, int num_tiles) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* slot_smem = smem;
+  unsigned char* band_smem = smem + kWgSlots * kWgSlotB + 2 * kWgGroupB;
+  C1WgBars* bars = reinterpret_cast<C1WgBars*>(band_smem + kWgBands * kWgBandB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgSlots; ++s) {
+      mbar_init(&bars->full[s], kWgGroups);
+      mbar_init(&bars->empty[s], 2);
+    }
+    for (int s = 0; s < kWgBands; ++s) {
+      mbar_init(&bars->band_full[s], 1);
+      mbar_init(&bars->band_empty[s], kWgGroups - 1);
+    }
+    mbar_init(&bars->done, 2);
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 64);
+  // k-rows past WO are never written by the builders and must contribute zero
+  for (int i = threadIdx.x; i < (kWgSlots * kWgSlotB + 2 * kWgGroupB) / 16; i += kWgThr) reinterpret_cast<float4*>(slot_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp < kEpiWarps) {
+    // ================================ epilogue: once, after the last tile ================================
+    mbar_wait(&bars->done, 0);
+    tc_fence_after_sync();
+    const int r = warp * 32 + lane;
+    float* dst = p.partial + (size_t)blockIdx.x * (kKtot * kCout);
+#pragma unroll
+    for (int acc = 0; acc < 2; ++acc) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * kCout), v);
+      tmem_ld_wait();
+      const int k = acc * kBM + r;
+      if (k < kKtot) {
+#pragma unroll
+        for (int j = 0; j < kCout; j += 4)
+          *reinterpret_cast<float4*>(dst + (size_t)k * kCout + j) =
+              my_tiles ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  } else if (warp < kWgLoader) {
+    // ================================ MMA issuers: me = 0 -> k 0..127, me = 1 -> k 128..191 (+ two phantom groups) ================================
+    if (lane == 0) {
+      const int me = warp - kEpiWarps;
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, kCout, true, true);
+      const uint32_t sb = smem_u32(slot_smem);
+      const uint32_t d = tmem_base + (uint32_t)(me * kCout);
+      const int ksteps = p.KR >> 3;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int slot = it % kWgSlots;
+        mbar_wait(&bars->full[slot], (it / kWgSlots) & 1);
+        tc_fence_after_sync();
+        const uint32_t a = sb + slot * kWgSlotB + me * 4 * kWgGroupB, b = sb + slot * kWgSlotB + 6 * kWgGroupB;
+        for (int k = 0; k < ksteps; ++k) {
+          // MN-major operands: 8 k-rows per MMA = two 512-byte swizzle atoms (SBO), 32-element groups kWgGroupB apart (LBO)
+          const uint64_t da = make_smem_desc(a + k * 1024, kWgGroupB, 512u, 1u), db = make_smem_desc(b + k * 1024, kWgGroupB, 512u, 1u);
+          umma_tf32(d, da, db, idesc, (uint32_t)(it != 0 || k != 0));
+        }
+        umma_commit(&bars->empty[slot]);
+      }
+      umma_commit(&bars->done);
+    }
+  } else if (warp == kWgLoader) {
+    // ================================ band loader ================================
+    if (lane == 0) {
+      const uint32_t rowbytes = (uint32_t)p.W * 4;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int slot = it % kWgBands;
+        mbar_wait(&bars->band_empty[slot], ((it / kWgBands) & 1) ^ 1);
+        const int n = tile / p.HO, y = tile - n * p.HO;
+        expect_tx(&bars->band_full[slot], 3 * 8 * rowbytes);
+        const uint32_t dst = smem_u32(band_smem) + slot * kWgBandB;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) bulk_load(dst + (uint32_t)(ci * 8) * rowbytes, p.x + ((size_t)(n * 3 + ci) * p.H + 4 * y) * p.W, 8 * rowbytes, &bars->band_full[slot]);
+      }
+    }
+  } else {
+    // ================================ builders: warp g fills group g of every tile slot ================================
+    const int g = warp - kWgBuilder0;  // 0..5: Xcol^T groups, 6: dY^T
+    const uint32_t rowbytes = (uint32_t)p.W * 4;
+    const int nchunks = p.WO * 8;      // 16-byte chunks of one group: pixel x = q / 8, chunk c = q % 8
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int slot = it % kWgSlots, bslot = it % kWgBands;
+      const int n = tile / p.HO, y = tile - n * p.HO;
+      const uint32_t dst = smem_u32(slot_smem) + slot * kWgSlotB + g * kWgGroupB;
+      mbar_wait(&bars->empty[slot], ((it / kWgSlots) & 1) ^ 1);
+      constexpr int kIters = kWgKR * 8 / 32;  // 14 chunks per lane at most; all loads are issued before the first store
+      float4 v[kIters];
+      if (g < 6) {
+        mbar_wait(&bars->band_full[bslot], (it / kWgBands) & 1);
+        const uint32_t band = smem_u32(band_smem) + bslot * kWgBandB;
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) {
+          const int q = lane + 32 * i, xx = q >> 3, c = q & 7;
+          const int pr = g * 4 + (c >> 1), ci = pr >> 3, ky = pr & 7;  // (ci, ky) pair of this chunk; kx half = c & 1
+          if (q < nchunks) v[i] = ld_shared16(band + (uint32_t)(ci * 8 + ky) * rowbytes + (uint32_t)((xx * 4 + (c & 1) * 4) * 4));
+        }
+      } else {
+        const float* src = p.dy + ((size_t)(n * p.HO + y) * p.WO) * kCout;
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) {
+          const int q = lane + 32 * i;
+          if (q < nchunks) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)q * 4));  // rows of 32 floats are contiguous: chunk q is at q * 16 B
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) {
+        const int q = lane + 32 * i;
+        if (q < nchunks) st_shared16(dst + swz32(q >> 3, q & 7), v[i]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->full[slot]);
+        if (g < 6) mbar_arrive(&bars->band_empty[bslot]);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 }  // namespace
 
 // Returns cudaErrorNotSupported when the geometry does not fit the band scheme (the caller then uses the gather kernel).
@@ -258,5 +435,23 @@ int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y
   if (tiles >= (1ll << 31) || (long long)N * 3 * H * W >= (1ll << 31)) return (int)cudaErrorNotSupported;
   HULC_TRY(cudaFuncSetAttribute(conv1_band_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   HULC_LAUNCH(conv1_band_fwd_kernel, dim3((unsigned)min((long long)kNumSMs, tiles)), dim3(kThr), kSmem, st, p, (int)tiles);
+  HULC_RETURN_LAST();
+}
+
+// Per-CTA partial weight gradients [ctas][192][32] of the first layer (k in the reference's (ci, ky, kx) order); *ctas_out = number of
+// partials to reduce.  cudaErrorNotSupported when the geometry does not fit (the caller then uses the gather kernel).
+int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int N, int H, int W, int* ctas_out, cudaStream_t st) {
+  const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
+  if (HO <= 0 || WO <= 0 || WO > kWgKR || (W & 3) || (size_t)3 * 8 * W * 4 > (size_t)kWgBandB) return (int)cudaErrorNotSupported;
+  if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(partial)) & 15) return (int)cudaErrorNotSupported;
+  const long long tiles = (long long)N * HO;
+  if (tiles >= (1ll << 31) || (long long)N * 3 * H * W >= (1ll << 31)) return (int)cudaErrorNotSupported;
+  const int ctas = (int)min((long long)kNumSMs, tiles);
+  if ((size_t)ctas * kKtot * kCout * sizeof(float) > partial_bytes) return (int)cudaErrorNotSupported;
+  C1WgParams p;
+  p.x = x; p.dy = dy; p.partial = partial; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.KR = (WO + 7) & ~7;
+  HULC_TRY(cudaFuncSetAttribute(conv1_band_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+  HULC_LAUNCH(conv1_band_wgrad_kernel, dim3(ctas), dim3(kWgThr), kWgSmem, st, p, (int)tiles);
+  *ctas_out = ctas;
   HULC_RETURN_LAST();
 }

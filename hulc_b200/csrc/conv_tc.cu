@@ -27,6 +27,7 @@ int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* 
 int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int COUT,
                               int HO, int WO, int R, int S, int py, int px, cudaStream_t st);
 
+int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int N, int H, int W, int* ctas_out, cudaStream_t st);
 int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st);  // conv1_tc.cu
 
 namespace {
@@ -497,7 +498,19 @@ HULC_API int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, fl
   Geom g{N, H, W, CIN, (H - KS) / S + 1, (W - KS) / S + 1, COUT};
   if ((long long)N * H * W * CIN >= (1ll << 32) / 4) return (int)cudaErrorInvalidValue;
   switch (conv_kind(CIN, COUT, KS, S)) {
-    case 1: return x_nchw ? wgrad<3, 8, 4, 32, true>(g, x, dy, dw, beta, ws, wsb, st) : (int)cudaErrorInvalidValue;
+    case 1: {
+      if (!x_nchw) return (int)cudaErrorInvalidValue;
+      if (g_use_tma) {  // band-staged kernel (conv1_tc.cu): per-CTA partials, reduced in a fixed order below
+        int ctas = 0;
+        const int rc = hulc_conv1_band_wgrad_partials(x, dy, ws, wsb, N, H, W, &ctas, st);
+        if (rc == 0) {
+          HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(192 * 32, 256)), dim3(256), 0, st, (const float*)ws, dw, ctas, 192, 32, 3, 8, 1, beta);
+          HULC_RETURN_LAST();
+        }
+        if (rc != (int)cudaErrorNotSupported) return rc;
+      }
+      return wgrad<3, 8, 4, 32, true>(g, x, dy, dw, beta, ws, wsb, st);
+    }
     case 2: return x_nchw ? (int)cudaErrorInvalidValue : wgrad<32, 4, 2, 64, false>(g, x, dy, dw, beta, ws, wsb, st);
     case 3: return x_nchw ? (int)cudaErrorInvalidValue : wgrad<64, 3, 1, 64, false>(g, x, dy, dw, beta, ws, wsb, st);
   }
