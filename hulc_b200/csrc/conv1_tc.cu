@@ -254,12 +254,16 @@ __global__ void __launch_bounds__(kThr, 1) conv1_band_fwd_kernel(C1Params p, int
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kWgKR = 56;                       // k-rows (pixels) per tile, multiple of 8
 constexpr int kWgGroupB = kWgKR * kRowBytes;    // one 32-element group of a tile: 7 KB
-constexpr int kWgGroups = 7;                    // 6 groups of Xcol^T + 1 group of dY^T
-constexpr int kWgSlotB = kWgGroups * kWgGroupB; // 49 KB
+constexpr int kWgGroups = 7;                    // builder warps: 6 groups of Xcol^T + 1 group of dY^T
+// slot = 8 groups: 0-5 Xcol^T, 6 = a constant group whose element 0 is 1 for every real pixel (k = 192: a row of ones appended to
+// the im2col matrix, so accumulator row 192 is sum_pixels dY = the BIAS gradient, for free), 7 = dY^T
+constexpr int kWgOnes = 6, kWgDy = 7;
+constexpr int kWgSlotB = 8 * kWgGroupB;         // 56 KB
 constexpr int kWgSlots = 3;
-constexpr int kWgBandB = 20 * 1024;             // 8 input rows x 3 channels x W floats (W <= 212)
+constexpr int kWgBandB = 19 * 1024;             // 8 input rows x 3 channels x W floats (W <= 202)
 constexpr int kWgBands = 3;
-constexpr int kWgSmem = kWgSlots * kWgSlotB + kWgBands * kWgBandB + 2 * kWgGroupB /*phantom groups of the second MMA*/ + 256 + 1024;
+constexpr int kWgSmem = kWgSlots * kWgSlotB + kWgBands * kWgBandB + 256 + 1024;
+static_assert(kWgSmem <= 227 * 1024, "shared memory budget");
 // warps: 0-3 epilogue (end of kernel only) | 4-5 MMA issuers | 6 band loader | 7-13 builders
 constexpr int kWgLoader = kEpiWarps + 2, kWgBuilder0 = kWgLoader + 1;
 constexpr int kWgThr = (kWgBuilder0 + kWgGroups) * 32;
@@ -268,6 +272,7 @@ struct C1WgParams {
   const float* x;    // [N, 3, H, W]
   const float* dy;   // [N, HO, WO, 32]
   float* partial;    // [gridDim.x][192][32]
+  float* bias_partial;  // [gridDim.x][32] or null
   int N, H, W, HO, WO, KR;  // KR = WO rounded up to 8
 };
 
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* slot_smem = smem;
-  unsigned char* band_smem = smem + kWgSlots * kWgSlotB + 2 * kWgGroupB;
+  unsigned char* band_smem = smem + kWgSlots * kWgSlotB;
   C1WgBars* bars = reinterpret_cast<C1WgBars*>(band_smem + kWgBands * kWgBandB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -302,7 +307,12 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
   }
   if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 64);
   // k-rows past WO are never written by the builders and must contribute zero
-  for (int i = threadIdx.x; i < (kWgSlots * kWgSlotB + 2 * kWgGroupB) / 16; i += kWgThr) reinterpret_cast<float4*>(slot_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < kWgSlots * kWgSlotB / 16; i += kWgThr) reinterpret_cast<float4*>(slot_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kWgSlots * p.WO; i += kWgThr) {  // the constant ones group of every slot
+    const int s_ = i / p.WO, xx = i - s_ * p.WO;
+    *reinterpret_cast<float*>(slot_smem + s_ * kWgSlotB + kWgOnes * kWgGroupB + swz32(xx, 0)) = 1.0f;
+  }
   fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
@@ -322,6 +332,10 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * kCout), v);
       tmem_ld_wait();
       const int k = acc * kBM + r;
+      if (k == kKtot && p.bias_partial) {  // the ones row: sum over this CTA's pixels of dY
+#pragma unroll
+        for (int j = 0; j < kCout; ++j) p.bias_partial[(size_t)blockIdx.x * kCout + j] = my_tiles ? __uint_as_float(v[j]) : 0.f;
+      }
       if (k < kKtot) {
 #pragma unroll
         for (int j = 0; j < kCout; j += 4)
@@ -341,7 +355,7 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
         const int slot = it % kWgSlots;
         mbar_wait(&bars->full[slot], (it / kWgSlots) & 1);
         tc_fence_after_sync();
-        const uint32_t a = sb + slot * kWgSlotB + me * 4 * kWgGroupB, b = sb + slot * kWgSlotB + 6 * kWgGroupB;
+        const uint32_t a = sb + slot * kWgSlotB + me * 4 * kWgGroupB, b = sb + slot * kWgSlotB + kWgDy * kWgGroupB;
         for (int k = 0; k < ksteps; ++k) {
           // MN-major operands: 8 k-rows per MMA = two 512-byte swizzle atoms (SBO), 32-element groups kWgGroupB apart (LBO)
           const uint64_t da = make_smem_desc(a + k * 1024, kWgGroupB, 512u, 1u), db = make_smem_desc(b + k * 1024, kWgGroupB, 512u, 1u);
@@ -375,7 +389,7 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
       const int tile = blockIdx.x + it * gridDim.x;
       const int slot = it % kWgSlots, bslot = it % kWgBands;
       const int n = tile / p.HO, y = tile - n * p.HO;
-      const uint32_t dst = smem_u32(slot_smem) + slot * kWgSlotB + g * kWgGroupB;
+      const uint32_t dst = smem_u32(slot_smem) + slot * kWgSlotB + (g < 6 ? g : kWgDy) * kWgGroupB;
       mbar_wait(&bars->empty[slot], ((it / kWgSlots) & 1) ^ 1);
       constexpr int kIters = kWgKR * 8 / 32;  // 14 chunks per lane at most; all loads are issued before the first store
       float4 v[kIters];
@@ -438,18 +452,20 @@ int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y
   HULC_RETURN_LAST();
 }
 
-// Per-CTA partial weight gradients [ctas][192][32] of the first layer (k in the reference's (ci, ky, kx) order); *ctas_out = number of
-// partials to reduce.  cudaErrorNotSupported when the geometry does not fit (the caller then uses the gather kernel).
-int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int N, int H, int W, int* ctas_out, cudaStream_t st) {
+// Per-CTA partial weight gradients [ctas][192][32] of the first layer (k in the reference's (ci, ky, kx) order), followed — when
+// want_bias — by per-CTA partial bias gradients [ctas][32]; *ctas_out = number of partials to reduce.  cudaErrorNotSupported when the geometry does not fit (the caller then uses the gather kernel).
+int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int want_bias, int N, int H, int W, int* ctas_out,
+                                   cudaStream_t st) {
   const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
   if (HO <= 0 || WO <= 0 || WO > kWgKR || (W & 3) || (size_t)3 * 8 * W * 4 > (size_t)kWgBandB) return (int)cudaErrorNotSupported;
   if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(partial)) & 15) return (int)cudaErrorNotSupported;
   const long long tiles = (long long)N * HO;
   if (tiles >= (1ll << 31) || (long long)N * 3 * H * W >= (1ll << 31)) return (int)cudaErrorNotSupported;
   const int ctas = (int)min((long long)kNumSMs, tiles);
-  if ((size_t)ctas * kKtot * kCout * sizeof(float) > partial_bytes) return (int)cudaErrorNotSupported;
+  if ((size_t)ctas * (kKtot + 1) * kCout * sizeof(float) > partial_bytes) return (int)cudaErrorNotSupported;
   C1WgParams p;
-  p.x = x; p.dy = dy; p.partial = partial; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.KR = (WO + 7) & ~7;
+  p.x = x; p.dy = dy; p.partial = partial; p.bias_partial = want_bias ? partial + (size_t)ctas * kKtot * kCout : nullptr;  // bias partials follow the weight partials
+  p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.KR = (WO + 7) & ~7;
   HULC_TRY(cudaFuncSetAttribute(conv1_band_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
   HULC_LAUNCH(conv1_band_wgrad_kernel, dim3(ctas), dim3(kWgThr), kWgSmem, st, p, (int)tiles);
   *ctas_out = ctas;

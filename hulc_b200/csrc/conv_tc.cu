@@ -27,7 +27,9 @@ int hulc_conv_tma_dgrad_s2_all(const float* dy, const float* wall, const float* 
 int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W, int COUT,
                               int HO, int WO, int R, int S, int py, int px, cudaStream_t st);
 
-int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int N, int H, int W, int* ctas_out, cudaStream_t st);
+int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int want_bias, int N, int H, int W, int* ctas_out,
+                                   cudaStream_t st);
+extern "C" int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, float* workspace, size_t workspace_bytes, void* stream);
 int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st);  // conv1_tc.cu
 
 namespace {
@@ -488,7 +490,7 @@ HULC_API int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* 
 }
 
 // dw = beta*dw + dL/dw.  x NHWC (x_nchw = 0) or the NCHW frames of the first layer (x_nchw = 1)
-HULC_API int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, float beta, int N, int CIN, int H, int W, int COUT, int KS, int S,
+HULC_API int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, float beta, float* db, int N, int CIN, int H, int W, int COUT, int KS, int S,
                                   int x_nchw, float* workspace, size_t workspace_bytes, void* stream) {
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -502,17 +504,28 @@ HULC_API int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, fl
       if (!x_nchw) return (int)cudaErrorInvalidValue;
       if (g_use_tma) {  // band-staged kernel (conv1_tc.cu): per-CTA partials, reduced in a fixed order below
         int ctas = 0;
-        const int rc = hulc_conv1_band_wgrad_partials(x, dy, ws, wsb, N, H, W, &ctas, st);
+        const int rc = hulc_conv1_band_wgrad_partials(x, dy, ws, wsb, db != nullptr, N, H, W, &ctas, st);
         if (rc == 0) {
           HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(192 * 32, 256)), dim3(256), 0, st, (const float*)ws, dw, ctas, 192, 32, 3, 8, 1, beta);
+          if (db) return hulc_colsum(ws + (size_t)ctas * 192 * 32, ctas, 32, 32, db, 1.0f, nullptr, 0, stream);  // the ones row of the same GEMM
           HULC_RETURN_LAST();
         }
         if (rc != (int)cudaErrorNotSupported) return rc;
       }
-      return wgrad<3, 8, 4, 32, true>(g, x, dy, dw, beta, ws, wsb, st);
+      HULC_TRY((wgrad<3, 8, 4, 32, true>(g, x, dy, dw, beta, ws, wsb, st)));
+      break;
     }
-    case 2: return x_nchw ? (int)cudaErrorInvalidValue : wgrad<32, 4, 2, 64, false>(g, x, dy, dw, beta, ws, wsb, st);
-    case 3: return x_nchw ? (int)cudaErrorInvalidValue : wgrad<64, 3, 1, 64, false>(g, x, dy, dw, beta, ws, wsb, st);
+    case 2:
+      if (x_nchw) return (int)cudaErrorInvalidValue;
+      HULC_TRY((wgrad<32, 4, 2, 64, false>(g, x, dy, dw, beta, ws, wsb, st)));
+      break;
+    case 3:
+      if (x_nchw) return (int)cudaErrorInvalidValue;
+      HULC_TRY((wgrad<64, 3, 1, 64, false>(g, x, dy, dw, beta, ws, wsb, st)));
+      break;
+    default: return (int)cudaErrorInvalidValue;
   }
-  return (int)cudaErrorInvalidValue;
+  // bias gradient by a column-sum pass over dY where the weight-gradient kernel did not produce it
+  if (db) return hulc_colsum(dy, N * g.HO * g.WO, COUT, COUT, db, 1.0f, workspace, workspace_bytes, stream);
+  return 0;
 }

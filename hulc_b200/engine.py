@@ -378,10 +378,9 @@ class HulcEngine:
         ops.conv2d_tc_wgrad(a1, da2, G[f"{pre}.conv_model.2.weight"], 2, beta=1.0)
         colsum(da2.view(-1, 64), G[f"{pre}.conv_model.2.bias"], beta=1.0)
         da1 = ops.conv2d_tc_dgrad(da2, P[f"{pre}.conv_model.2.weight"], self.buf(f"{which}.da1", *a1.shape), 2, gate=a1, gate_bits=ctx["a1_bits"])
-        colsum(da1.view(-1, 32), G[f"{pre}.conv_model.0.bias"], beta=1.0)
         n0 = 0
-        for f in ctx["frames"]:
-            ops.conv2d_tc_wgrad(f, da1[n0 : n0 + f.shape[0]], G[f"{pre}.conv_model.0.weight"], 4, beta=1.0)
+        for f in ctx["frames"]:  # the bias gradient (column sums of da1) comes out of the same tensor-core pass
+            ops.conv2d_tc_wgrad(f, da1[n0 : n0 + f.shape[0]], G[f"{pre}.conv_model.0.weight"], 4, beta=1.0, db=G[f"{pre}.conv_model.0.bias"])
             n0 += f.shape[0]
 
     # ------------------------------------------------------------------------------------------------------------------

@@ -239,14 +239,15 @@ def conv2d_tc_dgrad(dy, w, dx, stride, gate=None, gate_bits=None):
     return dx
 
 
-def conv2d_tc_wgrad(x, dy, dw, stride, beta=0.0):
-    _chk(x, dy, dw)
+def conv2d_tc_wgrad(x, dy, dw, stride, beta=0.0, db=None):
+    """dw = beta * dw + dL/dw; db (optional) += sum over pixels of dy (the bias gradient, from the same pass where possible)."""
+    _chk(x, dy, dw, db)
     COUT, CIN, KS, _ = dw.shape
     nchw = CIN == 3
     N, H, W = (x.shape[0], x.shape[2], x.shape[3]) if nchw else (x.shape[0], x.shape[1], x.shape[2])
     assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
     ws = workspace(x.device)
-    _L().hulc_conv2d_tc_wgrad(_ptr(x), _ptr(dy), _ptr(dw), float(beta), N, CIN, H, W, COUT, KS, stride, int(nchw), _ptr(ws), ws.numel() * 4, _stream())
+    _L().hulc_conv2d_tc_wgrad(_ptr(x), _ptr(dy), _ptr(dw), float(beta), _ptr(db), N, CIN, H, W, COUT, KS, stride, int(nchw), _ptr(ws), ws.numel() * 4, _stream())
     return dw
 
 

@@ -106,7 +106,9 @@ int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, float* y,
                        int relu, unsigned* relu_bits, float* workspace, size_t workspace_bytes, void* stream);
 int hulc_conv2d_tc_dgrad(const float* dy, const float* w, const float* gate, const unsigned* gate_bits, float* dx, int N, int CIN, int H, int W,
                          int COUT, int KS, int S, float* workspace, size_t workspace_bytes, void* stream);
-int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, float beta, int N, int CIN, int H, int W, int COUT, int KS, int S,
+/* db (optional): the bias gradient sum_pixels dy[.., co] is ADDED to db[co] — by a row of ones appended to the im2col matrix of the same
+ * tensor-core pass where the kernel has a spare GEMM row (first layer), otherwise by a column-sum pass over dy. */
+int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, float beta, float* db, int N, int CIN, int H, int W, int COUT, int KS, int S,
                          int x_nchw, float* workspace, size_t workspace_bytes, void* stream);
 /* out[c] += sum_{n,p} x[n,c,p] (conv bias gradient; accumulates like the other parameter-gradient outputs) */
 int hulc_nchw_channel_sum(const float* x, float* out, int N, int C, int P, void* stream);

@@ -50,7 +50,10 @@ def test_conv_tc(cin, cout, ks, st, hw, n):
     dy = (torch.randn(ref.shape, generator=g).cuda() * (ref.detach() > 0)).float()
     ref.backward(dy.double())
     dw = torch.zeros_like(w)
-    ops.conv2d_tc_wgrad(xin, nhwc(dy), dw, st)
+    db = torch.ones(cout, device="cuda")
+    ops.conv2d_tc_wgrad(xin, nhwc(dy), dw, st, db=db)  # db accumulates the bias gradient (sum of dy over pixels)
+    dbref = dy.double().sum((0, 2, 3)) + 1
+    assert float((db.double() - dbref).abs().max()) < 4e-3 * float(dbref.abs().max() + dy.abs().sum((0, 2, 3)).max() * 1e-3), "bias gradient"
     gs = float(wr.grad.abs().max())
     err = float((dw.double() - wr.grad).abs().max())
     assert err < 4e-3 * gs, f"wgrad err {err:.3e} (scale {gs:.2f})"
