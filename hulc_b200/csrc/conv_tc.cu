@@ -321,11 +321,17 @@ struct WgradEpilogue {
 // dw[co][ci][ky][kx] = beta*dw + sum_s partial[s][k][co];  k = (ky, kx, ci) (NHWC order) or the natural order (nchw3)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int KTOT, int COUT, int CIN, int KS,
                                     int nchw3, float beta) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= KTOT * COUT) return;
-  const int k = e / COUT, co = e - k * COUT;
+  // 8 lanes per output element: lane j adds partials j, j + 8, ... (independent loads in flight), then a fixed-order shuffle tree
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, j = threadIdx.x & 7;
+  const bool live = e < KTOT * COUT;
+  const int k = live ? e / COUT : 0, co = live ? e - k * COUT : 0;
   float s = 0.f;
-  for (int i = 0; i < splits; ++i) s += partial[((size_t)i * KTOT + k) * COUT + co];
+  if (live)
+    for (int i = j; i < splits; i += 8) s += partial[((size_t)i * KTOT + k) * COUT + co];
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (!live || j != 0) return;
   int ko = k;
   if (!nchw3) {
     const int tap = k / CIN, ci = k - tap * CIN;
@@ -439,7 +445,7 @@ int wgrad(const Geom& g, const float* x, const float* dy, float* dw, float beta,
   WgradDyLoader<COUT> bl{dy, t, 0, 0, 0};
   WgradEpilogue ep{ws, splits, KTOT, COUT};
   HULC_TRY(launch<COUT>(al, bl, ep, mt * splits, pps / tc::kBK, st));
-  HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(KTOT * COUT, 256)), dim3(256), 0, st, (const float*)ws, dw, splits, KTOT, COUT, CIN, KS, NCHW3 ? 1 : 0, beta);
+  HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(KTOT * COUT * 8, 256)), dim3(256), 0, st, (const float*)ws, dw, splits, KTOT, COUT, CIN, KS, NCHW3 ? 1 : 0, beta);
   HULC_RETURN_LAST();
 }
 
@@ -506,7 +512,7 @@ HULC_API int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, fl
         int ctas = 0;
         const int rc = hulc_conv1_band_wgrad_partials(x, dy, ws, wsb, db != nullptr, N, H, W, &ctas, st);
         if (rc == 0) {
-          HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(192 * 32, 256)), dim3(256), 0, st, (const float*)ws, dw, ctas, 192, 32, 3, 8, 1, beta);
+          HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(192 * 32 * 8, 256)), dim3(256), 0, st, (const float*)ws, dw, ctas, 192, 32, 3, 8, 1, beta);
           if (db) return hulc_colsum(ws + (size_t)ctas * 192 * 32, ctas, 32, 32, db, 1.0f, nullptr, 0, stream);  // the ones row of the same GEMM
           HULC_RETURN_LAST();
         }
