@@ -248,6 +248,8 @@ struct WgradTiling {
 };
 
 // A operand (MN-major, 128 k's x 32 pixels).  NCHW3 = first layer (k = ci*64 + ky*8 + kx), otherwise NHWC (k = tap*CIN + ci).
+// Thread (p = ptid >> 3, c4 = ptid & 7) owns pixel p of every k-block and chunk c4 of each of the 4 k-groups: the group offsets are
+// fixed per work item, the pixel advances by 32 per k-block (tracked incrementally: no divisions in issue()).
 template <int CIN, int KS, int S, bool NCHW3>
 struct WgradXLoader {
   static constexpr bool kMNMajor = true;
@@ -256,52 +258,72 @@ struct WgradXLoader {
   Geom g;
   WgradTiling t;
   int tm, pix0, pix_end;
-  __device__ __forceinline__ void start_tile(int tile, int) { t.decode(tile, tm, pix0, pix_end); }
-  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
-    const int c4 = ptid & 7, p = ptid >> 3;  // this thread: pixel p of the k-block, chunk c4 of each of the 4 k-groups
-    const int pix = pix0 + kb * tc::kBK + p;
-    const bool pv = pix < pix_end;
+  int pix, n, y, xx, next_kb;  // this thread's pixel of k-block next_kb
+  uint32_t goff[4];
+  uint32_t gokmask;
+  __device__ __forceinline__ void start_tile(int tile, int ptid) {
+    t.decode(tile, tm, pix0, pix_end);
+    const int c4 = ptid & 7;
+    pix = pix0 + (ptid >> 3);
     const int P = g.HO * g.WO;
-    const int n = pix / P, q = pix - n * P;
-    const int y = q / g.WO, xx = q - y * g.WO;
-    const uint32_t base = NCHW3 ? (uint32_t)((n * 3 * g.H + y * S) * g.W + xx * S) : (uint32_t)(((n * g.H + y * S) * g.W + xx * S) * CIN);
+    n = pix / P;
+    const int q = pix - n * P;
+    y = q / g.WO; xx = q - y * g.WO;
+    next_kb = 0;
+    gokmask = 0;
 #pragma unroll
     for (int grp = 0; grp < 4; ++grp) {
-      uint32_t off;
-      bool ok;
       if (NCHW3) {
         const int k = tm * tc::kBM + grp * 32 + (c4 >> 1) * 8;  // (ci, ky) pair start
         const int ci = k / (KS * KS), ky = (k / KS) % KS;
-        off = (uint32_t)((ci * g.H + ky) * g.W + (c4 & 1) * 4);
-        ok = pv && k < KTOT;
+        goff[grp] = (uint32_t)((ci * g.H + ky) * g.W + (c4 & 1) * 4);
+        gokmask |= (k < KTOT ? 1u : 0u) << grp;
       } else {
         const int k = tm * tc::kBM + grp * 32;
         const int tap = k / CIN, ci0 = k - tap * CIN;
         const int ky = tap / KS, kx = tap - ky * KS;
-        off = (uint32_t)((ky * g.W + kx) * CIN + ci0 + c4 * 4);
-        ok = pv && k < KTOT;
+        goff[grp] = (uint32_t)((ky * g.W + kx) * CIN + ci0 + c4 * 4);
+        gokmask |= (k < KTOT ? 1u : 0u) << grp;
       }
-      cp_async16(dst + (uint32_t)grp * (tc::kBK * tc::kRowBytes) + swz32(p, c4), ok ? (const void*)(x + base + off) : (const void*)x, ok);
+    }
+  }
+  __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) {
+    while (next_kb < kb) {  // k-blocks are visited in order: advance this thread's pixel by 32 per k-block
+      pix += tc::kBK; xx += tc::kBK;
+      while (xx >= g.WO) { xx -= g.WO; if (++y == g.HO) { y = 0; ++n; } }
+      ++next_kb;
+    }
+    const int c4 = ptid & 7, p = ptid >> 3;
+    const bool pv = pix < pix_end;
+    const uint32_t base = NCHW3 ? (uint32_t)((n * 3 * g.H + y * S) * g.W + xx * S) : (uint32_t)(((n * g.H + y * S) * g.W + xx * S) * CIN);
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+      const bool ok = pv && ((gokmask >> grp) & 1u);
+      cp_async16(dst + (uint32_t)grp * (tc::kBK * tc::kRowBytes) + swz32(p, c4), ok ? (const void*)(x + base + goff[grp]) : (const void*)x, ok);
     }
   }
 };
 
-// B operand (MN-major, COUT x 32 pixels) from dY stored [pixels][COUT]
+// B operand (MN-major, COUT x 32 pixels) from dY stored [pixels][COUT]: thread (p, c4) owns chunk c4 of pixel p in each 32-channel group
 template <int COUT>
 struct WgradDyLoader {
   static constexpr bool kMNMajor = true;
   const float* dy;
   WgradTiling t;
   int tm, pix0, pix_end;
-  __device__ __forceinline__ void start_tile(int tile, int) { t.decode(tile, tm, pix0, pix_end); }
+  const float* ptr;
+  int pix;
+  __device__ __forceinline__ void start_tile(int tile, int ptid) {
+    t.decode(tile, tm, pix0, pix_end);
+    pix = pix0 + (ptid >> 3);
+    ptr = dy + (size_t)pix * COUT + (ptid & 7) * 4;
+  }
   __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
+    const bool ok = pix + kb * tc::kBK < pix_end;
+    const float* p = ptr + (size_t)kb * tc::kBK * COUT;
 #pragma unroll
-    for (int q = ptid; q < COUT * 8; q += kProdThreads) {
-      const int c4 = q & 7, p = (q >> 3) & 31, grp = q >> 8;
-      const int pix = pix0 + kb * tc::kBK + p;
-      const bool ok = pix < pix_end;
-      cp_async16(dst + (uint32_t)grp * (tc::kBK * tc::kRowBytes) + swz32(p, c4), ok ? (const void*)(dy + (size_t)pix * COUT + grp * 32 + c4 * 4) : (const void*)dy, ok);
-    }
+    for (int grp = 0; grp < COUT / 32; ++grp)
+      cp_async16(dst + (uint32_t)grp * (tc::kBK * tc::kRowBytes) + swz32(ptid >> 3, ptid & 7), ok ? (const void*)(p + grp * 32) : (const void*)dy, ok);
   }
 };
 
@@ -442,7 +464,7 @@ int wgrad(const Geom& g, const float* x, const float* dy, float* dw, float beta,
   splits = hulc_cdiv(M, pps);
   WgradTiling t{splits, pps, M};
   WgradXLoader<CIN, KS, S, NCHW3> al{x, g, t, 0, 0, 0};
-  WgradDyLoader<COUT> bl{dy, t, 0, 0, 0};
+  WgradDyLoader<COUT> bl{dy, t, 0, 0, 0, nullptr, 0};
   WgradEpilogue ep{ws, splits, KTOT, COUT};
   HULC_TRY(launch<COUT>(al, bl, ep, mt * splits, pps / tc::kBK, st));
   HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(KTOT * COUT * 8, 256)), dim3(256), 0, st, (const float*)ws, dw, splits, KTOT, COUT, CIN, KS, NCHW3 ? 1 : 0, beta);

@@ -306,26 +306,43 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
 // ld % 4 == 0, K % 4 == 0 (K-major) / rows % 4 == 0 (MN-major), so every 16-byte chunk is entirely valid or entirely zero.
 // Work items: tile -> ((tm, tn), k-split).
 
+// Producer threads own a FIXED set of 16-byte chunks of every stage tile (chunk q = ptid + 256 i), so everything that does not
+// depend on the k-block — row pointers, bounds, swizzled destination offsets — is computed once per work item in start_tile and
+// issue() is one pointer bump, one predicate and one cp.async per chunk.  (The producers are bound by the latency of their own
+// instruction stream: the first version re-derived row / column / address per chunk per k-block, ~150 instructions per warp.)
+
 // stored rows x K row-major (K contiguous): K-major tile [ROWS][BK], 128-byte rows, SWIZZLE_128B
 template <int ROWS>
 struct KMajorLoader {
   static constexpr bool kMNMajor = false;
+  static constexpr int kChunks = ROWS * 8 / kProdThreads;  // per thread: rows (ptid >> 3) + 32 i, column chunk ptid & 7
   const float* base;
   int rows, K, ld, tiles_n, is_n, splits, kb_per_split;
   int row0, kb0;
-  __device__ __forceinline__ void start_tile(int tile, int) {
+  const float* ptr[kChunks];  // (row_i, first column of this thread's chunk in k-block 0 of the work item)
+  int kcol;                   // that column
+  uint32_t okmask;
+  __device__ __forceinline__ void start_tile(int tile, int ptid) {
     const int t2 = tile / splits;
     kb0 = (tile - t2 * splits) * kb_per_split;
     row0 = (is_n ? t2 % tiles_n : t2 / tiles_n) * ROWS;
+    kcol = kb0 * kBK + (ptid & 7) * 4;
+    okmask = 0;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      const int row = row0 + (ptid >> 3) + 32 * i;
+      const bool ok = row < rows;
+      okmask |= (ok ? 1u : 0u) << i;
+      ptr[i] = base + (size_t)(ok ? row : 0) * ld + kcol;
+    }
   }
   __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
-    const int k0 = (kb0 + kb) * kBK;
+    const bool kok = kcol + kb * kBK < K;
+    const int r = ptid >> 3, c = ptid & 7;
 #pragma unroll
-    for (int q = ptid; q < ROWS * 8; q += kProdThreads) {
-      const int r = q >> 3, c = q & 7;
-      const int row = row0 + r, k = k0 + c * 4;
-      const bool ok = row < rows && k < K;
-      cp_async16(dst + swz(r, c), ok ? (const void*)(base + (size_t)row * ld + k) : (const void*)base, ok);
+    for (int i = 0; i < kChunks; ++i) {
+      const bool ok = kok && ((okmask >> i) & 1u);
+      cp_async16(dst + swz(r + 32 * i, c), ok ? (const void*)(ptr[i] + kb * kBK) : (const void*)base, ok);
     }
   }
   __device__ __forceinline__ void split(uint32_t hi, uint32_t lo, int ptid) const {
@@ -339,28 +356,34 @@ struct KMajorLoader {
 template <int ROWS>
 struct MNMajorLoader {
   static constexpr bool kMNMajor = true;
+  static constexpr int RQ = ROWS / 4;                            // 16-byte chunks per k-row
+  static constexpr int kChunks = kBK * RQ / kProdThreads;        // per thread: column chunk ptid % RQ, k-rows ptid / RQ + (256 / RQ) i
+  static constexpr int kKStep = kProdThreads / RQ;
   const float* base;
   int rows, K, ld, tiles_n, is_n, splits, kb_per_split;
   int row0, kb0;
-  __device__ __forceinline__ void start_tile(int tile, int) {
+  const float* ptr;  // (k-row kb0 * 32 + ptid / RQ, column row0 + 4 (ptid % RQ))
+  int krow;
+  bool colok;
+  __device__ __forceinline__ void start_tile(int tile, int ptid) {
     const int t2 = tile / splits;
     kb0 = (tile - t2 * splits) * kb_per_split;
     row0 = (is_n ? t2 % tiles_n : t2 / tiles_n) * ROWS;
+    const int col = row0 + (ptid % RQ) * 4;
+    colok = col < rows;
+    krow = kb0 * kBK + ptid / RQ;
+    ptr = base + (size_t)krow * ld + (colok ? col : 0);
   }
   static __device__ __forceinline__ uint32_t offset(int q) {
-    constexpr int RQ = ROWS / 4;
     const int kk = q / RQ, r = (q % RQ) * 4;
     return (uint32_t)(r >> 5) * (kBK * kRowBytes) + swz32(kk, (r & 31) >> 2);
   }
   __device__ __forceinline__ void issue(int kb, uint32_t dst, int ptid) const {
-    const int k0 = (kb0 + kb) * kBK;
-    constexpr int RQ = ROWS / 4;
+    const float* p = ptr + (size_t)kb * kBK * ld;
 #pragma unroll
-    for (int q = ptid; q < kBK * RQ; q += kProdThreads) {
-      const int kk = q / RQ, r = (q % RQ) * 4;
-      const int row = row0 + r, k = k0 + kk;
-      const bool ok = row < rows && k < K;
-      cp_async16(dst + offset(q), ok ? (const void*)(base + (size_t)k * ld + row) : (const void*)base, ok);
+    for (int i = 0; i < kChunks; ++i) {
+      const bool ok = colok && (krow + kb * kBK + kKStep * i < K);
+      cp_async16(dst + offset(ptid + kProdThreads * i), ok ? (const void*)(p + (size_t)(kKStep * i) * ld) : (const void*)base, ok);
     }
   }
   __device__ __forceinline__ void split(uint32_t hi, uint32_t lo, int ptid) const {
