@@ -11,13 +11,15 @@
 //     [64 i, 64 i + 64); its CTA j owns the K-slice [512 j, 512 j + 512).  Each CTA loads ITS 64 x 512 block of W_hh once,
 //     rounds it to tf32 (round-to-nearest; the tensor core itself would truncate) and keeps it in shared memory (128 KB)
 //     in the UMMA operand layout for all S steps;
-//   * per step a CTA stages the B x 512 slice of the previous hidden state (producer warps: ld.global.cg -> cvt.rna.tf32
-//     -> swizzled st.shared, every load of the step in flight at once), issues 64 tcgen05.mma (kind::tf32, M=128 with the
-//     batch in the lower 64 rows, N=64, fp32 accumulator in TMEM), parks its partial tile in shared memory, and after ONE
-//     cluster barrier each CTA sums the four partials of its quarter of the rows through distributed shared memory in a
-//     fixed order, applies the epilogue and writes h_t;
-//   * steps are chained by per-tile arrival counters in global memory (release/acquire), not by a grid barrier: a CTA
-//     starts step s as soon as the 8 feature tiles that make up its K-slice have published step s-1.
+//   * per step sixteen producer warps — one per 32-wide k-block — each wait for the ONE feature tile of the previous step their
+//     k-block comes from (per-tile arrival counters in global memory, release / acquire: no grid barrier), fetch their B x 32
+//     piece of the previous hidden state (ld.global.cg, every load in flight at once), round it to tf32 and store it into the
+//     swizzled A tile; one thread issues 64 tcgen05.mma (kind::tf32, M = 64 batch rows, N = 64, fp32 accumulator in TMEM) with two
+//     barrier waits and three commits per step; the CTA parks its partial tile in shared memory and after ONE cluster barrier
+//     each CTA sums the four partials of its quarter of the rows through distributed shared memory in a fixed order, applies
+//     the epilogue (addend and gate prefetched while the MMAs run), writes h_t and publishes it with a release increment.
+// Measured (scripts/dbg_rnn_trace.py): 10.3 us per step — flag propagation 2.6, L2 load 1.1, stage + MMA 4.4, reduce + store +
+// release 2.2 — against 25 us (forward, 3xTF32) / 17 us (backward) for the same step as a split-K cluster GEMM launch.
 // A single tf32 pass with round-to-nearest on both operands keeps the action logits within 0.3 of the parity tolerance
 // (rtol 1e-3 / atol 1e-4) over the 32-step chain; accumulation, addend and activation are fp32.
 #include "common.cuh"

@@ -51,6 +51,13 @@ def test_step_matches_oracle(model, rnn_model, p, B, S, precision):
     assert rep["worst_grad"][1] < (1.5e-1 if precision == "tf32" else 2e-3), rep
 
 
+def test_gcbc_seq64_elman_tf32():
+    """BASELINE config 5 with the default ReLU-RNN decoder in the default (tensor-core) mode: the persistent recurrence kernel over a
+    64-step chain (single tf32 pass, round-to-nearest) must still hold the loss / logit tolerance."""
+    res = run_pair("gcbc", "rnn_decoder", B=2, S=64, p=0.0, device="cuda", max_window=64, precision="tf32")
+    compare(res, rtol=RTOL, atol=ATOL, **TF32)
+
+
 def test_gcbc_seq64_gru():
     """BASELINE config 5: GCBC, S=64 (needs max_position_embeddings=64), GRU decoder."""
     res = run_pair("gcbc", "gru_decoder", B=2, S=64, p=0.0, device="cuda", max_window=64, precision="fp32")
