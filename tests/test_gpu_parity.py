@@ -29,6 +29,7 @@ VARIANTS = [
     ("gcbc", "rnn_decoder", 0.0, 2, 8),
     ("mcil", "rnn_decoder", 0.0, 2, 8),
     ("hulc", "rnn_decoder", 0.1, 3, 32),  # full window, odd batch
+    ("mcil", "rnn_decoder", 0.0, 2, 32),  # bidirectional tanh posterior over the full window (persistent recurrence, both directions)
 ]
 
 
