@@ -24,6 +24,7 @@ struct TcEpilogue {
   int ldg;
   int BN, tiles_n;
   int splits;  // > 1: split-K over a thread-block cluster of that size (tile index = output tile * splits + k-slice)
+  unsigned vec;  // 16-byte-aligned rows: bit 0 = C, bit 1 = addend, bit 2 = gate (their epilogue reads go as float4)
 
   // The epilogue stages are applied as short vector passes over W contiguous columns of one row (uniform branches hoisted
   // out of the element loops keeps the unrolled code small — it is instruction-fetch bound otherwise).  Dropout is applied
@@ -38,13 +39,29 @@ struct TcEpilogue {
     }
     if (addend) {
       const float* a = addend + (size_t)(add_mod ? m % add_mod : m) * ldadd + n0;
+      if (W >= 4 && (vec & 2)) {
 #pragma unroll
-      for (int j = 0; j < W; ++j) o[j] += a[j];
+        for (int j = 0; j + 3 < W; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(a + j);
+          o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) o[j] += a[j];
+      }
     }
     if (beta != 0.f) {
       const float* c = C + (size_t)m * ldc + n0;
+      if (W >= 4 && (vec & 1)) {
 #pragma unroll
-      for (int j = 0; j < W; ++j) o[j] += beta * c[j];
+        for (int j = 0; j + 3 < W; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(c + j);
+          o[j] += beta * t.x; o[j + 1] += beta * t.y; o[j + 2] += beta * t.z; o[j + 3] += beta * t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) o[j] += beta * c[j];
+      }
     }
     if ((act & 3) == 1) {
 #pragma unroll
@@ -54,7 +71,18 @@ struct TcEpilogue {
       for (int j = 0; j < W; ++j) o[j] = tanhf(o[j]);
     }
     if (gate) {
-      const float* g = gate + (size_t)m * ldg + n0;
+      const float* gp = gate + (size_t)m * ldg + n0;
+      float g[W];
+      if (W >= 4 && (vec & 4)) {
+#pragma unroll
+        for (int j = 0; j + 3 < W; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(gp + j);
+          g[j] = t.x; g[j + 1] = t.y; g[j + 2] = t.z; g[j + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) g[j] = gp[j];
+      }
       if (act & 4) {
 #pragma unroll
         for (int j = 0; j < W; ++j) o[j] *= 1.f - g[j] * g[j];
@@ -257,6 +285,8 @@ HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N
   ep.C = C; ep.M = M; ep.N = N; ep.ldc = ldc; ep.alpha = alpha; ep.beta = beta; ep.bias = bias; ep.addend = addend; ep.ldadd = ldadd;
   ep.add_mod = add_mod; ep.act = act; ep.gate = gate; ep.ldg = ldg;
   ep.BN = 0; ep.tiles_n = 0;
+  auto aligned = [](const float* p, int ld) { return p && (reinterpret_cast<size_t>(p) & 15) == 0 && (ld & 3) == 0; };
+  ep.vec = (aligned(C, ldc) ? 1u : 0u) | (aligned(addend, ldadd) ? 2u : 0u) | (aligned(gate, ldg) ? 4u : 0u);
   cudaStream_t st = (cudaStream_t)stream;
   int bn;
   choose_config(M, N, K, bn, ep.splits);

@@ -25,7 +25,9 @@ RELU, TANH, GATE_TANH = 1, 2, 4
 _POISON = bool(int(os.environ.get("HULC_B200_POISON", "0")))
 
 # parameters that must sit next to each other in the flat buffer so one GEMM covers them (decoder heads:
-# logit_probs | means | log_scales | gripper — the row layout hulc_logistic_loss expects)
+# logit_probs | means | log_scales | gripper — the row layout hulc_logistic_loss expects).  The group is padded with zero
+# rows to a multiple of 4 (182 -> 184) so that the fused [rows, heads] activations have 16-byte-aligned rows and all three
+# head products run on the tensor cores; the pad rows belong to no state_dict key and stay zero under Adam (zero gradient).
 _HEAD_ORDER = ("prob_fc", "mean_fc", "log_scale_fc", "gripper_fc")
 
 
@@ -39,12 +41,16 @@ class ParamStore:
         groups = [[k] for k in keys] + [head_w, head_b]
         self.offsets: Dict[str, Tuple[int, tuple]] = {}
         off = 0
+        self.n_heads = sum(spec[k][0] for k in head_w)
+        self.n_heads_padded = (self.n_heads + 3) // 4 * 4
         for grp in groups:
             off = (off + 3) // 4 * 4  # 16-byte alignment per group
             for k in grp:
                 n = int(math.prod(spec[k])) if len(spec[k]) else 1
                 self.offsets[k] = (off, tuple(spec[k]))
                 off += n
+            if grp is head_w and head_w:
+                off += (self.n_heads_padded - self.n_heads) * spec[head_w[0]][1]
         self.numel = (off + 3) // 4 * 4
         self.device = torch.device(device)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
@@ -63,7 +69,7 @@ class ParamStore:
         self.g = {k: self._view(self.grad, k) for k in self.keys}
         if self._head_w:  # fused views over the decoder-head group
             o, (_, n_in) = self.offsets[self._head_w[0]]
-            rows = sum(self.offsets[k][1][0] for k in self._head_w)
+            rows = self.n_heads_padded
             self.heads_w = self.flat[o : o + rows * n_in].view(rows, n_in)
             self.heads_gw = self.grad[o : o + rows * n_in].view(rows, n_in)
             ob, _ = self.offsets[self._head_b[0]]
@@ -177,9 +183,13 @@ class HulcEngine:
     def _tc_mode(self, M, N, K, role):
         """0 = exact fp32 on CUDA cores; 1 = tf32 (backward products: they only feed gradients); 3 = 3xTF32 (forward
         products, whose outputs are held to the fp32 parity tolerance)."""
-        if not self.tc or 2.0 * M * N * K < 1e8 or K < 64 or N < 32:
-            return 0  # tiny products: the CUDA-core kernel's launch is as cheap and it needs no alignment
-        return 3 if role == "fwd" else 1
+        if not self.tc or N < 32 or K < 32:
+            return 0
+        # thresholds from scripts/dbg_gemm_small.py (B200, back-to-back launches): the 1-pass kernel beats the CUDA-core one
+        # from K = 64 up (and at K = 32 when there are >= 8 row tiles); the 3-pass kernel only on many rows or big products
+        if role == "bwd":
+            return 1 if (K >= 64 or M >= 1024) else 0
+        return 3 if K >= 64 and (M >= 256 or 2.0 * M * N * K >= 1e8) else 0
 
     def gemm_fwd(self, A, B, C=None, **kw):
         M, K = (A.shape[1], A.shape[0]) if kw.get("transA") else A.shape
@@ -592,9 +602,12 @@ class HulcEngine:
              addend=None if kind == "gru" else P[f"{rp}.bias_hh_l1"].view(1, -1), add_mod=1)
         sv1 = self._rnn_fwd("dec.l1", pre1, P[f"{rp}.weight_hh_l1"], P[f"{rp}.bias_hh_l1"], hb[1], 0, S, nB, kind=kind)
         h1_all = hb[1][1 : S + 1].view(S * nB, H)
-        n_heads = ps.heads_w.shape[0]
-        heads = self.gemm_fwd(h1_all, ps.heads_w, self.buf("dec.heads", S * nB, n_heads), transB=True, bias=ps.heads_b)
-        out["heads_tm"] = heads.view(S, nB, n_heads)
+        # heads and their gradient live in [rows, n_pad] buffers (n_pad = n_heads rounded up to 4: aligned rows for the
+        # tensor-core products); the pad columns are 0 (zero weight rows / never written) and hidden from the consumers
+        n_heads, n_pad = ps.n_heads, ps.n_heads_padded
+        heads_p = self.gemm_fwd(h1_all, ps.heads_w, self.buf("dec.heads", S * nB, n_pad), transB=True, bias=ps.heads_b)
+        heads = heads_p[:, :n_heads]
+        out["heads_tm"] = heads_p.view(S, nB, n_pad)[:, :, :n_heads]
 
         # ---- losses (logistic_decoder_rnn.py:121-155,184-231; gripper_control.py:16-36) ----------------------------------------
         has_grip = self.model != "mcil"
@@ -605,7 +618,8 @@ class HulcEngine:
             else:
                 ops.strided_copy(acts_all[b0 : b0 + Bm], batch[m]["actions"])
         out["actions_tcp"] = acts_all
-        dheads = self.buf("dec.dheads", S * nB, n_heads)
+        dheads_p = self.buf("dec.dheads", S * nB, n_pad, zero=True)
+        dheads = dheads_p[:, :n_heads]
         for i, (m, b0, Bm) in enumerate(zip(mods, b0s, Bs)):
             ops.logistic_loss(heads, acts_all, dheads, losses[4 * i : 4 * i + 2], nB, S, b0, Bm, time_major=True, n_dims=self.n_dims,
                               n_mix=self.n_mix, num_classes=self.num_classes, has_gripper=has_grip, gripper_alpha=self.gripper_alpha,
@@ -650,9 +664,9 @@ class HulcEngine:
         dgoal = self.buf("dgoal", nB, 32)
 
         # heads
-        self.gemm_bwd(dheads, h1_all, ps.heads_gw, transA=True, beta=1.0)
-        colsum(dheads, ps.heads_gb, beta=1.0)
-        dh1 = self.gemm_bwd(dheads, ps.heads_w, self.buf("dec.dh1", S * nB, H))
+        self.gemm_bwd(dheads_p, h1_all, ps.heads_gw, transA=True, beta=1.0)
+        colsum(dheads_p, ps.heads_gb, beta=1.0)
+        dh1 = self.gemm_bwd(dheads_p, ps.heads_w, self.buf("dec.dh1", S * nB, H))
         # layer 1
         dpre1, dgh1 = self._rnn_bwd("dec.l1", dh1, P[f"{rp}.weight_hh_l1"], hb[1], 0, S, nB, kind=kind, saved=sv1)
         self.gemm_bwd(dgh1, hb[1][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l1"], transA=True, beta=1.0)
