@@ -334,6 +334,29 @@ __global__ void drop_rows_kernel(float* __restrict__ C, int M, int N, int ldc, D
   C[(size_t)m * ldc + n] *= drop_factor(drop, (unsigned long long)i);
 }
 
+// same, four consecutive columns per thread: one Philox call yields the four keep decisions (philox_uniform(idx) reads word
+// idx & 3 of counter idx >> 2), and the row is read / written as float4
+__global__ void drop_rows_vec4_kernel(float* __restrict__ C, int M, int N4, int ldc, DropSpec drop) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)M * N4) return;
+  const int m = (int)(q / N4), n = (int)(q - (long long)m * N4) * 4;
+  float4* p = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
+  float4 v = *p;
+  bool k0, k1, k2, k3;
+  if (drop.keep) {
+    const uchar4 k = *reinterpret_cast<const uchar4*>(drop.keep + (unsigned long long)q * 4);
+    k0 = k.x != 0; k1 = k.y != 0; k2 = k.z != 0; k3 = k.w != 0;
+  } else {
+    const uint4 r = philox4x32(rng_seed(drop.seed, drop.seed_ptr), drop.site, (unsigned long long)q);
+    const float s = 1.0f / 16777216.0f;
+    k0 = (float)(r.x >> 8) * s >= drop.p; k1 = (float)(r.y >> 8) * s >= drop.p;
+    k2 = (float)(r.z >> 8) * s >= drop.p; k3 = (float)(r.w >> 8) * s >= drop.p;
+  }
+  v.x = k0 ? v.x * drop.scale : 0.f; v.y = k1 ? v.y * drop.scale : 0.f;
+  v.z = k2 ? v.z * drop.scale : 0.f; v.w = k3 ? v.w * drop.scale : 0.f;
+  *p = v;
+}
+
 // out[c] = beta*out[c] + sum_r X[r*ldx + c]
 // Column sums out[c] = beta*out[c] + sum_r X[r][c].  A block of 256 threads = CL column lanes (VEC columns each) x 256/CL row
 // lanes; the rows are split over gridDim.y blocks whose partial sums meet in `partial` and are added in a fixed order by the
@@ -429,6 +452,10 @@ __global__ void scale_vec_kernel(float* x, int n, float s) {
 // shared with gemm_tc.cu
 int hulc_apply_dropout_rows(float* C, int M, int N, int ldc, DropSpec drop, cudaStream_t st) {
   if (drop.p <= 0.f) return 0;
+  if (N % 4 == 0 && ldc % 4 == 0 && (reinterpret_cast<size_t>(C) & 15) == 0 && (reinterpret_cast<size_t>(drop.keep) & 3) == 0) {
+    HULC_LAUNCH(drop_rows_vec4_kernel, dim3(hulc_cdiv((long long)M * (N / 4), 256)), dim3(256), 0, st, C, M, N / 4, ldc, drop);
+    HULC_RETURN_LAST();
+  }
   HULC_LAUNCH(drop_rows_kernel, dim3(hulc_cdiv((long long)M * N, 256)), dim3(256), 0, st, C, M, N, ldc, drop);
   HULC_RETURN_LAST();
 }

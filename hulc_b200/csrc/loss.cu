@@ -319,29 +319,46 @@ __global__ void __launch_bounds__(256) clip_loss_kernel(const float* __restrict_
   float* L = nt + n;                           // [n][n] logits, then gradient G
   float* rlse = L + (size_t)n * n;             // [n] row logsumexp
   float* clse = rlse + n;                      // [n] column logsumexp
+  float* U = clse + n;                         // [2n][D] un-normalised feature gradients
+  float* pr = U + 2 * (size_t)n * D;           // [2n] their projections on the features
   const int tid = threadIdx.x;
+  int* flag = reinterpret_cast<int*>(pr);      // mask bytes fetched in parallel, compacted in row order by one thread
+  for (int i = tid; i < n; i += blockDim.x) flag[i] = (!mask || mask[i]) ? 1 : 0;
+  for (int i = tid; i < n * D; i += blockDim.x) { d_im[i] = 0.f; d_tx[i] = 0.f; }
+  __syncthreads();
   if (tid == 0) {
     int c = 0;
     for (int i = 0; i < n; ++i)
-      if (!mask || mask[i]) sel[c++] = i;
+      if (flag[i]) sel[c++] = i;
     s_nv = c;
   }
   __syncthreads();
   const int nv = s_nv;
-  for (int i = tid; i < n * D; i += blockDim.x) { d_im[i] = 0.f; d_tx[i] = 0.f; }
   if (nv == 0) {  // reference: dummy pass scaled by 0 -> zero loss, zero gradients
     if (tid == 0) { loss[0] = 0.f; d_logit_scale[0] = 0.f; }
     return;
   }
   const float s = expf(logit_scale[0]);
-  for (int r = tid; r < nv; r += blockDim.x) {
-    const float* pi = im + (size_t)sel[r] * D;
-    const float* pt = tx + (size_t)sel[r] * D;
-    float qi = 0.f, qt = 0.f;
-    for (int k = 0; k < D; ++k) { qi += pi[k] * pi[k]; qt += pt[k] * pt[k]; }
-    qi = sqrtf(qi); qt = sqrtf(qt);
-    na[r] = qi; nt[r] = qt;
-    for (int k = 0; k < D; ++k) { a[r * D + k] = pi[k] / qi; t[r * D + k] = pt[k] / qt; }
+  // selected rows -> shared memory (coalesced), then the norms and the normalisation work on shared memory only
+  for (int e = tid; e < nv * D; e += blockDim.x) {
+    const int r = e / D, k = e - r * D;
+    a[e] = im[(size_t)sel[r] * D + k];
+    t[e] = tx[(size_t)sel[r] * D + k];
+  }
+  __syncthreads();
+  for (int r = tid; r < 2 * nv; r += blockDim.x) {
+    const bool is_t = r >= nv;
+    const int i = is_t ? r - nv : r;
+    const float* p = (is_t ? t : a) + i * D;
+    float q = 0.f;
+    for (int k = 0; k < D; ++k) q += p[k] * p[k];
+    (is_t ? nt : na)[i] = sqrtf(q);
+  }
+  __syncthreads();
+  for (int e = tid; e < nv * D; e += blockDim.x) {
+    const int r = e / D;
+    a[e] = a[e] / na[r];
+    t[e] = t[e] / nt[r];
   }
   __syncthreads();
   for (int e = tid; e < nv * nv; e += blockDim.x) {
@@ -379,23 +396,31 @@ __global__ void __launch_bounds__(256) clip_loss_kernel(const float* __restrict_
   ds = block_sum(ds, red);
   if (tid == 0) d_logit_scale[0] = ds * s;
   __syncthreads();
-  // d a_i = s * sum_j G_ij t_j ; d t_j = s * sum_i G_ij a_i ; then through the L2 normalisation
-  for (int r = tid; r < 2 * nv; r += blockDim.x) {
-    bool is_t = r >= nv;
-    int i = is_t ? r - nv : r;
-    const float* self = (is_t ? t : a) + i * D;
+  // d a_i = s * sum_j G_ij t_j ; d t_j = s * sum_i G_ij a_i ; then through the L2 normalisation.  One (row, feature) pair per
+  // thread and pass; the un-normalised gradients are parked in shared memory.
+  for (int e = tid; e < 2 * nv * D; e += blockDim.x) {
+    const int r = e / D, k = e - r * D;
+    const bool is_t = r >= nv;
+    const int i = is_t ? r - nv : r;
     const float* other = is_t ? a : t;
-    float nrm = is_t ? nt[i] : na[i];
-    float* dst = (is_t ? d_tx : d_im) + (size_t)sel[i] * D;
+    float gk = 0.f;
+    for (int j = 0; j < nv; ++j) gk += (is_t ? L[j * nv + i] : L[i * nv + j]) * other[j * D + k];
+    U[e] = gk * s;
+  }
+  __syncthreads();
+  for (int r = tid; r < 2 * nv; r += blockDim.x) {
+    const float* self = r >= nv ? t + (r - nv) * D : a + r * D;
     float proj = 0.f;
-    for (int k = 0; k < D; ++k) {
-      float gk = 0.f;
-      for (int j = 0; j < nv; ++j) gk += (is_t ? L[j * nv + i] : L[i * nv + j]) * other[j * D + k];
-      gk *= s;
-      dst[k] = gk;  // stash un-normalised gradient
-      proj += gk * self[k];
-    }
-    for (int k = 0; k < D; ++k) dst[k] = (dst[k] - self[k] * proj) / nrm;
+    for (int k = 0; k < D; ++k) proj += U[r * D + k] * self[k];
+    pr[r] = proj;
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * nv * D; e += blockDim.x) {
+    const int r = e / D, k = e - r * D;
+    const bool is_t = r >= nv;
+    const int i = is_t ? r - nv : r;
+    const float self = (is_t ? t : a)[i * D + k];
+    (is_t ? d_tx : d_im)[(size_t)sel[i] * D + k] = (U[e] - self * pr[r]) / (is_t ? nt[i] : na[i]);
   }
 }
 
@@ -469,7 +494,7 @@ HULC_API int hulc_sum(const float* x, int n, float* out, float scale, void* stre
 HULC_API int hulc_clip_loss(const float* im, const float* tx, const float* logit_scale, const unsigned char* mask, float* loss, float* d_im,
                             float* d_tx, float* d_logit_scale, int n, int D, float grad_scale, void* stream) {
   if (n <= 0) return 0;
-  size_t smem = sizeof(float) * ((size_t)n + 2 * (size_t)n * D + 2 * n + (size_t)n * n + 2 * n);
+  size_t smem = sizeof(float) * ((size_t)n + 2 * (size_t)n * D + 2 * n + (size_t)n * n + 2 * n + 2 * (size_t)n * D + 2 * n);
   if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
   auto kfn = clip_loss_kernel;
   if (smem > 48 * 1024) HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
