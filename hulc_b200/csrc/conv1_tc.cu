@@ -18,6 +18,7 @@
 //   * four warps run the epilogue: sum the two accumulators, bias + ReLU, channels-last stores (128 B per pixel).
 #include "common.cuh"
 #include "tc_pipeline.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -432,6 +433,216 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward without an im2col copy: the tensor core reads the raw input rows.
+//
+// For a fixed (ci, ky) the im2col row of output pixel (oy, ox) is the 8 consecutive floats x[ci][4 oy + ky][4 ox .. 4 ox + 7]:
+// rows of consecutive ox start 16 bytes apart and overlap by half.  That IS a K-major, un-swizzled UMMA operand — core matrix
+// = 8 rows x 16 bytes at a 16-byte pitch (128 contiguous bytes), the second K core matrix 16 bytes further (LBO = 16), the
+// next 8 rows 128 bytes further (SBO = 128) — so an MMA of K = 8 per (ci, ky) needs no staging pass at all.  To keep the
+// 16-byte pitch across output rows the input rows of a work unit are laid out in shared memory by row phase: sub-band
+// (p = y mod 4, ci) holds rows y = 4 j + p for j = oy0 .. oy0 + R at a pitch of W floats = W/4 pixels, and with
+// m' = (W/4) * (oy - oy0) + ox the operand row of (oy, ox) for tap row ky sits at  sub-band(ky mod 4, ci) + (ky / 4) * 4W + 16 m'.
+// Four TMA boxes per unit (one per phase: every 4th row through the tensor map's element stride) write exactly that layout;
+// ox = WO .. W/4 - 1 are dummy pixels (1 in 50).
+//
+// A unit is R output rows of one frame (R * W/4 <= 256 = two M = 128 accumulators: 5 rows of the 200x200 camera, 12 of the 84x84
+// one).  Warps: 0-3 epilogue | 4-5 MMA issuers (one per accumulator half, 24 MMAs each per unit) | 6 TMA producer.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kVwSlots = 3;
+constexpr int kVwWBytes = 24 * 1024;   // weights: 24 (ci, ky) blocks of [2 k-halves][4 groups of 8 channels][8][4 floats]
+constexpr int kVwThr = (kEpiWarps + 3) * 32;
+
+struct V1Params {
+  const float* w;
+  const float* b;
+  float* y;
+  unsigned* bits;
+  int N, H, W, HO, WO;
+  int Wq, R, UPF;        // W / 4, output rows per unit, units per frame
+  int sub_bytes;         // (R + 1) * W * 4: one (phase, ci) sub-band
+  int ph_stride;         // three sub-bands rounded up to 128 bytes (TMA destinations are 128-byte aligned)
+  int slot_bytes;        // 12 sub-bands + slack for the reads of the dummy rows past the last one
+  int relu;
+};
+
+struct V1Bars {
+  uint64_t band_full[kVwSlots];
+  uint64_t band_empty[kVwSlots];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kVwThr, 1) conv1_view_fwd_kernel(const __grid_constant__ CUtensorMap xmap, V1Params p, int num_units) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* w_smem = smem;
+  unsigned char* band_smem = smem + kVwWBytes;
+  V1Bars* bars = reinterpret_cast<V1Bars*>(band_smem + (size_t)kVwSlots * p.slot_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kVwSlots; ++s) {
+      mbar_init(&bars->band_full[s], 1);
+      mbar_init(&bars->band_empty[s], 2);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], 2);
+      mbar_init(&bars->tmem_empty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+    tma::prefetch_map(&xmap);
+  }
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 128);
+  // the slack behind each slot is read (for dummy rows only) but never written by the TMA: keep it finite
+  for (int i = threadIdx.x; i < kVwSlots * p.slot_bytes / 16; i += kVwThr) reinterpret_cast<float4*>(band_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // resident weights, un-swizzled K-major core matrices: element (n, k = cky * 8 + kx) -> [cky][kx / 4][n / 8][n % 8][kx % 4]
+  for (int q = threadIdx.x; q < kCout * 48; q += kVwThr) {
+    const int n = q / 48, kq = q - n * 48;  // kq: 16-byte piece of the 192-float row
+    const int cky = kq >> 1, half = kq & 1;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * kKtot + kq * 4));
+    *reinterpret_cast<float4*>(w_smem + cky * 1024 + half * 512 + (n >> 3) * 128 + (n & 7) * 16) = v;
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp < kEpiWarps) {
+    // ================================ epilogue: thread = one pixel of each accumulator half ================================
+    const int r = warp * 32 + lane;
+    float bias[kCout];
+#pragma unroll
+    for (int j = 0; j < kCout; ++j) bias[j] = p.b ? __ldg(p.b + j) : 0.f;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int n = unit / p.UPF, oy0 = (unit - n * p.UPF) * p.R;
+      mbar_wait(&bars->tmem_full[a], (it >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t v[2][32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 64), v[0]);
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 64 + 32), v[1]);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);  // the values are in registers: the accumulators may be reused
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = h * 128 + r;
+        const int dy = m / p.Wq, ox = m - dy * p.Wq;
+        if (dy >= p.R || ox >= p.WO || oy0 + dy >= p.HO) continue;
+        const size_t pix = (size_t)(n * p.HO + oy0 + dy) * p.WO + ox;
+        float* dst = p.y + pix * kCout;
+        unsigned om = 0u;
+#pragma unroll
+        for (int j = 0; j < kCout; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[h][j]) + bias[j], __uint_as_float(v[h][j + 1]) + bias[j + 1], __uint_as_float(v[h][j + 2]) + bias[j + 2],
+                                 __uint_as_float(v[h][j + 3]) + bias[j + 3]);
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (o.x > 0.f) om |= 1u << j;
+          if (o.y > 0.f) om |= 1u << (j + 1);
+          if (o.z > 0.f) om |= 1u << (j + 2);
+          if (o.w > 0.f) om |= 1u << (j + 3);
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+        if (p.bits) p.bits[pix] = om;
+      }
+    }
+  } else if (warp < kEpiWarps + 2) {
+    // ================================ MMA issuers: accumulator half h = rows m' = 128 h .. 128 h + 127 ================================
+    if (lane == 0) {
+      const int h = warp - kEpiWarps;
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, kCout, false, false);
+      const uint64_t a0 = make_smem_desc(smem_u32(band_smem) + (uint32_t)h * 2048u, 16u, 128u, 0u);
+      const uint64_t b0 = make_smem_desc(smem_u32(w_smem), 512u, 128u, 0u);
+      uint32_t aoff[24];  // (ci, ky) -> offset of its operand in the slot, in 16-byte units
+#pragma unroll
+      for (int cky = 0; cky < 24; ++cky) {
+        const int ci = cky >> 3, ky = cky & 7;
+        aoff[cky] = (uint32_t)((ky & 3) * p.ph_stride + ci * p.sub_bytes + (ky >> 2) * p.W * 4) >> 4;
+      }
+      const uint32_t slot16 = (uint32_t)p.slot_bytes >> 4;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int a = it & 1, slot = it % kVwSlots;
+        mbar_wait(&bars->tmem_empty[a], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&bars->band_full[slot], (it / kVwSlots) & 1);
+        tc_fence_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)(a * 64 + h * 32);
+        const uint64_t as = a0 + (uint64_t)(slot * slot16);
+#pragma unroll
+        for (int cky = 0; cky < 24; ++cky) umma_tf32(d, as + aoff[cky], b0 + (uint32_t)(cky * 64), idesc, (uint32_t)(cky != 0));
+        umma_commit(&bars->band_empty[slot]);
+        umma_commit(&bars->tmem_full[a]);
+      }
+    }
+  } else {
+    // ================================ TMA producer: one box per row phase and unit ================================
+    if (lane == 0) {
+      const uint32_t box_bytes = 12u * (uint32_t)p.sub_bytes, ph_bytes = (uint32_t)p.ph_stride;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int slot = it % kVwSlots;
+        mbar_wait(&bars->band_empty[slot], ((it / kVwSlots) & 1) ^ 1);
+        const int n = unit / p.UPF, oy0 = (unit - n * p.UPF) * p.R;
+        tma::expect_tx(&bars->band_full[slot], box_bytes);
+        const uint32_t dst = smem_u32(band_smem) + (uint32_t)slot * (uint32_t)p.slot_bytes;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) tma::load_4d(dst + ph * ph_bytes, &xmap, &bars->band_full[slot], 0, 4 * oy0 + ph, 0, n);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+bool g_conv1_view = [] {
+  const char* e = getenv("HULC_B200_CONV1_VIEW");
+  return !(e && e[0] == '0');
+}();
+
+// cudaErrorNotSupported when the geometry does not fit (the caller then uses the band kernel below).
+int conv1_view_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st) {
+  const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
+  if (!g_conv1_view || HO <= 0 || WO <= 0 || (W & 3) || (H & 3) || W > 256 || (reinterpret_cast<size_t>(x) & 15) || (reinterpret_cast<size_t>(w) & 15) ||
+      (reinterpret_cast<size_t>(y) & 15))
+    return (int)cudaErrorNotSupported;
+  V1Params p;
+  p.w = w; p.b = b; p.y = y; p.bits = relu_bits; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.relu = relu;
+  p.Wq = W / 4;
+  p.R = min(HO, 256 / p.Wq);
+  if (p.R < 1) return (int)cudaErrorNotSupported;
+  p.UPF = hulc_cdiv(HO, p.R);
+  p.sub_bytes = (p.R + 1) * W * 4;
+  p.ph_stride = (3 * p.sub_bytes + 127) / 128 * 128;
+  // reads reach the last sub-band + one more row + 16 * 255 + 32 bytes into the slot
+  p.slot_bytes = (max(4 * p.ph_stride, 3 * p.ph_stride + 2 * p.sub_bytes + W * 4 + 16 * 256 + 32) + 1023) / 1024 * 1024;
+  const size_t smem = 1024 + kVwWBytes + (size_t)kVwSlots * p.slot_bytes + sizeof(V1Bars);
+  if (smem > 227 * 1024 || 4 * (p.R + 1) > 256) return (int)cudaErrorNotSupported;
+  const long long units = (long long)N * p.UPF;
+  if (units >= (1ll << 31)) return (int)cudaErrorNotSupported;
+  // x[n][ci][y][xx]; a box takes every 4th row (element stride 4) starting at row 4 oy0 + phase: [ci][j][xx] in shared memory.
+  // Rows past the frame read as zero.
+  CUtensorMap m;
+  const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)N};
+  const uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)3 * H * W * 4};
+  const uint32_t box[4] = {(uint32_t)W, (uint32_t)(4 * (p.R + 1)), 3, 1};
+  const uint32_t es[4] = {1, 4, 1, 1};
+  if (tma::make_map(&m, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, es) != 0) return (int)cudaErrorNotSupported;
+  HULC_TRY(cudaFuncSetAttribute(conv1_view_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HULC_LAUNCH(conv1_view_fwd_kernel, dim3((unsigned)min((long long)kNumSMs, units)), dim3(kVwThr), smem, st, m, p, (int)units);
+  HULC_RETURN_LAST();
+}
+
 }  // namespace
 
 // Returns cudaErrorNotSupported when the geometry does not fit the band scheme (the caller then uses the gather kernel).
@@ -439,6 +650,8 @@ int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y
   const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
   if (HO <= 0 || WO <= 0 || WO > kBM || (W & 3) || (reinterpret_cast<size_t>(x) & 15) || (reinterpret_cast<size_t>(w) & 15) || (reinterpret_cast<size_t>(y) & 15))
     return (int)cudaErrorNotSupported;
+  const int rc_view = conv1_view_fwd(x, w, b, y, relu_bits, N, H, W, relu, st);
+  if (rc_view != (int)cudaErrorNotSupported) return rc_view;
   C1Params p;
   p.x = x; p.w = w; p.b = b; p.y = y; p.bits = relu_bits; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.relu = relu;
   p.RT = min(HO, kBM / WO);
