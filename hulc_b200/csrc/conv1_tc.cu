@@ -449,6 +449,8 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
 //
 // A unit is R output rows of one frame (R * W/4 <= 256 = two M = 128 accumulators: 5 rows of the 200x200 camera, 12 of the 84x84
 // one).  Warps: 0-3 epilogue | 4-5 MMA issuers (one per accumulator half, 24 MMAs each per unit) | 6 TMA producer.
+// (The weight gradient cannot do the same: its operands are MN-major, and an un-swizzled MN-major tf32 descriptor reads zeros —
+// scripts/micro/mn_noswz_probe.cu — so conv1_band_wgrad_kernel keeps its staging warps.)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kVwSlots = 3;
 constexpr int kVwWBytes = 24 * 1024;   // weights: 24 (ci, ky) blocks of [2 k-halves][4 groups of 8 channels][8][4 floats]
