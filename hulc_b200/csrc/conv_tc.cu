@@ -485,7 +485,9 @@ HULC_API int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, 
   if ((long long)N * H * W * CIN >= (1ll << 32) / 4) return (int)cudaErrorInvalidValue;  // 32-bit element offsets
   switch (conv_kind(CIN, COUT, KS, S)) {
     case 1: {
-      if (g_use_tma) {  // band-staged kernel (conv1_tc.cu) when the geometry fits; otherwise the im2col gather below
+      // every kernel of the first layer reads the NCHW rows in 16-byte pieces
+      if ((W & 3) || (reinterpret_cast<size_t>(x) & 15)) return (int)cudaErrorInvalidValue;
+      if (g_use_tma) {  // view / band-staged kernel (conv1_tc.cu) when the geometry fits; otherwise the im2col gather below
         const int rc = hulc_conv1_band_fwd(x, w, b, y, relu_bits, N, H, W, relu, st);
         if (rc != (int)cudaErrorNotSupported) return rc;
       }
@@ -529,7 +531,7 @@ HULC_API int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, fl
   if ((long long)N * H * W * CIN >= (1ll << 32) / 4) return (int)cudaErrorInvalidValue;
   switch (conv_kind(CIN, COUT, KS, S)) {
     case 1: {
-      if (!x_nchw) return (int)cudaErrorInvalidValue;
+      if (!x_nchw || (W & 3) || (reinterpret_cast<size_t>(x) & 15)) return (int)cudaErrorInvalidValue;
       if (g_use_tma) {  // band-staged kernel (conv1_tc.cu): per-CTA partials, reduced in a fixed order below
         int ctas = 0;
         const int rc = hulc_conv1_band_wgrad_partials(x, dy, ws, wsb, db != nullptr, N, H, W, &ctas, st);

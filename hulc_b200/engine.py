@@ -258,8 +258,11 @@ class HulcEngine:
 
     def _encoder_fwd(self, which, frames: List[torch.Tensor], emb):
         frames = self._normalised_frames(which, frames)
-        if self.tc:
-            return self._encoder_fwd_tc(which, frames, emb)
+        # the tensor-core first layer reads the NCHW rows in 16-byte pieces: other widths take the exact-fp32 kernels
+        if self.tc and frames[0].shape[-1] % 4 == 0:
+            ctx = self._encoder_fwd_tc(which, frames, emb)
+            ctx["tc"] = True
+            return ctx
         P = self.ps.p
         pre = f"perceptual_encoder.rgb_{which}_encoder"
         N = sum(f.shape[0] for f in frames)
@@ -286,7 +289,7 @@ class HulcEngine:
         return dict(frames=frames, a1=a1, a2=a2, a3=a3, acts=acts, stats=stats, names=names, pre=pre)
 
     def _encoder_bwd(self, which, ctx, demb):
-        if self.tc:
+        if ctx.get("tc"):
             return self._encoder_bwd_tc(which, ctx, demb)
         P, G = self.ps.p, self.ps.g
         pre, a1, a2, a3 = ctx["pre"], ctx["a1"], ctx["a2"], ctx["a3"]

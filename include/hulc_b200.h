@@ -98,7 +98,9 @@ int hulc_conv2d_wgrad(const float* x, const float* dy, float* dw, float beta, in
                       float* workspace, size_t workspace_bytes, void* stream);
 /* The same three layers on the tensor cores (tcgen05.mma kind::tf32) with channels-last activations: x NHWC [N,H,W,CIN] (or,
  * for the 3-channel first layer, the reference's NCHW frames: fwd reads them as they are, wgrad with x_nchw = 1);
- * y / dy NHWC [N,HO,WO,COUT]; gate / dx NHWC; w / dw keep the reference layout [COUT,CIN,KS,KS]. */
+ * y / dy NHWC [N,HO,WO,COUT]; gate / dx NHWC; w / dw keep the reference layout [COUT,CIN,KS,KS].  The first layer reads the frames in
+ * 16-byte pieces: W must be a multiple of 4 and x 16-byte aligned (cudaErrorInvalidValue otherwise; the reference's cameras are 200 and 84
+ * pixels wide — other widths take the exact-fp32 hulc_conv2d_* kernels). */
 /* relu_bits (optional, fwd): the sign mask of y, bit c % 32 of word [pixel][c / 32] = (y > 0), written next to y; gate_bits (optional,
  * dgrad): the same mask of the gating activation — the data gradient then reads 4 bytes instead of 128 per (pixel, 32 channels); `gate`
  * must still be given (kernels that do not take the mask use it). */
