@@ -540,16 +540,19 @@ __global__ void __launch_bounds__(kVwThr, 1) conv1_view_fwd_kernel(const __grid_
         const size_t pix = (size_t)(n * p.HO + oy0 + dy) * p.WO + ox;
         float* dst = p.y + pix * kCout;
         unsigned om = 0u;
+        float o[kCout];
 #pragma unroll
-        for (int j = 0; j < kCout; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[h][j]) + bias[j], __uint_as_float(v[h][j + 1]) + bias[j + 1], __uint_as_float(v[h][j + 2]) + bias[j + 2],
-                                 __uint_as_float(v[h][j + 3]) + bias[j + 3]);
-          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (o.x > 0.f) om |= 1u << j;
-          if (o.y > 0.f) om |= 1u << (j + 1);
-          if (o.z > 0.f) om |= 1u << (j + 2);
-          if (o.w > 0.f) om |= 1u << (j + 3);
-          *reinterpret_cast<float4*>(dst + j) = o;
+        for (int j = 0; j < kCout; ++j) {
+          o[j] = __uint_as_float(v[h][j]) + bias[j];
+          if (p.relu) o[j] = fmaxf(o[j], 0.f);
+          if (o[j] > 0.f) om |= 1u << j;
+        }
+        if ((reinterpret_cast<size_t>(dst) & 31) == 0) {
+#pragma unroll
+          for (int j = 0; j < kCout; j += 8) st_global_v8(dst + j, o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kCout; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         }
         if (p.bits) p.bits[pix] = om;
       }

@@ -346,24 +346,34 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
           const size_t word = off >> 5;
           unsigned gm = 0xFFFFFFFFu, om = 0u;
           if (p.gate_bits) gm = __ldg(p.gate_bits + word);
+          float o[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            o.x += bias[c0 + j]; o.y += bias[c0 + j + 1]; o.z += bias[c0 + j + 2]; o.w += bias[c0 + j + 3];
-            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (p.gate_bits) {
-              o.x = (gm >> j) & 1u ? o.x : 0.f; o.y = (gm >> (j + 1)) & 1u ? o.y : 0.f; o.z = (gm >> (j + 2)) & 1u ? o.z : 0.f; o.w = (gm >> (j + 3)) & 1u ? o.w : 0.f;
-            } else if (p.gate) {
+          for (int j = 0; j < 32; ++j) {
+            o[j] = __uint_as_float(v[j]) + bias[c0 + j];
+            if (p.relu) o[j] = fmaxf(o[j], 0.f);
+          }
+          if (p.gate_bits) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = (gm >> j) & 1u ? o[j] : 0.f;
+          } else if (p.gate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
               const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + off + j));
-              o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+              o[j] = g.x > 0.f ? o[j] : 0.f; o[j + 1] = g.y > 0.f ? o[j + 1] : 0.f; o[j + 2] = g.z > 0.f ? o[j + 2] : 0.f; o[j + 3] = g.w > 0.f ? o[j + 3] : 0.f;
             }
-            if (p.relu_bits) {
-              if (o.x > 0.f) om |= 1u << j;
-              if (o.y > 0.f) om |= 1u << (j + 1);
-              if (o.z > 0.f) om |= 1u << (j + 2);
-              if (o.w > 0.f) om |= 1u << (j + 3);
-            }
-            *reinterpret_cast<float4*>(p.out + off + j) = o;
+          }
+          if (p.relu_bits) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (o[j] > 0.f) om |= 1u << j;
+          }
+          float* dst = p.out + off;
+          if ((reinterpret_cast<size_t>(dst) & 31) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
           }
           if (p.relu_bits) p.relu_bits[word] = om;
         }

@@ -110,7 +110,10 @@ struct TcEpilogue {
 #pragma unroll
       for (int j = 0; j < 32; ++j) o[j] = v[j];
       apply<32>(o, m, n0);
-      if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
+      if ((reinterpret_cast<size_t>(dst) & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) tc::st_global_v8(dst + j, o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+      } else if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
       } else {
