@@ -24,7 +24,7 @@ struct TcEpilogue {
   int ldg;
   int BN, tiles_n;
   int splits;  // > 1: split-K over a thread-block cluster of that size (tile index = output tile * splits + k-slice)
-  unsigned vec;  // 16-byte-aligned rows: bit 0 = C, bit 1 = addend, bit 2 = gate (their epilogue reads go as float4)
+  unsigned vec;  // 16-byte-aligned rows: bit 0 = C, bit 1 = addend, bit 2 = gate (epilogue reads go as float4); bits 3-5: 32-byte-aligned (256-bit reads)
 
   // The epilogue stages are applied as short vector passes over W contiguous columns of one row (uniform branches hoisted
   // out of the element loops keeps the unrolled code small — it is instruction-fetch bound otherwise).  Dropout is applied
@@ -39,7 +39,15 @@ struct TcEpilogue {
     }
     if (addend) {
       const float* a = addend + (size_t)(add_mod ? m % add_mod : m) * ldadd + n0;
-      if (W >= 4 && (vec & 2)) {
+      if (W >= 8 && (vec & 16)) {
+#pragma unroll
+        for (int j = 0; j + 7 < W; j += 8) {
+          float t[8];
+          tc::ld_global_v8(a + j, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[j + e] += t[e];
+        }
+      } else if (W >= 4 && (vec & 2)) {
 #pragma unroll
         for (int j = 0; j + 3 < W; j += 4) {
           const float4 t = *reinterpret_cast<const float4*>(a + j);
@@ -52,7 +60,15 @@ struct TcEpilogue {
     }
     if (beta != 0.f) {
       const float* c = C + (size_t)m * ldc + n0;
-      if (W >= 4 && (vec & 1)) {
+      if (W >= 8 && (vec & 8)) {
+#pragma unroll
+        for (int j = 0; j + 7 < W; j += 8) {
+          float t[8];
+          tc::ld_global_v8(c + j, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[j + e] += beta * t[e];
+        }
+      } else if (W >= 4 && (vec & 1)) {
 #pragma unroll
         for (int j = 0; j + 3 < W; j += 4) {
           const float4 t = *reinterpret_cast<const float4*>(c + j);
@@ -73,7 +89,10 @@ struct TcEpilogue {
     if (gate) {
       const float* gp = gate + (size_t)m * ldg + n0;
       float g[W];
-      if (W >= 4 && (vec & 4)) {
+      if (W >= 8 && (vec & 32)) {
+#pragma unroll
+        for (int j = 0; j + 7 < W; j += 8) tc::ld_global_v8(gp + j, g + j);
+      } else if (W >= 4 && (vec & 4)) {
 #pragma unroll
         for (int j = 0; j + 3 < W; j += 4) {
           const float4 t = *reinterpret_cast<const float4*>(gp + j);
@@ -289,7 +308,9 @@ HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N
   ep.add_mod = add_mod; ep.act = act; ep.gate = gate; ep.ldg = ldg;
   ep.BN = 0; ep.tiles_n = 0;
   auto aligned = [](const float* p, int ld) { return p && (reinterpret_cast<size_t>(p) & 15) == 0 && (ld & 3) == 0; };
-  ep.vec = (aligned(C, ldc) ? 1u : 0u) | (aligned(addend, ldadd) ? 2u : 0u) | (aligned(gate, ldg) ? 4u : 0u);
+  auto aligned32 = [](const float* p, int ld) { return p && (reinterpret_cast<size_t>(p) & 31) == 0 && (ld & 7) == 0; };
+  ep.vec = (aligned(C, ldc) ? 1u : 0u) | (aligned(addend, ldadd) ? 2u : 0u) | (aligned(gate, ldg) ? 4u : 0u) | (aligned32(C, ldc) ? 8u : 0u) |
+           (aligned32(addend, ldadd) ? 16u : 0u) | (aligned32(gate, ldg) ? 32u : 0u);
   cudaStream_t st = (cudaStream_t)stream;
   int bn;
   choose_config(M, N, K, bn, ep.splits);

@@ -79,6 +79,13 @@ __device__ __forceinline__ void st_global_v8(float* p, float a0, float a1, float
                : "memory");
 }
 
+// 256-bit global load (LDG.E.ENL2.256); p must be 32-byte aligned
+__device__ __forceinline__ void ld_global_v8(const float* p, float* o) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+               : "l"(p));
+}
+
 // ---- UMMA descriptors -----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), SWIZZLE_128B:
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 | [46,48) version = 1 |
