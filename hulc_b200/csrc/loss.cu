@@ -71,6 +71,97 @@ __global__ void world_to_tcp_kernel(const float* __restrict__ act, const float* 
   if (bad && nan_flag) atomicOr(nan_flag, 1);
 }
 
+// tcp_to_world_frame (decoders/utils/gripper_control.py:39-63): the inverse map, applied to SAMPLED actions on the validation path.
+// R = R(euler); pos_w = R pos_tcp; R_new = R * inv(R(0.01 * orn_tcp)); orn_w = 100 * wrap_pi(euler(R_new) - euler); gripper passes through.
+__global__ void tcp_to_world_kernel(const float* __restrict__ act, const float* __restrict__ robot_obs, int obs_dim, float* __restrict__ out, int n,
+                                    int* __restrict__ nan_flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* a = act + (size_t)i * 7;
+  const float* o = robot_obs + (size_t)i * obs_dim;
+  const float PI = 3.14159265358979323846f;
+  float R[9], Rrel[9], Rrelinv[9], M[9];
+  euler_xyz(o[3], o[4], o[5], R);
+  float r[7];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r[k] = R[k * 3] * a[0] + R[k * 3 + 1] * a[1] + R[k * 3 + 2] * a[2];
+  euler_xyz(a[3] * 0.01f, a[4] * 0.01f, a[5] * 0.01f, Rrel);
+  mat3_inv(Rrel, Rrelinv);
+  mat3_mul(R, Rrelinv, M);
+  float e[3] = {atan2f(-M[5], M[8]), asinf(M[2]), atan2f(-M[1], M[0])};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = e[k] - o[3 + k];
+    if (v < -PI) v += 2.f * PI;
+    if (v > PI) v -= 2.f * PI;
+    r[3 + k] = v * 100.f;
+  }
+  r[6] = a[6];
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { out[(size_t)i * 7 + k] = r[k]; bad |= (r[k] != r[k]); }
+  if (bad && nan_flag) atomicOr(nan_flag, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sampling from the logistic mixture (logistic_decoder_rnn.py:234-258, validation / inference): per (token, action dim) a Gumbel-max
+// choice of the mixture component, then inverse-CDF sampling of that logistic; the gripper command is gripper_bounds[argmax].
+// Uniforms: injected (u_mix [token][dim][mix], u_inv [token][dim], tokens in (b, t) order) or Philox(seed, site / site + 1).
+// One thread per (token, dim), dim == n_dims being the gripper.  out is [B][S][n_dims + has_gripper], batch-major.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void logistic_sample_kernel(const float* __restrict__ heads, int ldh, const float* __restrict__ u_mix, const float* __restrict__ u_inv,
+                                       float* __restrict__ out, int B, int S, int b0, int Bm, int time_major, int n_dims, int n_mix, float log_scale_min,
+                                       int has_gripper, float grip_lo, float grip_hi, unsigned long long seed, const unsigned long long* seed_ptr,
+                                       unsigned site) {
+  const int per_tok = n_dims + (has_gripper ? 1 : 0);
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= Bm * S * per_tok) return;
+  const int tok = gid / per_tok, d = gid - tok * per_tok;  // tok = bl * S + t over the Bm sequences of this call
+  const int bl = tok / S, t = tok - bl * S, b = b0 + bl;
+  const float* h = heads + (size_t)(time_major ? t * B + b : b * S + t) * ldh;
+  float* o = out + ((size_t)b * S + t) * per_tok;
+  const int NM = n_dims * n_mix;
+  if (d == n_dims) {  // gripper: argmax of the two logits (first index on ties, like torch.argmax)
+    o[d] = h[3 * NM + 1] > h[3 * NM] ? grip_hi : grip_lo;
+    return;
+  }
+  const float r1 = 1e-5f, r2 = 1.0f - 1e-5f;
+  const unsigned long long sd = rng_seed(seed, seed_ptr);
+  int best = 0;
+  float best_v = -FLT_MAX;
+  for (int k = 0; k < n_mix; ++k) {
+    const size_t e = ((size_t)tok * n_dims + d) * n_mix + k;
+    const float u = u_mix ? u_mix[e] : philox_uniform(sd, site, e);
+    const float v = h[d * n_mix + k] - logf(-logf((r1 - r2) * u + r2));
+    if (v > best_v) { best_v = v; best = k; }
+  }
+  const float mean = h[NM + d * n_mix + best];
+  const float scale = expf(fmaxf(h[2 * NM + d * n_mix + best], log_scale_min));
+  const size_t e2 = (size_t)tok * n_dims + d;
+  const float u = (r1 - r2) * (u_inv ? u_inv[e2] : philox_uniform(sd, site + 1, e2)) + r2;
+  o[d] = mean + scale * (logf(u) - logf(1.0f - u));
+}
+
+// Validation metrics (hulc.py:346-385): mae[b][d] = mean_t |pred - actions| for the first n_dims action dims; hits[b] = number of steps whose
+// sampled gripper command (sign of pred[..., -1]) equals the ground-truth one.  One block per sequence.
+__global__ void val_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ actions, float* __restrict__ mae, float* __restrict__ hits, int S,
+                                   int n_dims) {
+  const int b = blockIdx.x, d = threadIdx.x;
+  const int A = n_dims + 1;
+  if (d < n_dims) {
+    float s = 0.f;
+    for (int t = 0; t < S; ++t) s += fabsf(pred[((size_t)b * S + t) * A + d] - actions[((size_t)b * S + t) * A + d]);
+    mae[(size_t)b * n_dims + d] = s / (float)S;
+  } else if (d == n_dims) {
+    float c = 0.f;
+    for (int t = 0; t < S; ++t) {
+      const float g = pred[((size_t)b * S + t) * A + n_dims] > 0.f ? 1.f : -1.f;
+      c += (actions[((size_t)b * S + t) * A + n_dims] == g) ? 1.f : 0.f;
+    }
+    hits[b] = c;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Discretised logistic mixture NLL + gripper CE (decoders/logistic_decoder_rnn.py:136-155,184-231), forward + gradient
 // w.r.t. the head pre-activations in one pass.  One thread per (token, action dim).  heads holds B sequences (rows
@@ -430,6 +521,31 @@ HULC_API int hulc_world_to_tcp(const float* actions, const float* robot_obs, int
   if (n_tokens <= 0) return 0;
   HULC_LAUNCH(world_to_tcp_kernel, dim3(hulc_cdiv(n_tokens, 128)), dim3(128), 0, (cudaStream_t)stream, actions, robot_obs, obs_dim, out, n_tokens,
               nan_flag);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_tcp_to_world(const float* actions, const float* robot_obs, int obs_dim, float* out, int n_tokens, int* nan_flag, void* stream) {
+  if (n_tokens <= 0) return 0;
+  HULC_LAUNCH(tcp_to_world_kernel, dim3(hulc_cdiv(n_tokens, 128)), dim3(128), 0, (cudaStream_t)stream, actions, robot_obs, obs_dim, out, n_tokens,
+              nan_flag);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_logistic_sample(const float* heads, int ldh, const float* u_mix, const float* u_inv, float* out, int B, int S, int b0, int Bm,
+                                  int time_major, int n_dims, int n_mix, float log_scale_min, int has_gripper, float grip_lo, float grip_hi,
+                                  unsigned long long seed, unsigned site, void* stream) {
+  if (Bm * S <= 0) return 0;
+  if (b0 < 0 || b0 + Bm > B || n_mix <= 0) return (int)cudaErrorInvalidValue;
+  const int total = Bm * S * (n_dims + (has_gripper ? 1 : 0));
+  HULC_LAUNCH(logistic_sample_kernel, dim3(hulc_cdiv(total, 128)), dim3(128), 0, (cudaStream_t)stream, heads, ldh, u_mix, u_inv, out, B, S, b0, Bm,
+              time_major, n_dims, n_mix, log_scale_min, has_gripper, grip_lo, grip_hi, seed, g_hulc_rng_offset_ptr, site);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_val_metrics(const float* pred, const float* actions, float* mae, float* hits, int B, int S, int n_dims, void* stream) {
+  if (B <= 0 || S <= 0) return 0;
+  if (n_dims + 1 > 32) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(val_metrics_kernel, dim3(B), dim3(32), 0, (cudaStream_t)stream, pred, actions, mae, hits, S, n_dims);
   HULC_RETURN_LAST();
 }
 

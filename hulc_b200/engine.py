@@ -471,11 +471,14 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_u=None, plan_eps=None, dropout_masks=None, seed: Optional[int] = None,
-             backward: bool = True) -> Dict[str, torch.Tensor]:
+             backward: bool = True, plan_from: str = "posterior") -> Dict[str, torch.Tensor]:
         """One fused forward(+backward) over `batch` (the reference's {"vis": ..., "lang": ...} contract).  Gradients of
         total_loss land in `self.ps.grad` (zeroed first).  Randomness: `plan_idx[m]` / `plan_u[m]` / `plan_eps[m]` and
         `dropout_masks` (dict site -> uint8 keep mask over the whole batch, modalities concatenated in batch order)
-        inject it for parity runs; otherwise Philox streams keyed on `seed` (None: the previous seed + 1)."""
+        inject it for parity runs; otherwise Philox streams keyed on `seed` (None: the previous seed + 1).  `plan_from="prior"` (forward
+        only, validation path) draws the latent plan from the plan-proposal network instead of the recognition network; the KL it reports is
+        then meaningless and ignored by the caller."""
+        assert plan_from in ("posterior", "prior") and not (backward and plan_from == "prior")
         P, G, ps = self.ps.p, self.ps.g, self.ps
         self._step_shapes.clear()
         if seed is not None:
@@ -568,7 +571,8 @@ class HulcEngine:
                     r0, r1 = b0 * 32, (b0 + Bm) * 32
                     u = plan_u[m].reshape(-1) if plan_u is not None and plan_idx is None else None
                     idx_in = plan_idx[m].reshape(-1).to(torch.int32) if plan_idx is not None else None
-                    ops.plan_discrete_fwd(pr_state[b0 : b0 + Bm], pp_state[b0 : b0 + Bm], plan[b0 : b0 + Bm], kl_rows[r0:r1], u=u,
+                    src, oth = (pr_state, pp_state) if plan_from == "posterior" else (pp_state, pr_state)
+                    ops.plan_discrete_fwd(src[b0 : b0 + Bm], oth[b0 : b0 + Bm], plan[b0 : b0 + Bm], kl_rows[r0:r1], u=u,
                                           idx_in=idx_in, idx_out=idx_out[r0:r1], seed=seed, site=100 + i)
                     ops.sum_to(kl_rows[r0:r1], lview(4 * i + 2), 1.0 / Bm)
                 out["plan_idx"] = idx_out.view(nB, 32)
@@ -576,7 +580,8 @@ class HulcEngine:
                 kl_el = self.buf("kl_el", nB, PF)
                 for i, (m, b0, Bm) in enumerate(zip(mods, b0s, Bs)):
                     eps = plan_eps[m] if plan_eps is not None else None
-                    ops.plan_cont_fwd(pr_state[b0 : b0 + Bm], pp_state[b0 : b0 + Bm], plan[b0 : b0 + Bm], kl_el[b0 : b0 + Bm], eps=eps,
+                    src, oth = (pr_state, pp_state) if plan_from == "posterior" else (pp_state, pr_state)
+                    ops.plan_cont_fwd(src[b0 : b0 + Bm], oth[b0 : b0 + Bm], plan[b0 : b0 + Bm], kl_el[b0 : b0 + Bm], eps=eps,
                                       seed=seed, site=100 + i)
                     ops.sum_to(kl_el[b0 : b0 + Bm], lview(4 * i + 2), 1.0 / Bm)
             out["sampled_plan"] = plan
@@ -863,6 +868,68 @@ class HulcEngine:
         ops.strided_copy(demb3.transpose(0, 1), dabove.view(S, nB, 128), accumulate=True)
 
     # ------------------------------------------------------------------------------------------------------------------
+    # ------------------------------------------------------------------------------------------------------------------
+    # validation: lmp_val / validation_step, hulc/models/hulc.py:301-388, 739-841
+    # ------------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def validation_step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_eps=None, sample_u=None, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """The reference's validation metrics for one batch, dropout off (eval mode): for the plan drawn from the proposal network ("pp")
+        and from the recognition network ("pr") — action loss, actions sampled from the logistic mixture and mapped back to the world frame,
+        their per-sequence L1 error (mae_*: [B, 6]) and gripper success rate — plus the KL and (language modality) the CLIP loss.
+        Keys: "<name>_<pp|pr>_<modality>", "kl_loss_<modality>", "val_pred_clip_loss", "sampled_plan_<pp|pr>_<modality>".
+        Randomness for parity runs: plan_idx / plan_eps = {"pp" | "pr": {modality: ...}} as in `step`; sample_u = {"pp" | "pr": {modality:
+        (u_mix [B,S,n_dims,n_mix], u_inv [B,S,n_dims])}}; otherwise Philox streams keyed on `seed`.
+        The shared front of the network is evaluated once per plan source (two forward passes): this is not the hot path."""
+        mods = list(batch.keys())
+        Bs = [batch[m]["actions"].shape[0] for m in mods]
+        S = batch[mods[0]]["actions"].shape[1]
+        b0s = [sum(Bs[:i]) for i in range(len(mods))]
+        nB = sum(Bs)
+        has_grip = self.model != "mcil"
+        A = self.n_dims + (1 if has_grip else 0)
+        res: Dict[str, torch.Tensor] = {}
+        p_save, self.dropout_p = self.dropout_p, 0.0
+        try:
+            sources = ("pp", "pr") if self.model != "gcbc" else ("pr",)
+            for k, which in enumerate(sources):
+                out = self.step(batch, plan_idx=(plan_idx or {}).get(which), plan_eps=(plan_eps or {}).get(which), backward=False,
+                                seed=None if seed is None else 2 * int(seed) + k, plan_from="prior" if which == "pp" else "posterior")
+                rng = 0 if self.device.type == "cuda" else int(self.rng_dev.item())
+                heads = self._bufs["dec.heads"][:, : self.ps.n_heads]
+                pred_tcp = self.buf(f"val.pred_tcp", nB, S, A)
+                pred = self.buf(f"val.pred", nB, S, A)
+                mae = self.buf("val.mae", nB, A - 1)
+                hits = self.buf("val.hits", nB)
+                acts = self.buf("val.actions", nB, S, A)
+                for i, (m, b0, Bm) in enumerate(zip(mods, b0s, Bs)):
+                    u = (sample_u or {}).get(which, {}).get(m)
+                    ops.logistic_sample(heads, pred_tcp, nB, S, b0, Bm, time_major=True, n_dims=self.n_dims, n_mix=self.n_mix, has_gripper=has_grip,
+                                        u_mix=None if u is None else u[0].contiguous(), u_inv=None if u is None else u[1].contiguous(), seed=rng,
+                                        site=200 + 2 * i)
+                    ops.strided_copy(acts[b0 : b0 + Bm], batch[m]["actions"])
+                    if has_grip:
+                        ops.tcp_to_world(pred_tcp[b0 : b0 + Bm], batch[m]["state_info"]["robot_obs"].contiguous(), pred[b0 : b0 + Bm], self.nan_flag)
+                    else:
+                        ops.strided_copy(pred[b0 : b0 + Bm], pred_tcp[b0 : b0 + Bm])
+                ops.val_metrics(pred, acts, mae, hits)
+                tag = f"_{which}" if self.model != "gcbc" else ""
+                for m, b0, Bm in zip(mods, b0s, Bs):
+                    res[f"action_loss{tag}_{m}"] = out[f"action_loss_{m}"].clone()
+                    res[f"mae{tag}_{m}"] = mae[b0 : b0 + Bm].clone()
+                    res[f"gripper_sr{tag}_{m}"] = hits[b0 : b0 + Bm].sum() / float(Bm * S)
+                    res[f"sample_act{tag}_{m}"] = pred[b0 : b0 + Bm].clone()
+                    if "sampled_plan" in out:
+                        res[f"sampled_plan_{which}_{m}"] = out["sampled_plan"][b0 : b0 + Bm].clone()
+                    if which == "pr":
+                        res[f"kl_loss_{m}"] = out[f"kl_loss_{m}"].clone()
+                if which == "pr":
+                    res["seq_feat"] = out["seq_feat"].clone()
+                    if "lang_clip_loss" in out:
+                        res["val_pred_clip_loss"] = out["lang_clip_loss"].clone()
+        finally:
+            self.dropout_p = p_save
+        return res
+
     def optimizer_step(self, grad_scale=1.0):
         self.ps.adam_step(lr=self.lr, grad_scale=grad_scale)
 

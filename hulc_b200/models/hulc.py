@@ -318,6 +318,43 @@ class Hulc(_Base):
             return _StepLoss.apply(out["total_loss"], self.engine, *params)
         return out["total_loss"]
 
+    @torch.no_grad()
+    def validation_step(self, batch: Dict[str, Dict], batch_idx: int = 0, **inject) -> Dict[str, torch.Tensor]:
+        """hulc.py:739-841 (+ lmp_val, :301-388): logs the reference's validation keys and returns the sampled plans and episode indices.
+        Dropout is off as under `model.eval()`.  `clip_groundtruth` (a logging-only metric over the dataset's task annotations) is not
+        computed.  `inject`: see HulcEngine.validation_step."""
+        out = self.engine.validation_step(batch, **inject)
+        self.last_val_outputs = out
+        mods = list(batch.keys())
+        output: Dict[str, torch.Tensor] = {}
+        total_pp = None
+        gcbc = self.engine.model == "gcbc"
+        for m in mods:
+            if gcbc:  # gcbc.py:183-236: one decoder pass, no latent plan
+                self.log(f"val_act/{m}_act_loss", out[f"action_loss_{m}"], sync_dist=True)
+                self.log(f"val_total_mae/{m}_total_mae", out[f"mae_{m}"].mean(), sync_dist=True)
+                self.log(f"val_pos_mae/{m}_pos_mae", out[f"mae_{m}"][..., :3].mean(), sync_dist=True)
+                self.log(f"val_orn_mae/{m}_orn_mae", out[f"mae_{m}"][..., 3:6].mean(), sync_dist=True)
+                self.log(f"val_grip/{m}_grip_sr", out[f"gripper_sr_{m}"], sync_dist=True)
+                output[f"idx_{m}"] = batch[m]["idx"]
+                continue
+            if "lang" in m and "val_pred_clip_loss" in out:
+                self.log("val/val_pred_clip_loss", out["val_pred_clip_loss"], sync_dist=True)
+            total_pp = out[f"action_loss_pp_{m}"] if total_pp is None else total_pp + out[f"action_loss_pp_{m}"]
+            for w in ("pr", "pp"):
+                mae = out[f"mae_{w}_{m}"]
+                self.log(f"val_total_mae/{m}_total_mae_{w}", mae.mean(), sync_dist=True)
+                self.log(f"val_pos_mae/{m}_pos_mae_{w}", mae[..., :3].mean(), sync_dist=True)
+                self.log(f"val_orn_mae/{m}_orn_mae_{w}", mae[..., 3:6].mean(), sync_dist=True)
+                self.log(f"val_act/{m}_act_loss_{w}", out[f"action_loss_{w}_{m}"], sync_dist=True)
+                self.log(f"val_grip/{m}_grip_sr_{w}", out[f"gripper_sr_{w}_{m}"], sync_dist=True)
+                output[f"sampled_plan_{w}_{m}"] = out[f"sampled_plan_{w}_{m}"]
+            self.log(f"val_kl/{m}_kl_loss", out[f"kl_loss_{m}"], sync_dist=True)
+            # the reference logs the running sum over the modalities seen so far, divided by their total number (hulc.py:830-834)
+            self.log("val_act/action_loss_pp", total_pp / len(mods), sync_dist=True)
+            output[f"idx_{m}"] = batch[m]["idx"]
+        return output
+
     def lmp_train(self, perceptual_emb, latent_goal, train_acts, robot_obs):
         raise NotImplementedError(
             "lmp_train is fused into training_step here (one batched pass over both modalities); the per-block values it "

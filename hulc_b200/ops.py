@@ -409,6 +409,36 @@ def world_to_tcp(actions, robot_obs, out, nan_flag):
     return out
 
 
+def tcp_to_world(actions, robot_obs, out, nan_flag):
+    """Sampled actions (TCP frame) -> world frame (hulc_tcp_to_world; gripper_control.py:39-63)."""
+    _chk(actions, robot_obs, out)
+    _chk(nan_flag, dtype=torch.int32)
+    assert actions.is_contiguous() and robot_obs.is_contiguous() and out.is_contiguous() and actions.shape[-1] == 7
+    _L().hulc_tcp_to_world(_ptr(actions), _ptr(robot_obs), robot_obs.shape[-1], _ptr(out), actions.numel() // 7, _ptr(nan_flag), _stream())
+    return out
+
+
+def logistic_sample(heads, out, B, S, b0, Bm, *, time_major, n_dims, n_mix, log_scale_min=-7.0, has_gripper=True, grip_bounds=(-1.0, 1.0), u_mix=None,
+                    u_inv=None, seed=0, site=0):
+    """Actions sampled from the logistic mixture the heads describe (hulc_logistic_sample; logistic_decoder_rnn.py:234-258).
+    out: [B, S, n_dims + has_gripper] (only sequences [b0, b0 + Bm) are written); u_mix [Bm, S, n_dims, n_mix] / u_inv [Bm, S, n_dims] inject
+    the uniforms, otherwise Philox(seed, site)."""
+    _chk(heads, out, u_mix, u_inv)
+    assert out.is_contiguous() and (u_mix is None or u_mix.is_contiguous()) and (u_inv is None or u_inv.is_contiguous())
+    _L().hulc_logistic_sample(_ptr(heads), _rowmajor(heads), _ptr(u_mix), _ptr(u_inv), _ptr(out), B, S, b0, Bm, int(time_major), n_dims, n_mix,
+                              float(log_scale_min), int(has_gripper), float(grip_bounds[0]), float(grip_bounds[1]), int(seed), int(site), _stream())
+    return out
+
+
+def val_metrics(pred, actions, mae, hits):
+    """mae [B, n_dims] = mean over time of |pred - actions|; hits [B] = steps with the right gripper command (hulc_val_metrics)."""
+    _chk(pred, actions, mae, hits)
+    B, S, A = pred.shape
+    assert pred.is_contiguous() and actions.is_contiguous() and tuple(actions.shape) == (B, S, A) and mae.is_contiguous()
+    _L().hulc_val_metrics(_ptr(pred), _ptr(actions), _ptr(mae), _ptr(hits), B, S, A - 1, _stream())
+    return mae, hits
+
+
 def logistic_loss(heads, actions, dheads, losses, B, S, b0, Bm, *, time_major, n_dims, n_mix, num_classes, log_scale_min=-7.0, act_min=-1.0,
                   act_max=1.0, has_gripper=True, gripper_alpha=1.0, grad_scale=1.0):
     _chk(heads, actions, dheads, losses)

@@ -288,6 +288,19 @@ def plan_noise(batch: int, seq: int, modality: str, seed: int = 1, n_cat: int = 
     }
 
 
+def validation_noise(batch: int, seq: int, modality: str, which: str, seed: int = 1, n_dims: int = 6, n_mix: int = 10, n_cat: int = 32,
+                     n_cont: int = 256) -> Dict[str, torch.Tensor]:
+    """Injected randomness of the validation path for plan source `which` ("pp" | "pr"): the categorical-sample uniforms / Normal noise of
+    the latent plan and the two uniform draws of LogisticDecoderRNN._sample (Gumbel-max over the mixture, inverse-CDF logistic)."""
+    g = torch.Generator().manual_seed(seed * 4241 + (3 if modality == "vis" else 5) + (100 if which == "pp" else 200))
+    return {
+        "u": torch.rand(batch, n_cat, generator=g, dtype=torch.float32),
+        "eps": torch.randn(batch, n_cont, generator=g, dtype=torch.float32),
+        "u_mix": torch.rand(batch, seq, n_dims, n_mix, generator=g, dtype=torch.float32),
+        "u_inv": torch.rand(batch, seq, n_dims, generator=g, dtype=torch.float32),
+    }
+
+
 def dropout_masks(
     batch: int, seq: int, modality: str, p: float, seed: int = 1, d_model: int = 128, nhead: int = 8, ff: int = 2048, nlayers: int = 2
 ) -> Dict[str, torch.Tensor]:

@@ -171,6 +171,21 @@ int hulc_frames_u8_to_f32(const unsigned char* src, float* dst, long long n, flo
  * (the reference asserts on the host, :35; the flag is checked without stalling the stream). */
 int hulc_world_to_tcp(const float* actions, const float* robot_obs, int obs_dim, float* out, int n_tokens, int* nan_flag, void* stream);
 
+/* ---- validation path: tcp_to_world_frame (gripper_control.py:39-63), sampling from the logistic mixture
+ * (logistic_decoder_rnn.py:234-258) and the MAE / gripper-accuracy reductions of lmp_val (hulc/models/hulc.py:346-385) -------
+ * hulc_tcp_to_world: sampled actions [n,7] in the TCP frame + robot_obs -> world frame [n,7]; *nan_flag as in hulc_world_to_tcp.
+ * hulc_logistic_sample: heads rows as in hulc_logistic_loss (row = b*S+t or t*B+b); for the sequences [b0,b0+Bm) writes
+ *   out[b][t][0..n_dims) = mean_k + exp(max(log_scale_k, log_scale_min)) * (log u - log(1-u)), k = argmax_k(logit_k - log(-log u_k)),
+ *   and, with has_gripper, out[b][t][n_dims] = gripper logit 1 > logit 0 ? grip_hi : grip_lo.  u_mix [Bm*S][n_dims][n_mix] and
+ *   u_inv [Bm*S][n_dims] are U[0,1) draws (mapped to [1e-5, 1-1e-5] like the reference); NULL -> Philox(seed, site / site+1).
+ * hulc_val_metrics: pred / actions [B,S,n_dims+1] -> mae [B,n_dims] (mean over S of |pred - actions|), hits [B] (steps whose
+ *   sign(pred gripper) equals the ground-truth gripper command). */
+int hulc_tcp_to_world(const float* actions, const float* robot_obs, int obs_dim, float* out, int n_tokens, int* nan_flag, void* stream);
+int hulc_logistic_sample(const float* heads, int ldh, const float* u_mix, const float* u_inv, float* out, int B, int S, int b0, int Bm,
+                         int time_major, int n_dims, int n_mix, float log_scale_min, int has_gripper, float grip_lo, float grip_hi,
+                         unsigned long long seed, unsigned site, void* stream);
+int hulc_val_metrics(const float* pred, const float* actions, float* mae, float* hits, int B, int S, int n_dims, void* stream);
+
 /* ---- discretised logistic mixture NLL + gripper CE (decoders/logistic_decoder_rnn.py:136-155,184-231) ---------------------
  * heads rows: [logit_probs n_dims*n_mix | means | raw log_scales | gripper 2]; B sequences of S tokens, row = b*S+t or
  * t*B+b (time_major); the loss covers sequences [b0,b0+Bm).  losses[0] = NLL, losses[1] = CE (means over Bm*S tokens);

@@ -316,6 +316,44 @@ def world_to_tcp_frame(action: torch.Tensor, robot_obs: torch.Tensor) -> torch.T
     return out
 
 
+def tcp_to_world_frame(action: torch.Tensor, robot_obs: torch.Tensor) -> torch.Tensor:
+    """gripper_control.py:39-63: the inverse of world_to_tcp_frame, applied to sampled actions on the validation path."""
+    b, s, _ = action.shape
+    R = euler_xyz_to_matrix(robot_obs[..., 3:6]).float().view(-1, 3, 3)
+    pos = R @ action[..., :3].reshape(-1, 3, 1)
+    Rrel = euler_xyz_to_matrix(action[..., 3:6] * 0.01).float().view(-1, 3, 3)
+    orn = matrix_to_euler_xyz(R @ torch.linalg.inv(Rrel)).float() - robot_obs[..., 3:6].reshape(-1, 3)
+    orn = torch.where(orn < -math.pi, orn + 2 * math.pi, orn)
+    orn = torch.where(orn > math.pi, orn - 2 * math.pi, orn)
+    orn = orn * 100
+    out = torch.cat([pos.view(b, s, -1), orn.view(b, s, -1), action[..., -1:]], -1)
+    assert not torch.any(out.isnan())
+    return out
+
+
+def logistic_mixture_sample(logit_probs, log_scales, means, gripper_act, u_mix, u_inv, gripper_bounds=(-1.0, 1.0)) -> torch.Tensor:
+    """LogisticDecoderRNN._sample (logistic_decoder_rnn.py:234-258) with the two torch.rand draws passed in: Gumbel-max choice of the
+    mixture component, inverse-CDF sample of that logistic, gripper command = gripper_bounds[argmax]."""
+    r1, r2 = 1e-5, 1.0 - 1e-5
+    temp = logit_probs - torch.log(-torch.log((r1 - r2) * u_mix + r2))
+    dist = torch.nn.functional.one_hot(torch.argmax(temp, -1), logit_probs.shape[-1]).to(means.dtype)
+    ls = (dist * log_scales).sum(-1)
+    mu = (dist * means).sum(-1)
+    u = (r1 - r2) * u_inv + r2
+    actions = mu + torch.exp(ls) * (torch.log(u) - torch.log(1.0 - u))
+    if gripper_act is None:
+        return actions
+    cmd = torch.tensor(gripper_bounds, dtype=means.dtype)[gripper_act.argmax(-1)]
+    return torch.cat([actions, cmd.unsqueeze(-1)], 2)
+
+
+def validation_metrics(sample_act: torch.Tensor, actions: torch.Tensor):
+    """lmp_val (hulc.py:346-385): per-sequence L1 error of the six continuous dims (mean over time) and the gripper success rate."""
+    mae = (sample_act[..., :-1] - actions[..., :-1]).abs().mean(1)
+    grip = torch.where(sample_act[..., -1] > 0, 1.0, -1.0)
+    return mae, (actions[..., -1] == grip).float().mean()
+
+
 def decoder_heads(sd: SD, h: torch.Tensor, out_features: int, n_mix: int, log_scale_min: float, discrete_gripper: bool, prefix: str = "action_decoder"):
     """LogisticDecoderRNN.forward after the RNN (logistic_decoder_rnn.py:278-287)."""
     B, S, _ = h.shape
@@ -463,4 +501,50 @@ def training_step(
         total = total + clip_beta * clip
         out["lang_clip_loss"] = clip
     out["total_loss"], out["kl_loss"], out["action_loss"] = total, kl_tot / n_mod, act_tot / n_mod
+    return out
+
+
+@torch.no_grad()
+def validation_step(sd: SD, batch: Dict[str, Dict], *, model: str = "hulc", rnn_model: str = "rnn_decoder", plan_idx=None, plan_eps=None, sample_u=None,
+                    kl_beta: float = 0.01, kl_alpha: float = 0.8) -> Dict[str, torch.Tensor]:
+    """Hulc.validation_step / lmp_val (hulc.py:301-388, 739-841), eval mode (no dropout).  For the plan sampled from the proposal ("pp") and
+    from the recognition network ("pr"): action loss, actions sampled from the mixture (LogisticDecoderRNN.loss_and_act,
+    logistic_decoder_rnn.py:85-102) and their MAE / gripper success rate; plus KL and the CLIP loss of the language modality.
+    plan_idx[which][m] (B,32) / plan_eps[which][m] (B,256) and sample_u[which][m] = (u_mix, u_inv) inject the randomness."""
+    out: Dict[str, torch.Tensor] = {}
+    discrete = model != "mcil"
+    dg = model != "mcil"
+    for m, d in batch.items():
+        emb = perceptual_encoder(sd, d["rgb_obs"]["rgb_static"], d["rgb_obs"]["rgb_gripper"])
+        goal = goal_encoder(sd, "language_goal", d["lang"]) if "lang" in m else goal_encoder(sd, "visual_goal", emb[:, -1])
+        B, S, _ = emb.shape
+        actions, robot_obs = d["actions"], d["state_info"]["robot_obs"]
+        if model == "mcil":
+            seq_feat = birnn_tanh(sd, "plan_recognition.birnn_model", emb)[:, -1]
+            pr_state = linear(sd, "plan_recognition.fc_state.0", seq_feat)
+        else:
+            pr_state, seq_feat = plan_recognition_transformer(sd, emb, p=0.0, masks=None)
+        pp_state = plan_proposal(sd, emb[:, 0], goal)
+        for which, state in (("pp", pp_state), ("pr", pr_state)):
+            if discrete:
+                plan = torch.nn.functional.one_hot(plan_idx[which][m].long(), 32).to(emb.dtype).flatten(-2)
+            else:
+                mean, std = cont_state(state)
+                plan = mean + std * plan_eps[which][m]
+            percep = emb[..., 64:128] if model != "mcil" else emb
+            x = torch.cat([plan.unsqueeze(1).expand(-1, S, -1), percep, goal.unsqueeze(1).expand(-1, S, -1)], -1)
+            h = gru(sd, "action_decoder.rnn", x, 2) if rnn_model == "gru_decoder" else elman_rnn(sd, "action_decoder.rnn", x, 2, "relu")
+            lp, ls, mu, grip = decoder_heads(sd, h, 6 if dg else 7, 10, -7.0, dg)
+            u_mix, u_inv = sample_u[which][m]
+            pred = logistic_mixture_sample(lp, ls, mu, grip, u_mix, u_inv)
+            act_t = world_to_tcp_frame(actions, robot_obs) if dg else actions
+            out[f"action_loss_{which}_{m}"] = decoder_loss(lp, ls, mu, grip, act_t, discrete_gripper=dg, gripper_alpha=1.0, num_classes=10 if dg else 256,
+                                                           log_scale_min=-7.0)
+            pred_w = tcp_to_world_frame(pred, robot_obs) if dg else pred
+            out[f"sample_act_{which}_{m}"] = pred_w
+            out[f"mae_{which}_{m}"], out[f"gripper_sr_{which}_{m}"] = validation_metrics(pred_w, actions)
+            out[f"sampled_plan_{which}_{m}"] = plan
+        out[f"kl_loss_{m}"] = kl_loss_discrete(pp_state, pr_state, 32, 32, kl_beta, kl_alpha) if discrete else kl_loss_continuous(pp_state, pr_state, kl_beta, kl_alpha)
+        if "lang" in m and model != "mcil":
+            out["val_pred_clip_loss"] = clip_loss(sd, seq_feat, goal, d.get("use_for_aux_lang_loss"))
     return out

@@ -198,7 +198,112 @@ def run_case(name):
           f"worst oracle-vs-reference grad rel err={worst:.2e}  ({time.time() - t0:.1f}s)")
 
 
+VAL_CASES = {
+    # name: (model, rnn_model, B, S) — validation_step / lmp_val (hulc.py:301-388, 739-841), eval mode
+    "val_hulc_b2s8": ("hulc", "rnn_decoder", 2, 8),
+    "val_hulc_b4s32": ("hulc", "rnn_decoder", 4, 32),
+    "val_mcil_b2s8": ("mcil", "rnn_decoder", 2, 8),
+}
+
+
+def run_val_case(name):
+    """The reference's validation_step with its randomness injected (torch.multinomial / _standard_normal for the latent plan, torch.rand for
+    LogisticDecoderRNN._sample), the oracle's restatement on the same tensors, and the fixture with the reference's numbers."""
+    import types
+
+    model, rnn_model, B, S = VAL_CASES[name]
+    t0 = time.time()
+    net = build_reference(model, rnn_model, 0.1, 32)
+    net.eval()
+    batch = synthetic.make_batch(B, S, seed=1)
+    n_dims = 6 if model != "mcil" else 7
+    noise = {w: {m: synthetic.validation_noise(B, S, m, w, n_dims=n_dims) for m in batch} for w in ("pp", "pr")}
+    u_q, eps_q, rand_q = [], [], []
+    for m in batch:
+        for w in ("pp", "pr"):  # lmp_val samples from the proposal first (hulc.py:337-343), then from the recognition network (:360-366)
+            if model == "hulc":
+                u_q.append(noise[w][m]["u"])
+            else:
+                eps_q.append(noise[w][m]["eps"])
+            rand_q += [noise[w][m]["u_mix"], noise[w][m]["u_inv"]]
+    net.trainer = types.SimpleNamespace(datamodule=types.SimpleNamespace(modalities=list(batch)))
+    net.clip_groundtruth = lambda *a, **k: None  # needs the dataset's task annotations; a logging-only metric
+    captured = {}
+    orig_val = net.lmp_val
+
+    def spy_val(*a, **k):
+        r = orig_val(*a, **k)
+        captured[net.modality_scope] = r
+        return r
+
+    net.lmp_val = spy_val
+    orig_rand = torch.rand
+
+    def rand(*size, **kw):
+        u = rand_q.pop(0)
+        shape = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+        assert tuple(u.shape) == shape, (u.shape, shape)
+        return u.clone()
+
+    orig_normal = torch.normal
+
+    def normal(mean, std, *a, **kw):  # Normal.sample() (continuous latent) draws through torch.normal, not _standard_normal
+        e = eps_q.pop(0)
+        assert tuple(e.shape) == tuple(mean.shape), (e.shape, mean.shape)
+        return mean + std * e
+
+    torch.rand, torch.normal = rand, normal
+    try:
+        with injected_randomness(u_q, eps_q, [], 0.0), torch.no_grad():
+            net.validation_step(batch, 0)
+    finally:
+        torch.rand, torch.normal = orig_rand, orig_normal
+    assert not u_q and not eps_q and not rand_q, "injected randomness not fully consumed"
+    logged = net.logged
+
+    # --- oracle ----------------------------------------------------------------------------------------------------
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    plan_idx = {w: {} for w in ("pp", "pr")}
+    fx = {}
+    for m in batch:
+        pp_plan, _, pr_plan = captured[m][0], captured[m][1], captured[m][2]
+        if model == "hulc":
+            plan_idx["pp"][m] = pp_plan.view(B, 32, 32).argmax(-1)
+            plan_idx["pr"][m] = pr_plan.view(B, 32, 32).argmax(-1)
+            fx[f"plan_idx_pp_{m}"], fx[f"plan_idx_pr_{m}"] = plan_idx["pp"][m], plan_idx["pr"][m]
+    out = O.validation_step(sd, batch, model=model, rnn_model=rnn_model, plan_idx=plan_idx,
+                            plan_eps={w: {m: noise[w][m]["eps"] for m in batch} for w in ("pp", "pr")},
+                            sample_u={w: {m: (noise[w][m]["u_mix"], noise[w][m]["u_inv"]) for m in batch} for w in ("pp", "pr")})
+
+    def close(a, b, what, rtol=1e-4, atol=1e-5):
+        if not torch.allclose(a, b, rtol=rtol, atol=atol):
+            raise AssertionError(f"{name}: oracle != reference for {what}: max|d|={float((a - b).abs().max()):.3e}")
+
+    for m in batch:
+        (pp_plan, loss_pp, pr_plan, loss_pr, kl, mae_pp, mae_pr, sr_pp, sr_pr, _seq) = captured[m]
+        close(out[f"action_loss_pp_{m}"], loss_pp, f"action_loss_pp_{m}")
+        close(out[f"action_loss_pr_{m}"], loss_pr, f"action_loss_pr_{m}")
+        close(out[f"kl_loss_{m}"], kl, f"kl_loss_{m}", 1e-5, 1e-7)
+        close(out[f"mae_pp_{m}"], mae_pp, f"mae_pp_{m}", 1e-4, 1e-4)
+        close(out[f"mae_pr_{m}"], mae_pr, f"mae_pr_{m}", 1e-4, 1e-4)
+        close(out[f"gripper_sr_pp_{m}"], sr_pp, f"gripper_sr_pp_{m}")
+        close(out[f"gripper_sr_pr_{m}"], sr_pr, f"gripper_sr_pr_{m}")
+        close(out[f"sampled_plan_pp_{m}"], pp_plan, f"sampled_plan_pp_{m}")
+        close(out[f"sampled_plan_pr_{m}"], pr_plan, f"sampled_plan_pr_{m}")
+        fx.update({f"action_loss_pp_{m}": loss_pp, f"action_loss_pr_{m}": loss_pr, f"kl_loss_{m}": kl, f"mae_pp_{m}": mae_pp, f"mae_pr_{m}": mae_pr,
+                   f"gripper_sr_pp_{m}": sr_pp, f"gripper_sr_pr_{m}": sr_pr})
+    if "val/val_pred_clip_loss" in logged:
+        close(out["val_pred_clip_loss"], logged["val/val_pred_clip_loss"], "val_pred_clip_loss", 1e-5, 1e-6)
+        fx["val_pred_clip_loss"] = logged["val/val_pred_clip_loss"]
+    for k, v in logged.items():
+        if k.startswith("val"):
+            fx["logged/" + k] = torch.as_tensor(v)
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLDEN / f"{name}.npz", **{k: np.asarray(torch.as_tensor(v).detach().cpu().numpy()) for k, v in fx.items()})
+    print(f"[golden] {name}: act_loss_pp_vis={float(captured[list(batch)[0]][1]):.6f} keys={len(fx)}  ({time.time() - t0:.1f}s)")
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or list(CASES) + list(VAL_CASES)
     for n in names:
-        run_case(n)
+        (run_val_case if n in VAL_CASES else run_case)(n)

@@ -144,6 +144,59 @@ def test_world_to_tcp(K):
     assert int(flag) == 1
 
 
+def test_tcp_to_world(K):
+    from hulc_b200.utils import synthetic
+    d = synthetic.make_modality("vis", 3, 7)
+    obs = d["state_info"]["robot_obs"]
+    ref = O.tcp_to_world_frame(d["actions"], obs)
+    flag = torch.zeros(1, dtype=torch.int32)
+    out = K.tcp_to_world(d["actions"], obs, torch.empty(3, 7, 7), flag)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)
+    assert int(flag) == 0
+    # the two frame changes are inverses of each other (gripper_control.py:16-63)
+    back = K.world_to_tcp(out.contiguous(), obs, torch.empty(3, 7, 7), flag)
+    torch.testing.assert_close(back, d["actions"], rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("time_major,has_grip", [(True, True), (False, True), (True, False)])
+def test_logistic_sample(K, time_major, has_grip):
+    g = torch.Generator().manual_seed(11)
+    B, S, b0, Bm, n_dims, n_mix = 5, 6, 1, 3, 6, 10
+    nm = n_dims * n_mix
+    n = 3 * nm + (2 if has_grip else 0)
+    heads_b = torch.randn(B, S, n, generator=g)
+    heads_b[..., 2 * nm : 3 * nm] = heads_b[..., 2 * nm : 3 * nm] * 3 - 4  # some log-scales below the -7 clamp
+    sub = heads_b[b0 : b0 + Bm]
+    lp, mu, ls = [sub[..., i * nm : (i + 1) * nm].reshape(Bm, S, n_dims, n_mix) for i in range(3)]
+    grip = sub[..., 3 * nm :] if has_grip else None
+    u_mix, u_inv = torch.rand(Bm, S, n_dims, n_mix, generator=g), torch.rand(Bm, S, n_dims, generator=g)
+    ref = O.logistic_mixture_sample(lp, ls.clamp(min=-7.0), mu, grip, u_mix, u_inv)
+    ld = n + 2  # padded rows, like the engine's head buffer
+    hbuf = torch.zeros(B * S, ld)
+    hbuf[:, :n] = heads_b.transpose(0, 1).reshape(S * B, n) if time_major else heads_b.reshape(B * S, n)
+    A = n_dims + (1 if has_grip else 0)
+    out = torch.full((B, S, A), 7.0)
+    K.logistic_sample(hbuf[:, :n], out, B, S, b0, Bm, time_major=time_major, n_dims=n_dims, n_mix=n_mix, has_gripper=has_grip, u_mix=u_mix, u_inv=u_inv)
+    torch.testing.assert_close(out[b0 : b0 + Bm], ref, rtol=1e-5, atol=1e-5)
+    assert float((out[:b0] - 7.0).abs().max()) == 0.0 and float((out[b0 + Bm :] - 7.0).abs().max()) == 0.0  # other sequences untouched
+    # Philox path: reproducible for a seed, different across seeds, finite
+    o1, o2, o3 = (torch.zeros(B, S, A) for _ in range(3))
+    for o, sd in ((o1, 5), (o2, 5), (o3, 6)):
+        K.logistic_sample(hbuf[:, :n], o, B, S, 0, B, time_major=time_major, n_dims=n_dims, n_mix=n_mix, has_gripper=has_grip, seed=sd, site=40)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3) and bool(torch.isfinite(o1).all())
+
+
+def test_val_metrics(K):
+    g = torch.Generator().manual_seed(2)
+    B, S = 4, 9
+    pred, act = torch.randn(B, S, 7, generator=g), torch.rand(B, S, 7, generator=g) * 2 - 1
+    act[..., 6] = (torch.rand(B, S, generator=g) < 0.5).float() * 2 - 1
+    mae, hits = K.val_metrics(pred, act, torch.empty(B, 6), torch.empty(B))
+    ref_mae, ref_sr = O.validation_metrics(pred, act)
+    torch.testing.assert_close(mae, ref_mae, rtol=1e-5, atol=1e-6)
+    assert abs(float(hits.sum()) / (B * S) - float(ref_sr)) < 1e-6
+
+
 @pytest.mark.parametrize("time_major,n_dims,num_classes,has_grip", [(True, 6, 10, True), (False, 6, 10, True), (True, 7, 256, False)])
 def test_logistic_loss(K, time_major, n_dims, num_classes, has_grip):
     g = torch.Generator().manual_seed(3)
