@@ -191,7 +191,8 @@ def test_val_metrics(K):
     B, S = 4, 9
     pred, act = torch.randn(B, S, 7, generator=g), torch.rand(B, S, 7, generator=g) * 2 - 1
     act[..., 6] = (torch.rand(B, S, generator=g) < 0.5).float() * 2 - 1
-    mae, hits = K.val_metrics(pred, act, torch.empty(B, 6), torch.empty(B))
+    mae, hits = torch.empty(B, 6), torch.empty(B)
+    K.val_metrics(pred, act, mae, hits)  # results land in the caller's tensors (the cuda variant copies storages back)
     ref_mae, ref_sr = O.validation_metrics(pred, act)
     torch.testing.assert_close(mae, ref_mae, rtol=1e-5, atol=1e-6)
     assert abs(float(hits.sum()) / (B * S) - float(ref_sr)) < 1e-6
