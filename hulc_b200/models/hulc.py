@@ -330,7 +330,11 @@ class Hulc(_Base):
         total_pp = None
         gcbc = self.engine.model == "gcbc"
         for m in mods:
-            if gcbc:  # gcbc.py:183-236: one decoder pass, no latent plan
+            if gcbc:  # gcbc.py:183-281: one decoder pass, no latent plan
+                if "lang" in m and "val_pred_clip_loss" in out:
+                    self.log("val/val_pred_clip_loss", out["val_pred_clip_loss"], sync_dist=True)
+                total_pp = out[f"action_loss_{m}"] if total_pp is None else total_pp + out[f"action_loss_{m}"]
+                self.log("val_act/action_loss", total_pp / len(mods), sync_dist=True)
                 self.log(f"val_act/{m}_act_loss", out[f"action_loss_{m}"], sync_dist=True)
                 self.log(f"val_total_mae/{m}_total_mae", out[f"mae_{m}"].mean(), sync_dist=True)
                 self.log(f"val_pos_mae/{m}_pos_mae", out[f"mae_{m}"][..., :3].mean(), sync_dist=True)

@@ -524,6 +524,19 @@ def validation_step(sd: SD, batch: Dict[str, Dict], *, model: str = "hulc", rnn_
             pr_state = linear(sd, "plan_recognition.fc_state.0", seq_feat)
         else:
             pr_state, seq_feat = plan_recognition_transformer(sd, emb, p=0.0, masks=None)
+        if model == "gcbc":  # GCBC.validation_step (gcbc.py:183-281): one decoder pass on an empty plan, no KL
+            x = torch.cat([emb[..., 64:128], goal.unsqueeze(1).expand(-1, S, -1)], -1)
+            h = gru(sd, "action_decoder.rnn", x, 2) if rnn_model == "gru_decoder" else elman_rnn(sd, "action_decoder.rnn", x, 2, "relu")
+            lp, ls, mu, grip = decoder_heads(sd, h, 6, 10, -7.0, True)
+            u_mix, u_inv = sample_u["pr"][m]
+            pred_w = tcp_to_world_frame(logistic_mixture_sample(lp, ls, mu, grip, u_mix, u_inv), robot_obs)
+            out[f"action_loss_{m}"] = decoder_loss(lp, ls, mu, grip, world_to_tcp_frame(actions, robot_obs), discrete_gripper=True, gripper_alpha=1.0,
+                                                   num_classes=10, log_scale_min=-7.0)
+            out[f"sample_act_{m}"] = pred_w
+            out[f"mae_{m}"], out[f"gripper_sr_{m}"] = validation_metrics(pred_w, actions)
+            if "lang" in m:
+                out["val_pred_clip_loss"] = clip_loss(sd, seq_feat, goal, d.get("use_for_aux_lang_loss"))
+            continue
         pp_state = plan_proposal(sd, emb[:, 0], goal)
         for which, state in (("pp", pp_state), ("pr", pr_state)):
             if discrete:

@@ -203,6 +203,7 @@ VAL_CASES = {
     "val_hulc_b2s8": ("hulc", "rnn_decoder", 2, 8),
     "val_hulc_b4s32": ("hulc", "rnn_decoder", 4, 32),
     "val_mcil_b2s8": ("mcil", "rnn_decoder", 2, 8),
+    "val_gcbc_b2s8": ("gcbc", "rnn_decoder", 2, 8),  # GCBC.validation_step (gcbc.py:183-281)
 }
 
 
@@ -220,10 +221,10 @@ def run_val_case(name):
     noise = {w: {m: synthetic.validation_noise(B, S, m, w, n_dims=n_dims) for m in batch} for w in ("pp", "pr")}
     u_q, eps_q, rand_q = [], [], []
     for m in batch:
-        for w in ("pp", "pr"):  # lmp_val samples from the proposal first (hulc.py:337-343), then from the recognition network (:360-366)
+        for w in (("pp", "pr") if model != "gcbc" else ("pr",)):  # lmp_val samples from the proposal first (hulc.py:337-343), then from the recognition network (:360-366)
             if model == "hulc":
                 u_q.append(noise[w][m]["u"])
-            else:
+            elif model == "mcil":
                 eps_q.append(noise[w][m]["eps"])
             rand_q += [noise[w][m]["u_mix"], noise[w][m]["u_inv"]]
     net.trainer = types.SimpleNamespace(datamodule=types.SimpleNamespace(modalities=list(batch)))
@@ -236,7 +237,17 @@ def run_val_case(name):
         captured[net.modality_scope] = r
         return r
 
-    net.lmp_val = spy_val
+    if model != "gcbc":
+        net.lmp_val = spy_val
+    else:  # GCBC has no lmp_val: capture (loss, sampled actions) at the decoder
+        orig_la = net.action_decoder.loss_and_act
+
+        def spy_la(*a, **k):
+            r = orig_la(*a, **k)
+            captured[net.modality_scope] = (r[0].detach().clone(), r[1].detach().clone())
+            return r
+
+        net.action_decoder.loss_and_act = spy_la
     orig_rand = torch.rand
 
     def rand(*size, **kw):
@@ -265,6 +276,24 @@ def run_val_case(name):
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     plan_idx = {w: {} for w in ("pp", "pr")}
     fx = {}
+    if model == "gcbc":
+        out = O.validation_step(sd, batch, model=model, rnn_model=rnn_model, sample_u={"pr": {m: (noise["pr"][m]["u_mix"], noise["pr"][m]["u_inv"]) for m in batch}})
+        for m in batch:
+            loss, act = captured[m]
+            assert torch.allclose(out[f"action_loss_{m}"], loss, rtol=1e-4, atol=1e-5), f"{name}: action_loss_{m}"
+            assert torch.allclose(out[f"sample_act_{m}"], act, rtol=1e-4, atol=1e-4), f"{name}: sample_act_{m}"
+            for key, okey in ((f"val_total_mae/{m}_total_mae", None), (f"val_grip/{m}_grip_sr", f"gripper_sr_{m}")):
+                ov = out[f"mae_{m}"].mean() if okey is None else out[okey]
+                assert torch.allclose(ov, logged[key], rtol=1e-4, atol=1e-5), f"{name}: {key}"
+            fx[f"action_loss_{m}"], fx[f"mae_{m}"], fx[f"gripper_sr_{m}"] = loss, out[f"mae_{m}"], logged[f"val_grip/{m}_grip_sr"]
+        assert torch.allclose(out["val_pred_clip_loss"], logged["val/val_pred_clip_loss"], rtol=1e-5, atol=1e-6)
+        fx["val_pred_clip_loss"] = logged["val/val_pred_clip_loss"]
+        for k, v in logged.items():
+            if k.startswith("val"):
+                fx["logged/" + k] = torch.as_tensor(v)
+        np.savez_compressed(GOLDEN / f"{name}.npz", **{k: np.asarray(torch.as_tensor(v).detach().cpu().numpy()) for k, v in fx.items()})
+        print(f"[golden] {name}: act_loss_vis={float(captured[list(batch)[0]][0]):.6f} keys={len(fx)}  ({time.time() - t0:.1f}s)")
+        return
     for m in batch:
         pp_plan, _, pr_plan = captured[m][0], captured[m][1], captured[m][2]
         if model == "hulc":

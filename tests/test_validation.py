@@ -25,7 +25,7 @@ def _inputs(model, B, S, fx=None, hw=(200, 84)):
     kw = dict(sample_u={w: {m: (noise[w][m]["u_mix"], noise[w][m]["u_inv"]) for m in batch} for w in ("pp", "pr")})
     if model == "mcil":
         kw["plan_eps"] = {w: {m: noise[w][m]["eps"] for m in batch} for w in ("pp", "pr")}
-    elif fx is not None:
+    elif fx is not None and model != "gcbc":
         kw["plan_idx"] = {w: {m: torch.from_numpy(fx[f"plan_idx_{w}_{m}"]) for m in batch} for w in ("pp", "pr")}
     return batch, noise, kw
 
@@ -43,6 +43,15 @@ def _check(out, fx, mods, S, mae_atol=2e-3, sr_slack=1):
         np.testing.assert_allclose(cpu(out["val_pred_clip_loss"]), fx["val_pred_clip_loss"], rtol=RTOL, atol=ATOL)
 
 
+def _check_gcbc(out, fx, mods, S, mae_atol=2e-3, sr_slack=1):
+    cpu = lambda t: t.detach().float().cpu().numpy()
+    for m in mods:
+        np.testing.assert_allclose(cpu(out[f"action_loss_{m}"]), fx[f"action_loss_{m}"], rtol=RTOL, atol=ATOL, err_msg=f"action_loss_{m}")
+        np.testing.assert_allclose(cpu(out[f"mae_{m}"]), fx[f"mae_{m}"], rtol=RTOL, atol=mae_atol, err_msg=f"mae_{m}")
+        assert abs(float(out[f"gripper_sr_{m}"]) - float(fx[f"gripper_sr_{m}"])) <= sr_slack / S + 1e-6
+    np.testing.assert_allclose(cpu(out["val_pred_clip_loss"]), fx["val_pred_clip_loss"], rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize("name", list(VAL_CASES))
 def test_oracle_validation_matches_reference_fixture(name):
     model, rnn_model, B, S = VAL_CASES[name]
@@ -51,9 +60,12 @@ def test_oracle_validation_matches_reference_fixture(name):
     fx = np.load(GOLDEN / f"{name}.npz")
     batch, noise, kw = _inputs(model, B, S, fx)
     sd = synthetic.make_state_dict(model, rnn_model)
-    if model != "mcil":
+    if "plan_idx" in kw:
         kw["plan_idx"] = {w: {m: v.long() for m, v in d.items()} for w, d in kw["plan_idx"].items()}
     out = O.validation_step(sd, batch, model=model, rnn_model=rnn_model, **kw)
+    if model == "gcbc":
+        _check_gcbc(out, fx, list(batch), S, mae_atol=1e-4)
+        return
     _check(out, fx, list(batch), S, mae_atol=1e-4)
     # the logged aggregates of validation_step (hulc.py:806-829)
     for m in batch:
@@ -79,8 +91,13 @@ def test_emu_validation_step_matches_oracle(emu, monkeypatch, model):
     eng.load_state_dict(sd)
     if model == "gcbc":
         out = eng.validation_step(batch, sample_u={"pr": kw["sample_u"]["pr"]})
-        assert all(bool(torch.isfinite(v).all()) for v in out.values())
-        assert {"action_loss_vis", "mae_lang", "gripper_sr_vis", "sample_act_lang"} <= set(out)
+        ref = O.validation_step(sd, batch, model="gcbc", sample_u={"pr": kw["sample_u"]["pr"]})
+        for m in batch:
+            torch.testing.assert_close(out[f"action_loss_{m}"], ref[f"action_loss_{m}"], rtol=RTOL, atol=ATOL)
+            torch.testing.assert_close(out[f"sample_act_{m}"], ref[f"sample_act_{m}"], rtol=1e-3, atol=2e-3)
+            torch.testing.assert_close(out[f"mae_{m}"], ref[f"mae_{m}"], rtol=1e-3, atol=1e-3)
+            assert abs(float(out[f"gripper_sr_{m}"]) - float(ref[f"gripper_sr_{m}"])) < 1e-6
+        torch.testing.assert_close(out["val_pred_clip_loss"], ref["val_pred_clip_loss"], rtol=RTOL, atol=ATOL)
         return
     if model == "hulc":  # the engine samples by inverse CDF from injected uniforms; hand the same classes to the oracle
         o1 = eng.step(batch, backward=False, plan_u={m: noise["pr"][m]["u"] for m in batch})
@@ -126,8 +143,13 @@ def test_gpu_validation_step_matches_reference_fixture(name, precision):
         dkw["plan_eps"] = {w: {m: to(v) for m, v in d.items()} for w, d in kw["plan_eps"].items()}
     if "plan_idx" in kw:
         dkw["plan_idx"] = {w: {m: to(v) for m, v in d.items()} for w, d in kw["plan_idx"].items()}
+    if model == "gcbc":
+        dkw = {"sample_u": {"pr": dkw["sample_u"]["pr"]}}
     out = eng.validation_step(synthetic._to(batch, "cuda"), **dkw)
     eng.check_nan_flag()
+    if model == "gcbc":
+        _check_gcbc(out, fx, list(batch), S, mae_atol=0.3 if precision == "tf32" else 2e-3, sr_slack=3 if precision == "tf32" else 1)
+        return
     # tf32 products move the action logits by up to ~1e-4: enough to flip a Gumbel-max choice between two near-tied mixture components
     # for a handful of the B*S*6 draws, which moves that sample (not the distribution) by O(1) -> the L1 error is only held loosely there;
     # the exact-fp32 mode pins the whole chain (sampling kernel, frame change, reductions) tightly.
@@ -189,3 +211,23 @@ def test_emu_module_validation_logs_reference_values(emu):
         assert torch.equal(out[f"idx_{m}"], batch[m]["idx"])
         for w in ("pp", "pr"):
             assert torch.equal(out[f"sampled_plan_{w}_{m}"].view(B, 32, 32).argmax(-1), torch.from_numpy(fx[f"plan_idx_{w}_{m}"]).long())
+
+
+def test_emu_gcbc_module_validation_logs_reference_values(emu):
+    """GCBC.validation_step (gcbc.py:183-281) through hulc_b200.models.gcbc.GCBC on the emulator: the reference's logged keys and values."""
+    from hulc_b200.models.gcbc import GCBC
+
+    name = "val_gcbc_b2s8"
+    _, rnn_model, B, S = VAL_CASES[name]
+    fx = np.load(GOLDEN / f"{name}.npz")
+    batch, noise, kw = _inputs("gcbc", B, S, fx)
+    cfg = synthetic.model_config("gcbc", target_root="hulc_b200")
+    cfg.pop("_target_"); cfg.pop("_recursive_")
+    model = GCBC(**cfg, device=torch.device("cpu"), precision="fp32")
+    model.load_state_dict(synthetic.make_state_dict("gcbc"), strict=False)
+    out = model.validation_step(batch, 0, sample_u={"pr": kw["sample_u"]["pr"]})
+    ref_keys = [k[len("logged/"):] for k in fx.files if k.startswith("logged/")]
+    assert len(ref_keys) == 12
+    for k in ref_keys:
+        np.testing.assert_allclose(float(model.logged[k]), float(fx["logged/" + k]), rtol=1e-3, atol=1e-4, err_msg=k)
+    assert all(torch.equal(out[f"idx_{m}"], batch[m]["idx"]) for m in batch)
