@@ -12,6 +12,7 @@ Layouts: frames and posterior tokens are batch-first rows (b*S + s); everything 
 from __future__ import annotations
 
 import math
+import contextlib
 import os
 from typing import Dict, List, Optional, Tuple
 
@@ -146,6 +147,8 @@ class HulcEngine:
         self.H = 2048
         self.gates = 3 if rnn_model == "gru_decoder" else 1
         self._bufs: Dict[str, torch.Tensor] = {}
+        self._buf_namespaces: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._infer_state = None
         self._step_shapes: Dict[str, tuple] = {}
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
         # per-step Philox seed, device resident: advanced on the device so a captured step draws fresh randomness per replay
@@ -170,6 +173,17 @@ class HulcEngine:
         if t is None or tuple(t.shape) != tuple(shape):
             t = self._bufs[name] = torch.zeros(*shape, dtype=torch.int32, device=self.device)
         return t
+
+    @contextlib.contextmanager
+    def _buffers(self, namespace: str):
+        """Run a block on its own set of persistent buffers.  The training step's buffers are the static inputs / outputs of its captured CUDA
+        graphs: validation batches or single-frame inference re-using the same names with other shapes would re-allocate them under a graph."""
+        saved = self._bufs
+        self._bufs = self._buf_namespaces.setdefault(namespace, {})
+        try:
+            yield
+        finally:
+            self._bufs = saved
 
     def load_state_dict(self, sd, strict=True):
         self.ps.load_state_dict(sd, strict)
@@ -872,7 +886,13 @@ class HulcEngine:
     # validation: lmp_val / validation_step, hulc/models/hulc.py:301-388, 739-841
     # ------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def validation_step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_eps=None, sample_u=None, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    def validation_step(self, batch: Dict[str, Dict], **kw) -> Dict[str, torch.Tensor]:
+        """See _validation_step; runs on its own buffer set so that a validation batch of another size cannot re-allocate the buffers
+        the training step's CUDA graphs were captured on."""
+        with self._buffers("validation"):
+            return self._validation_step(batch, **kw)
+
+    def _validation_step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_eps=None, sample_u=None, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """The reference's validation metrics for one batch, dropout off (eval mode): for the plan drawn from the proposal network ("pp")
         and from the recognition network ("pr") — action loss, actions sampled from the logistic mixture and mapped back to the world frame,
         their per-sequence L1 error (mae_*: [B, 6]) and gripper success rate — plus the KL and (language modality) the CLIP loss.
@@ -929,6 +949,119 @@ class HulcEngine:
         finally:
             self.dropout_p = p_save
         return res
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # inference: Hulc.step / get_pp_plan_{lang,vision} / predict_with_plan (hulc.py:851-957),
+    # LogisticDecoderRNN.act with the carried hidden state (logistic_decoder_rnn.py:104-119)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _infer_embed(self, rgb_static, rgb_gripper):
+        n = rgb_static.shape[0]
+        emb = self.buf("emb", n, 128)
+        self._encoder_fwd("static", [rgb_static], emb)
+        self._encoder_fwd("gripper", [rgb_gripper], emb)
+        return emb
+
+    @torch.no_grad()
+    def infer_plan(self, rgb_static, rgb_gripper, *, lang=None, plan_idx=None, plan_u=None, plan_eps=None, seed: Optional[int] = None):
+        """Start (or re-plan) a rollout: encode the goal and sample a latent plan from the proposal network.  rgb_*: [T, 3, H, W] frames — the
+        current observation (T = 1, language goal `lang` [1, 384]) or observation + goal image (T = 2, visual goal = embedding of the last
+        frame).  Clears the decoder's hidden state like the reference (hulc.py:926,952).  GCBC: goal only, no plan."""
+        P = self.ps.p
+        H = self.H
+        with self._buffers("inference"):
+            self._step_shapes.clear()
+            if seed is not None:
+                self.rng_dev.fill_(int(seed))
+            else:
+                self.rng_dev.add_(1)
+            if self.device.type == "cuda":
+                ops.set_rng_offset(self.rng_dev)
+            rng = 0 if self.device.type == "cuda" else int(self.rng_dev.item())
+            emb = self._infer_embed(rgb_static, rgb_gripper)
+            n = emb.shape[0]
+            goal = self.buf("goal", 1, 32)
+            if lang is not None:
+                self._mlp_ln_fwd("goal.lang", lang, [f"language_goal.mlp.{i}" for i in (1, 3, 5)], "language_goal.ln", goal)
+            else:
+                self._mlp_ln_fwd("goal.vis", emb[n - 1 : n], [f"visual_goal.mlp.{i}" for i in (0, 2, 4)], "visual_goal.ln", goal)
+            plan = None
+            if self.model != "gcbc":
+                w0 = P["plan_proposal.fc_model.0.weight"]
+                x = self.buf("pp.a1", 1, H)
+                self.gemm_fwd(emb[0:1], w0[:, :128], x, transB=True, bias=P["plan_proposal.fc_model.0.bias"])
+                self.gemm_fwd(goal, w0[:, 128:], x, transB=True, beta=1.0, act=RELU)
+                for j, i in enumerate((2, 4, 6)):
+                    y = self.buf(f"pp.a{j + 2}", 1, H)
+                    self.gemm_fwd(x, P[f"plan_proposal.fc_model.{i}.weight"], y, transB=True, bias=P[f"plan_proposal.fc_model.{i}.bias"], act=RELU)
+                    x = y
+                state_dim = P["plan_proposal.fc_state.0.weight"].shape[0]
+                pp_state = self.gemm_fwd(x, P["plan_proposal.fc_state.0.weight"], self.buf("pp.state", 1, state_dim), transB=True,
+                                         bias=P["plan_proposal.fc_state.0.bias"])
+                plan = self.buf("plan", 1, self.plan_features)
+                if self.discrete:
+                    idx_out = self._bufs.get("plan_idx")
+                    if idx_out is None:
+                        idx_out = self._bufs["plan_idx"] = torch.zeros(32, dtype=torch.int32, device=self.device)
+                    ops.plan_discrete_fwd(pp_state, pp_state, plan, self.buf("kl_rows", 32), u=None if plan_u is None or plan_idx is not None else plan_u.reshape(-1),
+                                          idx_in=None if plan_idx is None else plan_idx.reshape(-1).to(torch.int32), idx_out=idx_out, seed=rng, site=300)
+                else:
+                    ops.plan_cont_fwd(pp_state, pp_state, plan, self.buf("kl_el", 1, self.plan_features), eps=plan_eps, seed=rng, site=300)
+            self._infer_state = dict(goal=goal.clone(), plan=None if plan is None else plan.clone(), hidden=torch.zeros(2, 1, H, device=self.device))
+        return self._infer_state["plan"], self._infer_state["goal"]
+
+    @torch.no_grad()
+    def infer_act(self, rgb_static, rgb_gripper, robot_obs_raw, *, sample_u=None, seed: Optional[int] = None) -> torch.Tensor:
+        """One control step: encode the observation ([1, 3, H, W] frames), advance the decoder RNN by one step from the carried hidden state,
+        sample an action from the mixture and map it to the world frame (robot_obs_raw [1, 15]).  Returns [1, 1, 7]."""
+        if self._infer_state is None:
+            raise RuntimeError("infer_plan() starts a rollout")
+        P, ps, st = self.ps.p, self.ps, self._infer_state
+        H, Gn, PF = self.H, self.gates, self.plan_features
+        kind = "gru" if self.rnn_model == "gru_decoder" else "relu"
+        has_grip = self.model != "mcil"
+        A = self.n_dims + (1 if has_grip else 0)
+        with self._buffers("inference"):
+            self._step_shapes.clear()
+            if seed is not None:
+                self.rng_dev.fill_(int(seed))
+            else:
+                self.rng_dev.add_(1)
+            if self.device.type == "cuda":
+                ops.set_rng_offset(self.rng_dev)
+            rng = 0 if self.device.type == "cuda" else int(self.rng_dev.item())
+            emb = self._infer_embed(rgb_static, rgb_gripper)
+            C = 128 - self.percep_lo
+            rp = "action_decoder.rnn"
+            w_ih0 = P[f"{rp}.weight_ih_l0"]
+            w_plan, w_pc, w_goal = w_ih0[:, :PF], w_ih0[:, PF : PF + C], w_ih0[:, PF + C :]
+            const = self.buf("dec.const", 1, Gn * H)
+            self.gemm_fwd(st["goal"], w_goal, const, transB=True, bias=P[f"{rp}.bias_ih_l0"])
+            if PF:
+                self.gemm_fwd(st["plan"], w_plan, const, transB=True, beta=1.0)
+            percep = self.buf("dec.percep", 1, C)
+            ops.strided_copy(percep, emb[0:1, self.percep_lo :])
+            hb = [self.buf(f"dec.h{l}", 3, 1, H, zero=True) for l in range(2)]
+            for l in range(2):
+                ops.strided_copy(hb[l][0], st["hidden"][l])  # slot 0 = the hidden state carried from the previous control step
+            pre0 = self.buf("dec.pre0", 1, Gn * H)
+            self.gemm_fwd(percep, w_pc, pre0, transB=True, addend=const, add_mod=1, bias=None if kind == "gru" else P[f"{rp}.bias_hh_l0"])
+            self._rnn_fwd("dec.l0", pre0, P[f"{rp}.weight_hh_l0"], P[f"{rp}.bias_hh_l0"], hb[0], 0, 1, 1, kind=kind)
+            pre1 = self.buf("dec.pre1", 1, Gn * H)
+            self.gemm_fwd(hb[0][1], P[f"{rp}.weight_ih_l1"], pre1, transB=True, bias=P[f"{rp}.bias_ih_l1"],
+                          addend=None if kind == "gru" else P[f"{rp}.bias_hh_l1"].view(1, -1), add_mod=1)
+            self._rnn_fwd("dec.l1", pre1, P[f"{rp}.weight_hh_l1"], P[f"{rp}.bias_hh_l1"], hb[1], 0, 1, 1, kind=kind)
+            heads_p = self.gemm_fwd(hb[1][1], ps.heads_w, self.buf("dec.heads", 1, ps.n_heads_padded), transB=True, bias=ps.heads_b)
+            for l in range(2):
+                ops.strided_copy(st["hidden"][l], hb[l][1])
+            pred_tcp = self.buf("pred_tcp", 1, 1, A)
+            ops.logistic_sample(heads_p[:, : ps.n_heads], pred_tcp, 1, 1, 0, 1, time_major=True, n_dims=self.n_dims, n_mix=self.n_mix, has_gripper=has_grip,
+                                u_mix=None if sample_u is None else sample_u[0].contiguous(), u_inv=None if sample_u is None else sample_u[1].contiguous(),
+                                seed=rng, site=310)
+            if not has_grip:
+                return pred_tcp.clone()
+            out = self.buf("pred_world", 1, 1, A)
+            ops.tcp_to_world(pred_tcp, robot_obs_raw.reshape(1, 1, -1).contiguous(), out, self.nan_flag)
+            return out.clone()
 
     def optimizer_step(self, grad_scale=1.0):
         self.ps.adam_step(lr=self.lr, grad_scale=grad_scale)

@@ -359,6 +359,43 @@ class Hulc(_Base):
             output[f"idx_{m}"] = batch[m]["idx"]
         return output
 
+    # ---- inference (hulc.py:843-957) ------------------------------------------------------------------------------------------
+    def reset(self):
+        """Call at the beginning of a rollout (hulc.py:843-849)."""
+        self.plan = None
+        self.latent_goal = None
+        self.rollout_step_counter = 0
+        self.engine._infer_state = None
+
+    def load_lang_embeddings(self, embeddings_path):
+        """hulc.py:872-882: <dataset>/validation/embeddings.npy -> {annotation: embedding}."""
+        import numpy as np
+
+        embeddings = np.load(embeddings_path, allow_pickle=True).item()
+        self.lang_embeddings = {v["ann"][0]: v["emb"] for k, v in embeddings.items()}
+
+    @torch.no_grad()
+    def step(self, obs, goal, *, plan_idx=None, plan_u=None, sample_u=None):
+        """One control step (hulc.py:851-870).  obs: {"rgb_obs": {"rgb_static": (1,1,3,H,W), "rgb_gripper": (1,1,3,h,w)}, "robot_obs_raw":
+        (1,1,15), ...}; goal: an annotation string (key of `lang_embeddings`) or a goal observation dict.  Every `replan_freq` steps the goal
+        is encoded and a plan sampled from the proposal network (the decoder's hidden state is cleared); then the decoder advances one step and
+        the sampled action (world frame, (1,1,7)) is returned.  plan_idx / plan_u / sample_u inject the randomness for parity runs."""
+        if not hasattr(self, "rollout_step_counter"):
+            self.reset()
+        dev = self.engine.device
+        st, gr = obs["rgb_obs"]["rgb_static"].to(dev).float(), obs["rgb_obs"]["rgb_gripper"].to(dev).float()
+        if self.rollout_step_counter % self.replan_freq == 0:
+            if isinstance(goal, str):
+                lang = torch.from_numpy(self.lang_embeddings[goal]).to(dev).squeeze(0).float()
+                self.plan, self.latent_goal = self.engine.infer_plan(st[0].contiguous(), gr[0].contiguous(), lang=lang.reshape(1, -1).contiguous(), plan_idx=plan_idx, plan_u=plan_u)
+            else:
+                gs, gg = goal["rgb_obs"]["rgb_static"].to(dev).float(), goal["rgb_obs"]["rgb_gripper"].to(dev).float()
+                self.plan, self.latent_goal = self.engine.infer_plan(torch.cat([st, gs], 1)[0].contiguous(), torch.cat([gr, gg], 1)[0].contiguous(), plan_idx=plan_idx,
+                                                                     plan_u=plan_u)
+        action = self.engine.infer_act(st[0].contiguous(), gr[0].contiguous(), obs["robot_obs_raw"].to(dev).float().reshape(1, -1), sample_u=sample_u)
+        self.rollout_step_counter += 1
+        return action
+
     def lmp_train(self, perceptual_emb, latent_goal, train_acts, robot_obs):
         raise NotImplementedError(
             "lmp_train is fused into training_step here (one batched pass over both modalities); the per-block values it "

@@ -301,6 +301,22 @@ def validation_noise(batch: int, seq: int, modality: str, which: str, seed: int 
     }
 
 
+def rollout_inputs(steps: int, goal_kind: str = "lang", seed: int = 1) -> Dict[str, torch.Tensor]:
+    """Seeded inputs of an inference rollout (Hulc.step, hulc.py:851-870): `steps` observations, a language embedding or a goal image, and
+    the injected randomness (one categorical-sample uniform vector per re-plan, the two _sample draws per control step)."""
+    vis = make_modality("vis", 1, steps, seed=seed + 50)
+    other = make_modality("lang", 1, 1, seed=seed + 51)
+    g = torch.Generator().manual_seed(seed * 6151 + (1 if goal_kind == "lang" else 2))
+    return {
+        "rgb_static": vis["rgb_obs"]["rgb_static"][0], "rgb_gripper": vis["rgb_obs"]["rgb_gripper"][0],          # (steps, 3, H, W)
+        "robot_obs": vis["robot_obs"][0], "robot_obs_raw": vis["state_info"]["robot_obs"][0],                      # (steps, 8) / (steps, 15)
+        "lang": other["lang"],                                                                                    # (1, 384)
+        "goal_static": other["rgb_obs"]["rgb_static"][0], "goal_gripper": other["rgb_obs"]["rgb_gripper"][0],      # (1, 3, H, W)
+        "goal_robot_obs": other["robot_obs"][0],
+        "plan_u": torch.rand(steps, 32, generator=g), "u_mix": torch.rand(steps, 1, 1, 6, 10, generator=g), "u_inv": torch.rand(steps, 1, 1, 6, generator=g),
+    }
+
+
 def dropout_masks(
     batch: int, seq: int, modality: str, p: float, seed: int = 1, d_model: int = 128, nhead: int = 8, ff: int = 2048, nlayers: int = 2
 ) -> Dict[str, torch.Tensor]:

@@ -332,7 +332,76 @@ def run_val_case(name):
     print(f"[golden] {name}: act_loss_pp_vis={float(captured[list(batch)[0]][1]):.6f} keys={len(fx)}  ({time.time() - t0:.1f}s)")
 
 
+INFER_CASES = {
+    # name: (goal kind, control steps, replan_freq) — Hulc.step (hulc.py:851-870): re-plans (and clears the decoder's hidden state) every replan_freq steps
+    "infer_hulc_lang": ("lang", 7, 3),
+    "infer_hulc_vision": ("vision", 5, 4),
+}
+
+
+def run_infer_case(name):
+    """A rollout of the reference's Hulc.step with its randomness injected, the oracle's restatement on the same tensors, the fixture."""
+    kind, T, replan = INFER_CASES[name]
+    t0 = time.time()
+    net = build_reference("hulc", "rnn_decoder", 0.1, 32)
+    net.eval()
+    net.replan_freq = replan
+    r = synthetic.rollout_inputs(T, kind)
+    net.lang_embeddings = {"the task": r["lang"].numpy()[None]}  # load_lang_embeddings stores (1, 1, 384) arrays per annotation (hulc.py:872-882)
+    n_replans = (T + replan - 1) // replan
+    u_q = [r["plan_u"][i : i + 1] for i in range(n_replans)]
+    rand_q = []
+    for t in range(T):
+        rand_q += [r["u_mix"][t], r["u_inv"][t]]
+    orig_rand = torch.rand
+
+    def rand(*size, **kw):
+        u = rand_q.pop(0)
+        shape = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+        assert tuple(u.shape) == shape, (u.shape, shape)
+        return u.clone()
+
+    def obs(t):
+        return {"rgb_obs": {"rgb_static": r["rgb_static"][t][None, None], "rgb_gripper": r["rgb_gripper"][t][None, None]}, "depth_obs": {},
+                "robot_obs": r["robot_obs"][t][None, None], "robot_obs_raw": r["robot_obs_raw"][t][None, None]}
+
+    goal = "the task" if kind == "lang" else {"rgb_obs": {"rgb_static": r["goal_static"][None], "rgb_gripper": r["goal_gripper"][None]}, "depth_obs": {},
+                                              "robot_obs": r["goal_robot_obs"][None]}
+    plans, actions = [], []
+    net.reset()
+    torch.rand = rand
+    try:
+        with injected_randomness(u_q, [], [], 0.0), torch.no_grad():
+            for t in range(T):
+                a = net.step(obs(t), goal)
+                actions.append(a.detach().clone().reshape(7))
+                if t % replan == 0:
+                    plans.append(net.plan.detach().clone().view(32, 32).argmax(-1))
+    finally:
+        torch.rand = orig_rand
+    assert not u_q and not rand_q, "injected randomness not fully consumed"
+    actions, plan_idx = torch.stack(actions), torch.stack(plans)
+
+    # --- oracle ----------------------------------------------------------------------------------------------------
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    hidden = plan = goal_t = None
+    for t in range(T):
+        if t % replan == 0:
+            if kind == "lang":
+                plan, goal_t, _ = O.inference_plan(sd, r["rgb_static"][t : t + 1], r["rgb_gripper"][t : t + 1], lang=r["lang"], plan_idx=plan_idx[t // replan][None])
+            else:
+                plan, goal_t, _ = O.inference_plan(sd, torch.cat([r["rgb_static"][t : t + 1], r["goal_static"]]), torch.cat([r["rgb_gripper"][t : t + 1], r["goal_gripper"]]),
+                                                   plan_idx=plan_idx[t // replan][None])
+            hidden = torch.zeros(2, 1, 2048)
+        a, hidden = O.inference_act(sd, r["rgb_static"][t : t + 1], r["rgb_gripper"][t : t + 1], r["robot_obs_raw"][t : t + 1], plan, goal_t, hidden, r["u_mix"][t], r["u_inv"][t])
+        if not torch.allclose(a.reshape(7), actions[t], rtol=1e-4, atol=1e-4):
+            raise AssertionError(f"{name}: oracle != reference at step {t}: max|d|={float((a.reshape(7) - actions[t]).abs().max()):.3e}")
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLDEN / f"{name}.npz", actions=actions.numpy(), plan_idx=plan_idx.numpy())
+    print(f"[golden] {name}: {T} steps, {len(plans)} plans, |a|max={float(actions.abs().max()):.3f}  ({time.time() - t0:.1f}s)")
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES) + list(VAL_CASES)
+    names = sys.argv[1:] or list(CASES) + list(VAL_CASES) + list(INFER_CASES)
     for n in names:
-        (run_val_case if n in VAL_CASES else run_case)(n)
+        (run_val_case if n in VAL_CASES else run_infer_case if n in INFER_CASES else run_case)(n)
