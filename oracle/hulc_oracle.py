@@ -567,27 +567,45 @@ def validation_step(sd: SD, batch: Dict[str, Dict], *, model: str = "hulc", rnn_
 # inference: Hulc.step / get_pp_plan_{lang,vision} / predict_with_plan (hulc.py:851-957), LogisticDecoderRNN.act (:104-119)
 # ----------------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def inference_plan(sd: SD, rgb_static: torch.Tensor, rgb_gripper: torch.Tensor, *, lang: Optional[torch.Tensor] = None, plan_idx: torch.Tensor):
+def inference_plan(sd: SD, rgb_static: torch.Tensor, rgb_gripper: torch.Tensor, *, lang: Optional[torch.Tensor] = None, plan_idx: Optional[torch.Tensor] = None,
+                   plan_eps: Optional[torch.Tensor] = None, model: str = "hulc"):
     """get_pp_plan_lang (T = 1 frame, `lang` (1,384)) / get_pp_plan_vision (T = 2: observation + goal image; the goal is encoded from the last
-    frame): latent goal and a plan drawn from the proposal network (class indices `plan_idx` (1,32) injected).  rgb_*: (T,3,H,W)."""
+    frame): latent goal and a plan drawn from the proposal network (class indices `plan_idx` (1,32) or Normal noise `plan_eps` (1,256)
+    injected); GCBC (gcbc.py:287-317): the goal only, an empty plan.  rgb_*: (T,3,H,W)."""
     emb = perceptual_encoder(sd, rgb_static[None], rgb_gripper[None])
     goal = goal_encoder(sd, "language_goal", lang) if lang is not None else goal_encoder(sd, "visual_goal", emb[:, -1])
+    if model == "gcbc":
+        return emb.new_zeros(1, 0), goal, None
     pp_state = plan_proposal(sd, emb[:, 0], goal)
-    plan = torch.nn.functional.one_hot(plan_idx.long(), 32).to(emb.dtype).flatten(-2)
+    if model == "mcil":
+        mean, std = cont_state(pp_state)
+        plan = mean + std * plan_eps
+    else:
+        plan = torch.nn.functional.one_hot(plan_idx.long(), 32).to(emb.dtype).flatten(-2)
     return plan, goal, pp_state
 
 
 @torch.no_grad()
-def inference_act(sd: SD, rgb_static, rgb_gripper, robot_obs_raw, plan, goal, hidden, u_mix, u_inv):
-    """predict_with_plan -> LogisticDecoderRNN.act: one step of the 2-layer ReLU RNN from the carried hidden state (2,1,H), sampled action
-    mapped to the world frame.  Returns (action (1,1,7), new hidden)."""
+def inference_act(sd: SD, rgb_static, rgb_gripper, robot_obs_raw, plan, goal, hidden, u_mix, u_inv, *, model: str = "hulc", rnn_model: str = "rnn_decoder"):
+    """predict_with_plan -> LogisticDecoderRNN.act: one step of the 2-layer decoder RNN (ReLU Elman cell or GRU) from the carried hidden state
+    (2,1,H), sampled action mapped to the world frame (not for MCIL: no gripper control).  Returns (action (1,1,7), new hidden)."""
     emb = perceptual_encoder(sd, rgb_static[None], rgb_gripper[None])
-    x = torch.cat([plan, emb[:, 0, 64:128], goal], -1)
+    dg = model != "mcil"
+    x = torch.cat([plan, emb[:, 0, 64:128] if dg else emb[:, 0], goal], -1)
     new_hidden = []
+    p = "action_decoder.rnn"
     for l in range(2):
-        p = f"action_decoder.rnn"
-        x = torch.relu(x @ sd[f"{p}.weight_ih_l{l}"].t() + sd[f"{p}.bias_ih_l{l}"] + hidden[l] @ sd[f"{p}.weight_hh_l{l}"].t() + sd[f"{p}.bias_hh_l{l}"])
+        Wi, Wh, bi, bh = sd[f"{p}.weight_ih_l{l}"], sd[f"{p}.weight_hh_l{l}"], sd[f"{p}.bias_ih_l{l}"], sd[f"{p}.bias_hh_l{l}"]
+        if rnn_model == "gru_decoder":
+            H = Wh.shape[1]
+            gi, gh = x @ Wi.t() + bi, hidden[l] @ Wh.t() + bh
+            r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+            z = torch.sigmoid(gi[:, H : 2 * H] + gh[:, H : 2 * H])
+            n = torch.tanh(gi[:, 2 * H :] + r * gh[:, 2 * H :])
+            x = (1 - z) * n + z * hidden[l]
+        else:
+            x = torch.relu(x @ Wi.t() + bi + hidden[l] @ Wh.t() + bh)
         new_hidden.append(x)
-    lp, ls, mu, grip = decoder_heads(sd, x[:, None], 6, 10, -7.0, True)
+    lp, ls, mu, grip = decoder_heads(sd, x[:, None], 6 if dg else 7, 10, -7.0, dg)
     pred = logistic_mixture_sample(lp, ls, mu, grip, u_mix, u_inv)
-    return tcp_to_world_frame(pred, robot_obs_raw.reshape(1, 1, -1)), torch.stack(new_hidden)
+    return (tcp_to_world_frame(pred, robot_obs_raw.reshape(1, 1, -1)) if dg else pred), torch.stack(new_hidden)
