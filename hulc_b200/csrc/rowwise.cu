@@ -431,6 +431,20 @@ __global__ void scale_kernel(float* __restrict__ x, long long n, float alpha) {
   if (i < n) x[i] *= alpha;
 }
 
+// x *= *alpha_ptr; every block returns at once when the factor is exactly 1 (the common case: autograd's root gradient)
+__global__ void scale_dev_kernel(float* __restrict__ x, long long n, const float* __restrict__ alpha_ptr) {
+  const float alpha = *alpha_ptr;
+  if (alpha == 1.0f) return;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<float4*>(x + i);
+    v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+    *reinterpret_cast<float4*>(x + i) = v;
+  } else {
+    for (; i < n; ++i) x[i] *= alpha;
+  }
+}
+
 }  // namespace
 
 HULC_API int hulc_layernorm_fwd(const float* x, int ldx, const float* res, int ldres, const float* w, const float* b, float* y, int ldy,
@@ -584,5 +598,12 @@ HULC_API int hulc_frames_u8_to_f32(const unsigned char* src, float* dst, long lo
 HULC_API int hulc_scale(float* x, long long n, float alpha, void* stream) {
   if (n <= 0) return 0;
   HULC_LAUNCH(scale_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, n, alpha);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_scale_dev(float* x, long long n, const float* alpha_ptr, void* stream) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<size_t>(x) & 15) != 0 || !alpha_ptr) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(scale_dev_kernel, dim3(hulc_cdiv(hulc_cdiv(n, 4), 256)), dim3(256), 0, (cudaStream_t)stream, x, n, alpha_ptr);
   HULC_RETURN_LAST();
 }

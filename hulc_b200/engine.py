@@ -20,7 +20,7 @@ import torch
 
 from . import ops
 from .ops import Drop, NO_DROP, gemm, colsum
-from .utils.synthetic import param_spec
+from .spec import ModelDims, param_spec
 
 RELU, TANH, GATE_TANH = 1, 2, 4
 _POISON = bool(int(os.environ.get("HULC_B200_POISON", "0")))
@@ -108,9 +108,10 @@ class ParamStore:
 class StepGraph:
     """A captured training step (see HulcEngine.capture)."""
 
-    def __init__(self, engine, graph, out, optimizer, launches):
+    def __init__(self, engine, graph, out, optimizer, launches, namespace=None):
         self.engine, self.graph, self.out, self.optimizer = engine, graph, out, optimizer
         self.launches = launches  # kernels of libhulc_b200.so inside one replay
+        self.namespace = namespace  # the engine's buffer set this graph's pointers refer to
 
     def replay(self) -> Dict[str, torch.Tensor]:
         self.graph.replay()
@@ -123,31 +124,40 @@ class HulcEngine:
     """Owns the parameters and runs fused forward+backward steps.  `model` in {"hulc", "gcbc", "mcil"}."""
 
     def __init__(self, model="hulc", rnn_model="rnn_decoder", max_window=32, device="cuda", dropout_p=0.1, kl_beta=0.01,
-                 kl_balancing_mix=0.8, clip_beta=3.0, gripper_alpha=1.0, nhead=8, nlayers=2, lr=2e-4, precision="tf32"):
+                 kl_balancing_mix=0.8, clip_beta=3.0, gripper_alpha=1.0, nhead=8, nlayers=2, lr=2e-4, precision="tf32", dims: Optional[ModelDims] = None):
         """precision: "tf32" (default) runs the convolutions and the large backward GEMMs on the tensor cores with tf32
         operands and the large forward GEMMs as 3xTF32 (fp32-level accuracy); "fp32" keeps every product on the exact-fp32
-        CUDA-core kernels (also the only mode of the host-emulated build used by the CPU tests)."""
+        CUDA-core kernels (also the only mode of the host-emulated build used by the CPU tests).  `dims` (hulc_b200.spec.ModelDims,
+        normally read from the Hydra config tree by `dims_from_configs`) overrides the individual size arguments."""
+        if dims is None:
+            dims = ModelDims(model=model, rnn_model=rnn_model, max_window=max_window, dropout_p=float(dropout_p) if model != "mcil" else 0.0, nhead=nhead,
+                             nlayers=nlayers, gripper_alpha=float(gripper_alpha))
+        model, rnn_model = dims.model, dims.rnn_model
         assert model in ("hulc", "gcbc", "mcil") and rnn_model in ("rnn_decoder", "gru_decoder")
         assert precision in ("tf32", "fp32")
+        self.dims = dims
         self.tc = precision == "tf32"
         self.persistent_rnn = os.environ.get("HULC_B200_PERSISTENT_RNN", "1") != "0"  # whole recurrence in one launch (csrc/rnn_tc.cu)
         self.model, self.rnn_model = model, rnn_model
         self.device = torch.device(device)
-        self.spec = param_spec(model, rnn_model, max_window)
+        self.spec = param_spec(dims=dims)
         self.ps = ParamStore(self.spec, device)
-        self.dropout_p = float(dropout_p) if model != "mcil" else 0.0
-        self.kl_beta, self.kl_alpha, self.clip_beta, self.gripper_alpha = float(kl_beta), float(kl_balancing_mix), float(clip_beta), float(gripper_alpha)
-        self.nhead, self.nlayers, self.lr = nhead, nlayers, lr
-        self.discrete = model != "mcil"
-        self.plan_features = {"hulc": 1024, "gcbc": 0, "mcil": 256}[model]
-        self.percep_lo = 64 if model != "mcil" else 0  # decoder sees emb[..., 64:128] (gripper features) unless MCIL
-        self.n_dims = 6 if model != "mcil" else 7
-        self.n_mix = 10
-        self.num_classes = 10 if model != "mcil" else 256
-        self.H = 2048
+        self.dropout_p = float(dims.dropout_p) if model != "mcil" else 0.0
+        self.kl_beta, self.kl_alpha, self.clip_beta, self.gripper_alpha = float(kl_beta), float(kl_balancing_mix), float(clip_beta), float(dims.gripper_alpha)
+        self.nhead, self.nlayers, self.lr = dims.nhead, dims.nlayers, lr
+        self.discrete = dims.discrete
+        self.plan_features = dims.plan_features
+        self.percep_lo = dims.percep_lo  # decoder sees emb[..., 64:128] (gripper features) unless MCIL
+        self.n_dims = dims.n_dims
+        self.n_mix = dims.n_mix
+        self.num_classes = dims.num_classes
+        self.H = dims.dec_hidden
+        self.H_prior = dims.prior_hidden
+        self.H_bi = 2048  # hidden size of the MCIL BiRNN posterior (plan_recognition_net.py:27-34)
         self.gates = 3 if rnn_model == "gru_decoder" else 1
         self._bufs: Dict[str, torch.Tensor] = {}
-        self._buf_namespaces: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._train_root = self._bufs  # the dictionary in place outside any namespace
+        self._buf_namespaces: Dict[object, Dict[str, torch.Tensor]] = {}
         self._infer_state = None
         self._step_shapes: Dict[str, tuple] = {}
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
@@ -175,7 +185,7 @@ class HulcEngine:
         return t
 
     @contextlib.contextmanager
-    def _buffers(self, namespace: str):
+    def _buffers(self, namespace):
         """Run a block on its own set of persistent buffers.  The training step's buffers are the static inputs / outputs of its captured CUDA
         graphs: validation batches or single-frame inference re-using the same names with other shapes would re-allocate them under a graph."""
         saved = self._bufs
@@ -292,7 +302,7 @@ class HulcEngine:
         a2 = ops.conv2d_fwd(a1, P[f"{pre}.conv_model.2.weight"], P[f"{pre}.conv_model.2.bias"], 2, self.buf(f"{which}.a2", N, 64, sizes[2], sizes[2]))
         a3 = ops.conv2d_fwd(a2, P[f"{pre}.conv_model.4.weight"], P[f"{pre}.conv_model.4.bias"], 1, self.buf(f"{which}.a3", N, 64, sizes[3], sizes[3]))
         if which == "static":
-            feat = ops.spatial_softmax_fwd(a3, self.buf("static.ss", N, 128))
+            feat = ops.spatial_softmax_fwd(a3, self.buf("static.ss", N, 128), temperature=self.dims.spatial_softmax_temp)
             names = [f"{pre}.fc1.0", f"{pre}.fc2"]
             out = emb[:, 0:64]
         else:
@@ -311,7 +321,7 @@ class HulcEngine:
         N = a3.shape[0]
         if which == "static":
             dss = self._mlp_ln_bwd(which, ctx["acts"], ctx["stats"], ctx["names"], f"{pre}.ln", dout, self.buf("static.dss", N, 128))
-            da3 = ops.spatial_softmax_bwd(a3, dss, self.buf("static.da3", *a3.shape), relu_gate=True)
+            da3 = ops.spatial_softmax_bwd(a3, dss, self.buf("static.da3", *a3.shape), temperature=self.dims.spatial_softmax_temp, relu_gate=True)
         else:
             # dgrad of the flatten-FC, gated by conv3's ReLU
             acts, names = ctx["acts"], ctx["names"]
@@ -358,7 +368,7 @@ class HulcEngine:
         a3 = ops.conv2d_tc_fwd(a2, P[f"{pre}.conv_model.4.weight"], P[f"{pre}.conv_model.4.bias"], 1, self.buf(f"{which}.a3", N, sizes[3], sizes[3], 64))
         w0 = None
         if which == "static":
-            feat = ops.spatial_softmax_nhwc_fwd(a3, self.buf("static.ss", N, 128))
+            feat = ops.spatial_softmax_nhwc_fwd(a3, self.buf("static.ss", N, 128), temperature=self.dims.spatial_softmax_temp)
             names = [f"{pre}.fc1.0", f"{pre}.fc2"]
             out = emb[:, 0:64]
         else:
@@ -381,7 +391,7 @@ class HulcEngine:
         N = a3.shape[0]
         if which == "static":
             dss = self._mlp_ln_bwd(which, ctx["acts"], ctx["stats"], ctx["names"], f"{pre}.ln", dout, self.buf("static.dss", N, 128))
-            da3 = ops.spatial_softmax_nhwc_bwd(a3, dss, self.buf("static.da3", *a3.shape), relu_gate=True)
+            da3 = ops.spatial_softmax_nhwc_bwd(a3, dss, self.buf("static.da3", *a3.shape), temperature=self.dims.spatial_softmax_temp, relu_gate=True)
         else:
             acts, names, w0 = ctx["acts"], ctx["names"], ctx["w0"]
             d = self.buf(f"{which}.mlp_dz", *acts[-1].shape)
@@ -417,7 +427,7 @@ class HulcEngine:
         """Run one direction of one layer.  pre [S*B, G*H] holds x W_ih^T + b_ih (+ b_hh for Elman cells); hbuf has S+2
         time slots of [B, ld] (slot 0 and S+1 stay zero), h_t is written to slot t+1, columns col0:col0+H.
         Tensor-core mode: every step is a split-K 3xTF32 product (fp32-level accuracy on the 32-step chain)."""
-        H = self.H
+        H = w_hh.shape[1]
         h = lambda slot: hbuf[slot, :, col0 : col0 + H]
         pre3 = pre.view(S, B, -1)
         saved = self.buf(f"{tag}.saved", S, B, 4 * H) if kind == "gru" else None
@@ -447,7 +457,7 @@ class HulcEngine:
         """BPTT through one direction of one layer.  dh_above [S*B, ld_above] (a column view is fine) is dL/dh_t from the
         consumer.  Returns (dpre [S*B, G*H], dgh [S*B, G*H]): gradients w.r.t. the input-side and hidden-side
         pre-activations (identical tensors for Elman cells)."""
-        H, Gn = self.H, self.gates if kind == "gru" else 1
+        H, Gn = w_hh.shape[1], self.gates if kind == "gru" else 1
         h = lambda slot: hbuf[slot, :, col0 : col0 + H]
         ab = lambda t: dh_above[t * B : (t + 1) * B]
         if kind == "gru":
@@ -483,16 +493,44 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     # the step
     # ------------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def batch_signature(batch: Dict[str, Dict]) -> tuple:
+        """Shapes that size the step's activation buffers: (modality, sequences, window, frame shapes / dtypes)."""
+        sig = []
+        for m, d in batch.items():
+            rgb = d.get("rgb_obs", {})
+            sig.append((m, tuple(d["actions"].shape[:2])) + tuple((k, tuple(v.shape[2:]), str(v.dtype)) for k, v in sorted(rgb.items())))
+        return tuple(sig)
+
     @torch.no_grad()
-    def step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_u=None, plan_eps=None, dropout_masks=None, seed: Optional[int] = None,
-             backward: bool = True, plan_from: str = "posterior") -> Dict[str, torch.Tensor]:
+    def step(self, batch: Dict[str, Dict], **kw) -> Dict[str, torch.Tensor]:
+        """See _step.  Every distinct batch signature gets its own set of persistent activation buffers: a CUDA graph captured on one shape keeps
+        valid pointers when a batch of another shape (the last, partial batch of an epoch) comes through in between."""
+        if self._bufs is not self._train_root:  # already inside a namespace (validation / inference / lmp_train)
+            return self._step(batch, **kw)
+        with self._buffers(("train", self.batch_signature(batch))):
+            return self._step(batch, **kw)
+
+    def train_buffers(self, batch) -> Dict[str, torch.Tensor]:
+        """The persistent activation buffers of the training step for batches shaped like `batch` (after a step ran)."""
+        return self._buf_namespaces[("train", self.batch_signature(batch))]
+
+    def release_buffers(self, namespace) -> None:
+        """Drop a buffer namespace (its graphs were evicted)."""
+        self._buf_namespaces.pop(namespace, None)
+
+    def _step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_u=None, plan_eps=None, dropout_masks=None, seed: Optional[int] = None,
+              backward: bool = True, plan_from: str = "posterior", emb_override: Optional[torch.Tensor] = None,
+              goal_override: Optional[torch.Tensor] = None, with_clip: bool = True) -> Dict[str, torch.Tensor]:
         """One fused forward(+backward) over `batch` (the reference's {"vis": ..., "lang": ...} contract).  Gradients of
         total_loss land in `self.ps.grad` (zeroed first).  Randomness: `plan_idx[m]` / `plan_u[m]` / `plan_eps[m]` and
         `dropout_masks` (dict site -> uint8 keep mask over the whole batch, modalities concatenated in batch order)
         inject it for parity runs; otherwise Philox streams keyed on `seed` (None: the previous seed + 1).  `plan_from="prior"` (forward
         only, validation path) draws the latent plan from the plan-proposal network instead of the recognition network; the KL it reports is
-        then meaningless and ignored by the caller."""
+        then meaningless and ignored by the caller.  `emb_override` [nB, S, 128] / `goal_override` [nB, 32] (forward only) replace the outputs of
+        the perceptual / goal encoders — the entry point of `Hulc.lmp_train`, which receives them from its caller (hulc.py:254-299)."""
         assert plan_from in ("posterior", "prior") and not (backward and plan_from == "prior")
+        assert not (backward and (emb_override is not None or goal_override is not None))
         P, G, ps = self.ps.p, self.ps.g, self.ps
         self._step_shapes.clear()
         if seed is not None:
@@ -523,12 +561,17 @@ class HulcEngine:
         if backward:
             ps.zero_grad()
         losses = self.buf("losses", 16, zero=True)  # per modality m: [4m] nll, [4m+1] ce, [4m+2] kl, [4m+3] clip
+        losses.zero_()  # slots of a modality order / count seen on an earlier step must not leak into this step's totals
         lview = lambda i: losses[i : i + 1]
 
         # ---- perceptual encoders --------------------------------------------------------------------------------------
         emb = self.buf("emb", N, 128)
-        ctx_s = self._encoder_fwd("static", [batch[m]["rgb_obs"]["rgb_static"].flatten(0, 1) for m in mods], emb)
-        ctx_g = self._encoder_fwd("gripper", [batch[m]["rgb_obs"]["rgb_gripper"].flatten(0, 1) for m in mods], emb)
+        if emb_override is not None:
+            ops.strided_copy(emb.view(nB, S, 128), emb_override)
+            ctx_s = ctx_g = None
+        else:
+            ctx_s = self._encoder_fwd("static", [batch[m]["rgb_obs"]["rgb_static"].flatten(0, 1) for m in mods], emb)
+            ctx_g = self._encoder_fwd("gripper", [batch[m]["rgb_obs"]["rgb_gripper"].flatten(0, 1) for m in mods], emb)
         emb3 = emb.view(nB, S, 128)
         out["perceptual_emb"] = emb3
 
@@ -536,6 +579,9 @@ class HulcEngine:
         goal = self.buf("goal", nB, 32)
         goal_ctx = []
         for m, b0, Bm in zip(mods, b0s, Bs):
+            if goal_override is not None:
+                ops.strided_copy(goal[b0 : b0 + Bm], goal_override[b0 : b0 + Bm])
+                continue
             if "lang" in m:
                 x, names, ln = batch[m]["lang"], [f"language_goal.mlp.{i}" for i in (1, 3, 5)], "language_goal.ln"
             else:
@@ -547,11 +593,11 @@ class HulcEngine:
         # ---- plan proposal = prior (plan_proposal_net.py:42-47): cat(emb[:,0], goal) never materialised ----------------------
         if self.model != "gcbc":
             w0 = P["plan_proposal.fc_model.0.weight"]
-            pp = [None, self.buf("pp.a1", nB, H)]
+            pp = [None, self.buf("pp.a1", nB, self.H_prior)]
             self.gemm_fwd(emb3[:, 0, :], w0[:, :128], pp[1], transB=True, bias=P["plan_proposal.fc_model.0.bias"])
             self.gemm_fwd(goal, w0[:, 128:], pp[1], transB=True, beta=1.0, act=RELU)
             for j, i in enumerate((2, 4, 6)):
-                y = self.buf(f"pp.a{j + 2}", nB, H)
+                y = self.buf(f"pp.a{j + 2}", nB, self.H_prior)
                 self.gemm_fwd(pp[-1], P[f"plan_proposal.fc_model.{i}.weight"], y, transB=True, bias=P[f"plan_proposal.fc_model.{i}.bias"], act=RELU)
                 pp.append(y)
             state_dim = P["plan_proposal.fc_state.0.weight"].shape[0]
@@ -645,22 +691,23 @@ class HulcEngine:
         for i, (m, b0, Bm) in enumerate(zip(mods, b0s, Bs)):
             ops.logistic_loss(heads, acts_all, dheads, losses[4 * i : 4 * i + 2], nB, S, b0, Bm, time_major=True, n_dims=self.n_dims,
                               n_mix=self.n_mix, num_classes=self.num_classes, has_gripper=has_grip, gripper_alpha=self.gripper_alpha,
-                              grad_scale=1.0 / n_mod)
+                              grad_scale=1.0 / n_mod, log_scale_min=self.dims.log_scale_min, act_min=self.dims.act_min, act_max=self.dims.act_max)
 
         # ---- CLIP auxiliary loss (hulc.py:650-695, proj_vis_lang.py:23-27), language modality only --------------------------------
         clip_ctx = None
-        if self.model != "mcil":
+        if self.model != "mcil" and with_clip:
             for i, (m, b0, Bm) in enumerate(zip(mods, b0s, Bs)):
                 if "lang" not in m:
                     continue
                 sf, gl = seq_feat[b0 : b0 + Bm], goal[b0 : b0 + Bm]
-                im1 = self.gemm_fwd(sf, P["proj_vis_lang.mlp_im.0.weight"], self.buf("clip.im1", Bm, 128), transB=True, bias=P["proj_vis_lang.mlp_im.0.bias"], act=RELU)
-                im2 = self.gemm_fwd(im1, P["proj_vis_lang.mlp_im.2.weight"], self.buf("clip.im2", Bm, 32), transB=True, bias=P["proj_vis_lang.mlp_im.2.bias"])
-                tx1 = self.gemm_fwd(gl, P["proj_vis_lang.mlp_lang.0.weight"], self.buf("clip.tx1", Bm, 128), transB=True, bias=P["proj_vis_lang.mlp_lang.0.bias"], act=RELU)
-                tx2 = self.gemm_fwd(tx1, P["proj_vis_lang.mlp_lang.2.weight"], self.buf("clip.tx2", Bm, 32), transB=True, bias=P["proj_vis_lang.mlp_lang.2.bias"])
+                H1, Dc = P["proj_vis_lang.mlp_im.0.weight"].shape[0], P["proj_vis_lang.mlp_im.2.weight"].shape[0]
+                im1 = self.gemm_fwd(sf, P["proj_vis_lang.mlp_im.0.weight"], self.buf("clip.im1", Bm, H1), transB=True, bias=P["proj_vis_lang.mlp_im.0.bias"], act=RELU)
+                im2 = self.gemm_fwd(im1, P["proj_vis_lang.mlp_im.2.weight"], self.buf("clip.im2", Bm, Dc), transB=True, bias=P["proj_vis_lang.mlp_im.2.bias"])
+                tx1 = self.gemm_fwd(gl, P["proj_vis_lang.mlp_lang.0.weight"], self.buf("clip.tx1", Bm, H1), transB=True, bias=P["proj_vis_lang.mlp_lang.0.bias"], act=RELU)
+                tx2 = self.gemm_fwd(tx1, P["proj_vis_lang.mlp_lang.2.weight"], self.buf("clip.tx2", Bm, Dc), transB=True, bias=P["proj_vis_lang.mlp_lang.2.bias"])
                 mask = batch[m].get("use_for_aux_lang_loss")
                 mask8 = mask.to(torch.uint8) if mask is not None else None
-                d_im2, d_tx2 = self.buf("clip.dim2", Bm, 32), self.buf("clip.dtx2", Bm, 32)
+                d_im2, d_tx2 = self.buf("clip.dim2", Bm, Dc), self.buf("clip.dtx2", Bm, Dc)
                 ops.clip_loss(im2, tx2, P["logit_scale"].view(1), mask8, lview(4 * i + 3), d_im2, d_tx2, G["logit_scale"].view(1), grad_scale=self.clip_beta)
                 clip_ctx = (i, b0, Bm, sf, gl, im1, tx1, d_im2, d_tx2)
 
@@ -668,7 +715,7 @@ class HulcEngine:
         L = losses.view(4, 4)[:n_mod]
         act_m = L[:, 0] + (self.gripper_alpha * L[:, 1] if has_grip else 0.0)
         kl_m = self.kl_beta * L[:, 2] if self.model != "gcbc" else torch.zeros_like(L[:, 2])
-        clip = L[:, 3].sum() if self.model != "mcil" else None
+        clip = L[:, 3].sum() if (self.model != "mcil" and with_clip) else None
         total = (act_m + kl_m).sum() / n_mod
         if clip is not None:
             total = total + self.clip_beta * clip
@@ -719,9 +766,9 @@ class HulcEngine:
         dseq.zero_()
         if clip_ctx is not None:
             i, b0, Bm, sf, gl, im1, tx1, d_im2, d_tx2 = clip_ctx
-            d_im1 = self._linear_bwd("proj_vis_lang.mlp_im.2", im1, d_im2, self.buf("clip.dim1", Bm, 128), gate=im1)
+            d_im1 = self._linear_bwd("proj_vis_lang.mlp_im.2", im1, d_im2, self.buf("clip.dim1", *im1.shape), gate=im1)
             self._linear_bwd("proj_vis_lang.mlp_im.0", sf, d_im1, dseq[b0 : b0 + Bm])
-            d_tx1 = self._linear_bwd("proj_vis_lang.mlp_lang.2", tx1, d_tx2, self.buf("clip.dtx1", Bm, 128), gate=tx1)
+            d_tx1 = self._linear_bwd("proj_vis_lang.mlp_lang.2", tx1, d_tx2, self.buf("clip.dtx1", *tx1.shape), gate=tx1)
             self._linear_bwd("proj_vis_lang.mlp_lang.0", gl, d_tx1, dgoal[b0 : b0 + Bm], dx_beta=1.0)
 
         # latent plan
@@ -752,7 +799,7 @@ class HulcEngine:
             names = ["plan_proposal.fc_state.0"] + [f"plan_proposal.fc_model.{i}" for i in (6, 4, 2)]
             for j, n in enumerate(names):
                 x = pp[len(pp) - 1 - j]
-                nd = self.buf(f"pp.d{j}", nB, H)
+                nd = self.buf(f"pp.d{j}", nB, self.H_prior)
                 self._linear_bwd(n, x, d, nd, gate=x)
                 d = nd
             g0 = G["plan_proposal.fc_model.0.weight"]
@@ -839,7 +886,7 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     def _birnn_fwd(self, emb3, S, nB):
         P = self.ps.p
-        H = self.H
+        H = self.H_bi
         rp = "plan_recognition.birnn_model"
         x_tm = self.buf("bi.x", S, nB, 128)
         ops.strided_copy(x_tm, emb3.transpose(0, 1))
@@ -860,7 +907,7 @@ class HulcEngine:
 
     def _birnn_bwd(self, post, dseq, demb3, S, nB):
         P, G = self.ps.p, self.ps.g
-        H = self.H
+        H = self.H_bi
         rp = "plan_recognition.birnn_model"
         dabove = self.buf("bi.dabove1", S, nB, 2 * H)
         dabove.zero_()
@@ -923,7 +970,7 @@ class HulcEngine:
                 acts = self.buf("val.actions", nB, S, A)
                 for i, (m, b0, Bm) in enumerate(zip(mods, b0s, Bs)):
                     u = (sample_u or {}).get(which, {}).get(m)
-                    ops.logistic_sample(heads, pred_tcp, nB, S, b0, Bm, time_major=True, n_dims=self.n_dims, n_mix=self.n_mix, has_gripper=has_grip,
+                    ops.logistic_sample(heads, pred_tcp, nB, S, b0, Bm, time_major=True, n_dims=self.n_dims, n_mix=self.n_mix, has_gripper=has_grip, log_scale_min=self.dims.log_scale_min,
                                         u_mix=None if u is None else u[0].contiguous(), u_inv=None if u is None else u[1].contiguous(), seed=rng,
                                         site=200 + 2 * i)
                     ops.strided_copy(acts[b0 : b0 + Bm], batch[m]["actions"])
@@ -949,6 +996,40 @@ class HulcEngine:
         finally:
             self.dropout_p = p_save
         return res
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # the blocks behind Hulc.lmp_train / Hulc.clip_auxiliary_loss as stand-alone forward passes (hulc.py:254-299, 650-695)
+    # ------------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def lmp_forward(self, perceptual_emb, latent_goal, actions, robot_obs, **inject) -> Dict[str, torch.Tensor]:
+        """Prior, posterior, plan sample, decoder and losses for ONE modality from already-encoded inputs: perceptual_emb [B, S, 128],
+        latent_goal [B, 32], actions [B, S, 7], robot_obs [B, S, 15] (raw).  Forward only — the training step fuses this block with the
+        encoders and the backward pass.  `inject`: plan_idx / plan_u / plan_eps / dropout_masks / seed as in `step`, keyed by "vis"."""
+        batch = {"vis": {"actions": actions.contiguous(), "state_info": {"robot_obs": robot_obs.contiguous()}}}
+        with self._buffers(("lmp", tuple(actions.shape[:2]))):
+            out = self._step(batch, backward=False, emb_override=perceptual_emb.contiguous(), goal_override=latent_goal.contiguous(), with_clip=False, **inject)
+            return {k: v.clone() for k, v in out.items()}
+
+    @torch.no_grad()
+    def clip_forward(self, seq_feat, latent_goal, mask=None) -> torch.Tensor:
+        """CLIP-style contrastive loss of the projected sequence features and language goals (hulc.py:650-695, proj_vis_lang.py:23-27);
+        `mask` [B] bool selects the rows (none selected: 0, as the reference's dummy pass)."""
+        P, G = self.ps.p, self.ps.g
+        Bm = seq_feat.shape[0]
+        with self._buffers(("clip", Bm)):
+            self._step_shapes.clear()
+            sf, gl = seq_feat.contiguous(), latent_goal.contiguous()
+            H1, Dc = P["proj_vis_lang.mlp_im.0.weight"].shape[0], P["proj_vis_lang.mlp_im.2.weight"].shape[0]
+            im1 = self.gemm_fwd(sf, P["proj_vis_lang.mlp_im.0.weight"], self.buf("clip.im1", Bm, H1), transB=True, bias=P["proj_vis_lang.mlp_im.0.bias"], act=RELU)
+            im2 = self.gemm_fwd(im1, P["proj_vis_lang.mlp_im.2.weight"], self.buf("clip.im2", Bm, Dc), transB=True, bias=P["proj_vis_lang.mlp_im.2.bias"])
+            tx1 = self.gemm_fwd(gl, P["proj_vis_lang.mlp_lang.0.weight"], self.buf("clip.tx1", Bm, H1), transB=True, bias=P["proj_vis_lang.mlp_lang.0.bias"], act=RELU)
+            tx2 = self.gemm_fwd(tx1, P["proj_vis_lang.mlp_lang.2.weight"], self.buf("clip.tx2", Bm, Dc), transB=True, bias=P["proj_vis_lang.mlp_lang.2.bias"])
+            loss = self.buf("clip.loss", 1, zero=True)
+            loss.zero_()
+            scratch = self.buf("clip.dscale", 1)  # the kernel also emits gradients: they go to scratch here
+            ops.clip_loss(im2, tx2, P["logit_scale"].view(1), None if mask is None else mask.to(torch.uint8), loss, self.buf("clip.dim2", Bm, Dc), self.buf("clip.dtx2", Bm, Dc),
+                          scratch, grad_scale=1.0)
+            return loss[0].clone()
 
     # ------------------------------------------------------------------------------------------------------------------
     # inference (SURVEY §8f rank 2): Hulc.step / get_pp_plan_{lang,vision} / predict_with_plan (hulc.py:851-957),
@@ -987,11 +1068,11 @@ class HulcEngine:
             plan = None
             if self.model != "gcbc":
                 w0 = P["plan_proposal.fc_model.0.weight"]
-                x = self.buf("pp.a1", 1, H)
+                x = self.buf("pp.a1", 1, self.H_prior)
                 self.gemm_fwd(emb[0:1], w0[:, :128], x, transB=True, bias=P["plan_proposal.fc_model.0.bias"])
                 self.gemm_fwd(goal, w0[:, 128:], x, transB=True, beta=1.0, act=RELU)
                 for j, i in enumerate((2, 4, 6)):
-                    y = self.buf(f"pp.a{j + 2}", 1, H)
+                    y = self.buf(f"pp.a{j + 2}", 1, self.H_prior)
                     self.gemm_fwd(x, P[f"plan_proposal.fc_model.{i}.weight"], y, transB=True, bias=P[f"plan_proposal.fc_model.{i}.bias"], act=RELU)
                     x = y
                 state_dim = P["plan_proposal.fc_state.0.weight"].shape[0]
@@ -1054,7 +1135,7 @@ class HulcEngine:
             for l in range(2):
                 ops.strided_copy(st["hidden"][l], hb[l][1])
             pred_tcp = self.buf("pred_tcp", 1, 1, A)
-            ops.logistic_sample(heads_p[:, : ps.n_heads], pred_tcp, 1, 1, 0, 1, time_major=True, n_dims=self.n_dims, n_mix=self.n_mix, has_gripper=has_grip,
+            ops.logistic_sample(heads_p[:, : ps.n_heads], pred_tcp, 1, 1, 0, 1, time_major=True, n_dims=self.n_dims, n_mix=self.n_mix, has_gripper=has_grip, log_scale_min=self.dims.log_scale_min,
                                 u_mix=None if sample_u is None else sample_u[0].contiguous(), u_inv=None if sample_u is None else sample_u[1].contiguous(),
                                 seed=rng, site=310)
             if not has_grip:
@@ -1081,7 +1162,7 @@ class HulcEngine:
                 self.ps.adam_step(lr=self.lr, grad_scale=grad_scale)
         if optimizer:
             self.ps.step_count -= 1  # the capture itself did not execute the update
-        return StepGraph(self, g, out, optimizer, ops.launch_count() - n0)
+        return StepGraph(self, g, out, optimizer, ops.launch_count() - n0, namespace=("train", self.batch_signature(batch)))
 
     def check_nan_flag(self):
         """The reference asserts on NaNs inside world_to_tcp_frame every step (gripper_control.py:35), which stalls the

@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from ..engine import HulcEngine
+from ..spec import dims_from_configs
 
 try:  # Lightning is optional: the reference's trainer needs it, the kernels do not
     import pytorch_lightning as pl
@@ -70,8 +71,11 @@ class _Block(nn.Module):
 
 
 class _StepLoss(torch.autograd.Function):
-    """Connects the engine's fused forward+backward to autograd: forward returns the loss the kernels computed,
-    backward hands out the parameter gradients the kernels already produced (scaled by the incoming gradient)."""
+    """Connects the engine's fused forward+backward to autograd: forward returns the loss the kernels computed, backward hands out
+    the parameter gradients the kernels already produced.  Zero-copy: the gradients handed to autograd are fresh VIEWS of the flat
+    gradient buffer (so `p.grad` aliases it and `FusedAdam.step` has nothing to copy back); the incoming gradient (1 for a plain
+    `loss.backward()`, 1/k under gradient accumulation, the loss scale under AMP) is applied to the flat buffer in place by one
+    launch that reads the factor from the device and returns immediately when it is 1."""
 
     @staticmethod
     def forward(ctx, loss, engine, *params):
@@ -80,20 +84,31 @@ class _StepLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        eng = ctx.engine
-        grads = tuple(eng.ps.g[k] * grad_out for k in eng.ps.keys)
-        return (None, None) + grads
+        from .. import ops
+
+        ps = ctx.engine.ps
+        ops.scale_dev_(ps.grad, grad_out.reshape(1).to(torch.float32))
+        return (None, None) + tuple(ps._view(ps.grad, k) for k in ps.keys)
+
+
+_ADAM_DEFAULTS = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                      differentiable=False, fused=None)
 
 
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (hulc.py:240 instantiates `torch.optim.Adam(lr=2e-4)`) as ONE kernel launch over the
-    engine's flat parameter / gradient / moment buffers.  Uses the gradients the engine wrote (or, when autograd / DDP
-    populated `.grad` on the parameters, those — they are views of / copies into the same layout)."""
+    engine's flat parameter / gradient / moment buffers.  Gradients: the ones the engine wrote; when autograd / DDP put other
+    tensors into `p.grad` (DDP's bucket views, already averaged across ranks) those are copied into the flat layout first —
+    gradients that already alias the flat buffer (the normal `loss.backward()` path, see _StepLoss) cost nothing.
+    `state_dict()` / `load_state_dict()` use torch.optim.Adam's own layout ({"state": {i: {"step", "exp_avg", "exp_avg_sq"}},
+    "param_groups": [...]}, parameters numbered in `module.parameters()` order), so optimizer checkpoints interchange with the
+    reference's and resuming restores the moments and the bias-correction step (hulc/training.py resumes via trainer.fit(ckpt_path))."""
 
     def __init__(self, module: "Hulc", lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if weight_decay:
             raise NotImplementedError("the reference trains with weight_decay=0 (conf/model/optimizer/adam.yaml)")
         self._module = module
+        self._gptrs = None
         super().__init__(list(module.parameters()), dict(lr=lr, betas=betas, eps=eps))
 
     @torch.no_grad()
@@ -104,16 +119,94 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         mod, eng = self._module, self._module.engine
         g = self.param_groups[0]
-        # gradients that reached the parameters through autograd/DDP (already averaged across ranks) win over the raw
-        # local ones in the flat buffer
-        for k, p in mod._param_by_key.items():
-            if p.grad is not None and p.grad.data_ptr() != eng.ps.g[k].data_ptr():
-                eng.ps.g[k].copy_(p.grad)
-        eng.ps.adam_step(lr=g["lr"], betas=g["betas"], eps=g["eps"])
+        ps = eng.ps
+        if self._gptrs is None or self._gptrs[0] is not ps.grad:  # (re)build after the flat buffers moved
+            self._gptrs = (ps.grad, [(k, p, ps.g[k].data_ptr()) for k, p in mod._param_by_key.items()])
+        for k, p, ptr in self._gptrs[1]:
+            pg = p.grad
+            if pg is not None and pg.data_ptr() != ptr:
+                ps.g[k].copy_(pg)
+        ps.adam_step(lr=g["lr"], betas=g["betas"], eps=g["eps"])
         return loss
 
     def zero_grad(self, set_to_none: bool = True):
         super().zero_grad(set_to_none=set_to_none)
+
+    # ---- checkpointing: torch.optim.Adam's layout --------------------------------------------------------------------------
+    def _keys_in_param_order(self):
+        by_id = {id(p): k for k, p in self._module._param_by_key.items()}
+        return [by_id[id(p)] for p in self.param_groups[0]["params"]]
+
+    def state_dict(self):
+        ps = self._module.engine.ps
+        keys = self._keys_in_param_order()
+        state = {}
+        if ps.step_count > 0:
+            for i, k in enumerate(keys):
+                state[i] = {"step": torch.tensor(float(ps.step_count)), "exp_avg": ps._view(ps.exp_avg, k).detach().clone(),
+                            "exp_avg_sq": ps._view(ps.exp_avg_sq, k).detach().clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        for k, v in _ADAM_DEFAULTS.items():
+            group.setdefault(k, v)
+        group["params"] = list(range(len(keys)))
+        return {"state": state, "param_groups": [group]}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        ps = self._module.engine.ps
+        keys = self._keys_in_param_order()
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(keys):
+            raise ValueError("optimizer state does not match this model: one parameter group over all parameters expected")
+        for name in ("lr", "betas", "eps"):
+            if name in groups[0]:
+                self.param_groups[0][name] = tuple(groups[0][name]) if name == "betas" else groups[0][name]
+        if "initial_lr" in groups[0]:
+            self.param_groups[0]["initial_lr"] = groups[0]["initial_lr"]
+        if groups[0].get("weight_decay", 0) or groups[0].get("amsgrad", False):
+            raise NotImplementedError("weight_decay / amsgrad optimizer state is not supported")
+        state = state_dict["state"]
+        steps = set()
+        ps.exp_avg.zero_(); ps.exp_avg_sq.zero_()
+        for i, pid in enumerate(groups[0]["params"]):
+            st = state.get(pid, state.get(str(pid)))
+            if st is None:
+                continue
+            k = keys[i]
+            ps._view(ps.exp_avg, k).copy_(st["exp_avg"].to(ps.device, torch.float32))
+            ps._view(ps.exp_avg_sq, k).copy_(st["exp_avg_sq"].to(ps.device, torch.float32))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise NotImplementedError(f"per-parameter step counts differ ({sorted(steps)}): the fused update keeps one step count")
+        ps.step_count = steps.pop() if steps else 0
+        ps.step_dev.fill_(ps.step_count)
+
+
+def _lr_lambda(cfg, num_training_steps_fn):
+    """The three schedules the reference ships (conf/model/lr_scheduler/*.yaml -> transformers.get_*_schedule*), as LambdaLR factors."""
+    target = str(_get(cfg, "_target_", "transformers.get_constant_schedule"))
+    name = target.rsplit(".", 1)[-1]
+    if name == "get_constant_schedule":
+        return lambda step: 1.0
+    if name not in ("get_cosine_schedule_with_warmup", "get_linear_schedule_with_warmup"):
+        raise NotImplementedError(f"lr_scheduler._target_={target!r}: constant, linear-with-warmup and cosine-with-warmup are supported")
+    total, warm = _get(cfg, "num_training_steps", -1), _get(cfg, "num_warmup_steps", 0)
+    if total is None or total < 0:  # hulc.py:218-237 (compute_warmup): infer from the trainer
+        total = num_training_steps_fn()
+    if isinstance(warm, float):
+        warm = warm * total
+    total, warm = int(total), int(warm)
+    if name == "get_linear_schedule_with_warmup":
+        return lambda step: step / max(1, warm) if step < warm else max(0.0, (total - step) / max(1, total - warm))
+    cycles = float(_get(cfg, "num_cycles", 0.5))
+
+    def cosine(step):
+        if step < warm:
+            return step / max(1, warm)
+        progress = (step - warm) / max(1, total - warm)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * cycles * 2.0 * progress)))
+
+    return cosine
 
 
 class Hulc(_Base):
@@ -151,27 +244,17 @@ class Hulc(_Base):
         super().__init__()
         if state_recons or use_bc_z_auxiliary_loss or use_mia_auxiliary_loss:
             raise NotImplementedError("state reconstruction / BC-Z / MIA auxiliary losses are off in every shipped model yaml and are not built (DESIGN.md, out of scope)")
-        for name, enc in (("depth_static", None), ("depth_gripper", None), ("proprio", None), ("tactile", None)):
-            if _get(perceptual_encoder, name) not in (None, {}, "none"):
-                raise NotImplementedError(f"perceptual_encoder.{name} is disabled in conf/model/perceptual_encoder/gripper_cam.yaml and not built")
-        continuous = _get(distribution, "dist", "discrete") == "continuous"
         birnn = str(_get(plan_recognition, "_target_", "")).endswith("PlanRecognitionBiRNNNetwork")
-        if continuous != birnn:
-            raise NotImplementedError("supported latent plans: transformer posterior + discrete latent (hulc/gcbc) or BiRNN posterior + continuous latent (mcil)")
         model = "mcil" if birnn else self.MODEL
-        if model != "mcil" and (_get(distribution, "category_size", 32), _get(distribution, "class_size", 32)) != (32, 32):
-            raise NotImplementedError("the plan kernels are specialised for 32 categoricals x 32 classes (conf/model/distribution/discrete.yaml)")
         if bool(use_clip_auxiliary_loss) != (model != "mcil"):
             raise NotImplementedError("CLIP auxiliary loss is on for hulc/gcbc and off for mcil in the shipped configs")
-        rnn_model = _get(action_decoder, "rnn_model", "rnn_decoder")
-        max_window = int(_get(plan_recognition, "max_position_embeddings", 32))
+        # every size of the network comes from the config tree (hulc.py:86-187 wires the sub-configs the same way); values the kernels
+        # cannot honour raise NotImplementedError naming the key
+        dims = dims_from_configs(model, perceptual_encoder, plan_proposal, plan_recognition, language_goal, visual_goal, action_decoder, distribution, proj_vis_lang)
+        self._check_optimizer_config(optimizer)
         dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        self.engine = HulcEngine(
-            model, rnn_model, max_window=max_window, device=dev, dropout_p=float(_get(plan_recognition, "dropout_p", 0.0) or 0.0),
-            kl_beta=kl_beta, kl_balancing_mix=kl_balancing_mix, clip_beta=clip_auxiliary_loss_beta,
-            gripper_alpha=float(_get(action_decoder, "gripper_alpha", 1.0)), nhead=int(_get(plan_recognition, "num_heads", 8)),
-            nlayers=int(_get(plan_recognition, "num_layers", 2)), lr=float(_get(optimizer, "lr", 2e-4)), precision=precision,
-        )
+        self.engine = HulcEngine(device=dev, kl_beta=kl_beta, kl_balancing_mix=kl_balancing_mix, clip_beta=clip_auxiliary_loss_beta,
+                                 lr=float(_get(optimizer, "lr", 2e-4)), precision=precision, dims=dims)
         self._param_by_key: Dict[str, nn.Parameter] = {}
         for k in self.engine.ps.keys:
             self._register(k, nn.Parameter(self.engine.ps.p[k]))
@@ -184,6 +267,8 @@ class Hulc(_Base):
         self.replan_freq = replan_freq
         self.val_instructions = val_instructions
         self._graphs = None
+        self._graph_hyper = None
+        self.max_graphs = 4  # captured steps kept (least recently used goes first)
         self.save_hyperparameters()
 
     # ---- parameter plumbing ---------------------------------------------------------------------------------------------
@@ -224,7 +309,8 @@ class Hulc(_Base):
     @torch.no_grad()
     def _init_parameters(self):
         """PyTorch's default initialisers for the reference's module types (Linear/Conv: kaiming-uniform(a=sqrt 5) ==
-        U(+-1/sqrt(fan_in)) for weight and bias; RNN/GRU: U(+-1/sqrt(hidden)); LayerNorm: 1/0; Embedding: N(0,1);
+        U(+-1/sqrt(fan_in)) for weight and bias; RNN/GRU: U(+-1/sqrt(hidden)); LayerNorm: 1/0; Embedding: N(0,1); the attention
+        in-projection: xavier-uniform weight, zero bias, zero out-projection bias (nn.MultiheadAttention._reset_parameters);
         logit_scale = ln(1/0.07), hulc.py:115)."""
         for k, p in self._param_by_key.items():
             if k == "logit_scale":
@@ -237,28 +323,39 @@ class Hulc(_Base):
                 p.uniform_(-1.0 / math.sqrt(self.engine.H), 1.0 / math.sqrt(self.engine.H))
             else:
                 wkey = k[: -len("bias")] + "weight" if k.endswith("bias") else k
-                wkey = wkey.replace("in_proj_weight", "in_proj_weight")
                 w = self._param_by_key.get(wkey, p)
                 fan_in = int(math.prod(w.shape[1:])) if w.dim() > 1 else w.shape[0]
                 if k.endswith("in_proj_bias") or k.endswith("out_proj.bias"):
                     p.zero_()
+                elif k.endswith("in_proj_weight"):  # nn.MultiheadAttention._reset_parameters: xavier_uniform_
+                    bound = math.sqrt(6.0 / (p.shape[0] + p.shape[1]))
+                    p.uniform_(-bound, bound)
                 else:
                     p.uniform_(-1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
 
     def _apply(self, fn, *a, **kw):
-        """`.to(device)` / `.cuda()`: move the flat buffers and re-point every parameter at its view."""
+        """`.to(device)` / `.cuda()`: move the flat buffers AND every other piece of device state the kernels dereference (the Adam
+        step counter, the RNG seed, the NaN flag), re-point every parameter at its view, and forget everything that was bound to the old
+        device (activation buffers, captured graphs, a rollout's carried state).  Lightning builds the module before it picks the device
+        (hulc/training.py:44 then trainer.fit), so every DDP rank goes through here."""
         ps = self.engine.ps
         new_flat = fn(ps.flat)
         if new_flat.device != ps.flat.device or new_flat.dtype != ps.flat.dtype:
             if new_flat.dtype != torch.float32:
                 raise NotImplementedError("parameters are kept in fp32 (the kernels compute in fp32)")
             ps.flat, ps.grad, ps.exp_avg, ps.exp_avg_sq = new_flat, fn(ps.grad), fn(ps.exp_avg), fn(ps.exp_avg_sq)
+            ps.step_dev = fn(ps.step_dev)
             ps.device = new_flat.device
             ps.rebuild_views()
             eng = self.engine
             eng.device = new_flat.device
-            eng._bufs.clear()
+            eng.rng_dev = fn(eng.rng_dev)
             eng.nan_flag = fn(eng.nan_flag)
+            eng._bufs.clear()
+            eng._buf_namespaces.clear()
+            eng._infer_state = None
+            if self._graphs is not None:
+                self._graphs = {}
             for k, p in self._param_by_key.items():
                 p.data = ps.p[k]
                 p.grad = None
@@ -269,50 +366,103 @@ class Hulc(_Base):
         return self
 
     # ---- reference surface ----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _check_optimizer_config(optimizer):
+        target = str(_get(optimizer, "_target_", "torch.optim.Adam"))
+        if target != "torch.optim.Adam":
+            raise NotImplementedError(f"optimizer._target_={target!r}: the fused update implements torch.optim.Adam (conf/model/optimizer/adam.yaml)")
+        for k in (optimizer.keys() if hasattr(optimizer, "keys") else []):
+            if k in ("_target_", "_recursive_", "_partial_", "lr", "betas", "eps"):
+                continue
+            if k in _ADAM_DEFAULTS and (_get(optimizer, k) == _ADAM_DEFAULTS[k] or not _get(optimizer, k)):
+                continue
+            raise NotImplementedError(f"optimizer.{k}={_get(optimizer, k)!r} is not supported by the fused Adam update")
+
+    @property
+    def num_training_steps(self) -> int:
+        """Total optimizer steps, inferred from the trainer like the reference (hulc.py:189-216)."""
+        tr = getattr(self, "trainer", None)
+        if tr is None:
+            raise RuntimeError("lr_scheduler.num_training_steps=-1 needs an attached Lightning trainer to infer the number of steps")
+        if getattr(tr, "max_steps", None) and tr.max_steps > 0:
+            est = getattr(tr, "estimated_stepping_batches", None)
+            return int(min(tr.max_steps, est)) if est else int(tr.max_steps)
+        return int(tr.estimated_stepping_batches)
+
     def configure_optimizers(self):
-        """hulc.py:239-252: Adam + constant schedule stepped every iteration."""
-        opt = FusedAdam(self, lr=float(_get(self.optimizer_config, "lr", 2e-4)))
-        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda _: 1.0)  # transformers.get_constant_schedule
+        """hulc.py:239-252: the configured Adam + the configured schedule (constant by default), stepped every iteration."""
+        cfg = self.optimizer_config
+        betas = tuple(_get(cfg, "betas", (0.9, 0.999)))
+        opt = FusedAdam(self, lr=float(_get(cfg, "lr", 2e-4)), betas=(float(betas[0]), float(betas[1])), eps=float(_get(cfg, "eps", 1e-8)))
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, _lr_lambda(self.lr_scheduler, lambda: self.num_training_steps))
         return {"optimizer": opt, "lr_scheduler": {"scheduler": sched, "interval": "step", "frequency": 1}}
 
     def set_kl_beta(self, kl_beta):
-        """Called by the KL-annealing callbacks (hulc/utils/kl_callbacks.py:22)."""
+        """Called by the KL-annealing callbacks once per epoch (hulc/utils/kl_callbacks.py:19-22).  The coefficient is a by-value kernel
+        argument, i.e. baked into captured graphs: graphs captured under another value are dropped and re-captured on their next use."""
         self.kl_beta = kl_beta
         self.engine.kl_beta = float(kl_beta)
 
     def enable_cuda_graphs(self, flag: bool = True):
         """Replay the training step from a CUDA graph captured per distinct set of input buffers (the batch tensors are the
-        graph's static inputs: a loader that re-uses its device staging buffers hits the same graph every step)."""
+        graph's static inputs: a loader that re-uses its device staging buffers hits the same graph every step).  At most
+        `max_graphs` graphs are kept; every batch shape has its own activation buffers (HulcEngine.step)."""
         self._graphs = {} if flag else None
 
     def fused_step(self, batch, **inject) -> Dict[str, torch.Tensor]:
         """Forward + backward in the kernels; gradients land in the flat gradient buffer.  No autograd graph."""
         if self._graphs is not None and not inject:
-            key = tuple((t.data_ptr(), tuple(t.shape)) for t in _tensors(batch))
-            sg = self._graphs.get(key)
+            eng = self.engine
+            hyper = (eng.kl_beta, eng.kl_alpha, eng.clip_beta, eng.dropout_p)
+            if hyper != self._graph_hyper:  # by-value kernel arguments changed (KL schedule): captured graphs are stale
+                self._graphs.clear()
+                self._graph_hyper = hyper
+            key = tuple((t.data_ptr(), tuple(t.shape), str(t.dtype)) for t in _tensors(batch))
+            sg = self._graphs.pop(key, None)
             if sg is None:
-                sg = self._graphs[key] = self.engine.capture(batch, optimizer=False)
+                while len(self._graphs) >= self.max_graphs:  # least recently used first
+                    old_key = next(iter(self._graphs))
+                    old = self._graphs.pop(old_key)
+                    if not any(g.namespace == old.namespace for g in self._graphs.values()):
+                        eng.release_buffers(old.namespace)
+                sg = eng.capture(batch, optimizer=False)
+            self._graphs[key] = sg  # most recently used last
             return sg.replay()
         return self.engine.step(batch, **inject)
+
+    def _unalias_accumulated_grads(self):
+        """Gradient accumulation (`accumulate_grad_batches > 1`): `p.grad` of the previous micro-batch aliases the flat gradient buffer this
+        step is about to overwrite — move the accumulated values into tensors of their own first (autograd then adds this step's views)."""
+        ps = self.engine.ps
+        first = self._param_by_key[ps.keys[0]]
+        if first.grad is None or first.grad.data_ptr() != ps.g[ps.keys[0]].data_ptr():
+            return
+        for k, p in self._param_by_key.items():
+            if p.grad is not None and p.grad.data_ptr() == ps.g[k].data_ptr():
+                p.grad = p.grad.clone()
 
     def training_step(self, batch: Dict[str, Dict], batch_idx: int = 0, **inject) -> torch.Tensor:
         """hulc.py:390-537.  Returns total_loss with an autograd edge to every parameter, so Lightning's
         `loss.backward()` (and DDP's gradient hooks) work unchanged; the gradients themselves were computed by the
         kernels' backward pass during this call."""
+        self._unalias_accumulated_grads()
         out = self.fused_step(batch, **inject)
         self.last_outputs = out
         mods = list(batch.keys())
         kl, act = out["kl_loss"], out["action_loss"]
+        total_bs = 0
         for m in mods:
-            # key names as logged by the reference (hulc.py:470-490); kl is logged once unscaled-by-beta there ("kl_loss")
-            # and once scaled per modality
-            self.log(f"train/kl_loss_scaled_{m}", out[f"kl_loss_{m}"], on_step=False, on_epoch=True)
-            self.log(f"train/action_loss_{m}", out[f"action_loss_{m}"], on_step=False, on_epoch=True)
-        self.log("train/kl_loss", kl, on_step=False, on_epoch=True, sync_dist=True)
-        self.log("train/action_loss", act, on_step=False, on_epoch=True, sync_dist=True)
+            # key names and batch sizes as logged by the reference (hulc.py:470-490)
+            bs = batch[m]["actions"].shape[0]
+            total_bs += bs
+            self.log(f"train/kl_loss_scaled_{m}", out[f"kl_loss_{m}"], on_step=False, on_epoch=True, batch_size=bs)
+            self.log(f"train/action_loss_{m}", out[f"action_loss_{m}"], on_step=False, on_epoch=True, batch_size=bs)
+            self.log(f"train/total_loss_{m}", out[f"action_loss_{m}"] + out[f"kl_loss_{m}"], on_step=False, on_epoch=True, batch_size=bs)
         if "lang_clip_loss" in out:
             self.log("train/lang_clip_loss", self.clip_auxiliary_loss_beta * out["lang_clip_loss"], on_step=False, on_epoch=True, sync_dist=True)
-        self.log("train/total_loss", out["total_loss"], on_step=False, on_epoch=True, sync_dist=True)
+        self.log("train/kl_loss", kl, on_step=False, on_epoch=True, batch_size=total_bs)
+        self.log("train/action_loss", act, on_step=False, on_epoch=True, batch_size=total_bs)
+        self.log("train/total_loss", out["total_loss"], on_step=False, on_epoch=True, batch_size=total_bs)
         params = [self._param_by_key[k] for k in self.engine.ps.keys]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _StepLoss.apply(out["total_loss"], self.engine, *params)
@@ -396,10 +546,39 @@ class Hulc(_Base):
         self.rollout_step_counter += 1
         return action
 
-    def lmp_train(self, perceptual_emb, latent_goal, train_acts, robot_obs):
-        raise NotImplementedError(
-            "lmp_train is fused into training_step here (one batched pass over both modalities); the per-block values it "
-            "returned in the reference are in `self.last_outputs` (pp_state, pr_state, seq_feat, kl/action losses)")
+    def _dist(self, state: torch.Tensor):
+        """Distribution.get_dist (hulc/utils/distributions.py:38-47) on a state tensor: logits [B, 1024] or [mean | raw std] [B, 512]."""
+        import torch.distributions as D
+
+        if self.engine.discrete:
+            d = self.engine.dims
+            logits = state.view(*state.shape[:-1], d.category_size, d.class_size)
+            return D.Independent(D.OneHotCategoricalStraightThrough(logits=logits), 1)
+        mean, raw = state.chunk(2, dim=-1)
+        return D.Independent(D.Normal(mean, torch.nn.functional.softplus(raw) + 1e-4), 1)
+
+    @torch.no_grad()
+    def lmp_train(self, perceptual_emb, latent_goal, train_acts, robot_obs, **inject):
+        """hulc.py:254-299 for one modality, from already-encoded inputs: returns `(kl_loss, action_loss, total_loss, pp_dist, pr_dist,
+        seq_feat)` — prior, posterior, a plan sampled from the posterior, the decoder's mixture NLL (+ gripper CE) and the balanced, scaled
+        KL, all on the same kernels as `training_step`.  Forward values: `training_step` does not call this method, it runs the same block
+        fused with the encoders, both modalities batched, and with the hand-written backward; the intermediate tensors of this call are kept
+        in `self.last_lmp_outputs`.  `inject` (plan_idx / plan_u / plan_eps / dropout_masks, keyed by "vis") pins the randomness for parity runs."""
+        if self.engine.model == "gcbc":
+            raise NotImplementedError("GCBC has no latent plan: its training_step calls the decoder directly (gcbc.py:50-181)")
+        out = self.engine.lmp_forward(perceptual_emb, latent_goal, train_acts, robot_obs, **inject)
+        self.last_lmp_outputs = out
+        kl, act = out["kl_loss_vis"], out["action_loss_vis"]
+        return kl, act, act + kl, self._dist(out["pp_state"]), self._dist(out["pr_state"]), out["seq_feat"]
+
+    @torch.no_grad()
+    def clip_auxiliary_loss(self, seq_vis_feat, encoded_lang, use_for_aux_loss=None):
+        """hulc.py:650-695: symmetric cross-entropy over the cosine-similarity logits of the projected sequence features and language
+        goals of the rows `use_for_aux_loss` selects (0 when it selects none).  Forward value; inside `training_step` the same kernel
+        also emits the gradient."""
+        if not self.use_clip_auxiliary_loss:
+            raise RuntimeError("use_clip_auxiliary_loss is off")
+        return self.engine.clip_forward(seq_vis_feat, encoded_lang, use_for_aux_loss)
 
     def compute_kl_loss(self, pp_state, pr_state):
         """hulc.py:539-561 on device tensors of logits (discrete) / [mean|raw_std] (continuous): returns the scaled,
@@ -420,5 +599,7 @@ class Hulc(_Base):
             ops.sum_to(kl_el, out, float(self.kl_beta) / Bn)
         return out[0]
 
-    def on_load_checkpoint(self, checkpoint):  # state_dict keys are the reference's; nothing to translate
-        pass
+    def on_load_checkpoint(self, checkpoint):
+        """state_dict keys are the reference's, nothing to translate; the optimizer state (torch.optim.Adam layout) is restored by
+        FusedAdam.load_state_dict, which Lightning calls with `checkpoint["optimizer_states"][0]`."""
+

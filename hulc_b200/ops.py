@@ -46,11 +46,15 @@ def _stream():
 
 
 def _chk(*ts, dtype=torch.float32):
+    """Every tensor argument must live on the device the kernels are about to be launched on (the CURRENT device, index included:
+    a module built on cuda:0 and moved to cuda:1 must not hand the kernels a stale cuda:0 pointer) and have the expected dtype."""
+    cur = torch.cuda.current_device() if _DEVICE_TYPE == "cuda" else None
     for t in ts:
         if t is None:
             continue
-        if t.device.type != _DEVICE_TYPE:
-            raise _lib.HulcError(f"hulc_b200 kernels need {_DEVICE_TYPE} tensors, got {t.device}")
+        if t.device.type != _DEVICE_TYPE or (cur is not None and t.device.index != cur):
+            want = _DEVICE_TYPE if cur is None else f"{_DEVICE_TYPE}:{cur} (the current device)"
+            raise _lib.HulcError(f"hulc_b200 kernels need tensors on {want}, got {t.device}")
         if dtype is not None and t.dtype != dtype:
             raise TypeError(f"expected {dtype}, got {t.dtype}")
 
@@ -395,6 +399,14 @@ def scale_(x, alpha):
     _chk(x)
     assert x.is_contiguous()
     _L().hulc_scale(_ptr(x), x.numel(), float(alpha), _stream())
+    return x
+
+
+def scale_dev_(x, alpha_dev):
+    """x *= alpha with alpha a 1-element device tensor (no host read; a factor of exactly 1 costs one empty launch)."""
+    _chk(x, alpha_dev)
+    assert x.is_contiguous() and alpha_dev.numel() == 1
+    _L().hulc_scale_dev(_ptr(x), x.numel(), _ptr(alpha_dev), _stream())
     return x
 
 

@@ -17,6 +17,8 @@ from typing import Dict, Optional
 
 import torch
 
+from ..spec import param_spec  # noqa: F401  (re-exported: tests and tools reach it through this module too)
+
 
 class AttrDict(dict):
     """Attribute-style dict (stands in for omegaconf.DictConfig when omegaconf is not installed)."""
@@ -335,74 +337,6 @@ def dropout_masks(
         m[f"l{i}.ffn"] = keep(batch, seq, ff)
         m[f"l{i}.drop2"] = keep(batch, seq, d_model)
     return m
-
-
-def param_spec(model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: int = 32) -> Dict[str, tuple]:
-    """state_dict contract of the reference: parameter key -> shape, in registration order, for
-    `conf/model/{hulc,gcbc,mcil}.yaml`.  Buffers are not listed."""
-    spec: Dict[str, tuple] = {}
-
-    def lin(name, n_out, n_in):
-        spec[f"{name}.weight"] = (n_out, n_in)
-        spec[f"{name}.bias"] = (n_out,)
-
-    def convs(p):
-        spec[f"{p}.conv_model.0.weight"], spec[f"{p}.conv_model.0.bias"] = (32, 3, 8, 8), (32,)
-        spec[f"{p}.conv_model.2.weight"], spec[f"{p}.conv_model.2.bias"] = (64, 32, 4, 4), (64,)
-        spec[f"{p}.conv_model.4.weight"], spec[f"{p}.conv_model.4.bias"] = (64, 64, 3, 3), (64,)
-
-    def rnn(p, n_in, hidden, layers, gates=1, bidir=False):
-        for l in range(layers):
-            for sfx in ("", "_reverse") if bidir else ("",):
-                i = n_in if l == 0 else hidden * (2 if bidir else 1)
-                spec[f"{p}.weight_ih_l{l}{sfx}"] = (gates * hidden, i)
-                spec[f"{p}.weight_hh_l{l}{sfx}"] = (gates * hidden, hidden)
-                spec[f"{p}.bias_ih_l{l}{sfx}"] = (gates * hidden,)
-                spec[f"{p}.bias_hh_l{l}{sfx}"] = (gates * hidden,)
-
-    if model != "mcil":
-        spec["logit_scale"] = ()
-    pe = "perceptual_encoder.rgb_static_encoder"
-    convs(pe)
-    lin(f"{pe}.fc1.0", 512, 128), lin(f"{pe}.fc2", 64, 512)
-    spec[f"{pe}.ln.weight"], spec[f"{pe}.ln.bias"] = (64,), (64,)
-    pg = "perceptual_encoder.rgb_gripper_encoder"
-    convs(pg)
-    lin(f"{pg}.conv_model.7", 128, 3136), lin(f"{pg}.fc1.0", 512, 128), lin(f"{pg}.fc2", 64, 512)
-    spec[f"{pg}.ln.weight"], spec[f"{pg}.ln.bias"] = (64,), (64,)
-    plan = 1024 if model != "mcil" else 256
-    state = plan if model != "mcil" else 2 * plan
-    lin("plan_proposal.fc_model.0", 2048, 160)
-    for i in (2, 4, 6):
-        lin(f"plan_proposal.fc_model.{i}", 2048, 2048)
-    lin("plan_proposal.fc_state.0", state, 2048)
-    if model == "mcil":
-        rnn("plan_recognition.birnn_model", 128, 2048, 2, bidir=True)
-        lin("plan_recognition.fc_state.0", state, 4096)
-    else:
-        spec["plan_recognition.position_embeddings.weight"] = (max_window, 128)
-        for l in range(2):
-            p = f"plan_recognition.transformer_encoder.layers.{l}"
-            spec[f"{p}.self_attn.in_proj_weight"], spec[f"{p}.self_attn.in_proj_bias"] = (384, 128), (384,)
-            lin(f"{p}.self_attn.out_proj", 128, 128)
-            lin(f"{p}.linear1", 2048, 128), lin(f"{p}.linear2", 128, 2048)
-            spec[f"{p}.norm1.weight"], spec[f"{p}.norm1.bias"] = (128,), (128,)
-            spec[f"{p}.norm2.weight"], spec[f"{p}.norm2.bias"] = (128,), (128,)
-        lin("plan_recognition.fc", 4096, 128)
-        lin("plan_recognition.fc_state.0", state, 4096)
-    lin("visual_goal.mlp.0", 2048, 128), lin("visual_goal.mlp.2", 2048, 2048), lin("visual_goal.mlp.4", 32, 2048)
-    spec["visual_goal.ln.weight"], spec["visual_goal.ln.bias"] = (32,), (32,)
-    lin("language_goal.mlp.1", 2048, 384), lin("language_goal.mlp.3", 2048, 2048), lin("language_goal.mlp.5", 32, 2048)
-    spec["language_goal.ln.weight"], spec["language_goal.ln.bias"] = (32,), (32,)
-    dec_in = {"hulc": 1024 + 64 + 32, "gcbc": 64 + 32, "mcil": 256 + 128 + 32}[model]
-    rnn("action_decoder.rnn", dec_in, 2048, 2, gates=3 if rnn_model == "gru_decoder" else 1)
-    n_out = 60 if model != "mcil" else 70
-    lin("action_decoder.mean_fc", n_out, 2048), lin("action_decoder.log_scale_fc", n_out, 2048), lin("action_decoder.prob_fc", n_out, 2048)
-    if model != "mcil":
-        lin("action_decoder.gripper_fc", 2, 2048)
-        lin("proj_vis_lang.mlp_im.0", 128, 4096), lin("proj_vis_lang.mlp_im.2", 32, 128)
-        lin("proj_vis_lang.mlp_lang.0", 128, 32), lin("proj_vis_lang.mlp_lang.2", 32, 128)
-    return spec
 
 
 def make_state_dict(model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: int = 32, salt: int = 0) -> Dict[str, torch.Tensor]:

@@ -159,6 +159,9 @@ int hulc_strided_copy(float* dst, const float* src, int n0, int n1, int n2, long
 int hulc_reduce_mid(const float* x, float* out, int B, int S, int D, float scale, void* stream);
 int hulc_sum(const float* x, int n, float* out, float scale, void* stream);
 int hulc_scale(float* x, long long n, float alpha, void* stream);
+/* x *= *alpha_ptr with the factor in device memory (the gradient autograd hands to `loss.backward()`, hulc/training.py ->
+ * Lightning's backward of the tensor returned by Hulc.training_step, hulc.py:537); a factor of exactly 1 leaves x untouched. */
+int hulc_scale_dev(float* x, long long n, const float* alpha_ptr, void* stream);
 
 /* ---- uint8 camera frames -> normalised fp32 (the input pipeline on the device) ---------------------------
  * dst[i] = ((src[i] / 255) - mean) / std in fp32, the deterministic part of the reference's image transforms (ScaleImageTensor +
