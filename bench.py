@@ -29,6 +29,15 @@ B_PER_MODALITY, SEQ_LEN = 32, 32
 GFLOP_PER_SEQ = 13.03  # fwd+bwd, SURVEY.md §8(d) / BASELINE.md §3
 MB_PER_SEQ = 41.6      # mandatory HBM bytes per sequence, ibid.
 
+# BASELINE.json configs: name -> (model, rnn_model, seq_len, workload text).  `hulc` is the one the metric is quoted on (config 2; with
+# --dtype bf16: config 3); the others are the ablations of configs 4 and 5 at their full shapes.
+CONFIGS = {
+    "hulc": ("hulc", "rnn_decoder", 32, "HULC full model"),
+    "mcil": ("mcil", "rnn_decoder", 32, "MCIL ablation (BiRNN posterior, continuous latent; BASELINE config 4)"),
+    "gcbc64": ("gcbc", "rnn_decoder", 64, "GCBC ablation, seq_len=64, ReLU-RNN decoder (BASELINE config 5)"),
+    "gcbc64-gru": ("gcbc", "gru_decoder", 64, "GCBC ablation, seq_len=64, GRU decoder (BASELINE config 5)"),
+}
+
 
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -83,52 +92,73 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def oracle_step_fn(B, S, threads):
-    """The oracle (CPU restatement of the reference, oracle/hulc_oracle.py) as a training step: forward + autograd
-    backward + torch.optim.Adam, fp32 — BASELINE.md §4's CPU-baseline recipe."""
+def oracle_step_fn(B, S, threads, model="hulc", rnn_model="rnn_decoder", device="cpu", autocast=None):
+    """The oracle (restatement of the reference in plain torch, oracle/hulc_oracle.py) as a training step: forward + autograd
+    backward + torch.optim.Adam — BASELINE.md §4's baseline recipe.  device="cpu": the CPU baseline (fp32, `threads` host threads);
+    device="cuda": the same eager torch program on the GPU through cuDNN / cuBLAS (`eager_b200`), fp32 with
+    torch's default TF32 convolutions or under bf16 autocast."""
     import torch
 
     from hulc_b200.utils import synthetic
     from oracle import hulc_oracle as O
 
-    torch.set_num_threads(threads)
-    sd = {k: v.requires_grad_(True) for k, v in synthetic.make_state_dict("hulc").items()}
+    if device == "cpu":
+        torch.set_num_threads(threads)
+    mw = max(32, S)
+    sd = {k: v.to(device).requires_grad_(True) for k, v in synthetic.make_state_dict(model, rnn_model, max_window=mw).items()}
     opt = torch.optim.Adam(list(sd.values()), lr=2e-4)
-    batch = synthetic.make_batch(B, S, seed=1)
+    batch = synthetic._to(synthetic.make_batch(B, S, seed=1), device)
     noise = {m: synthetic.plan_noise(B, S, m) for m in batch}
-    masks = {m: synthetic.dropout_masks(B, S, m, 0.1) for m in batch}
+    p = 0.1 if model != "mcil" else 0.0
+    masks = {m: {k: v.to(device) for k, v in synthetic.dropout_masks(B, S, m, p).items()} for m in batch} if p > 0 else None
+    kw = dict(model=model, rnn_model=rnn_model, dropout_p=p, plan_u={m: noise[m]["u"].to(device) for m in batch}, plan_eps={m: noise[m]["eps"].to(device) for m in batch},
+              dropout_masks=masks)
 
     def step():
         opt.zero_grad(set_to_none=True)
-        out = O.training_step(sd, batch, dropout_p=0.1, plan_u={m: noise[m]["u"] for m in batch}, dropout_masks=masks)
+        if autocast is not None:
+            with torch.autocast("cuda", dtype=autocast):
+                out = O.training_step(sd, batch, **kw)
+        else:
+            out = O.training_step(sd, batch, **kw)
         out["total_loss"].backward()
         opt.step()
-        return float(out["total_loss"].detach())
+        return out["total_loss"].detach()
 
     return step
 
 
+def workload_text(args):
+    model, rnn_model, S, what = CONFIGS[args.config]
+    prec = "fp32 (BASELINE config 2)" if args.dtype == "fp32" else "bf16 storage / tensor-core operands, fp32 master weights (BASELINE config 3)"
+    if args.config != "hulc":
+        prec = args.dtype
+    return f"{what}, batch=32 vis + 32 lang sequences per GPU, seq_len={S}, 200x200 + 84x84 RGB fp32 frames, 384-d lang emb, {prec}, fwd+bwd+Adam"
+
+
 def run_reference(args):
     """`--impl reference`: the reference's algorithm on the host cores.  The reference is pure Python/PyTorch and is not
-    present on the GPU box, so this arm times the oracle port with every host thread (kind "port")."""
+    present on the GPU box, so this arm times the oracle port with every host thread (kind "port") on the SAME workload as
+    our arm: the full 32 + 32 sequences per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    Bs = 8  # bounded sample: 8 + 8 sequences of 32 frames per step (the workload has 32 + 32)
-    step = oracle_step_fn(Bs, SEQ_LEN, cores)
-    for _ in range(max(1, args.warmup)):
+    model, rnn_model, S, _ = CONFIGS[args.config]
+    Bs = B_PER_MODALITY
+    step = oracle_step_fn(Bs, S, cores, model, rnn_model)
+    for _ in range(max(1, min(args.warmup, 2))):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = 2 * Bs / dt
-    sample = f"{Bs}+{Bs} sequences x {SEQ_LEN} frames per step (1/4 of the workload's batch), fwd+bwd+Adam, fp32, torch CPU"
+    sample = f"the full step: {Bs}+{Bs} sequences x {S} frames, fwd+bwd+Adam, fp32, torch CPU ({cores} threads), {args.steps} timed steps"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "HULC full model, batch=32+32 seq_len=32, 200x200+84x84 RGB, fp32 (BASELINE config 2)", "sample": sample},
+        "config": {"workload": workload_text(args), "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -145,7 +175,7 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     pre = "perceptual_encoder.rgb_static_encoder"
     x = batch["vis"]["rgb_obs"]["rgb_static"].flatten(0, 1)  # one modality: 1024 frames (conv1 runs once per modality)
     n_mod = len(batch)
-    B_ = eng._bufs
+    B_ = eng.train_buffers(batch)
     a1, a2, a3, da1, da2, da3 = (B_[f"static.{k}"] for k in ("a1", "a2", "a3", "da1", "da2", "da3"))
     n1, N = x.shape[0], a1.shape[0]
     w0, w2, w4 = (P[f"{pre}.conv_model.{i}.weight"] for i in (0, 2, 4))
@@ -176,16 +206,20 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
         }
     # decoder: the recurrent step (64 sequences x 2048 hidden, 2 layers x 32 steps, forward + backward = 128 per step) and
     # the large dense products (dW_hh x2, dW_ih1, dh0 as tf32; the layer-1 input projection as 3xTF32)
-    H, S, nB = eng.H, SEQ_LEN, 2 * B_PER_MODALITY
+    H, S, nB = eng.H, batch["vis"]["actions"].shape[1], sum(d["actions"].shape[0] for d in batch.values())
     whh = P["action_decoder.rnn.weight_hh_l1"]
     hb, pre1 = B_["dec.h1"], B_["dec.pre1"]
     big_a, big_c = B_["dec.dh0"], torch.empty(H, H, device=x.device)
-    if eng.tc and eng.persistent_rnn:
+    elman = eng.rnn_model == "rnn_decoder"
+    if not elman:
+        pass  # GRU decoder: per-step GEMM + gate kernels (not timed one by one here)
+    elif eng.tc and eng.persistent_rnn:
         # the whole 32-step chain of one layer is one persistent launch (csrc/rnn_tc.cu); 2 layers forward + 2 backward per step
         st, sp = hb.stride(0), pre1.view(S, nB, -1).stride(0)
         pre3 = pre1.view(S, nB, -1)
-        cands["rnn_seq_fwd_32steps"] = (lambda: ops.rnn_tc_seq(whh, hb[0], hb[1], pre3[0], S, prev_step=st, out_step=st, add_step=sp, act=1),
-                                        2.0 * nB * H * H * S, 2)
+        if S <= 32:
+            cands["rnn_seq_fwd_32steps"] = (lambda: ops.rnn_tc_seq(whh, hb[0], hb[1], pre3[0], S, prev_step=st, out_step=st, add_step=sp, act=1),
+                                            2.0 * nB * H * H * S, 2)
         dbuf = B_["dec.l1.dpre"]
         sd = dbuf.stride(0)
         dh = big_a.view(S, nB, H)
@@ -198,8 +232,9 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     else:
         cands["rnn_step_gemm"] = (lambda: ops.gemm(hb[1], whh, hb[2], transB=True, addend=pre1[:nB], act=1), 2.0 * nB * H * H, 4 * S)
     mode = 1 if eng.tc else 0
-    cands["dense_wgrad_2048^3"] = (lambda: ops.gemm(big_a, hb[1 : S + 1].view(S * nB, H), big_c, transA=True, tc=mode), 2.0 * H * H * S * nB, 4)
-    cands["dense_fwd_2048^3"] = (lambda: ops.gemm(big_a, whh, pre1, transB=True, tc=3 if eng.tc else 0), 2.0 * H * H * S * nB, 1)
+    if elman:
+        cands["dense_wgrad_2048^3"] = (lambda: ops.gemm(big_a, hb[1 : S + 1].view(S * nB, H), big_c, transA=True, tc=mode), 2.0 * H * H * S * nB, 4)
+        cands["dense_fwd_2048^3"] = (lambda: ops.gemm(big_a, whh, pre1, transB=True, tc=3 if eng.tc else 0), 2.0 * H * H * S * nB, 1)
     res = {}
     for name, (fn, flops, per_step) in cands.items():
         try:
@@ -251,11 +286,104 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
             "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); the kernel runs tf32 operands, whose tensor-core peak is half of it", **common}
 
 
+def eager_b200(torch, args, dev):
+    """BASELINE.md §4 step 4 / SURVEY §8d: the same algorithm as an EAGER torch program on this GPU (cuDNN convolutions, cuBLAS GEMMs,
+    autograd, torch.optim.Adam) — the "existing Blackwell kernels" bar.  Full batch, CUDA-event timed, resident inputs."""
+    import warnings
+
+    from oracle import hulc_oracle as O
+
+    model, rnn_model, S, _ = CONFIGS[args.config]
+
+    # the reference's recurrent layers are nn.RNN / nn.GRU modules, i.e. cuDNN's fused kernels on a GPU: run them that way (the oracle
+    # unrolls them step by step in Python, which would understate this bar)
+    def flat(sd, prefix, layers, sfxs=("",)):
+        return [sd[f"{prefix}.{n}_l{l}{sfx}"] for l in range(layers) for sfx in sfxs for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+
+    def elman(sd, prefix, x, num_layers, nonlinearity, reverse_suffix="", h0=None):
+        w = flat(sd, prefix, num_layers)
+        h0 = x.new_zeros(num_layers, x.shape[0], w[1].shape[1]) if h0 is None else h0
+        return (torch._VF.rnn_relu if nonlinearity == "relu" else torch._VF.rnn_tanh)(x, h0, w, True, num_layers, 0.0, True, False, True)[0]
+
+    def birnn(sd, prefix, x, num_layers=2):
+        w = flat(sd, prefix, num_layers, ("", "_reverse"))
+        return torch._VF.rnn_tanh(x, x.new_zeros(2 * num_layers, x.shape[0], w[1].shape[1]), w, True, num_layers, 0.0, True, True, True)[0]
+
+    def gru(sd, prefix, x, num_layers):
+        w = flat(sd, prefix, num_layers)
+        return torch._VF.gru(x, x.new_zeros(num_layers, x.shape[0], w[1].shape[1]), w, True, num_layers, 0.0, True, False, True)[0]
+
+    saved = (O.elman_rnn, O.birnn_tanh, O.gru)
+    O.elman_rnn, O.birnn_tanh, O.gru = elman, birnn, gru
+    warnings.filterwarnings("ignore", message=".*weights are not part of single contiguous chunk.*")
+    res = {}
+    for name, ac in (("fp32_tf32conv", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            step = oracle_step_fn(B_PER_MODALITY, S, 1, model, rnn_model, device=str(dev), autocast=ac)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 10
+            e0.record()
+            for _ in range(n):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            res[name] = {"ms_per_step": ms, "value": 2 * B_PER_MODALITY / (ms * 1e-3), "unit": UNIT, "loss": float(loss)}
+        except Exception as e:  # a comparator must never take the bench line down
+            res[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    O.elman_rnn, O.birnn_tanh, O.gru = saved
+    res["what"] = ("oracle/hulc_oracle.py (plain torch restatement of the reference) run eagerly on cuda: cuDNN convolutions and cuDNN nn.RNN/nn.GRU kernels, cuBLAS, autograd, torch.optim.Adam, "
+                   "torch defaults (TF32 convolutions, fp32 matmuls) and under torch.autocast(bfloat16); 32+32 sequences, 3 warm-up + 10 timed steps")
+    return res
+
+
+def inference_latency(torch, args, dev):
+    """batch-1 latency of the rollout path `Hulc.step` (hulc.py:851-870) — observation on the host -> action on the host,
+    per control step, with the control step replayed from a CUDA graph; re-planning steps (every `replan_freq` = 30) reported apart."""
+    from hulc_b200.models.hulc import Hulc
+    from hulc_b200.utils import synthetic
+
+    cfg = synthetic.model_config("hulc", target_root="hulc_b200")
+    cfg.pop("_target_"); cfg.pop("_recursive_")
+    model = Hulc(**cfg, device=dev)
+    model.load_state_dict(synthetic.make_state_dict("hulc"), strict=False)
+    steps = 240
+    r = synthetic.rollout_inputs(steps, "lang", seed=3)
+    import numpy as np
+
+    model.lang_embeddings = {"goal": r["lang"].numpy()[None]}
+    obs = [{"rgb_obs": {"rgb_static": r["rgb_static"][t][None, None].pin_memory(), "rgb_gripper": r["rgb_gripper"][t][None, None].pin_memory()},
+            "robot_obs_raw": r["robot_obs_raw"][t][None, None].pin_memory()} for t in range(steps)]
+    out = {}
+    for mode in ("eager", "graph"):
+        model.enable_cuda_graph_inference(mode == "graph")
+        model.reset()
+        for t in range(35):  # warm-up incl. one re-plan and the graph capture
+            model.step(obs[t], "goal")
+        model.reset()
+        torch.cuda.synchronize()
+        act_us, plan_us = [], []
+        for t in range(steps):
+            t0 = time.perf_counter()
+            a = model.step(obs[t], "goal").cpu()
+            dt = (time.perf_counter() - t0) * 1e6
+            (plan_us if t % model.replan_freq == 0 else act_us).append(dt)
+        q = lambda v, p: float(np.percentile(v, p))
+        out[mode] = {"p50_us": q(act_us, 50), "p99_us": q(act_us, 99), "mean_us": float(np.mean(act_us)), "replan_step_p50_us": q(plan_us, 50), "steps": len(act_us)}
+    out["what"] = "Hulc.step: pinned-host observation (200x200 + 84x84 fp32 frames, 15-d robot state) -> sampled world-frame action on the host, batch 1, wall clock per control step"
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from hulc_b200 import ops
+    from hulc_b200.models.gcbc import GCBC
     from hulc_b200.models.hulc import Hulc
     from hulc_b200.utils import synthetic
 
@@ -270,15 +398,17 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     peaks = measured_peaks()
+    mname, rnn_model, S, _ = CONFIGS[args.config]
+    precision = "tf32" if args.dtype == "fp32" else args.dtype
 
-    cfg = synthetic.model_config("hulc", target_root="hulc_b200")
+    cfg = synthetic.model_config(mname, rnn_model=rnn_model, max_window=max(32, S), target_root="hulc_b200")
     cfg.pop("_target_"); cfg.pop("_recursive_")
-    model = Hulc(**cfg, device=dev)
-    model.load_state_dict(synthetic.make_state_dict("hulc"), strict=False)  # identical weights on every rank
+    model = (GCBC if mname == "gcbc" else Hulc)(**cfg, device=dev, precision=precision)
+    model.load_state_dict(synthetic.make_state_dict(mname, rnn_model, max_window=max(32, S)), strict=False)  # identical weights on every rank
     eng = model.engine
     opt = model.configure_optimizers()["optimizer"]
 
-    host = synthetic.make_batch(B_PER_MODALITY, SEQ_LEN, seed=1 + rank)  # per-rank data (weak scaling)
+    host = synthetic.make_batch(B_PER_MODALITY, S, seed=1 + rank)  # per-rank data (weak scaling)
     batch = synthetic._to(host, dev)
 
     from hulc_b200.ddp import FlatGradientSync
@@ -341,8 +471,10 @@ def run_ours(args):
             elif torch.is_tensor(v):
                 yield v
 
-    def run_e2e(host_batch):
-        """Pinned host batch -> double-buffered H2D on a copy stream -> model.training_step (graph replay) -> all-reduce + Adam -> loss D2H."""
+    def run_e2e(host_batch, lightning_contract=False):
+        """Pinned host batch -> double-buffered H2D on a copy stream -> model.training_step (graph replay) -> all-reduce + Adam -> loss D2H.
+        lightning_contract: what Lightning's loop does with the module on one GPU, autograd enabled —
+        `loss = training_step(batch); loss.backward(); optimizer.step(); optimizer.zero_grad()`."""
         hostp = pin(host_batch)
         nbytes = sum(t_.numel() * t_.element_size() for t_ in tensors(hostp))
         copy_stream = torch.cuda.Stream()
@@ -367,20 +499,24 @@ def run_ours(args):
                 torch.cuda.current_stream().wait_event(ready[slot])
                 loss_t = model.training_step(stage[slot], i)
                 consumed[slot].record()
-                allreduce_and_adam()
+                if lightning_contract:
+                    loss_t.backward()
+                    opt.step()
+                    opt.zero_grad()
+                else:
+                    allreduce_and_adam()
                 losses.append(loss_t.item())  # device -> host read of the step's result
             return losses
 
         for ev in consumed:
             ev.record()
         model.enable_cuda_graphs()
-        with torch.no_grad():
+        with torch.set_grad_enabled(lightning_contract):
             e2e_loop(4)  # captures one graph per staging slot, then warm replays
-        barrier()
-        t0 = time.perf_counter()
-        with torch.no_grad():
+            barrier()
+            t0 = time.perf_counter()
             e2e_loop(args.steps)
-        barrier()
+            barrier()
         ms_ = (time.perf_counter() - t0) / args.steps * 1e3
         t_ = torch.tensor([ms_], device=dev)
         if world > 1:
@@ -395,6 +531,12 @@ def run_ours(args):
     for m in host_u8:
         host_u8[m]["rgb_obs"] = {k: ((v * 0.5 + 0.5) * 255).round().clamp(0, 255).to(torch.uint8) for k, v in host[m]["rgb_obs"].items()}
     u8_ms, u8_bytes = run_e2e(host_u8)
+    lc = None
+    if world == 1:
+        lc_ms, lc_bytes = run_e2e(host_u8, lightning_contract=True)
+        lc = {"value": seqs / (lc_ms * 1e-3), "unit": UNIT, "ms_per_step": lc_ms, "h2d_bytes_per_step": lc_bytes, "d2h_bytes_per_step": 4,
+              "api": "autograd enabled: loss = Hulc.training_step(batch); loss.backward(); FusedAdam.step(); zero_grad() — uint8 frames; the gradients autograd "
+                     "hands to the parameters are views of the engine's flat buffer (no copies)"}
 
     if rank == 0:
         roof = dominant_kernel_roofline(torch, eng, batch, peaks, ms)
@@ -402,13 +544,13 @@ def run_ours(args):
         roof["step"] = {
             "tensor_frac": per_gpu * GFLOP_PER_SEQ * 1e9 / (peaks["tf_sustained"] * 1e12),
             "hbm_frac": per_gpu * MB_PER_SEQ * 1e6 / (peaks["hbm"] * 1e9),
-            "note": "whole step vs SURVEY.md §8(d) bounds: 13.03 GFLOP and 41.6 MB per sequence; sustained bf16 peak",
+            "note": "whole step vs SURVEY.md §8(d) bounds: 13.03 GFLOP and 41.6 MB per sequence (HULC, S=32); sustained bf16 peak",
         }
-        cpu = None
+        cpu = eager = lat = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            Bs = 8
-            ostep = oracle_step_fn(Bs, SEQ_LEN, cores)
+            Bs = B_PER_MODALITY
+            ostep = oracle_step_fn(Bs, S, cores, mname, rnn_model)
             ostep()
             t0 = time.perf_counter()
             n = 2
@@ -416,18 +558,30 @@ def run_ours(args):
                 ostep()
             dt = (time.perf_counter() - t0) / n
             cpu = {"value": 2 * Bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{Bs}+{Bs} sequences x {SEQ_LEN} frames, fwd+bwd+Adam fp32, 1 warm-up + {n} timed steps of the oracle (torch CPU, {cores} threads)"}
+                   "sample": f"the full step ({Bs}+{Bs} sequences x {S} frames, fwd+bwd+Adam fp32), 1 warm-up + {n} timed steps of the oracle (torch CPU, {cores} threads)"}
+        if world == 1 and not args.no_eager:
+            del sg
+            eager = eager_b200(torch, args, dev)
+        if world == 1 and not args.no_latency and args.config == "hulc":
+            try:
+                lat = inference_latency(torch, args, dev)
+            except Exception as e:
+                lat = {"error": f"{type(e).__name__}: {e}"[:300]}
+        dtype = {"tf32": "f32 storage/accumulate; tf32 tensor-core convs and backward GEMMs, 3xTF32 forward GEMMs, fp32 CUDA-core elsewhere",
+                 "fp32": "f32", "bf16": "bf16 activations / weight copies on the tensor cores (kind::f16), fp32 accumulate, fp32 master weights + Adam, fp32 losses / LayerNorm / softmax"}[precision]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage/accumulate; tf32 tensor-core convs and backward GEMMs, 3xTF32 forward GEMMs, fp32 CUDA-core elsewhere" if eng.tc else "f32", "data": "synthetic",
-            "config": {"workload": "HULC full model, batch=32 vis + 32 lang sequences per GPU, seq_len=32, 200x200 + 84x84 RGB fp32 frames, 384-d lang emb (BASELINE config 2), fwd+bwd+Adam",
-                       "parallelism": f"dp{world}", "launch": "forward+backward(+Adam) replayed from one CUDA graph", "l2": "per-step inputs are 1.16 GB per GPU (> 126 MB L2); no explicit flush", "dropout_p": 0.1},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": workload_text(args), "name": args.config,
+                       "parallelism": f"dp{world}", "launch": "forward+backward(+Adam) replayed from one CUDA graph", "l2": "per-step inputs are 1.16 GB per GPU (> 126 MB L2); no explicit flush",
+                       "dropout_p": eng.dropout_p},
             "clocks": clk.summary(), "gpu_launches": launches, "launches_per_step": launches / args.steps, "loss": loss,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "api": "hulc_b200.models.hulc.Hulc.training_step (CUDA-graph replay per staging slot) + fused Adam; double-buffered pinned-host uploads on a copy stream"},
             "e2e_uint8_frames": {"value": seqs / (u8_ms * 1e-3), "unit": UNIT, "ms_per_step": u8_ms, "h2d_bytes_per_step": u8_bytes, "d2h_bytes_per_step": 4,
                                  "note": "same API, frames handed over as the uint8 the dataset stores; (x/255-0.5)/0.5 runs on the device (hulc_frames_u8_to_f32)"},
-            "roofline": roof, "cpu_baseline": cpu,
+            "e2e_lightning_contract": lc,
+            "roofline": roof, "cpu_baseline": cpu, "eager_b200": eager, "latency": lat,
         }
         print(json.dumps(line))
     if world > 1:
@@ -442,6 +596,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-torch-on-this-GPU comparator")
+    ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 inference latency block")
+    ap.add_argument("--config", default="hulc", choices=sorted(CONFIGS))
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,6 +24,21 @@ from .spec import ModelDims, param_spec
 
 RELU, TANH, GATE_TANH = 1, 2, 4
 _POISON = bool(int(os.environ.get("HULC_B200_POISON", "0")))
+# HULC_B200_NVTX=1: one NVTX range per block of the step (encoders, goal, prior, posterior, plan, decoder, losses, and their backward
+# counterparts), so a timeline (nsys / ncu --nvtx) reads in the reference's vocabulary
+_NVTX = bool(int(os.environ.get("HULC_B200_NVTX", "0")))
+_nvtx_open = [False]
+
+
+def _mark(name: Optional[str]):
+    """Close the current NVTX range and open `name` (None: just close)."""
+    if not _NVTX:
+        return
+    if _nvtx_open[0]:
+        torch.cuda.nvtx.range_pop()
+    _nvtx_open[0] = name is not None
+    if name is not None:
+        torch.cuda.nvtx.range_push(name)
 
 # parameters that must sit next to each other in the flat buffer so one GEMM covers them (decoder heads:
 # logit_probs | means | log_scales | gripper — the row layout hulc_logistic_loss expects).  The group is padded with zero
@@ -130,8 +145,8 @@ class HulcEngine:
         CUDA-core kernels (also the only mode of the host-emulated build used by the CPU tests).  `dims` (hulc_b200.spec.ModelDims,
         normally read from the Hydra config tree by `dims_from_configs`) overrides the individual size arguments."""
         if dims is None:
-            dims = ModelDims(model=model, rnn_model=rnn_model, max_window=max_window, dropout_p=float(dropout_p) if model != "mcil" else 0.0, nhead=nhead,
-                             nlayers=nlayers, gripper_alpha=float(gripper_alpha))
+            dims = ModelDims.shipped(model, rnn_model, max_window, nhead=nhead, nlayers=nlayers, gripper_alpha=float(gripper_alpha),
+                                     **({} if model == "mcil" else {"dropout_p": float(dropout_p)}))
         model, rnn_model = dims.model, dims.rnn_model
         assert model in ("hulc", "gcbc", "mcil") and rnn_model in ("rnn_decoder", "gru_decoder")
         assert precision in ("tf32", "fp32")
@@ -158,7 +173,9 @@ class HulcEngine:
         self._bufs: Dict[str, torch.Tensor] = {}
         self._train_root = self._bufs  # the dictionary in place outside any namespace
         self._buf_namespaces: Dict[object, Dict[str, torch.Tensor]] = {}
-        self._infer_state = None
+        self._infer_state = None   # persistent rollout tensors (goal, plan, hidden, const); allocated by the first infer_plan
+        self._infer_planned = False
+        self._infer_graph = None
         self._step_shapes: Dict[str, tuple] = {}
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
         # per-step Philox seed, device resident: advanced on the device so a captured step draws fresh randomness per replay
@@ -564,6 +581,7 @@ class HulcEngine:
         losses.zero_()  # slots of a modality order / count seen on an earlier step must not leak into this step's totals
         lview = lambda i: losses[i : i + 1]
 
+        _mark("fwd/perceptual_encoders")
         # ---- perceptual encoders --------------------------------------------------------------------------------------
         emb = self.buf("emb", N, 128)
         if emb_override is not None:
@@ -575,6 +593,7 @@ class HulcEngine:
         emb3 = emb.view(nB, S, 128)
         out["perceptual_emb"] = emb3
 
+        _mark("fwd/goal_encoders")
         # ---- goal encoders (goal_encoders.py:31-36, 64-69) ---------------------------------------------------------------
         goal = self.buf("goal", nB, 32)
         goal_ctx = []
@@ -590,6 +609,7 @@ class HulcEngine:
             goal_ctx.append((acts, stats, names, ln))
         out["latent_goal"] = goal
 
+        _mark("fwd/plan_proposal")
         # ---- plan proposal = prior (plan_proposal_net.py:42-47): cat(emb[:,0], goal) never materialised ----------------------
         if self.model != "gcbc":
             w0 = P["plan_proposal.fc_model.0.weight"]
@@ -605,6 +625,7 @@ class HulcEngine:
                             bias=P["plan_proposal.fc_state.0.bias"])
             out["pp_state"] = pp_state
 
+        _mark("fwd/plan_recognition")
         # ---- plan recognition = posterior -----------------------------------------------------------------------------------
         if self.model == "mcil":
             post = self._birnn_fwd(emb3, S, nB)
@@ -617,6 +638,7 @@ class HulcEngine:
                         bias=P["plan_recognition.fc_state.0.bias"])
         out["pr_state"], out["seq_feat"] = pr_state, seq_feat
 
+        _mark("fwd/latent_plan_kl")
         # ---- latent plan sample + KL (hulc.py:289-291, 539-561; distributions.py:23-60) ---------------------------------------
         PF = self.plan_features
         plan = None
@@ -646,6 +668,7 @@ class HulcEngine:
                     ops.sum_to(kl_el[b0 : b0 + Bm], lview(4 * i + 2), 1.0 / Bm)
             out["sampled_plan"] = plan
 
+        _mark("fwd/action_decoder")
         # ---- action decoder forward (logistic_decoder_rnn.py:260-287) ------------------------------------------------------------
         kind = "gru" if self.rnn_model == "gru_decoder" else "relu"
         Gn = self.gates
@@ -677,6 +700,7 @@ class HulcEngine:
         heads = heads_p[:, :n_heads]
         out["heads_tm"] = heads_p.view(S, nB, n_pad)[:, :, :n_heads]
 
+        _mark("fwd/losses")
         # ---- losses (logistic_decoder_rnn.py:121-155,184-231; gripper_control.py:16-36) ----------------------------------------
         has_grip = self.model != "mcil"
         acts_all = self.buf("dec.actions", nB, S, 7)
@@ -693,6 +717,7 @@ class HulcEngine:
                               n_mix=self.n_mix, num_classes=self.num_classes, has_gripper=has_grip, gripper_alpha=self.gripper_alpha,
                               grad_scale=1.0 / n_mod, log_scale_min=self.dims.log_scale_min, act_min=self.dims.act_min, act_max=self.dims.act_max)
 
+        _mark("fwd/clip_aux")
         # ---- CLIP auxiliary loss (hulc.py:650-695, proj_vis_lang.py:23-27), language modality only --------------------------------
         clip_ctx = None
         if self.model != "mcil" and with_clip:
@@ -711,6 +736,7 @@ class HulcEngine:
                 ops.clip_loss(im2, tx2, P["logit_scale"].view(1), mask8, lview(4 * i + 3), d_im2, d_tx2, G["logit_scale"].view(1), grad_scale=self.clip_beta)
                 clip_ctx = (i, b0, Bm, sf, gl, im1, tx1, d_im2, d_tx2)
 
+        _mark("totals")
         # ---- totals (hulc.py:464-491,525) ------------------------------------------------------------------------------------------
         L = losses.view(4, 4)[:n_mod]
         act_m = L[:, 0] + (self.gripper_alpha * L[:, 1] if has_grip else 0.0)
@@ -724,6 +750,7 @@ class HulcEngine:
         for i, m in enumerate(mods):
             out[f"action_loss_{m}"], out[f"kl_loss_{m}"] = act_m[i], kl_m[i]
         if not backward:
+            _mark(None)
             return out
 
         # ============================================ backward =====================================================================
@@ -732,6 +759,7 @@ class HulcEngine:
         demb3 = demb.view(nB, S, 128)
         dgoal = self.buf("dgoal", nB, 32)
 
+        _mark("bwd/action_decoder")
         # heads
         self.gemm_bwd(dheads_p, h1_all, ps.heads_gw, transA=True, beta=1.0)
         colsum(dheads_p, ps.heads_gb, beta=1.0)
@@ -761,6 +789,7 @@ class HulcEngine:
         dpercep = self.gemm_bwd(dpre0, w_pc, self.buf("dec.dpercep", S * nB, C))
         ops.strided_copy(demb3[:, :, self.percep_lo :].transpose(0, 1), dpercep.view(S, nB, C), accumulate=True)
 
+        _mark("bwd/clip_aux")
         # CLIP head
         dseq = self.buf("dseq", nB, seq_feat.shape[1])
         dseq.zero_()
@@ -771,6 +800,7 @@ class HulcEngine:
             d_tx1 = self._linear_bwd("proj_vis_lang.mlp_lang.2", tx1, d_tx2, self.buf("clip.dtx1", *tx1.shape), gate=tx1)
             self._linear_bwd("proj_vis_lang.mlp_lang.0", gl, d_tx1, dgoal[b0 : b0 + Bm], dx_beta=1.0)
 
+        _mark("bwd/latent_plan_kl")
         # latent plan
         d_pr = self.buf("d_pr", *pr_state.shape)
         if self.model == "gcbc":
@@ -786,6 +816,7 @@ class HulcEngine:
                     eps = plan_eps[m] if plan_eps is not None else None
                     ops.plan_cont_bwd(pr_state[sl], pp_state[sl], dplan[sl], d_pr[sl], d_pp[sl], cl, cr, eps=eps, seed=seed, site=100 + i)
 
+        _mark("bwd/plan_recognition")
         # posterior
         self._linear_bwd("plan_recognition.fc_state.0", seq_feat, d_pr, dseq, dx_beta=1.0)
         if self.model == "mcil":
@@ -793,6 +824,7 @@ class HulcEngine:
         else:
             self._transformer_bwd(post, dseq, demb3, S, nB, drop)
 
+        _mark("bwd/plan_proposal")
         # prior
         if self.model != "gcbc":
             d = d_pp
@@ -809,6 +841,7 @@ class HulcEngine:
             self.gemm_bwd(d, w0[:, :128], demb3[:, 0, :], beta=1.0)
             self.gemm_bwd(d, w0[:, 128:], dgoal, beta=1.0)
 
+        _mark("bwd/goal_encoders")
         # goal encoders
         for (m, b0, Bm), (acts, stats, names, ln) in zip(zip(mods, b0s, Bs), goal_ctx):
             if "lang" in m:
@@ -816,9 +849,11 @@ class HulcEngine:
             else:
                 self._mlp_ln_bwd(f"goal.{m}", acts, stats, names, ln, dgoal[b0 : b0 + Bm], demb3[b0 : b0 + Bm, S - 1, :], dx_beta=1.0)
 
+        _mark("bwd/perceptual_encoders")
         # perceptual encoders
         self._encoder_bwd("static", ctx_s, demb)
         self._encoder_bwd("gripper", ctx_g, demb)
+        _mark(None)
         return out
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -1087,15 +1122,65 @@ class HulcEngine:
                                           idx_in=None if plan_idx is None else plan_idx.reshape(-1).to(torch.int32), idx_out=idx_out, seed=rng, site=300)
                 else:
                     ops.plan_cont_fwd(pp_state, pp_state, plan, self.buf("kl_el", 1, self.plan_features), eps=plan_eps, seed=rng, site=300)
-            self._infer_state = dict(goal=goal.clone(), plan=None if plan is None else plan.clone(), hidden=torch.zeros(2, 1, H, device=self.device))
+            # rollout state in PERSISTENT tensors (a captured control step keeps pointing at them across re-plans): goal, plan, the decoder's
+            # carried hidden state (cleared here) and the part of the first layer's input projection that is constant between re-plans
+            st = self._infer_state
+            if st is None:
+                st = self._infer_state = dict(goal=torch.empty(1, 32, device=self.device), plan=None if plan is None else torch.empty_like(plan),
+                                              hidden=torch.zeros(2, 1, H, device=self.device), const=torch.empty(1, self.gates * H, device=self.device))
+            ops.strided_copy(st["goal"], goal)
+            if plan is not None:
+                ops.strided_copy(st["plan"], plan)
+            st["hidden"].zero_()
+            PF, C, rp = self.plan_features, 128 - self.percep_lo, "action_decoder.rnn"
+            w_ih0 = P[f"{rp}.weight_ih_l0"]
+            self.gemm_fwd(st["goal"], w_ih0[:, PF + C :], st["const"], transB=True, bias=P[f"{rp}.bias_ih_l0"])
+            if PF:
+                self.gemm_fwd(st["plan"], w_ih0[:, :PF], st["const"], transB=True, beta=1.0)
+            self._infer_planned = True
         return self._infer_state["plan"], self._infer_state["goal"]
+
+    def infer_reset(self):
+        """Forget the current rollout (the persistent state tensors stay: captured control steps point at them)."""
+        self._infer_planned = False
+
+    def enable_infer_graph(self, flag: bool = True):
+        """Replay the control step (`infer_act`) from a CUDA graph: the observation is copied into static input buffers, one
+        cudaGraphLaunch runs the ~60 kernels of the step, the carried hidden state and the RNG seed advance on the device."""
+        self._infer_graph = {} if flag else None
 
     @torch.no_grad()
     def infer_act(self, rgb_static, rgb_gripper, robot_obs_raw, *, sample_u=None, seed: Optional[int] = None) -> torch.Tensor:
         """One control step: encode the observation ([1, 3, H, W] frames), advance the decoder RNN by one step from the carried hidden state,
         sample an action from the mixture and map it to the world frame (robot_obs_raw [1, 15]).  Returns [1, 1, 7]."""
-        if self._infer_state is None:
+        if not self._infer_planned:
             raise RuntimeError("infer_plan() starts a rollout")
+        graphs = self._infer_graph
+        if graphs is None or sample_u is not None or seed is not None or self.device.type != "cuda":
+            return self._infer_act_body(rgb_static, rgb_gripper, robot_obs_raw, sample_u=sample_u, seed=seed).clone()
+        key = (tuple(rgb_static.shape), tuple(rgb_gripper.shape), str(rgb_static.dtype))
+        ent = graphs.get(key)
+        if ent is None:
+            ins = (torch.empty(rgb_static.shape, dtype=rgb_static.dtype, device=self.device), torch.empty(rgb_gripper.shape, dtype=rgb_gripper.dtype, device=self.device),
+                   torch.empty(1, robot_obs_raw.numel(), device=self.device))
+            for dst, src in zip(ins, (rgb_static, rgb_gripper, robot_obs_raw.reshape(1, -1))):
+                dst.copy_(src, non_blocking=True)
+            st = self._infer_state
+            keep = (st["hidden"].clone(), self.rng_dev.clone())
+            self._infer_act_body(*ins)  # eager warm-up (allocates the buffers); undo its effect on the rollout state
+            st["hidden"].copy_(keep[0]); self.rng_dev.copy_(keep[1])
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._infer_act_body(*ins)
+            ent = graphs[key] = (g, ins, out)
+        g, ins, out = ent
+        for dst, src in zip(ins, (rgb_static, rgb_gripper, robot_obs_raw.reshape(1, -1))):
+            dst.copy_(src, non_blocking=True)
+        g.replay()
+        return out.clone()
+
+    def _infer_act_body(self, rgb_static, rgb_gripper, robot_obs_raw, *, sample_u=None, seed: Optional[int] = None) -> torch.Tensor:
         P, ps, st = self.ps.p, self.ps, self._infer_state
         H, Gn, PF = self.H, self.gates, self.plan_features
         kind = "gru" if self.rnn_model == "gru_decoder" else "relu"
@@ -1113,19 +1198,14 @@ class HulcEngine:
             emb = self._infer_embed(rgb_static, rgb_gripper)
             C = 128 - self.percep_lo
             rp = "action_decoder.rnn"
-            w_ih0 = P[f"{rp}.weight_ih_l0"]
-            w_plan, w_pc, w_goal = w_ih0[:, :PF], w_ih0[:, PF : PF + C], w_ih0[:, PF + C :]
-            const = self.buf("dec.const", 1, Gn * H)
-            self.gemm_fwd(st["goal"], w_goal, const, transB=True, bias=P[f"{rp}.bias_ih_l0"])
-            if PF:
-                self.gemm_fwd(st["plan"], w_plan, const, transB=True, beta=1.0)
+            w_pc = P[f"{rp}.weight_ih_l0"][:, PF : PF + C]
             percep = self.buf("dec.percep", 1, C)
             ops.strided_copy(percep, emb[0:1, self.percep_lo :])
             hb = [self.buf(f"dec.h{l}", 3, 1, H, zero=True) for l in range(2)]
             for l in range(2):
                 ops.strided_copy(hb[l][0], st["hidden"][l])  # slot 0 = the hidden state carried from the previous control step
             pre0 = self.buf("dec.pre0", 1, Gn * H)
-            self.gemm_fwd(percep, w_pc, pre0, transB=True, addend=const, add_mod=1, bias=None if kind == "gru" else P[f"{rp}.bias_hh_l0"])
+            self.gemm_fwd(percep, w_pc, pre0, transB=True, addend=st["const"], add_mod=1, bias=None if kind == "gru" else P[f"{rp}.bias_hh_l0"])
             self._rnn_fwd("dec.l0", pre0, P[f"{rp}.weight_hh_l0"], P[f"{rp}.bias_hh_l0"], hb[0], 0, 1, 1, kind=kind)
             pre1 = self.buf("dec.pre1", 1, Gn * H)
             self.gemm_fwd(hb[0][1], P[f"{rp}.weight_ih_l1"], pre1, transB=True, bias=P[f"{rp}.bias_ih_l1"],
@@ -1139,10 +1219,10 @@ class HulcEngine:
                                 u_mix=None if sample_u is None else sample_u[0].contiguous(), u_inv=None if sample_u is None else sample_u[1].contiguous(),
                                 seed=rng, site=310)
             if not has_grip:
-                return pred_tcp.clone()
+                return pred_tcp
             out = self.buf("pred_world", 1, 1, A)
             ops.tcp_to_world(pred_tcp, robot_obs_raw.reshape(1, 1, -1).contiguous(), out, self.nan_flag)
-            return out.clone()
+            return out
 
     def optimizer_step(self, grad_scale=1.0):
         self.ps.adam_step(lr=self.lr, grad_scale=grad_scale)
@@ -1152,7 +1232,9 @@ class HulcEngine:
         cudaGraphLaunch, which removes the host launch cost that otherwise bounds the 128 dependent recurrent steps.  The
         tensors of `batch` are the graph's static inputs (copy new data into them before each replay); the per-step RNG
         seed and the Adam step count advance on the device."""
+        seed0 = self.rng_dev.clone()
         self.step(batch)  # eager warm-up: allocates every activation buffer the step needs
+        self.rng_dev.copy_(seed0)  # capture + first replay consume ONE seed increment, like an eager step
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()

@@ -10,7 +10,7 @@ class GCBC(Hulc):
     # ---- inference (gcbc.py:281-317): the goal is encoded once per rollout, there is no plan and no re-planning -------------------
     def reset(self):
         self.latent_goal = None
-        self.engine._infer_state = None
+        self.engine.infer_reset()
 
     def step(self, obs, goal, *, sample_u=None):
         """One control step.  Unlike the reference, whose decoder keeps its hidden state across `reset()` calls (nothing clears it), a new

@@ -353,7 +353,9 @@ class Hulc(_Base):
             eng.nan_flag = fn(eng.nan_flag)
             eng._bufs.clear()
             eng._buf_namespaces.clear()
-            eng._infer_state = None
+            eng._infer_state, eng._infer_planned = None, False
+            if eng._infer_graph is not None:
+                eng._infer_graph = {}
             if self._graphs is not None:
                 self._graphs = {}
             for k, p in self._param_by_key.items():
@@ -515,7 +517,7 @@ class Hulc(_Base):
         self.plan = None
         self.latent_goal = None
         self.rollout_step_counter = 0
-        self.engine._infer_state = None
+        self.engine.infer_reset()
 
     def load_lang_embeddings(self, embeddings_path):
         """hulc.py:872-882: <dataset>/validation/embeddings.npy -> {annotation: embedding}."""
@@ -542,9 +544,18 @@ class Hulc(_Base):
                 gs, gg = goal["rgb_obs"]["rgb_static"].to(dev).float(), goal["rgb_obs"]["rgb_gripper"].to(dev).float()
                 self.plan, self.latent_goal = self.engine.infer_plan(torch.cat([st, gs], 1)[0].contiguous(), torch.cat([gr, gg], 1)[0].contiguous(), plan_idx=plan_idx,
                                                                      plan_u=plan_u)
-        action = self.engine.infer_act(st[0].contiguous(), gr[0].contiguous(), obs["robot_obs_raw"].to(dev).float().reshape(1, -1), sample_u=sample_u)
+        if self.engine._infer_graph is not None and sample_u is None:
+            # graph replay: the observation goes straight from where it is (host memory in a rollout) into the graph's static input buffers
+            ro = obs["robot_obs_raw"]
+            action = self.engine.infer_act(obs["rgb_obs"]["rgb_static"][0], obs["rgb_obs"]["rgb_gripper"][0], ro if ro.dtype == torch.float32 else ro.float())
+        else:
+            action = self.engine.infer_act(st[0].contiguous(), gr[0].contiguous(), obs["robot_obs_raw"].to(dev).float().reshape(1, -1), sample_u=sample_u)
         self.rollout_step_counter += 1
         return action
+
+    def enable_cuda_graph_inference(self, flag: bool = True):
+        """Replay `step`'s per-control-step work (encoders, one decoder step, sampling, frame change) from one CUDA graph."""
+        self.engine.enable_infer_graph(flag)
 
     def _dist(self, state: torch.Tensor):
         """Distribution.get_dist (hulc/utils/distributions.py:38-47) on a state tensor: logits [B, 1024] or [mean | raw std] [B, 512]."""

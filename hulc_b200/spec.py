@@ -47,6 +47,15 @@ class ModelDims:
     clip_hidden: int = 128              # ProjVisLang's hidden width (proj_vis_lang.py:10-21, fixed in the reference)
     clip_out: int = 32
 
+    @classmethod
+    def shipped(cls, model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: int = 32, **kw) -> "ModelDims":
+        """The shipped configuration of `model` (conf/model/{hulc,gcbc,mcil}.yaml): MCIL discretises into 256 classes and has no dropout."""
+        base = dict(model=model, rnn_model=rnn_model, max_window=max_window)
+        if model == "mcil":
+            base.update(num_classes=256, dropout_p=0.0)
+        base.update(kw)
+        return cls(**base)
+
     @property
     def latent_size(self) -> int:
         return 2 * self.visual_features
@@ -101,7 +110,7 @@ def _require(cfg, path: str, key: str, allowed, default):
 def dims_from_configs(model: str, perceptual_encoder, plan_proposal, plan_recognition, language_goal, visual_goal, action_decoder, distribution,
                       proj_vis_lang=None) -> ModelDims:
     """Every size of the network from the config tree; raises on anything the kernels cannot run."""
-    d = ModelDims(model=model)
+    d = ModelDims.shipped(model)
     # ---- perceptual encoders (concat_encoders.py:20-57, vision_network.py:17-53, vision_network_gripper.py:24-47) ----
     for name in ("depth_static", "depth_gripper", "proprio", "tactile"):
         if _get(perceptual_encoder, name) not in (None, {}, "none"):
@@ -195,7 +204,7 @@ def dims_from_configs(model: str, perceptual_encoder, plan_proposal, plan_recogn
 def param_spec(model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: int = 32, dims: Optional[ModelDims] = None) -> Dict[str, tuple]:
     """state_dict contract of the reference: parameter key -> shape, in registration order, for
     `conf/model/{hulc,gcbc,mcil}.yaml` (or the sizes in `dims`).  Buffers are not listed."""
-    d = dims if dims is not None else ModelDims(model=model, rnn_model=rnn_model, max_window=max_window, dropout_p=0.1 if model != "mcil" else 0.0)
+    d = dims if dims is not None else ModelDims.shipped(model, rnn_model, max_window)
     model, rnn_model = d.model, d.rnn_model
     spec: Dict[str, tuple] = {}
     D, G = d.latent_size, d.latent_goal

@@ -343,7 +343,7 @@ def logistic_mixture_sample(logit_probs, log_scales, means, gripper_act, u_mix, 
     actions = mu + torch.exp(ls) * (torch.log(u) - torch.log(1.0 - u))
     if gripper_act is None:
         return actions
-    cmd = torch.tensor(gripper_bounds, dtype=means.dtype)[gripper_act.argmax(-1)]
+    cmd = torch.tensor(gripper_bounds, dtype=means.dtype, device=means.device)[gripper_act.argmax(-1)]
     return torch.cat([actions, cmd.unsqueeze(-1)], 2)
 
 
@@ -415,7 +415,7 @@ def clip_loss(sd: SD, seq_feat: torch.Tensor, goal: torch.Tensor, mask: Optional
     im = im / im.norm(dim=-1, keepdim=True)
     tx = tx / tx.norm(dim=-1, keepdim=True)
     logits = sd["logit_scale"].exp() * im @ tx.t()
-    labels = torch.arange(logits.shape[0])
+    labels = torch.arange(logits.shape[0], device=logits.device)
     loss = (F.cross_entropy(logits, labels) + F.cross_entropy(logits.t(), labels)) / 2
     return loss * 0 if skip else loss
 
