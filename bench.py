@@ -232,7 +232,11 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     else:
         cands["rnn_step_gemm"] = (lambda: ops.gemm(hb[1], whh, hb[2], transB=True, addend=pre1[:nB], act=1), 2.0 * nB * H * H, 4 * S)
     mode = 1 if eng.tc else 0
-    if elman:
+    if elman and eng.bf16:  # bf16 path: bf16 operands (TMA-fed kind::f16 kernel), fp32 result
+        a16, h16, w16 = big_a.to(torch.bfloat16), hb[1 : S + 1].reshape(S * nB, H).to(torch.bfloat16), whh.to(torch.bfloat16)
+        cands["dense_wgrad_2048^3"] = (lambda: ops.gemm_bf16(a16, h16, big_c, transA=True), 2.0 * H * H * S * nB, 4)
+        cands["dense_fwd_2048^3"] = (lambda: ops.gemm_bf16(a16, w16, pre1, transB=True), 2.0 * H * H * S * nB, 1)
+    elif elman:
         cands["dense_wgrad_2048^3"] = (lambda: ops.gemm(big_a, hb[1 : S + 1].view(S * nB, H), big_c, transA=True, tc=mode), 2.0 * H * H * S * nB, 4)
         cands["dense_fwd_2048^3"] = (lambda: ops.gemm(big_a, whh, pre1, transB=True, tc=3 if eng.tc else 0), 2.0 * H * H * S * nB, 1)
     res = {}
@@ -262,13 +266,17 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
         "rnn_step_fwd_3xtf32": 4.0 * (H * H + 3 * nB * H), "rnn_step_bwd_tf32": 4.0 * (H * H + 4 * nB * H), "rnn_step_gemm": 4.0 * (H * H + 3 * nB * H),
         "dense_wgrad_2048^3": 4.0 * (2 * S * nB * H + H * H), "dense_fwd_2048^3": 4.0 * (2 * S * nB * H + H * H),
     }
+    if eng.bf16:  # bf16 operands, fp32 result
+        abytes["dense_wgrad_2048^3"] = 2.0 * 2 * S * nB * H + 4.0 * H * H
+        abytes["dense_fwd_2048^3"] = 2.0 * (S * nB * H + H * H) + 4.0 * S * nB * H
     top = max(res, key=lambda k: res[k]["ms"] * res[k]["per_step"])
     r = res[top]
     tflops = r["flops"] / (r["ms"] * 1e-3) / 1e12
     gbs = abytes[top] / (r["ms"] * 1e-3) / 1e9
     # the kernel runs tf32 operands: its tensor ceiling is half the measured bf16 rate; it is HBM-bound when its arithmetic
     # intensity is below that ridge
-    tf32_peak = peaks["tf_burst"] / 2.0
+    is_bf16_kernel = eng.bf16 and top.startswith("dense")
+    tf32_peak = peaks["tf_burst"] / (1.0 if is_bf16_kernel else 2.0)
     hbm_bound = (r["flops"] / abytes[top]) < (tf32_peak * 1e12) / (peaks["hbm"] * 1e9)
     kern = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "gbs": round(abytes[k] / (v["ms"] * 1e-3) / 1e9, 1),
                 "per_step": v["per_step"], "share_of_step": round(v["share"], 4)} for k, v in res.items()}

@@ -385,8 +385,18 @@ __global__ void __launch_bounds__(256) nchw_channel_sum_kernel(const float* __re
 }
 
 // torch.optim.Adam (no weight decay, no amsgrad): one launch over the flat parameter buffer
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
-                            float b1, float b2, float eps, int step, const int* __restrict__ step_ptr, float grad_scale) {
+// bf16 (round to nearest even) of a finite or infinite fp32; NaN stays NaN
+__device__ __forceinline__ unsigned short f32_to_bf16_bits(float f) {
+  unsigned u = __float_as_uint(f);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (unsigned short)((u >> 16) | 0x40u);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
+
+// BF16: also write the updated parameters as bf16 into pb (the operand copy of the bf16 path: one pass instead of Adam + a cast)
+template <bool BF16>
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, unsigned short* __restrict__ pb,
+                            long long n, float lr, float b1, float b2, float eps, int step, const int* __restrict__ step_ptr, float grad_scale) {
   if (step_ptr) step = *step_ptr;  // device-resident step count: the launch can live in a replayed CUDA graph
   const float bc1 = 1.f - powf(b1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
@@ -399,7 +409,16 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     pi -= step_size * (mi / denom);
   };
   // 16-byte accesses, two independent quads per thread and trip (the kernel streams 7 x 4 bytes per parameter: HBM bound)
-  const long long n4 = (((reinterpret_cast<size_t>(p) | reinterpret_cast<size_t>(g) | reinterpret_cast<size_t>(m) | reinterpret_cast<size_t>(v)) & 15) == 0) ? n / 4 : 0;
+  const long long n4 = (((reinterpret_cast<size_t>(p) | reinterpret_cast<size_t>(g) | reinterpret_cast<size_t>(m) | reinterpret_cast<size_t>(v)) & 15) == 0 &&
+                        (!BF16 || (reinterpret_cast<size_t>(pb) & 7) == 0)) ? n / 4 : 0;
+  auto stb = [&](long long q, const float4& x) {  // four bf16 = 8 bytes
+    if (BF16) {
+      uint2 o;
+      o.x = (unsigned)f32_to_bf16_bits(x.x) | ((unsigned)f32_to_bf16_bits(x.y) << 16);
+      o.y = (unsigned)f32_to_bf16_bits(x.z) | ((unsigned)f32_to_bf16_bits(x.w) << 16);
+      reinterpret_cast<uint2*>(pb)[q] = o;
+    }
+  };
   float4* p4 = reinterpret_cast<float4*>(p);
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(m);
@@ -408,21 +427,24 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + stride < n4; i += 2 * stride) {
     float4 pa = p4[i], ga = g4[i], ma = m4[i], va = v4[i];
-    float4 pb = p4[i + stride], gb = g4[i + stride], mb = m4[i + stride], vb = v4[i + stride];
+    float4 pb2 = p4[i + stride], gb = g4[i + stride], mb = m4[i + stride], vb = v4[i + stride];
     upd(pa.x, ga.x, ma.x, va.x); upd(pa.y, ga.y, ma.y, va.y); upd(pa.z, ga.z, ma.z, va.z); upd(pa.w, ga.w, ma.w, va.w);
-    upd(pb.x, gb.x, mb.x, vb.x); upd(pb.y, gb.y, mb.y, vb.y); upd(pb.z, gb.z, mb.z, vb.z); upd(pb.w, gb.w, mb.w, vb.w);
+    upd(pb2.x, gb.x, mb.x, vb.x); upd(pb2.y, gb.y, mb.y, vb.y); upd(pb2.z, gb.z, mb.z, vb.z); upd(pb2.w, gb.w, mb.w, vb.w);
     p4[i] = pa; m4[i] = ma; v4[i] = va;
-    p4[i + stride] = pb; m4[i + stride] = mb; v4[i + stride] = vb;
+    p4[i + stride] = pb2; m4[i + stride] = mb; v4[i + stride] = vb;
+    stb(i, pa); stb(i + stride, pb2);
   }
   for (; i < n4; i += stride) {
     float4 pa = p4[i], ga = g4[i], ma = m4[i], va = v4[i];
     upd(pa.x, ga.x, ma.x, va.x); upd(pa.y, ga.y, ma.y, va.y); upd(pa.z, ga.z, ma.z, va.z); upd(pa.w, ga.w, ma.w, va.w);
     p4[i] = pa; m4[i] = ma; v4[i] = va;
+    stb(i, pa);
   }
   for (long long e = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
     float pi = p[e], mi = m[e], vi = v[e];
     upd(pi, g[e], mi, vi);
     p[e] = pi; m[e] = mi; v[e] = vi;
+    if (BF16) pb[e] = f32_to_bf16_bits(pi);
   }
 }
 
@@ -558,7 +580,17 @@ HULC_API int hulc_adam_step(float* p, const float* g, float* m, float* v, long l
                             const int* step_ptr, float grad_scale, void* stream) {
   if (n <= 0) return 0;
   int blocks = (int)min((long long)kNumSMs * 8, (n + 255) / 256);
-  HULC_LAUNCH(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, step, step_ptr, grad_scale);
+  HULC_LAUNCH(adam_kernel<false>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (unsigned short*)nullptr, n, lr, beta1, beta2, eps, step, step_ptr, grad_scale);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_adam_step_bf16(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2, float eps, int step,
+                                 const int* step_ptr, float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  if (!p_bf16) return (int)cudaErrorInvalidValue;
+  int blocks = (int)min((long long)kNumSMs * 8, (n + 255) / 256);
+  HULC_LAUNCH(adam_kernel<true>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, reinterpret_cast<unsigned short*>(p_bf16), n, lr, beta1, beta2, eps, step,
+              step_ptr, grad_scale);
   HULC_RETURN_LAST();
 }
 

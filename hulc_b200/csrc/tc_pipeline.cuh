@@ -143,6 +143,12 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
       mbar_wait(&bars->tmem_full[a], aphase);
       tc_fence_after_sync();
       if (warp == 0) trace(4);  // accumulator ready
+      if constexpr (CLUSTER > 1) {
+        // the partial tile is parked in the stage buffers below: meet the producer and MMA warps (which are done: one work item per CTA,
+        // and its accumulator is complete) at a CTA barrier first.  The mbarrier chain full -> tcgen05.commit -> tmem_full already orders
+        // the producers' last stage writes before this point; the barrier makes that ordering explicit (and visible to racecheck).
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kThreads) : "memory");
+      }
       const int row = warp * 32 + lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -261,6 +267,9 @@ __device__ __forceinline__ void run_pipeline(ALoader& al, BLoader& bl, const Epi
     }
     cp_async_wait<0>();
     for (int jj = j > L ? j - L : 0; jj < j; ++jj) publish(jj);
+  }
+  if constexpr (CLUSTER > 1) {
+    if (warp >= kEpiWarps && (int)blockIdx.x < num_tiles) asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kThreads) : "memory");  // see the epilogue
   }
 
   if (warp == 0) trace(5);  // epilogue warp 0 done with its role loop

@@ -22,18 +22,18 @@ inline EncodeFn encode_fn() {
   return fn;
 }
 
-// fp32 tensor of `rank` dims (innermost first): dims[i] elements, strides_bytes[i] = byte stride of dim i+1 (rank-1 entries,
+// tensor (fp32 unless `dtype` says otherwise) of `rank` dims (innermost first): dims[i] elements, strides_bytes[i] = byte stride of dim i+1 (rank-1 entries,
 // multiples of 16; views with overlapping windows are fine), box[i] = extent traversed per copy, elem_strides[i] = traversal step
 // (a box of N elements with step s has extent N*s).  OOB elements read as zero.
 inline int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
-                    const uint32_t* elem_strides = nullptr) {
+                    const uint32_t* elem_strides = nullptr, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
   EncodeFn fn = encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }

@@ -77,7 +77,20 @@ class ParamStore:
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)  # device copy of step_count (read by the Adam kernel)
         self._head_w, self._head_b = head_w, head_b
+        self.flat_bf16: Optional[torch.Tensor] = None  # bf16 operand copy of `flat` (bf16 path), refreshed by the Adam kernel
+        self.bf16_stale = True
         self.rebuild_views()
+
+    def enable_bf16(self):
+        """Keep a bf16 copy of the parameters next to the fp32 master weights (what torch.autocast re-creates on every use)."""
+        if self.flat_bf16 is None or self.flat_bf16.device != self.flat.device:
+            self.flat_bf16 = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.flat.device)
+            self.bf16_stale = True
+
+    def refresh_bf16(self):
+        if self.flat_bf16 is not None and self.bf16_stale:
+            ops.cast_bf16(self.flat, self.flat_bf16)
+            self.bf16_stale = False
 
     def rebuild_views(self):
         """(Re)create the named views after the flat buffers were allocated or moved to another device."""
@@ -104,6 +117,7 @@ class ParamStore:
         for k in self.keys:
             if k in sd:
                 self.p[k].copy_(sd[k].to(torch.float32))
+        self.bf16_stale = True
 
     def state_dict(self):
         return {k: self.p[k].detach().clone() for k in self.keys}
@@ -117,7 +131,7 @@ class ParamStore:
         self.step_count += 1
         self.step_dev.add_(1)
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
-                      step=0, step_dev=self.step_dev, grad_scale=grad_scale)
+                      step=0, step_dev=self.step_dev, grad_scale=grad_scale, p_bf16=self.flat_bf16)
 
 
 class StepGraph:
@@ -149,14 +163,21 @@ class HulcEngine:
                                      **({} if model == "mcil" else {"dropout_p": float(dropout_p)}))
         model, rnn_model = dims.model, dims.rnn_model
         assert model in ("hulc", "gcbc", "mcil") and rnn_model in ("rnn_decoder", "gru_decoder")
-        assert precision in ("tf32", "fp32")
+        assert precision in ("tf32", "fp32", "bf16")
         self.dims = dims
-        self.tc = precision == "tf32"
+        self.precision = precision
+        self.bf16 = precision == "bf16"        # bf16 tensor-core operands for every Linear product (and bf16 activations between the conv layers)
+        self.tc = precision in ("tf32", "bf16")
         self.persistent_rnn = os.environ.get("HULC_B200_PERSISTENT_RNN", "1") != "0"  # whole recurrence in one launch (csrc/rnn_tc.cu)
         self.model, self.rnn_model = model, rnn_model
         self.device = torch.device(device)
         self.spec = param_spec(dims=dims)
         self.ps = ParamStore(self.spec, device)
+        if self.bf16:
+            self.ps.enable_bf16()
+        self._twins: Dict[tuple, list] = {}     # (ptr, shape, strides) of an fp32 tensor -> [bf16 twin, generation it is valid for, byte range]
+        self._twin_gen = 0
+        self._bf16_only: set = set()            # keys whose fp32 storage was never written this step (the producer emitted bf16 only)
         self.dropout_p = float(dims.dropout_p) if model != "mcil" else 0.0
         self.kl_beta, self.kl_alpha, self.clip_beta, self.gripper_alpha = float(kl_beta), float(kl_balancing_mix), float(clip_beta), float(dims.gripper_alpha)
         self.nhead, self.nlayers, self.lr = dims.nhead, dims.nlayers, lr
@@ -232,15 +253,105 @@ class HulcEngine:
             return 1 if (K >= 64 or M >= 1024) else 0
         return 3 if K >= 64 and (M >= 256 or 2.0 * M * N * K >= 1e8) else 0
 
-    def gemm_fwd(self, A, B, C=None, **kw):
+    def gemm_fwd(self, A, B, C=None, out="f32", **kw):
+        """out (bf16 mode only): "f32" writes C; "bf16" writes only C's bf16 twin (C stays a handle: for activations that are consumed by
+        further products and ReLU gates only); "both" writes the two."""
+        if self.bf16:
+            return self._gemm16(A, B, C, out=out, **kw)
         M, K = (A.shape[1], A.shape[0]) if kw.get("transA") else A.shape
         N = B.shape[0] if kw.get("transB") else B.shape[1]
         return gemm(A, B, C, tc=self._tc_mode(M, N, K, "fwd"), **kw)
 
-    def gemm_bwd(self, A, B, C=None, **kw):
+    def gemm_bwd(self, A, B, C=None, out="f32", **kw):
+        if self.bf16:
+            return self._gemm16(A, B, C, out=out, **kw)
         M, K = (A.shape[1], A.shape[0]) if kw.get("transA") else A.shape
         N = B.shape[0] if kw.get("transB") else B.shape[1]
         return gemm(A, B, C, tc=self._tc_mode(M, N, K, "bwd"), **kw)
+
+    def gemm_rec(self, A, B, C, role, **kw):
+        """The per-step products of the recurrences that do not run in the persistent kernel (GRU, windows above 32 steps)."""
+        if self.bf16:
+            return self._gemm16(A, B, C, **kw)
+        return gemm(A, B, C, tc=(3 if role == "fwd" else 1) if self.tc else 0, **kw)
+
+    # ---- bf16 path: operand twins ---------------------------------------------------------------------------------------
+    # Every product of the bf16 path reads bf16 operands (hulc_gemm_bf16).  Parameters have a persistent bf16 copy (ParamStore.flat_bf16,
+    # refreshed by the Adam kernel).  An fp32 activation gets a bf16 "twin": written by the producing product's epilogue (out="bf16" /
+    # "both") or by one cast launch the first time a product consumes it in a step; the twin is remembered for the rest of the step and
+    # dropped when a product writes the memory again.
+    @staticmethod
+    def _key(t):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+
+    @staticmethod
+    def _span(t):
+        return (t.data_ptr(), t.data_ptr() + 4 * (sum((n - 1) * st for n, st in zip(t.shape, t.stride())) + 1))
+
+    def _twin_buffer(self, t, key):
+        ent = self._twins.get(key)
+        if ent is None:
+            if t.dim() == 2:
+                ld = (t.shape[1] + 7) // 8 * 8  # 16-byte aligned rows (TMA)
+                tw = torch.zeros(t.shape[0], ld, dtype=torch.bfloat16, device=t.device)[:, : t.shape[1]]
+            else:
+                tw = torch.zeros(t.shape, dtype=torch.bfloat16, device=t.device)
+            ent = self._twins[key] = [tw, -1, self._span(t)]
+        return ent
+
+    def _tw(self, t, produce=False):
+        """bf16 twin of the fp32 tensor `t` (a parameter view or an activation).  produce=True: the caller is about to write it."""
+        ps = self.ps
+        off = t.data_ptr() - ps.flat.data_ptr()
+        if 0 <= off < 4 * ps.numel:
+            return torch.as_strided(ps.flat_bf16, t.shape, t.stride(), off // 4)
+        key = self._key(t)
+        ent = self._twin_buffer(t, key)
+        if produce:
+            ent[1] = self._twin_gen
+        elif ent[1] != self._twin_gen:
+            assert key not in self._bf16_only
+            ops.cast_bf16(t, ent[0])
+            ent[1] = self._twin_gen
+        return ent[0]
+
+    def _written(self, t, keep=None):
+        """fp32 memory of `t` is (re)written: twins of anything overlapping it are stale."""
+        lo, hi = self._span(t)
+        for k, ent in self._twins.items():
+            if ent[1] == self._twin_gen and k != keep and ent[2][0] < hi and lo < ent[2][1]:
+                ent[1] = -1
+                self._bf16_only.discard(k)
+
+    def _new_generation(self):
+        self._twin_gen += 1
+        self._bf16_only.clear()
+        if self.bf16:
+            self.ps.enable_bf16()  # (no-op once allocated; a replaced / moved ParamStore gets its copy here)
+            self.ps.refresh_bf16()
+
+    def _gemm16(self, A, B, C, *, out="f32", gate=None, **kw):
+        A16, B16 = self._tw(A), self._tw(B)
+        if not ops.gemm_bf16_ok(A16, B16):
+            raise ops._lib.HulcError(f"bf16 product with operands the TMA cannot address: A {tuple(A.shape)} strides {A.stride()}, B {tuple(B.shape)} strides {B.stride()}")
+        key = self._key(C)
+        self._written(C, keep=key if out != "f32" else None)
+        Cb = self._tw(C, produce=True) if out != "f32" else None
+        if out == "f32":
+            ent = self._twins.get(key)
+            if ent is not None:
+                ent[1] = -1
+            self._bf16_only.discard(key)
+        elif out == "bf16":
+            if kw.get("beta", 0.0) != 0.0:
+                raise ValueError("beta accumulates into the fp32 result")
+            self._bf16_only.add(key)
+        else:
+            self._bf16_only.discard(key)
+        if gate is not None and self._key(gate) in self._bf16_only:
+            gate = self._tw(gate)
+        ops.gemm_bf16(A16, B16, None if out == "bf16" else C, Cb, gate=gate, **kw)
+        return C
 
     # ------------------------------------------------------------------------------------------------------------------
     # small composites
@@ -263,7 +374,7 @@ class HulcEngine:
             last = i == len(names) - 1
             y = self.buf(f"{tag}.mlp{i}", x.shape[0], P[n + ".weight"].shape[0])
             w = w0 if (i == 0 and w0 is not None) else P[n + ".weight"]
-            self.gemm_fwd(acts[-1], w, y, transB=True, bias=P[n + ".bias"], act=0 if last else RELU)
+            self.gemm_fwd(acts[-1], w, y, transB=True, bias=P[n + ".bias"], act=0 if last else RELU, out="f32" if last else "bf16")
             acts.append(y)
         stats = self.buf(f"{tag}.mlp_stats", x.shape[0], 2)
         ops.layernorm_fwd(acts[-1], P[ln + ".weight"], P[ln + ".bias"], out, stats)
@@ -449,7 +560,6 @@ class HulcEngine:
         pre3 = pre.view(S, B, -1)
         saved = self.buf(f"{tag}.saved", S, B, 4 * H) if kind == "gru" else None
         gh = self.buf(f"{tag}.gh", B, 3 * H) if kind == "gru" else None
-        tc = 3 if self.tc else 0
         if self.tc and self.persistent_rnn and kind != "gru" and ops.rnn_tc_seq_ok(B, H) and S <= 32:
             # one persistent launch for the whole chain (W_hh resident in shared memory, csrc/rnn_tc.cu).  Forward only up to 32
             # steps: the kernel makes ONE tf32 pass per step, whose rounding of W_hh accumulates along the chain — 0.28 of the
@@ -464,10 +574,10 @@ class HulcEngine:
         for t in (range(S - 1, -1, -1) if reverse else range(S)):
             prev = h(t + 2) if reverse else h(t)
             if kind == "gru":
-                gemm(prev, w_hh, gh, transB=True, bias=b_hh, tc=tc)
+                self.gemm_rec(prev, w_hh, gh, "fwd", transB=True, bias=b_hh)
                 ops.gru_gates_fwd(pre3[t], gh, prev, h(t + 1), saved[t])
             else:
-                gemm(prev, w_hh, h(t + 1), transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH, tc=tc)
+                self.gemm_rec(prev, w_hh, h(t + 1), "fwd", transB=True, addend=pre3[t], act=RELU if kind == "relu" else TANH)
         return saved
 
     def _rnn_bwd(self, tag, dh_above, w_hh, hbuf, col0, S, B, *, kind, saved=None, reverse=False):
@@ -486,7 +596,7 @@ class HulcEngine:
             for t in (range(S) if reverse else range(S - 1, -1, -1)):
                 prev = h(t + 2) if reverse else h(t)
                 ops.gru_gates_bwd(ab(t), None if first else rec, saved[t], prev, dgi[t], dgh[t], carry)
-                gemm(dgh[t], w_hh, rec, addend=carry, tc=1 if self.tc else 0)
+                self.gemm_rec(dgh[t], w_hh, rec, "bwd", addend=carry)
                 first = False
             return dgi.view(S * B, 3 * H), dgh.view(S * B, 3 * H)
         # Elman: dpre_t = (dh_above_t + dpre_{t+1} W_hh) * act'(h_t); slot S (or slot 0 for reverse) of dbuf stays zero
@@ -503,7 +613,7 @@ class HulcEngine:
             return d, d
         for t in (range(S) if reverse else range(S - 1, -1, -1)):
             nxt, cur = (dbuf[t], dbuf[t + 1]) if reverse else (dbuf[t + 1], dbuf[t])
-            gemm(nxt, w_hh, cur, addend=ab(t), gate=h(t + 1), act=act, tc=1 if self.tc else 0)
+            self.gemm_rec(nxt, w_hh, cur, "bwd", addend=ab(t), gate=h(t + 1), act=act)
         d = (dbuf[1:] if reverse else dbuf[:S]).reshape(S * B, H)
         return d, d
 
@@ -550,6 +660,7 @@ class HulcEngine:
         assert not (backward and (emb_override is not None or goal_override is not None))
         P, G, ps = self.ps.p, self.ps.g, self.ps
         self._step_shapes.clear()
+        self._new_generation()
         if seed is not None:
             self.rng_dev.fill_(int(seed))
         else:
@@ -615,10 +726,10 @@ class HulcEngine:
             w0 = P["plan_proposal.fc_model.0.weight"]
             pp = [None, self.buf("pp.a1", nB, self.H_prior)]
             self.gemm_fwd(emb3[:, 0, :], w0[:, :128], pp[1], transB=True, bias=P["plan_proposal.fc_model.0.bias"])
-            self.gemm_fwd(goal, w0[:, 128:], pp[1], transB=True, beta=1.0, act=RELU)
+            self.gemm_fwd(goal, w0[:, 128:], pp[1], transB=True, beta=1.0, act=RELU, out="both")
             for j, i in enumerate((2, 4, 6)):
                 y = self.buf(f"pp.a{j + 2}", nB, self.H_prior)
-                self.gemm_fwd(pp[-1], P[f"plan_proposal.fc_model.{i}.weight"], y, transB=True, bias=P[f"plan_proposal.fc_model.{i}.bias"], act=RELU)
+                self.gemm_fwd(pp[-1], P[f"plan_proposal.fc_model.{i}.weight"], y, transB=True, bias=P[f"plan_proposal.fc_model.{i}.bias"], act=RELU, out="bf16")
                 pp.append(y)
             state_dim = P["plan_proposal.fc_state.0.weight"].shape[0]
             pp_state = self.gemm_fwd(pp[-1], P["plan_proposal.fc_state.0.weight"], self.buf("pp.state", nB, state_dim), transB=True,
@@ -874,7 +985,7 @@ class HulcEngine:
             c["z1"], c["st1"], c["y1"] = self.buf(f"tr{l}.z1", T, D), self.buf(f"tr{l}.st1", T, 2), self.buf(f"tr{l}.y1", T, D)
             ops.layernorm_fwd(o, P[f"{pre}.norm1.weight"], P[f"{pre}.norm1.bias"], c["y1"], c["st1"], res=x, z=c["z1"], drop=drop(f"l{l}.drop1", 2 + 4 * l))
             c["h"] = self.gemm_fwd(c["y1"], P[f"{pre}.linear1.weight"], self.buf(f"tr{l}.h", T, P[f"{pre}.linear1.weight"].shape[0]), transB=True,
-                          bias=P[f"{pre}.linear1.bias"], act=RELU, drop=drop(f"l{l}.ffn", 3 + 4 * l))
+                          bias=P[f"{pre}.linear1.bias"], act=RELU, drop=drop(f"l{l}.ffn", 3 + 4 * l), out="bf16")
             f = self.gemm_fwd(c["h"], P[f"{pre}.linear2.weight"], self.buf(f"tr{l}.f", T, D), transB=True, bias=P[f"{pre}.linear2.bias"])
             c["z2"], c["st2"], c["y2"] = self.buf(f"tr{l}.z2", T, D), self.buf(f"tr{l}.st2", T, 2), self.buf(f"tr{l}.y2", T, D)
             ops.layernorm_fwd(f, P[f"{pre}.norm2.weight"], P[f"{pre}.norm2.bias"], c["y2"], c["st2"], res=c["y1"], z=c["z2"], drop=drop(f"l{l}.drop2", 4 + 4 * l))
@@ -1053,6 +1164,7 @@ class HulcEngine:
         Bm = seq_feat.shape[0]
         with self._buffers(("clip", Bm)):
             self._step_shapes.clear()
+            self._new_generation()
             sf, gl = seq_feat.contiguous(), latent_goal.contiguous()
             H1, Dc = P["proj_vis_lang.mlp_im.0.weight"].shape[0], P["proj_vis_lang.mlp_im.2.weight"].shape[0]
             im1 = self.gemm_fwd(sf, P["proj_vis_lang.mlp_im.0.weight"], self.buf("clip.im1", Bm, H1), transB=True, bias=P["proj_vis_lang.mlp_im.0.bias"], act=RELU)
@@ -1086,6 +1198,7 @@ class HulcEngine:
         H = self.H
         with self._buffers("inference"):
             self._step_shapes.clear()
+            self._new_generation()
             if seed is not None:
                 self.rng_dev.fill_(int(seed))
             else:
@@ -1188,6 +1301,7 @@ class HulcEngine:
         A = self.n_dims + (1 if has_grip else 0)
         with self._buffers("inference"):
             self._step_shapes.clear()
+            self._new_generation()
             if seed is not None:
                 self.rng_dev.fill_(int(seed))
             else:

@@ -353,6 +353,10 @@ class Hulc(_Base):
             eng.nan_flag = fn(eng.nan_flag)
             eng._bufs.clear()
             eng._buf_namespaces.clear()
+            eng._twins.clear()
+            if eng.bf16:
+                ps.flat_bf16 = None
+                ps.enable_bf16()
             eng._infer_state, eng._infer_planned = None, False
             if eng._infer_graph is not None:
                 eng._infer_graph = {}
@@ -366,6 +370,12 @@ class Hulc(_Base):
                     if b is not None:
                         mod._buffers[name] = fn(b)
         return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """nn.Module.load_state_dict copies into the parameter views directly: the bf16 operand copy of the parameters must follow."""
+        res = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.engine.ps.bf16_stale = True
+        return res
 
     # ---- reference surface ----------------------------------------------------------------------------------------------------
     @staticmethod

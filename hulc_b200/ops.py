@@ -116,6 +116,52 @@ def gemm(A, B, C=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=
     return C
 
 
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = bf16(x) (hulc_cast_bf16 / hulc_cast_bf16_rows): the narrowing torch.autocast applies to the inputs of nn.Linear / nn.Conv2d."""
+    _chk(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _chk(out, dtype=torch.bfloat16)
+    assert out.shape == x.shape
+    if x.is_contiguous() and out.is_contiguous() and x.data_ptr() % 32 == 0 and out.data_ptr() % 16 == 0:
+        _L().hulc_cast_bf16(_ptr(x), _ptr(out), x.numel(), _stream())
+    else:
+        x2, o2 = (x, out) if x.dim() == 2 else (x.reshape(-1, x.shape[-1]) if x.dim() > 2 else x.view(1, -1), out.reshape(-1, out.shape[-1]) if out.dim() > 2 else out.view(1, -1))
+        assert x2.data_ptr() == x.data_ptr() and o2.data_ptr() == out.data_ptr(), "views that cannot be flattened to rows need a contiguous copy first"
+        _L().hulc_cast_bf16_rows(_ptr(x2), _rowmajor(x2), _ptr(o2), _rowmajor(o2), x2.shape[0], x2.shape[1], _stream())
+    return out
+
+
+def gemm_bf16_ok(A, B) -> bool:
+    """Operand requirements of the TMA-fed bf16 kernel: 16-byte aligned bases and rows."""
+    return A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and _rowmajor(A) % 8 == 0 and _rowmajor(B) % 8 == 0
+
+
+def gemm_bf16(A, B, C=None, Cb=None, *, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, addend=None, add_mod=0, act=0, gate=None,
+              drop: Drop = NO_DROP):
+    """C (fp32) and / or Cb (bf16) = epi(alpha * op(A) @ op(B)) with bf16 operands on the tensor cores (hulc_gemm_bf16); the epilogue
+    contract of `gemm`.  `gate` may be fp32 or bf16.  At least one of C / Cb must be given."""
+    _chk(A, B, dtype=torch.bfloat16)
+    _chk(C, bias, addend)
+    _chk(Cb, dtype=torch.bfloat16)
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    N = B.shape[0] if transB else B.shape[1]
+    assert (B.shape[1] if transB else B.shape[0]) == K, (A.shape, B.shape, transA, transB)
+    assert C is not None or Cb is not None
+    assert (C is None or C.shape == (M, N)) and (Cb is None or Cb.shape == (M, N))
+    g32 = g16 = None
+    if gate is not None:
+        _chk(gate, dtype=None)
+        g32, g16 = (gate, None) if gate.dtype == torch.float32 else (None, gate)
+        assert gate.dtype in (torch.float32, torch.bfloat16)
+    _L().hulc_gemm_bf16(
+        _ptr(A), _ptr(B), _ptr(C), _ptr(Cb), M, N, K, _rowmajor(A), _rowmajor(B), _rowmajor(C) if C is not None else 0, _rowmajor(Cb) if Cb is not None else 0,
+        int(transA), int(transB), float(alpha), float(beta), _ptr(bias), _ptr(addend), _rowmajor(addend) if addend is not None else 0, int(add_mod), int(act),
+        _ptr(g32), _ptr(g16), _rowmajor(gate) if gate is not None else 0, *drop.args(), _stream(),
+    )
+    return C if C is not None else Cb
+
+
 def _tc_ok(A, B, M, N, K, transA, transB) -> bool:
     lda, ldb = _rowmajor(A), _rowmajor(B)
     return (A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0
@@ -505,9 +551,14 @@ def set_rng_offset(t: Optional[torch.Tensor]):
     _L().hulc_set_rng_offset_ptr(_ptr(t))
 
 
-def adam_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, grad_scale=1.0, step_dev=None):
+def adam_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, grad_scale=1.0, step_dev=None, p_bf16=None):
     _chk(p, g, m, v)
     _chk(step_dev, dtype=torch.int32)
     assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    if p_bf16 is not None:
+        assert p_bf16.dtype in (torch.bfloat16, torch.int16) and p_bf16.numel() == p.numel() and p_bf16.is_contiguous()
+        _L().hulc_adam_step_bf16(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                 _ptr(step_dev), float(grad_scale), _stream())
+        return
     _L().hulc_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
                         _ptr(step_dev), float(grad_scale), _stream())

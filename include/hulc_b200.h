@@ -219,11 +219,27 @@ int hulc_plan_cont_bwd(const float* pr_state, const float* pp_state, const float
 int hulc_clip_loss(const float* im, const float* tx, const float* logit_scale, const unsigned char* mask, float* loss, float* d_im,
                    float* d_tx, float* d_logit_scale, int n, int D, float grad_scale, void* stream);
 
+/* ---- bf16 path (BASELINE config 3: the reference trains under 16-bit autocast, conf/trainer/play_trainer.yaml:3) ------------------
+ * hulc_cast_bf16(_rows): y = bf16(x), round to nearest even — what torch.autocast does to the inputs of every nn.Linear / nn.Conv2d.
+ * hulc_gemm_bf16: the nn.Linear products (forward x W^T, data gradient dY W, weight gradient dY^T x — the same call sites as hulc_gemm)
+ * with bf16 operands A, B on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation, operands staged by TMA) and hulc_gemm's fused
+ * epilogue in fp32.  The result goes to C (fp32; beta*C is added first when beta != 0) and / or Cb (bf16, the operand of the next
+ * product); the gate is read from `gate` (fp32) or `gate_bf16`.  Requirements: 16-byte aligned A / B, lda % 8 == ldb % 8 == 0. */
+int hulc_cast_bf16(const float* x, void* y, long long n, void* stream);
+int hulc_cast_bf16_rows(const float* x, int ldx, void* y, int ldy, int rows, int cols, void* stream);
+int hulc_gemm_bf16(const void* A, const void* B, float* C, void* Cb, int M, int N, int K, int lda, int ldb, int ldc, int ldcb, int transA, int transB,
+                   float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate, const void* gate_bf16,
+                   int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, void* stream);
+
 /* ---- optimizer: torch.optim.Adam(lr, betas, eps), no weight decay (hulc/models/hulc.py:239-252) over a flat buffer ---------
  * g is multiplied by grad_scale first (1/world after the all-reduce); `step` is the 1-based step count, read from the device
  * integer *step_ptr instead when step_ptr != NULL (so the launch can be replayed from a CUDA graph). */
 int hulc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, int step,
                    const int* step_ptr, float grad_scale, void* stream);
+/* same update; additionally writes the new parameters as bf16 into p_bf16 (n elements) — the tensor-core operand copy of the bf16
+ * path, refreshed in the same pass (fp32 master weights stay the source of truth, as under torch.autocast). */
+int hulc_adam_step_bf16(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2, float eps, int step,
+                        const int* step_ptr, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

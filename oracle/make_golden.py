@@ -198,6 +198,76 @@ def run_case(name):
           f"worst oracle-vs-reference grad rel err={worst:.2e}  ({time.time() - t0:.1f}s)")
 
 
+AUTOCAST_CASES = {
+    # name: fp32 case whose inputs / sampled plan classes it shares.  The UNMODIFIED reference under torch.autocast(bfloat16) — the
+    # yardstick of the bf16 path (BASELINE config 3; the reference trains at 16-bit precision, conf/trainer/play_trainer.yaml:3).
+    "hulc_b2s8_bf16": "hulc_b2s8",
+    "hulc_b4s32_bf16": "hulc_b4s32",
+    "hulc_b32s32_bf16": "hulc_b32s32",  # BASELINE config 3's per-GPU batch
+}
+
+
+def run_autocast_case(name):
+    """The reference's training_step under bf16 autocast on the same inputs, weights and sampled plan classes as the fp32 fixture.
+    As on the GPU: the distribution objects get fp32 logits (bf16 logits fail OneHotCategorical's simplex check) and
+    world_to_tcp_frame runs in fp32 (the reference forces that with its own autocast(dtype=float32) context, gripper_control.py:17).
+    CPU autocast keeps softmax / layer_norm / loss arithmetic in bf16 where CUDA autocast would promote them to fp32, so the deviation
+    recorded here is an upper bound of what the reference shows on a GPU."""
+    import hulc.models.decoders.logistic_decoder_rnn as ldr
+
+    base = AUTOCAST_CASES[name]
+    model, rnn_model, B, S, p = CASES[base]
+    assert p == 0.0 and model == "hulc"
+    t0 = time.time()
+    fp32 = dict(np.load(GOLDEN / f"{base}.npz"))
+    net = build_reference(model, rnn_model, p, 32)
+    batch = synthetic.make_batch(B, S, seed=1)
+    idx_q = [torch.from_numpy(fp32[f"plan_idx_{m}"]).long() for m in batch]
+
+    orig_mn, orig_get, orig_w2t = torch.multinomial, net.dist.get_dist, ldr.world_to_tcp_frame
+
+    def multinomial(probs_2d, n, replacement=False, **kw):  # the fp32 run's sampled classes: the deviation measured is arithmetic, not a re-draw
+        return idx_q.pop(0).reshape(-1, 1)
+
+    def get_dist(state):
+        return orig_get(type(state)(*[x.float() for x in state]))
+
+    def w2t(action, robot_obs):
+        with torch.autocast("cpu", enabled=False):
+            return orig_w2t(action.float(), robot_obs.float())
+
+    captured = {}
+    dec = net.action_decoder
+    orig_loss = dec._loss
+
+    def spy_loss(logit_probs, log_scales, means, gripper_act, actions):
+        captured[net.modality_scope] = (logit_probs, log_scales, means, gripper_act, actions)
+        return orig_loss(logit_probs, log_scales, means, gripper_act, actions)
+
+    dec._loss = spy_loss
+    torch.multinomial, net.dist.get_dist, ldr.world_to_tcp_frame = multinomial, get_dist, w2t
+    try:
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            loss = net.training_step(batch, 0)
+    finally:
+        torch.multinomial, ldr.world_to_tcp_frame = orig_mn, orig_w2t
+    assert not idx_q
+    logged = net.logged
+    fx = {"total_loss": loss.detach().float()}
+    for k in ("train/kl_loss", "train/action_loss", "train/lang_clip_loss", "train/action_loss_vis", "train/action_loss_lang"):
+        fx[k.replace("train/", "")] = logged[k].float()
+    nseq = min(B, 2)
+    for m in batch:
+        lp, ls, mu, grip, act = captured[m]
+        fx[f"logit_probs_{m}"], fx[f"log_scales_{m}"], fx[f"means_{m}"] = lp[:nseq].detach().float(), ls[:nseq].detach().float(), mu[:nseq].detach().float()
+        fx[f"gripper_act_{m}"] = grip[:nseq].detach().float()
+    np.savez_compressed(GOLDEN / f"{name}.npz", **{k: np.asarray(v.detach().cpu().numpy()) for k, v in fx.items()})
+    dev = {k: abs(float(fx[k]) - float(fp32[k])) / abs(float(fp32[k])) for k in ("total_loss", "action_loss", "kl_loss", "lang_clip_loss")}
+    rms = lambda a: float(np.sqrt(np.mean(np.square(a))))
+    ldev = {k: rms(fx[f"{k}_vis"].numpy() - fp32[f"{k}_vis"]) / rms(fp32[f"{k}_vis"]) for k in ("logit_probs", "means", "log_scales")}
+    print(f"[golden] {name}: reference under bf16 autocast vs its fp32 run: relative loss deviations {dev}; logits rms deviation / rms {ldev}  ({time.time() - t0:.1f}s)")
+
+
 VAL_CASES = {
     # name: (model, rnn_model, B, S) — validation_step / lmp_val (hulc.py:301-388, 739-841), eval mode
     "val_hulc_b2s8": ("hulc", "rnn_decoder", 2, 8),
@@ -402,6 +472,6 @@ def run_infer_case(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES) + list(VAL_CASES) + list(INFER_CASES)
+    names = sys.argv[1:] or list(CASES) + list(VAL_CASES) + list(INFER_CASES) + list(AUTOCAST_CASES)
     for n in names:
-        (run_val_case if n in VAL_CASES else run_infer_case if n in INFER_CASES else run_case)(n)
+        (run_val_case if n in VAL_CASES else run_infer_case if n in INFER_CASES else run_autocast_case if n in AUTOCAST_CASES else run_case)(n)

@@ -18,8 +18,8 @@ R = lambda *s: torch.randn(*s, generator=g).to(dev)
 
 
 def check(name, got, want, tol):
-    err = (got.double() - want.double()).abs().max().item()
-    print(f"{name:40s} max err {err:.3e}", flush=True)
+    err = (got.double() - want.double()).abs().max().item() / max(want.double().abs().max().item(), 1e-12)
+    print(f"{name:40s} max err / max |ref| {err:.3e}", flush=True)
     assert err < tol, name
 
 
@@ -29,9 +29,9 @@ for tA, tB in ((False, True), (False, False), (True, True), (True, False)):
         M, N, K = 200, 136, 96
         A, B = R(*((K, M) if tA else (M, K))), R(*((N, K) if tB else (K, N)))
         C = ops.gemm(A, B, transA=tA, transB=tB, tc=passes)
-        check(f"gemm_tc tA={tA} tB={tB} passes={passes}", C, (A.t() if tA else A).double() @ (B.t() if tB else B).double(), 0.3 if passes == 1 else 1e-3)
+        check(f"gemm_tc tA={tA} tB={tB} passes={passes}", C, (A.t() if tA else A).double() @ (B.t() if tB else B).double(), 2e-2 if passes == 1 else 1e-4)
 A, B = R(64, 1024), R(128, 1024)
-check("gemm_tc split-K cluster", ops.gemm(A, B, transB=True, tc=3), A.double() @ B.double().t(), 2e-3)
+check("gemm_tc split-K cluster", ops.gemm(A, B, transB=True, tc=3), A.double() @ B.double().t(), 1e-4)
 
 # convolutions of the perceptual encoders: forward, data gradient, weight gradient (tensor-core path, channels-last)
 n, hw = 2, 84
@@ -57,7 +57,7 @@ d3g = d3 * (a3 > 0)
 d2 = ops.conv2d_tc_dgrad(d3g, w3, torch.empty_like(a2), 1, gate=a2, gate_bits=bits2)
 d1 = ops.conv2d_tc_dgrad(d2, w2, torch.empty_like(a1), 2, gate=a1, gate_bits=bits1)
 ops.conv2d_tc_wgrad(a2, d3g, g3, 1); ops.conv2d_tc_wgrad(a1, d2, g2, 2); gb1.zero_(); ops.conv2d_tc_wgrad(x, d1, g1, 4, db=gb1)
-check("conv3 wgrad", g3, ws[4].grad, 5e-2); check("conv2 wgrad", g2, ws[2].grad, 5e-2); check("conv1 wgrad", g1, ws[0].grad, 1e-1); check("conv1 bias grad", gb1, ws[1].grad, 5e-2)
+check("conv3 wgrad", g3, ws[4].grad, 2e-2); check("conv2 wgrad", g2, ws[2].grad, 2e-2); check("conv1 wgrad", g1, ws[0].grad, 2e-2); check("conv1 bias grad", gb1, ws[1].grad, 2e-2)
 
 # persistent recurrence (flag-chained steps, cluster split-K through DSMEM): forward and backward, 3 steps
 B, S, H = 8, 3, 2048
@@ -68,7 +68,7 @@ ops.rnn_tc_seq(W, hbuf[0], hbuf[1], pre[0], S, prev_step=hbuf.stride(0), out_ste
 h = torch.zeros(B, H, device=dev)
 for t in range(S):
     h = F.relu(pre[t] + h @ W.t())
-check("rnn_tc_seq forward", hbuf[S], h, 5e-2)
+check("rnn_tc_seq forward", hbuf[S], h, 1e-2)
 
 # one whole training step, tensor-core mode, B=1+1, S=2
 from engine_check import compare, run_pair  # noqa: E402

@@ -1,0 +1,154 @@
+"""The bf16 path (BASELINE config 3; engine precision="bf16": bf16 tensor-core operands for every Linear product, bf16 activations between
+the conv layers, fp32 accumulation, fp32 master weights / Adam / losses / LayerNorm / softmax) against
+
+  * the fp32 fixtures written by the unmodified reference (tests/golden/hulc_*.npz), with the YARDSTICK the reference itself sets: the
+    same reference run under torch.autocast(bfloat16) (tests/golden/hulc_*_bf16.npz, oracle/make_golden.py::run_autocast_case).  The
+    bf16 path must deviate from the fp32 reference no more than a small multiple of what the reference's own 16-bit run does;
+  * the fp32 engine modes (gradient direction);
+  * itself (repeatability, CUDA-graph replay, Adam with the fused bf16 parameter copy)."""
+import numpy as np
+import pytest
+import torch
+
+from hulc_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"hulc_b2s8": (2, 8), "hulc_b4s32": (4, 32), "hulc_b32s32": (32, 32)}
+# tolerated deviation = FACTOR x the reference's own bf16-autocast deviation (floored: a deviation can be small by luck)
+FACTOR, LOSS_FLOOR, LOGIT_FLOOR = 3.0, 2e-3, 5e-3
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked tests need a CUDA device; hulc_b200 has no CPU fallback")
+
+
+def _engine(precision, p=0.0):
+    from hulc_b200.engine import HulcEngine
+
+    eng = HulcEngine("hulc", "rnn_decoder", device="cuda", dropout_p=p, precision=precision)
+    eng.load_state_dict(synthetic.make_state_dict("hulc", "rnn_decoder"))
+    return eng
+
+
+rms = lambda a: float(np.sqrt(np.mean(np.square(np.asarray(a, dtype=np.float64)))))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_bf16_step_within_the_references_own_bf16_deviation(name, golden_dir):
+    B, S = CASES[name]
+    fx, ac = np.load(golden_dir / f"{name}.npz"), np.load(golden_dir / f"{name}_bf16.npz")
+    eng = _engine("bf16")
+    batch = synthetic.make_batch(B, S, seed=1, device="cuda")
+    mods = list(batch)
+    out = eng.step(batch, plan_idx={m: torch.from_numpy(fx[f"plan_idx_{m}"]).cuda() for m in mods})
+    eng.check_nan_flag()
+    rep = {}
+    for k, scale in (("total_loss", 1.0), ("action_loss", 1.0), ("kl_loss", 1.0), ("lang_clip_loss", 3.0)):
+        ours, ref, auto = scale * out[k].item(), float(fx[k]), float(ac[k])
+        dev, yard = abs(ours - ref) / abs(ref), abs(auto - ref) / abs(ref)
+        rep[k] = (dev, yard)
+        assert dev <= max(FACTOR * yard, LOSS_FLOOR), f"{k}: ours {ours:.6f} vs fp32 reference {ref:.6f} ({dev:.2e}); the reference under autocast deviates {yard:.2e}"
+    heads = out["heads_tm"].transpose(0, 1).cpu().numpy()  # (nB, S, n)
+    nm = eng.n_dims * eng.n_mix
+    for i, m in enumerate(mods):
+        n = fx[f"logit_probs_{m}"].shape[0]
+        h = heads[i * B : i * B + n]
+        for k, sl in (("logit_probs", slice(0, nm)), ("means", slice(nm, 2 * nm)), ("log_scales", slice(2 * nm, 3 * nm)), ("gripper_act", slice(3 * nm, 3 * nm + 2))):
+            ref, auto = fx[f"{k}_{m}"].reshape(n, S, -1), ac[f"{k}_{m}"].reshape(n, S, -1)
+            ours = h[..., sl] if k != "log_scales" else np.maximum(h[..., sl], -7.0)
+            dev, yard = rms(ours - ref) / rms(ref), rms(auto - ref) / rms(ref)
+            rep[f"{k}_{m}"] = (dev, yard)
+            assert dev <= max(FACTOR * yard, LOGIT_FLOOR), f"{k}_{m}: rms deviation {dev:.2e} of the fp32 reference's rms; the reference under autocast: {yard:.2e}"
+    # gradients: norms within 5 % and direction (cosine) of every parameter gradient against the reference's fp32 numbers
+    worst = ("", 0.0)
+    for k in eng.ps.keys:
+        gn = float(fx[f"gradnorm/{k}"])
+        g = eng.ps.g[k].float().cpu()
+        if gn < 0:
+            assert float(g.abs().max()) == 0.0, k
+            continue
+        rel = abs(float(g.norm()) - gn) / gn
+        if rel > worst[1]:
+            worst = (k, rel)
+        assert rel < 0.1, f"|grad {k}| = {float(g.norm()):.4e}, reference {gn:.4e}"
+    print(name, {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in rep.items()}, "worst |grad| deviation", worst)
+
+
+@pytest.mark.parametrize("model,rnn_model,S", [("hulc", "rnn_decoder", 8), ("hulc", "gru_decoder", 8), ("gcbc", "rnn_decoder", 8), ("mcil", "rnn_decoder", 8),
+                                               ("gcbc", "gru_decoder", 64)])
+def test_bf16_gradients_point_the_same_way_as_fp32(model, rnn_model, S):
+    """Every model variant: losses within 1 % and every parameter gradient within 20 % (relative L2; cosine > 0.98) of the exact-fp32 engine
+    on the same inputs and injected randomness (B = 2: the scalar CLIP temperature gradient, a difference of near-equal terms, is left out)."""
+    from hulc_b200.engine import HulcEngine
+
+    sd = synthetic.make_state_dict(model, rnn_model, max_window=max(32, S))
+    batch = synthetic.make_batch(2, S, seed=1, device="cuda")
+    noise = {m: synthetic.plan_noise(2, S, m) for m in batch}
+    res = {}
+    for prec in ("fp32", "bf16"):
+        eng = HulcEngine(model, rnn_model, max_window=max(32, S), device="cuda", dropout_p=0.0, precision=prec)
+        eng.load_state_dict(sd)
+        kw = {}
+        if model == "hulc":
+            kw["plan_idx"] = res["idx"] if "idx" in res else None
+            if kw["plan_idx"] is None:
+                kw = {"plan_u": {m: noise[m]["u"].cuda() for m in batch}}
+        if model == "mcil":
+            kw["plan_eps"] = {m: noise[m]["eps"].cuda() for m in batch}
+        out = eng.step(batch, **kw)
+        if model == "hulc" and "idx" not in res:
+            res["idx"] = {m: out["plan_idx"][i * 2 : (i + 1) * 2].clone() for i, m in enumerate(batch)}
+        res[prec] = (out["total_loss"].item(), {k: eng.ps.g[k].clone() for k in eng.ps.keys})
+    (l32, g32), (l16, g16) = res["fp32"], res["bf16"]
+    assert abs(l16 - l32) <= 1e-2 * abs(l32), (l16, l32)
+    worst = ("", 0.0)
+    for k, a in g32.items():
+        b = g16[k]
+        na = float(a.norm())
+        if na == 0:
+            assert float(b.abs().max()) == 0
+            continue
+        if k == "logit_scale":
+            continue
+        rel = float((a - b).norm()) / na
+        cos = float((a * b).sum()) / (na * float(b.norm()) + 1e-30)
+        if rel > worst[1]:
+            worst = (k, rel)
+        assert rel < 0.2 and cos > 0.98, f"{k}: relative error {rel:.3e}, cosine {cos:.4f}"
+    print(model, rnn_model, "loss", l16, l32, "worst gradient", worst)
+
+
+def test_bf16_graph_replay_adam_and_parameter_copy():
+    """Replay of the captured step == eager; the Adam kernel keeps the bf16 parameter copy equal to bf16(master weights); the loss goes down."""
+    a, b = _engine("bf16", 0.1), _engine("bf16", 0.1)
+    batch = synthetic.make_batch(4, 16, seed=5, device="cuda")
+    sg = b.capture(batch, optimizer=True)
+    b.rng_dev.fill_(10)
+    lg, le = [], []
+    for i in range(4):
+        lg.append(sg.replay()["total_loss"].item())
+        oe = a.step(batch, seed=11 + i)
+        a.optimizer_step()
+        le.append(oe["total_loss"].item())
+    np.testing.assert_allclose(lg, le, rtol=1e-4)
+    assert lg[-1] < lg[0]
+    for eng in (a, b):
+        assert torch.equal(eng.ps.flat_bf16, eng.ps.flat.to(torch.bfloat16))
+    # loading a state dict marks the copy stale; the next step refreshes it
+    a.load_state_dict(synthetic.make_state_dict("hulc", "rnn_decoder", salt=1))
+    a.step(batch, seed=1)
+    assert torch.equal(a.ps.flat_bf16, a.ps.flat.to(torch.bfloat16))
+
+
+def test_bf16_full_size_repeatable():
+    eng = _engine("bf16", 0.1)
+    batch = synthetic.make_batch(32, 32, seed=3, device="cuda")
+    x = eng.step(batch, seed=11)["total_loss"].item()
+    g1 = eng.ps.grad.clone()
+    y = eng.step(batch, seed=11)["total_loss"].item()
+    assert abs(x - y) <= 1e-6 * abs(x)
+    assert float((eng.ps.grad - g1).norm()) <= 1e-4 * float(g1.norm())
+    eng.check_nan_flag()
