@@ -271,7 +271,8 @@ constexpr int kWgThr = (kWgBuilder0 + kWgGroups) * 32;
 
 struct C1WgParams {
   const float* x;    // [N, 3, H, W]
-  const float* dy;   // [N, HO, WO, 32]
+  const float* dy;   // [N, HO, WO, 32] fp32, or bf16 when dy_bf16 = 1 (converted while the tile is built: the products stay tf32 x tf32)
+  int dy_bf16;
   float* partial;    // [gridDim.x][192][32]
   float* bias_partial;  // [gridDim.x][32] or null
   int N, H, W, HO, WO, KR;  // KR = WO rounded up to 8
@@ -404,11 +405,23 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
           if (q < nchunks) v[i] = ld_shared16(band + (uint32_t)(ci * 8 + ky) * rowbytes + (uint32_t)((xx * 4 + (c & 1) * 4) * 4));
         }
       } else {
-        const float* src = p.dy + ((size_t)(n * p.HO + y) * p.WO) * kCout;
+        if (p.dy_bf16) {
+          const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(p.dy) + ((size_t)(n * p.HO + y) * p.WO) * (kCout * 2));
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-          const int q = lane + 32 * i;
-          if (q < nchunks) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)q * 4));  // rows of 32 floats are contiguous: chunk q is at q * 16 B
+          for (int i = 0; i < kIters; ++i) {
+            const int q = lane + 32 * i;
+            if (q < nchunks) {  // four bf16 = 8 bytes -> four fp32 (a 16-bit shift)
+              const uint2 t = __ldg(src + q);
+              v[i] = make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xFFFF0000u), __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xFFFF0000u));
+            }
+          }
+        } else {
+          const float* src = p.dy + ((size_t)(n * p.HO + y) * p.WO) * kCout;
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            const int q = lane + 32 * i;
+            if (q < nchunks) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)q * 4));  // rows of 32 floats are contiguous: chunk q is at q * 16 B
+          }
         }
       }
 #pragma unroll
@@ -459,7 +472,8 @@ constexpr int kVwThr = (kEpiWarps + 3) * 32;
 struct V1Params {
   const float* w;
   const float* b;
-  float* y;
+  float* y;           // channels-last output: fp32, or bf16 (y_bf16 = 1: 32 channels = 64 bytes per pixel)
+  int y_bf16;
   unsigned* bits;
   int N, H, W, HO, WO;
   int Wq, R, UPF;        // W / 4, output rows per unit, units per frame
@@ -547,7 +561,17 @@ __global__ void __launch_bounds__(kVwThr, 1) conv1_view_fwd_kernel(const __grid_
           if (p.relu) o[j] = fmaxf(o[j], 0.f);
           if (o[j] > 0.f) om |= 1u << j;
         }
-        if ((reinterpret_cast<size_t>(dst) & 31) == 0) {
+        if (p.y_bf16) {
+          uint32_t w16[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w16[j]) : "f"(o[2 * j + 1]), "f"(o[2 * j]));
+          unsigned char* d16 = reinterpret_cast<unsigned char*>(p.y) + pix * (kCout * 2);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d16 + 32 * h2), "r"(w16[8 * h2]), "r"(w16[8 * h2 + 1]), "r"(w16[8 * h2 + 2]),
+                         "r"(w16[8 * h2 + 3]), "r"(w16[8 * h2 + 4]), "r"(w16[8 * h2 + 5]), "r"(w16[8 * h2 + 6]), "r"(w16[8 * h2 + 7])
+                         : "memory");
+        } else if ((reinterpret_cast<size_t>(dst) & 31) == 0) {
 #pragma unroll
           for (int j = 0; j < kCout; j += 8) st_global_v8(dst + j, o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
         } else {
@@ -616,13 +640,13 @@ bool g_conv1_view = [] {
 }();
 
 // cudaErrorNotSupported when the geometry does not fit (the caller then uses the band kernel below).
-int conv1_view_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st) {
+int conv1_view_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st, int y_bf16 = 0) {
   const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
   if (!g_conv1_view || HO <= 0 || WO <= 0 || (W & 3) || (H & 3) || W > 256 || (reinterpret_cast<size_t>(x) & 15) || (reinterpret_cast<size_t>(w) & 15) ||
       (reinterpret_cast<size_t>(y) & 15))
     return (int)cudaErrorNotSupported;
   V1Params p;
-  p.w = w; p.b = b; p.y = y; p.bits = relu_bits; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.relu = relu;
+  p.w = w; p.b = b; p.y = y; p.y_bf16 = y_bf16; p.bits = relu_bits; p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.relu = relu;
   p.Wq = W / 4;
   p.R = min(HO, 256 / p.Wq);
   if (p.R < 1) return (int)cudaErrorNotSupported;
@@ -673,7 +697,7 @@ int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y
 // Per-CTA partial weight gradients [ctas][192][32] of the first layer (k in the reference's (ci, ky, kx) order), followed — when
 // want_bias — by per-CTA partial bias gradients [ctas][32]; *ctas_out = number of partials to reduce.  cudaErrorNotSupported when the geometry does not fit (the caller then uses the gather kernel).
 int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int want_bias, int N, int H, int W, int* ctas_out,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, int dy_bf16) {
   const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
   if (HO <= 0 || WO <= 0 || WO > kWgKR || (W & 3) || (size_t)3 * 8 * W * 4 > (size_t)kWgBandB) return (int)cudaErrorNotSupported;
   if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(partial)) & 15) return (int)cudaErrorNotSupported;
@@ -682,10 +706,15 @@ int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* parti
   const int ctas = (int)min((long long)kNumSMs, tiles);
   if ((size_t)ctas * (kKtot + 1) * kCout * sizeof(float) > partial_bytes) return (int)cudaErrorNotSupported;
   C1WgParams p;
-  p.x = x; p.dy = dy; p.partial = partial; p.bias_partial = want_bias ? partial + (size_t)ctas * kKtot * kCout : nullptr;  // bias partials follow the weight partials
+  p.x = x; p.dy = dy; p.dy_bf16 = dy_bf16; p.partial = partial; p.bias_partial = want_bias ? partial + (size_t)ctas * kKtot * kCout : nullptr;  // bias partials follow the weight partials
   p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.KR = (WO + 7) & ~7;
   HULC_TRY(cudaFuncSetAttribute(conv1_band_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
   HULC_LAUNCH(conv1_band_wgrad_kernel, dim3(ctas), dim3(kWgThr), kWgSmem, st, p, (int)tiles);
   *ctas_out = ctas;
   HULC_RETURN_LAST();
+}
+
+// first layer with a bf16 channels-last output (bf16 path): the view kernel only (H, W multiples of 4)
+int hulc_conv1_view_fwd_bf16(const float* x, const float* w, const float* b, void* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st) {
+  return conv1_view_fwd(x, w, b, reinterpret_cast<float*>(y), relu_bits, N, H, W, relu, st, 1);
 }

@@ -28,7 +28,7 @@ int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float*
                               int HO, int WO, int R, int S, int py, int px, cudaStream_t st);
 
 int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int want_bias, int N, int H, int W, int* ctas_out,
-                                   cudaStream_t st);
+                                   cudaStream_t st, int dy_bf16 = 0);
 extern "C" int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, float* workspace, size_t workspace_bytes, void* stream);
 int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y, unsigned* relu_bits, int N, int H, int W, int relu, cudaStream_t st);  // conv1_tc.cu
 
@@ -473,6 +473,13 @@ int wgrad(const Geom& g, const float* x, const float* dy, float* dw, float beta,
 
 }  // namespace
 
+// Fixed-order reduction of the first layer's per-CTA partials [ctas][192][32] (+ [ctas][32] bias partials behind them when db != NULL)
+int hulc_conv1_wgrad_reduce(const float* partial, float* dw, float* db, int ctas, float beta, cudaStream_t st) {
+  HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(192 * 32 * 8, 256)), dim3(256), 0, st, partial, dw, ctas, 192, 32, 3, 8, 1, beta);
+  if (db) return hulc_colsum(partial + (size_t)ctas * 192 * 32, ctas, 32, 32, db, 1.0f, nullptr, 0, (void*)st);  // the ones row of the same GEMM
+  HULC_RETURN_LAST();
+}
+
 // Channels-last convolutions on the tensor cores.  x is NHWC [N,H,W,CIN] (or, for the 3-channel first layer, the
 // reference's NCHW [N,3,H,W]); y / dy are NHWC [N,HO,WO,COUT]; w, dw keep the reference layout [COUT,CIN,KS,KS].
 HULC_API int hulc_conv2d_tc_fwd(const float* x, const float* w, const float* b, float* y, int N, int CIN, int H, int W, int COUT, int KS, int S,
@@ -535,11 +542,7 @@ HULC_API int hulc_conv2d_tc_wgrad(const float* x, const float* dy, float* dw, fl
       if (g_use_tma) {  // band-staged kernel (conv1_tc.cu): per-CTA partials, reduced in a fixed order below
         int ctas = 0;
         const int rc = hulc_conv1_band_wgrad_partials(x, dy, ws, wsb, db != nullptr, N, H, W, &ctas, st);
-        if (rc == 0) {
-          HULC_LAUNCH(wgrad_reduce_kernel, dim3(hulc_cdiv(192 * 32 * 8, 256)), dim3(256), 0, st, (const float*)ws, dw, ctas, 192, 32, 3, 8, 1, beta);
-          if (db) return hulc_colsum(ws + (size_t)ctas * 192 * 32, ctas, 32, 32, db, 1.0f, nullptr, 0, stream);  // the ones row of the same GEMM
-          HULC_RETURN_LAST();
-        }
+        if (rc == 0) return hulc_conv1_wgrad_reduce(ws, dw, db, ctas, beta, st);
         if (rc != (int)cudaErrorNotSupported) return rc;
       }
       HULC_TRY((wgrad<3, 8, 4, 32, true>(g, x, dy, dw, beta, ws, wsb, st)));

@@ -235,8 +235,8 @@ struct BandParams {
   int nbands, es, flip;  // bands per tile; element stride of the source walk; flip = 1 for a data gradient
   int bc[kMaxBands], bx[kMaxBands], by[kMaxBands];  // TMA corner of band b: (bc, bx, es * y0 + by, n)
   int wkb[kMaxBands * kMaxTaps];                    // weight k-block of (band, local tap)
-  const float* wprep;    // [BN][NKB * 32] K-major
-  float* out;            // NHWC [N][out_H][out_W][BN]; grid point (y, x) -> pixel (o_mul y + oy_add, o_mul x + ox_add)
+  const void* wprep;     // [BN][NKB k-blocks of 128 bytes] K-major: 32 fp32 or 64 bf16 per k-block
+  void* out;             // NHWC [N][out_H][out_W][BN] (fp32, or bf16 in the BF16 kernels); grid point (y, x) -> pixel (o_mul y + oy_add, o_mul x + ox_add)
   int out_H, out_W, o_mul, oy_add, ox_add;
   int scatter;           // 1: the BN = 128 columns are 4 stride phases x 32 channels; chunk ph goes to pixel (2 y + ph / 2, 2 x + ph % 2)
   const float* bias;
@@ -254,8 +254,34 @@ struct BandBars {
   uint32_t tmem_base;
 };
 
+// bf16 operand helpers (BF16 = true: the band and the weights are bf16, 64 channels per 128-byte row, tcgen05.mma kind::f16 with K = 16
+// per instruction — the same 32 bytes of every row as a K = 8 tf32 instruction, so every descriptor offset below is shared)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_kk(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_kk(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {  // round to nearest even
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void st_global_v8_u32(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+               "r"(v[7])
+               : "memory");
+}
+
 // R = local taps per axis of one band (3 or 2); NI = MMA-issuing threads (local taps me, me + NI, ... of every band)
-template <int BN, int NKB, int R, int NI>
+template <int BN, int NKB, int R, int NI, bool BF16 = false>
 __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel(const __grid_constant__ CUtensorMap smap, BandParams p, int num_tiles) {
   constexpr int kWTileB = BN * kRowBytes, kTaps = R * R, kThreadsB = (kEpiWarps + NI + 1) * 32;
   static_assert(kTaps % NI == 0 && 2 * NI * BN <= 512, "issuer split / TMEM columns");
@@ -279,10 +305,11 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
   }
   if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 512);
   for (int i = threadIdx.x; i < kBandSlots * kBandB / 16; i += kThreadsB) reinterpret_cast<float4*>(band_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int q = threadIdx.x; q < NKB * BN * 8; q += kThreadsB) {
+  for (int q = threadIdx.x; q < NKB * BN * 8; q += kThreadsB) {  // 16-byte chunks: row n of the prepared weights is NKB * 128 bytes in either type
     const int kb = q / (BN * 8), qq = q - kb * (BN * 8);
     const int n = qq >> 3, c = qq & 7;
-    st_shared16(smem_u32(w_smem) + kb * kWTileB + swz(n, c), __ldg(reinterpret_cast<const float4*>(p.wprep + (size_t)n * (NKB * kBK) + kb * kBK + c * 4)));
+    st_shared16(smem_u32(w_smem) + kb * kWTileB + swz(n, c),
+                __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.wprep) + ((size_t)n * NKB + kb) * kRowBytes + c * 16)));
   }
   fence_proxy_async();
   tc_fence_before_sync();
@@ -303,7 +330,7 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
       const int n = tile / p.TPF, y0 = (tile - n * p.TPF) * p.RT;
       const bool valid0 = yl < p.RT && xx < p.OWv && y0 + yl < p.OH;
       const size_t off0 = (((size_t)n * p.out_H + (p.o_mul * (y0 + yl) + p.oy_add)) * p.out_W + (p.o_mul * xx + p.ox_add)) * BN;
-      if (p.gate && !p.gate_bits && valid0) {
+      if (!BF16 && p.gate && !p.gate_bits && valid0) {
         // the ReLU masks this thread will need come from DRAM: pull their lines into L2 while the tile's MMAs are still running
         // (four epilogue warps cannot hide one DRAM latency per 32-column chunk)
 #pragma unroll
@@ -355,7 +382,7 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
           if (p.gate_bits) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = (gm >> j) & 1u ? o[j] : 0.f;
-          } else if (p.gate) {
+          } else if (!BF16 && p.gate) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + off + j));
@@ -367,13 +394,22 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
             for (int j = 0; j < 32; ++j)
               if (o[j] > 0.f) om |= 1u << j;
           }
-          float* dst = p.out + off;
-          if ((reinterpret_cast<size_t>(dst) & 31) == 0) {
+          if (BF16) {  // 32 channels = 64 bytes of the channels-last bf16 tensor
+            uint32_t w16[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+            for (int j = 0; j < 16; ++j) w16[j] = pack2_bf16(o[2 * j], o[2 * j + 1]);
+            unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + off * 2;
+            st_global_v8_u32(dst, w16);
+            st_global_v8_u32(dst + 32, w16 + 8);
           } else {
+            float* dst = reinterpret_cast<float*>(p.out) + off;
+            if ((reinterpret_cast<size_t>(dst) & 31) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
           }
           if (p.relu_bits) p.relu_bits[word] = om;
         }
@@ -383,7 +419,7 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
     // ================================ MMA issuers ================================
     if (lane == 0) {
       const int me = warp - kEpiWarps;
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, false, false);
+      constexpr uint32_t idesc = BF16 ? make_idesc_bf16_kk(kBM, BN) : make_idesc_tf32(kBM, BN, false, false);
       const uint64_t a0 = make_desc<false, kBM, kBK>(smem_u32(band_smem), 0), b0 = make_desc<false, BN, kBK>(smem_u32(w_smem), 0);
       int it = 0, u = 0;  // u: band sequence number of this CTA
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -401,7 +437,10 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
             const int shift = p.flip ? (R - 1 - ty) * p.PW + (R - 1 - tx) : ty * p.PW + tx;  // rows of 128 B
             const uint64_t da = a0 + (uint32_t)((slot * kBandB + shift * kRowBytes) >> 4), db = b0 + (uint32_t)((p.wkb[b * kMaxTaps + tap] * kWTileB) >> 4);
 #pragma unroll
-            for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (uint32_t)(b != 0 || tap != me || k != 0));
+            for (int k = 0; k < kBK / 8; ++k) {  // four 32-byte k-steps of the 128-byte rows (K = 8 tf32 or 16 bf16 each)
+              if (BF16) umma_bf16_kk(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (uint32_t)(b != 0 || tap != me || k != 0));
+              else umma_tf32(d, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, (uint32_t)(b != 0 || tap != me || k != 0));
+            }
           }
           umma_commit(&bars->empty[slot]);
         }
@@ -513,6 +552,31 @@ int band_dgrad(const float* dy, const float* wphase, const float* gate, const un
   return (int)cudaErrorNotSupported;
 }
 
+// ---- bf16 bands: 64 channels (or, for the 32-channel stride-2 layer, a PAIR of horizontally adjacent pixels) per 128-byte row -------
+// pos_w positions of 64 bf16 per source row; row / frame strides in bytes; es_y = element stride of the walk in y (the stride-2 forward
+// takes every second row: one band per row phase).
+template <int BN, int NKB, int R, int NI>
+int launch_band_bf16(const void* src, int N, int SH, int pos_w, size_t row_bytes, size_t frame_bytes, int es_y, BandParams& p, cudaStream_t st) {
+  if (p.PW > kBM || p.PW > 256 || p.PH * es_y > 256) return (int)cudaErrorNotSupported;
+  if (p.PW * p.PH > kBandRows || 127 + (R - 1) * p.PW + R - 1 >= kBandRows) return (int)cudaErrorNotSupported;
+  if ((row_bytes & 15) || (frame_bytes & 15) || (reinterpret_cast<size_t>(src) & 15)) return (int)cudaErrorNotSupported;
+  CUtensorMap m;
+  const uint64_t dims[4] = {64, (uint64_t)pos_w, (uint64_t)SH, (uint64_t)N};
+  const uint64_t strides[3] = {128, (uint64_t)row_bytes, (uint64_t)frame_bytes};
+  const uint32_t box[4] = {64, (uint32_t)p.PW, (uint32_t)(p.PH * es_y), 1};
+  const uint32_t es[4] = {1, 1, (uint32_t)es_y, 1};
+  if (tma::make_map(&m, src, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, es, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) != 0) return (int)cudaErrorNotSupported;
+  const long long tiles = (long long)N * p.TPF;
+  if (tiles >= (1ll << 31)) return (int)cudaErrorNotSupported;
+  p.es = es_y;
+  constexpr int smem = NKB * BN * kRowBytes + kBandSlots * kBandB + 256 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kfn = conv_band_kernel<BN, NKB, R, NI, true>;
+  HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  HULC_LAUNCH(kfn, dim3((unsigned)min((long long)kNumSMs, tiles)), dim3((kEpiWarps + NI + 1) * 32), smem, st, m, p, (int)tiles);
+  HULC_RETURN_LAST();
+}
+
 template <int BN, int NKB>
 int launch(const CUtensorMap& smap, const TcParams& p, int num_tiles, cudaStream_t st) {
   constexpr int kW = NKB * BN * kRowBytes;
@@ -603,5 +667,63 @@ int hulc_conv_tma_dgrad_phase(const float* dy, const float* wphase, const float*
   }
   if (CIN == 32 && COUT == 64 && R == 2) return launch<32, 8>(m, p, num_tiles, st);
   if (CIN == 64 && COUT == 64 && R == 3) return launch<64, 18>(m, p, num_tiles, st);
+  return (int)cudaErrorNotSupported;
+}
+
+// ---- bf16 activations (BASELINE config 3): x / y / dy / dx are channels-last bf16, prepared weights are bf16 in the same K order as the
+// fp32 kernels use (forward [COUT][(ky, kx, ci)], data gradient [phase][CIN][(jy, jx, co)]), bias fp32, ReLU sign masks as above.
+int hulc_conv_band_bf16_fwd(const void* x, const void* wprep, const float* b, void* y, unsigned* relu_bits, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                            int relu, cudaStream_t st) {
+  const int OH = (H - KS) / S + 1, OW = (W - KS) / S + 1;
+  if (COUT != 64 || OH <= 0 || OW <= 0) return (int)cudaErrorNotSupported;
+  BandParams p{};
+  p.N = N; p.OH = OH; p.OWv = OW; p.flip = 0;
+  p.wprep = wprep; p.out = y; p.out_H = OH; p.out_W = OW; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = b; p.gate = nullptr; p.gate_bits = nullptr; p.relu_bits = relu_bits; p.relu = relu;
+  if (KS == 3 && S == 1 && CIN == 64) {  // one band of 64 channels per tile; k-block = tap
+    p.PW = W; p.RT = min(OH, kBM / p.PW); p.PH = p.RT + 2; p.TPF = hulc_cdiv(OH, p.RT); p.nbands = 1;
+    p.bc[0] = 0; p.bx[0] = 0; p.by[0] = 0;
+    for (int tap = 0; tap < 9; ++tap) p.wkb[tap] = tap;
+    return launch_band_bf16<64, 9, 3, 3>(x, N, H, W, (size_t)W * 128, (size_t)H * W * 128, 1, p, st);
+  }
+  if (KS == 4 && S == 2 && CIN == 32) {
+    // a row of the band = the pixel PAIR (2 q, 2 q + 1) x 32 channels = kernel columns kx = 2 tx, 2 tx + 1 of local tap tx, so a k-block is
+    // (ky, tx) x (px, ci) — 64 contiguous elements of the (ky, kx, ci)-ordered weights; one band per row phase py, local tap (ty, tx) is
+    // kernel row ky = 2 ty + py.  The pair view needs no de-interleave in x (a row of W pixels is W / 2 whole pairs; an odd last pixel is
+    // never read by a stride-2 window).
+    p.PW = W / 2; p.RT = min(OH, kBM / p.PW); p.PH = p.RT + 1; p.TPF = hulc_cdiv(OH, p.RT); p.nbands = 2;
+    if (p.PW < OW + 1) return (int)cudaErrorNotSupported;
+    for (int py = 0; py < 2; ++py) {
+      p.bc[py] = 0; p.bx[py] = 0; p.by[py] = py;
+      for (int tap = 0; tap < 4; ++tap) p.wkb[py * kMaxTaps + tap] = (2 * (tap >> 1) + py) * 2 + (tap & 1);
+    }
+    return launch_band_bf16<64, 8, 2, 2>(x, N, H, W / 2, (size_t)W * 64, (size_t)H * W * 64, 2, p, st);
+  }
+  return (int)cudaErrorNotSupported;
+}
+
+// dx (bf16 NHWC [N][H][W][CIN]) = conv_transpose(dy bf16 [N][HO][WO][64], w), masked by the ReLU sign bits of the activation that fed the layer.
+// KS = 3, S = 1: wprep = [CIN = 64][(jy, jx, co)]; KS = 4, S = 2: wprep = the four phase matrices [4][CIN = 32][(jy, jx, co)], all phases in one launch.
+int hulc_conv_band_bf16_dgrad(const void* dy, const void* wprep, const unsigned* gate_bits, void* dx, int N, int CIN, int H, int W, int COUT, int HO, int WO, int KS,
+                              int S, cudaStream_t st) {
+  if (COUT != 64) return (int)cudaErrorNotSupported;
+  BandParams p{};
+  p.N = N; p.flip = 1;
+  p.wprep = wprep; p.out = dx; p.out_H = H; p.out_W = W; p.o_mul = 1; p.oy_add = 0; p.ox_add = 0; p.bias = nullptr; p.gate = nullptr; p.gate_bits = gate_bits; p.relu_bits = nullptr; p.relu = 0;
+  p.nbands = 1; p.bc[0] = 0;
+  if (KS == 3 && S == 1 && CIN == 64) {
+    constexpr int R = 3;
+    p.OH = H; p.OWv = W; p.PW = W + R - 1; p.RT = min(p.OH, kBM / p.PW); p.PH = p.RT + R - 1; p.TPF = hulc_cdiv(p.OH, p.RT);
+    p.bx[0] = -(R - 1); p.by[0] = -(R - 1);
+    for (int tap = 0; tap < 9; ++tap) p.wkb[tap] = tap;
+    return launch_band_bf16<64, 9, 3, 3>(dy, N, HO, WO, (size_t)WO * 128, (size_t)HO * WO * 128, 1, p, st);
+  }
+  if (KS == 4 && S == 2 && CIN == 32) {  // the four stride phases stacked along N = 128, scattered by the epilogue
+    constexpr int R = 2;
+    p.OH = (H + 1) / 2; p.OWv = (W + 1) / 2; p.scatter = 1;
+    p.PW = p.OWv + R - 1; p.RT = min(p.OH, kBM / p.PW); p.PH = p.RT + R - 1; p.TPF = hulc_cdiv(p.OH, p.RT);
+    p.bx[0] = -(R - 1); p.by[0] = -(R - 1);
+    for (int tap = 0; tap < 4; ++tap) p.wkb[tap] = tap;
+    return launch_band_bf16<128, 4, 2, 2>(dy, N, HO, WO, (size_t)WO * 128, (size_t)HO * WO * 128, 1, p, st);
+  }
   return (int)cudaErrorNotSupported;
 }

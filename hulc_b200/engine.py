@@ -60,14 +60,14 @@ class ParamStore:
         self.n_heads = sum(spec[k][0] for k in head_w)
         self.n_heads_padded = (self.n_heads + 3) // 4 * 4
         for grp in groups:
-            off = (off + 3) // 4 * 4  # 16-byte alignment per group
+            off = (off + 7) // 8 * 8  # 32-byte alignment per group: its bf16 copy (same element offsets) is then 16-byte aligned, as TMA needs
             for k in grp:
                 n = int(math.prod(spec[k])) if len(spec[k]) else 1
                 self.offsets[k] = (off, tuple(spec[k]))
                 off += n
             if grp is head_w and head_w:
                 off += (self.n_heads_padded - self.n_heads) * spec[head_w[0]][1]
-        self.numel = (off + 3) // 4 * 4
+        self.numel = (off + 7) // 8 * 8
         self.device = torch.device(device)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.grad = torch.zeros_like(self.flat)

@@ -231,6 +231,17 @@ int hulc_gemm_bf16(const void* A, const void* B, float* C, void* Cb, int M, int 
                    float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate, const void* gate_bf16,
                    int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, void* stream);
 
+/* bf16 activations between the conv layers (vision_network.py:36-47 under autocast): the same three layers as hulc_conv2d_tc_*, with
+ * y / dy / dx (and x of layers 2, 3) channels-last bf16; layer 1 still reads the reference's fp32 NCHW frames.  Weights, bias and both
+ * gradients dw / db stay fp32 (reference layout); relu_bits / gate_bits as above (the data gradient gates on the sign bits only).
+ * wgrad: dw = beta * dw + dL/dw; db (optional) += column sums of dy, out of the same tensor-core pass. */
+int hulc_conv2d_bf16_fwd(const void* x, const float* w, const float* b, void* y, int N, int CIN, int H, int W, int COUT, int KS, int S, int relu,
+                         unsigned* relu_bits, float* workspace, size_t workspace_bytes, void* stream);
+int hulc_conv2d_bf16_dgrad(const void* dy, const float* w, const unsigned* gate_bits, void* dx, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                           float* workspace, size_t workspace_bytes, void* stream);
+int hulc_conv2d_bf16_wgrad(const void* x, const void* dy, float* dw, float beta, float* db, int N, int CIN, int H, int W, int COUT, int KS, int S,
+                           float* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- optimizer: torch.optim.Adam(lr, betas, eps), no weight decay (hulc/models/hulc.py:239-252) over a flat buffer ---------
  * g is multiplied by grad_scale first (1/world after the all-reduce); `step` is the 1-based step count, read from the device
  * integer *step_ptr instead when step_ptr != NULL (so the launch can be replayed from a CUDA graph). */

@@ -19,8 +19,9 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--seq", type=int, default=32)
 ap.add_argument("--model", default="hulc")
 ap.add_argument("--rnn", default="rnn_decoder")
+ap.add_argument("--precision", default="tf32")
 args = ap.parse_args()
-eng = HulcEngine(args.model, args.rnn, device="cuda", dropout_p=0.1)
+eng = HulcEngine(args.model, args.rnn, device="cuda", dropout_p=0.1, precision=args.precision)
 eng.load_state_dict(synthetic.make_state_dict(args.model, args.rnn))
 batch = synthetic.make_batch(args.batch, args.seq, seed=1, device="cuda")
 for i in range(args.steps):
