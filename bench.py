@@ -176,13 +176,25 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     x = batch["vis"]["rgb_obs"]["rgb_static"].flatten(0, 1)  # one modality: 1024 frames (conv1 runs once per modality)
     n_mod = len(batch)
     B_ = eng.train_buffers(batch)
-    a1, a2, a3, da1, da2, da3 = (B_[f"static.{k}"] for k in ("a1", "a2", "a3", "da1", "da2", "da3"))
+    sfx = "h" if eng.bf16_conv else ""  # bf16 path: the conv stack's activations are bf16 buffers
+    a1, a2, a3, da1, da2, da3 = (B_[f"static.{k}{sfx}"] for k in ("a1", "a2", "a3", "da1", "da2", "da3"))
     n1, N = x.shape[0], a1.shape[0]
     w0, w2, w4 = (P[f"{pre}.conv_model.{i}.weight"] for i in (0, 2, 4))
     b0, b2, b4 = (P[f"{pre}.conv_model.{i}.bias"] for i in (0, 2, 4))
     s0, s2, s4 = torch.empty_like(w0), torch.empty_like(w2), torch.empty_like(w4)
     fl = lambda n, co, ho, k: 2.0 * n * co * ho * ho * k
-    if eng.tc:
+    if eng.bf16_conv:  # bf16 activations between the conv layers; layer 1 reads the fp32 frames
+        cands = {
+            "conv1_fwd": (lambda: ops.conv2d_bf16_fwd(x, w0, b0, 4, a1[:n1], relu_bits=B_["static.a1_bits"][:n1]), fl(n1, 32, 49, 192), n_mod),
+            "conv2_fwd": (lambda: ops.conv2d_bf16_fwd(a1, w2, b2, 2, a2, relu_bits=B_["static.a2_bits"]), fl(N, 64, 23, 512), 1),
+            "conv3_fwd": (lambda: ops.conv2d_bf16_fwd(a2, w4, b4, 1, a3), fl(N, 64, 21, 576), 1),
+            "conv3_dgrad": (lambda: ops.conv2d_bf16_dgrad(da3, w4, da2, 1, B_["static.a2_bits"]), fl(N, 64, 21, 576), 1),
+            "conv2_dgrad": (lambda: ops.conv2d_bf16_dgrad(da2, w2, da1, 2, B_["static.a1_bits"]), fl(N, 64, 23, 512), 1),
+            "conv3_wgrad": (lambda: ops.conv2d_bf16_wgrad(a2, da3, s4, 1), fl(N, 64, 21, 576), 1),
+            "conv2_wgrad": (lambda: ops.conv2d_bf16_wgrad(a1, da2, s2, 2), fl(N, 64, 23, 512), 1),
+            "conv1_wgrad": (lambda: ops.conv2d_bf16_wgrad(x, da1[:n1], s0, 4), fl(n1, 32, 49, 192), n_mod),
+        }
+    elif eng.tc:
         cands = {
             "conv1_fwd": (lambda: ops.conv2d_tc_fwd(x, w0, b0, 4, a1[:n1], relu_bits=B_["static.a1_bits"][:n1]), fl(n1, 32, 49, 192), n_mod),
             "conv2_fwd": (lambda: ops.conv2d_tc_fwd(a1, w2, b2, 2, a2, relu_bits=B_["static.a2_bits"]), fl(N, 64, 23, 512), 1),
@@ -266,6 +278,13 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
         "rnn_step_fwd_3xtf32": 4.0 * (H * H + 3 * nB * H), "rnn_step_bwd_tf32": 4.0 * (H * H + 4 * nB * H), "rnn_step_gemm": 4.0 * (H * H + 3 * nB * H),
         "dense_wgrad_2048^3": 4.0 * (2 * S * nB * H + H * H), "dense_fwd_2048^3": 4.0 * (2 * S * nB * H + H * H),
     }
+    if eng.bf16_conv:  # bf16 activations (2 bytes); layer 1 still reads the fp32 frames
+        f2 = lambda n, c, hw: 2.0 * n * c * hw * hw
+        abytes.update({
+            "conv1_fwd": fr(n1, 3, 200) + f2(n1, 32, 49), "conv1_wgrad": fr(n1, 3, 200) + f2(n1, 32, 49),
+            "conv2_fwd": f2(N, 32, 49) + f2(N, 64, 23), "conv2_wgrad": f2(N, 32, 49) + f2(N, 64, 23), "conv2_dgrad": f2(N, 64, 23) + (1 + 1 / 16) * f2(N, 32, 49),
+            "conv3_fwd": f2(N, 64, 23) + f2(N, 64, 21), "conv3_wgrad": f2(N, 64, 23) + f2(N, 64, 21), "conv3_dgrad": f2(N, 64, 21) + (1 + 1 / 16) * f2(N, 64, 23),
+        })
     if eng.bf16:  # bf16 operands, fp32 result
         abytes["dense_wgrad_2048^3"] = 2.0 * 2 * S * nB * H + 4.0 * H * H
         abytes["dense_fwd_2048^3"] = 2.0 * (S * nB * H + H * H) + 4.0 * S * nB * H
@@ -275,7 +294,7 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     gbs = abytes[top] / (r["ms"] * 1e-3) / 1e9
     # the kernel runs tf32 operands: its tensor ceiling is half the measured bf16 rate; it is HBM-bound when its arithmetic
     # intensity is below that ridge
-    is_bf16_kernel = eng.bf16 and top.startswith("dense")
+    is_bf16_kernel = eng.bf16 and (top.startswith("dense") or (eng.bf16_conv and top.startswith(("conv2", "conv3"))))
     tf32_peak = peaks["tf_burst"] / (1.0 if is_bf16_kernel else 2.0)
     hbm_bound = (r["flops"] / abytes[top]) < (tf32_peak * 1e12) / (peaks["hbm"] * 1e9)
     kern = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "gbs": round(abytes[k] / (v["ms"] * 1e-3) / 1e9, 1),

@@ -447,6 +447,58 @@ __global__ void scale_vec_kernel(float* x, int n, float s) {
   if (i < n) x[i] *= s;
 }
 
+// Many column sums in ONE launch (the bias gradients of a whole backward pass: ~45 small reductions that are otherwise launch-bound).
+// Job j (8 x int64 in `table`): X, out, rows, cols, ldx, beta (float bits), first block, unused.  A block owns 32 consecutive columns of one
+// job for all of its rows: 8 column lanes x 4 columns, 32 row lanes whose partial sums meet in shared memory in lane order (fixed
+// summation order, no atomics).
+__global__ void __launch_bounds__(256) colsum_multi_kernel(const long long* __restrict__ table, int njobs) {
+  __shared__ float red[32][33];
+  __shared__ int s_job;
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < njobs && (int)table[(j + 1) * 8 + 6] <= (int)blockIdx.x) ++j;
+    s_job = j;
+  }
+  __syncthreads();
+  const long long* t = table + (size_t)s_job * 8;
+  const float* X = reinterpret_cast<const float*>(t[0]);
+  float* out = reinterpret_cast<float*>(t[1]);
+  const int rows = (int)t[2], cols = (int)t[3], ldx = (int)t[4];
+  const float beta = __int_as_float((int)t[5]);
+  const int c0 = ((int)blockIdx.x - (int)t[6]) * 32;
+  const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c = c0 + cl * 4;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c + 3 < cols && (ldx & 3) == 0 && (reinterpret_cast<size_t>(X) & 15) == 0) {
+    int r = rl;
+    for (; r + 32 < rows; r += 64) {  // two independent 16-byte loads in flight per trip
+      const float4 a = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + c);
+      const float4 b = *reinterpret_cast<const float4*>(X + (size_t)(r + 32) * ldx + c);
+      s0[0] += a.x; s0[1] += a.y; s0[2] += a.z; s0[3] += a.w;
+      s1[0] += b.x; s1[1] += b.y; s1[2] += b.z; s1[3] += b.w;
+    }
+    if (r < rows) {
+      const float4 a = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + c);
+      s0[0] += a.x; s0[1] += a.y; s0[2] += a.z; s0[3] += a.w;
+    }
+  } else {
+    for (int r = rl; r < rows; r += 32)
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (c + v < cols) s0[v] += X[(size_t)r * ldx + c + v];
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) red[rl][cl * 4 + v] = s0[v] + s1[v];
+  __syncthreads();
+  if (threadIdx.x < 32 && c0 + (int)threadIdx.x < cols) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc += red[i][threadIdx.x];
+    float* o = out + c0 + threadIdx.x;
+    *o = (beta != 0.f ? beta * *o : 0.f) + acc;
+  }
+}
+
 }  // namespace
 
 // shared with gemm_tc.cu
@@ -514,5 +566,11 @@ HULC_API int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out
   float* partial = workspace ? workspace + 1024 : nullptr;
   if (vec) HULC_LAUNCH(colsum_kernel<4>, dim3(gx, gy), dim3(256), 0, st, X, rows, cols, ldx, out, beta, rpb, CL, partial, counters);
   else HULC_LAUNCH(colsum_kernel<1>, dim3(gx, gy), dim3(256), 0, st, X, rows, cols, ldx, out, beta, rpb, CL, partial, counters);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_colsum_multi(const void* table, int njobs, int total_blocks, void* stream) {
+  if (njobs <= 0 || total_blocks <= 0) return 0;
+  HULC_LAUNCH(colsum_multi_kernel, dim3(total_blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const long long*>(table), njobs);
   HULC_RETURN_LAST();
 }

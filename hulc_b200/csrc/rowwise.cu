@@ -266,15 +266,27 @@ __global__ void __launch_bounds__(256) spatial_softmax_nhwc_bwd_kernel(const flo
 // PL x 32 threads per (frame, 32 channels), thread (pl, c) keeps positions pl, pl+PL, ... of channel c in registers, so every load of the
 // frame is issued before the first use (the serial online-softmax chain above is latency bound) and the backward pass reads
 // x once.  Statistics of the PL position lanes meet in shared memory and are added in lane order.
-template <int PL, int MAXV, bool BWD>
-__global__ void __launch_bounds__(PL * 32, 2) spatial_softmax_nhwc_reg_kernel(const float* __restrict__ x, const float* __restrict__ dout, float* __restrict__ out,
-                                                                           float* __restrict__ dx, int C, int H, int W, float inv_temp, int relu_gate) {
+// bf16 (round to nearest even) of a finite or infinite fp32; NaN stays NaN
+__device__ __forceinline__ unsigned short f32_to_bf16_bits(float f) {
+  unsigned u = __float_as_uint(f);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (unsigned short)((u >> 16) | 0x40u);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
+
+// BF: the map x (and its gradient dx) are bf16 (the bf16 path's channels-last activations); statistics and outputs stay fp32.
+template <int PL, int MAXV, bool BWD, bool BF = false>
+__global__ void __launch_bounds__(PL * 32, 2) spatial_softmax_nhwc_reg_kernel(const void* __restrict__ x_, const float* __restrict__ dout, float* __restrict__ out,
+                                                                           void* __restrict__ dx_, int C, int H, int W, float inv_temp, int relu_gate) {
+  const float* x = reinterpret_cast<const float*>(x_);
+  const unsigned short* x16 = reinterpret_cast<const unsigned short*>(x_);
   static_assert(MAXV <= 32, "the ReLU signs of a thread's values are kept in one 32-bit mask");
   __shared__ float sh_m[PL][32], sh_s[PL][32], sh_a[PL][32], sh_b[PL][32];
   __shared__ float cxs[PL * MAXV], cys[PL * MAXV];  // coordinate maps of the flattened positions (no per-element divisions)
   const int n = blockIdx.x, P = H * W;
   const int lc = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const float* xf = x + (size_t)n * P * C;
+  const unsigned short* xh = x16 + (size_t)n * P * C;
   for (int p = threadIdx.x; p < P; p += PL * 32) { cxs[p] = lin_coord(p / W, H); cys[p] = lin_coord(p % W, W); }
   const int c = blockIdx.y * 32 + lc;  // one CTA per (frame, group of 32 channels): two CTAs share an SM
   const bool cv = c < C;
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(PL * 32, 2) spatial_softmax_nhwc_reg_kernel(co
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int p = pl + PL * i;
-    v[i] = (cv && p < P) ? xf[(size_t)p * C + c] * inv_temp : -FLT_MAX;
+    v[i] = (cv && p < P) ? (BF ? __uint_as_float((unsigned)xh[(size_t)p * C + c] << 16) : xf[(size_t)p * C + c]) * inv_temp : -FLT_MAX;
     mx = fmaxf(mx, v[i]);
     pos_mask |= (v[i] > 0.f ? 1u : 0u) << i;  // inv_temp > 0: sign(v) == sign(x)
   }
@@ -319,14 +331,16 @@ __global__ void __launch_bounds__(PL * 32, 2) spatial_softmax_nhwc_reg_kernel(co
     }
   } else if (cv) {
     const float scale = inv_temp / s, mean_c = a / s;
-    float* df = dx + (size_t)n * P * C;
+    float* df = reinterpret_cast<float*>(dx_) + (size_t)n * P * C;
+    unsigned short* dh = reinterpret_cast<unsigned short*>(dx_) + (size_t)n * P * C;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int p = pl + PL * i;
       if (p < P) {
         float g = v[i] * scale * (gx * cxs[p] + gy * cys[p] - mean_c);
         if (relu_gate && !((pos_mask >> i) & 1u)) g = 0.f;
-        df[(size_t)p * C + c] = g;
+        if (BF) dh[(size_t)p * C + c] = f32_to_bf16_bits(g);
+        else df[(size_t)p * C + c] = g;
       }
     }
   }
@@ -385,14 +399,6 @@ __global__ void __launch_bounds__(256) nchw_channel_sum_kernel(const float* __re
 }
 
 // torch.optim.Adam (no weight decay, no amsgrad): one launch over the flat parameter buffer
-// bf16 (round to nearest even) of a finite or infinite fp32; NaN stays NaN
-__device__ __forceinline__ unsigned short f32_to_bf16_bits(float f) {
-  unsigned u = __float_as_uint(f);
-  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (unsigned short)((u >> 16) | 0x40u);
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return (unsigned short)(u >> 16);
-}
-
 // BF16: also write the updated parameters as bf16 into pb (the operand copy of the bf16 path: one pass instead of Adam + a cast)
 template <bool BF16>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, unsigned short* __restrict__ pb,
@@ -514,8 +520,8 @@ HULC_API int hulc_spatial_softmax_bwd(const float* x, const float* dout, float* 
 HULC_API int hulc_spatial_softmax_nhwc_fwd(const float* x, float* out, int N, int C, int H, int W, float inv_temp, void* stream) {
   if (N <= 0) return 0;
   if (H * W <= 16 * 28 && inv_temp > 0.f) {
-    HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, false>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, x, (const float*)nullptr, out,
-                (float*)nullptr, C, H, W, inv_temp, 0);
+    HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, false>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, (const void*)x, (const float*)nullptr, out,
+                (void*)nullptr, C, H, W, inv_temp, 0);
     HULC_RETURN_LAST();
   }
   HULC_LAUNCH(spatial_softmax_nhwc_fwd_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, x, out, C, H, W, inv_temp);
@@ -526,11 +532,27 @@ HULC_API int hulc_spatial_softmax_nhwc_bwd(const float* x, const float* dout, fl
                                            void* stream) {
   if (N <= 0) return 0;
   if (H * W <= 16 * 28 && inv_temp > 0.f) {
-    HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, true>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, x, dout, (float*)nullptr, dx, C, H, W,
+    HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, true>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, (const void*)x, dout, (float*)nullptr, (void*)dx, C, H, W,
                 inv_temp, relu_gate);
     HULC_RETURN_LAST();
   }
   HULC_LAUNCH(spatial_softmax_nhwc_bwd_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, x, dout, dx, C, H, W, inv_temp, relu_gate);
+  HULC_RETURN_LAST();
+}
+
+// bf16 maps (x, dx channels-last bf16); maps of up to 448 positions (the 21x21 map of the static camera)
+HULC_API int hulc_spatial_softmax_nhwc_bf16_fwd(const void* x, float* out, int N, int C, int H, int W, float inv_temp, void* stream) {
+  if (N <= 0) return 0;
+  if (H * W > 16 * 28 || !(inv_temp > 0.f)) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, false, true>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, x, (const float*)nullptr, out,
+              (void*)nullptr, C, H, W, inv_temp, 0);
+  HULC_RETURN_LAST();
+}
+HULC_API int hulc_spatial_softmax_nhwc_bf16_bwd(const void* x, const float* dout, void* dx, int N, int C, int H, int W, float inv_temp, int relu_gate, void* stream) {
+  if (N <= 0) return 0;
+  if (H * W > 16 * 28 || !(inv_temp > 0.f)) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH((spatial_softmax_nhwc_reg_kernel<16, 28, true, true>), dim3(N, hulc_cdiv(C, 32)), dim3(512), 0, (cudaStream_t)stream, x, dout, (float*)nullptr, dx, C, H, W,
+              inv_temp, relu_gate);
   HULC_RETURN_LAST();
 }
 

@@ -168,6 +168,8 @@ class HulcEngine:
         self.precision = precision
         self.bf16 = precision == "bf16"        # bf16 tensor-core operands for every Linear product (and bf16 activations between the conv layers)
         self.tc = precision in ("tf32", "bf16")
+        # bf16 activations between the conv layers (HULC_B200_BF16_CONV=0 keeps the fp32 / tf32 conv stack under the bf16 Linear products)
+        self.bf16_conv = self.bf16 and os.environ.get("HULC_B200_BF16_CONV", "1") != "0"
         self.persistent_rnn = os.environ.get("HULC_B200_PERSISTENT_RNN", "1") != "0"  # whole recurrence in one launch (csrc/rnn_tc.cu)
         self.model, self.rnn_model = model, rnn_model
         self.device = torch.device(device)
@@ -177,6 +179,7 @@ class HulcEngine:
             self.ps.enable_bf16()
         self._twins: Dict[tuple, list] = {}     # (ptr, shape, strides) of an fp32 tensor -> [bf16 twin, generation it is valid for, byte range]
         self._twin_gen = 0
+        self._bias_jobs: list = []
         self._bf16_only: set = set()            # keys whose fp32 storage was never written this step (the producer emitted bf16 only)
         self.dropout_p = float(dims.dropout_p) if model != "mcil" else 0.0
         self.kl_beta, self.kl_alpha, self.clip_beta, self.gripper_alpha = float(kl_beta), float(kl_balancing_mix), float(clip_beta), float(dims.gripper_alpha)
@@ -213,6 +216,13 @@ class HulcEngine:
             if _POISON and not zero:
                 t.fill_(float("nan"))  # debugging aid: any read of a never-written element surfaces as NaN
             self._bufs[name] = t
+        return t
+
+    def hbuf(self, name, *shape):
+        """persistent bf16 buffer (bf16 path: the channels-last activations of the conv stack and their gradients)"""
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != torch.bfloat16:
+            t = self._bufs[name] = torch.zeros(*shape, dtype=torch.bfloat16, device=self.device)
         return t
 
     def ibuf(self, name, *shape):
@@ -301,6 +311,8 @@ class HulcEngine:
 
     def _tw(self, t, produce=False):
         """bf16 twin of the fp32 tensor `t` (a parameter view or an activation).  produce=True: the caller is about to write it."""
+        if t.dtype == torch.bfloat16:
+            return t
         ps = self.ps
         off = t.data_ptr() - ps.flat.data_ptr()
         if 0 <= off < 4 * ps.numel:
@@ -331,6 +343,12 @@ class HulcEngine:
             self.ps.refresh_bf16()
 
     def _gemm16(self, A, B, C, *, out="f32", gate=None, **kw):
+        if C.dtype == torch.bfloat16:  # a bf16 activation buffer (conv stack): the result goes there directly
+            A16, B16 = self._tw(A), self._tw(B)
+            if gate is not None and gate.dtype != torch.bfloat16 and self._key(gate) in self._bf16_only:
+                gate = self._tw(gate)
+            ops.gemm_bf16(A16, B16, None, C, gate=gate, **kw)
+            return C
         A16, B16 = self._tw(A), self._tw(B)
         if not ops.gemm_bf16_ok(A16, B16):
             raise ops._lib.HulcError(f"bf16 product with operands the TMA cannot address: A {tuple(A.shape)} strides {A.stride()}, B {tuple(B.shape)} strides {B.stride()}")
@@ -356,11 +374,20 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     # small composites
     # ------------------------------------------------------------------------------------------------------------------
+    def bias_grad(self, dy, gb):
+        """gb += column sums of dy (the bias gradient of a Linear / conv layer).  Deferred: all of a backward pass's bias gradients are summed
+        by ONE launch at its end (`_flush_bias_grads`; every dy lives in its own persistent buffer until then)."""
+        self._bias_jobs.append((dy, gb, 1.0))
+
+    def _flush_bias_grads(self):
+        jobs, self._bias_jobs = self._bias_jobs, []
+        ops.colsum_multi(jobs)
+
     def _linear_bwd(self, name, x, dy, dx=None, *, gate=None, dx_beta=0.0, need_dx=True, act=0, addend=None, drop=NO_DROP):
         """Gradients of y = x W^T + b: accumulates dW, db; returns dx = dy W (optionally gated by the producer's ReLU)."""
         P, G = self.ps.p, self.ps.g
         self.gemm_bwd(dy, x, G[name + ".weight"], transA=True, beta=1.0)
-        colsum(dy, G[name + ".bias"], beta=1.0)
+        self.bias_grad(dy, G[name + ".bias"])
         if not need_dx:
             return None
         return self.gemm_bwd(dy, P[name + ".weight"], dx, beta=dx_beta, gate=gate, act=act, addend=addend, drop=drop)
@@ -411,6 +438,10 @@ class HulcEngine:
     def _encoder_fwd(self, which, frames: List[torch.Tensor], emb):
         frames = self._normalised_frames(which, frames)
         # the tensor-core first layer reads the NCHW rows in 16-byte pieces: other widths take the exact-fp32 kernels
+        if self.bf16_conv and frames[0].shape[-1] % 4 == 0:
+            ctx = self._encoder_fwd_bf16(which, frames, emb)
+            ctx["bf16"] = True
+            return ctx
         if self.tc and frames[0].shape[-1] % 4 == 0:
             ctx = self._encoder_fwd_tc(which, frames, emb)
             ctx["tc"] = True
@@ -441,6 +472,8 @@ class HulcEngine:
         return dict(frames=frames, a1=a1, a2=a2, a3=a3, acts=acts, stats=stats, names=names, pre=pre)
 
     def _encoder_bwd(self, which, ctx, demb):
+        if ctx.get("bf16"):
+            return self._encoder_bwd_bf16(which, ctx, demb)
         if ctx.get("tc"):
             return self._encoder_bwd_tc(which, ctx, demb)
         P, G = self.ps.p, self.ps.g
@@ -535,17 +568,84 @@ class HulcEngine:
             self.gemm_bwd(d, acts[0], dw0, transA=True)
             g7 = G[f"{pre}.conv_model.7.weight"]
             ops.strided_copy(g7.view(-1, 64, PP).transpose(1, 2), dw0.view(-1, PP, 64), accumulate=True)
-            colsum(d, G[f"{pre}.conv_model.7.bias"], beta=1.0)
+            self.bias_grad(d, G[f"{pre}.conv_model.7.bias"])
             self.gemm_bwd(d, w0, da3.view(N, -1), gate=acts[0])
         ops.conv2d_tc_wgrad(a2, da3, G[f"{pre}.conv_model.4.weight"], 1, beta=1.0)
-        colsum(da3.view(-1, 64), G[f"{pre}.conv_model.4.bias"], beta=1.0)
+        self.bias_grad(da3.view(-1, 64), G[f"{pre}.conv_model.4.bias"])
         da2 = ops.conv2d_tc_dgrad(da3, P[f"{pre}.conv_model.4.weight"], self.buf(f"{which}.da2", *a2.shape), 1, gate=a2, gate_bits=ctx["a2_bits"])
         ops.conv2d_tc_wgrad(a1, da2, G[f"{pre}.conv_model.2.weight"], 2, beta=1.0)
-        colsum(da2.view(-1, 64), G[f"{pre}.conv_model.2.bias"], beta=1.0)
+        self.bias_grad(da2.view(-1, 64), G[f"{pre}.conv_model.2.bias"])
         da1 = ops.conv2d_tc_dgrad(da2, P[f"{pre}.conv_model.2.weight"], self.buf(f"{which}.da1", *a1.shape), 2, gate=a1, gate_bits=ctx["a1_bits"])
         n0 = 0
         for f in ctx["frames"]:  # the bias gradient (column sums of da1) comes out of the same tensor-core pass
             ops.conv2d_tc_wgrad(f, da1[n0 : n0 + f.shape[0]], G[f"{pre}.conv_model.0.weight"], 4, beta=1.0, db=G[f"{pre}.conv_model.0.bias"])
+            n0 += f.shape[0]
+
+    # bf16 variant (BASELINE config 3): the first layer reads the fp32 frames, everything between the conv layers is channels-last bf16
+    def _encoder_fwd_bf16(self, which, frames: List[torch.Tensor], emb):
+        P = self.ps.p
+        pre = f"perceptual_encoder.rgb_{which}_encoder"
+        N = sum(f.shape[0] for f in frames)
+        sizes = [frames[0].shape[-1]]
+        for (_, s), k in zip(self._CONVS, (8, 4, 3)):
+            sizes.append((sizes[-1] - k) // s + 1)
+        a1 = self.hbuf(f"{which}.a1h", N, sizes[1], sizes[1], 32)
+        a1_bits = self.ibuf(f"{which}.a1_bits", N, sizes[1], sizes[1], 1)
+        a2_bits = self.ibuf(f"{which}.a2_bits", N, sizes[2], sizes[2], 2)
+        n0 = 0
+        for f in frames:
+            ops.conv2d_bf16_fwd(f, P[f"{pre}.conv_model.0.weight"], P[f"{pre}.conv_model.0.bias"], 4, a1[n0 : n0 + f.shape[0]], relu_bits=a1_bits[n0 : n0 + f.shape[0]])
+            n0 += f.shape[0]
+        a2 = ops.conv2d_bf16_fwd(a1, P[f"{pre}.conv_model.2.weight"], P[f"{pre}.conv_model.2.bias"], 2, self.hbuf(f"{which}.a2h", N, sizes[2], sizes[2], 64), relu_bits=a2_bits)
+        a3 = ops.conv2d_bf16_fwd(a2, P[f"{pre}.conv_model.4.weight"], P[f"{pre}.conv_model.4.bias"], 1, self.hbuf(f"{which}.a3h", N, sizes[3], sizes[3], 64))
+        w0 = None
+        if which == "static":
+            feat = ops.spatial_softmax_nhwc_bf16_fwd(a3, self.buf("static.ss", N, 128), temperature=self.dims.spatial_softmax_temp)
+            names = [f"{pre}.fc1.0", f"{pre}.fc2"]
+            out = emb[:, 0:64]
+        else:
+            feat = a3.view(N, -1)  # bf16: the operand of the flatten-FC as it is
+            PP = sizes[3] * sizes[3]
+            w7 = P[f"{pre}.conv_model.7.weight"]
+            w0 = self.buf("gripper.w7p", w7.shape[0], PP * 64)
+            ops.strided_copy(w0.view(-1, PP, 64), w7.view(-1, 64, PP).transpose(1, 2))
+            names = [f"{pre}.conv_model.7", f"{pre}.fc1.0", f"{pre}.fc2"]
+            out = emb[:, 64:128]
+        acts, stats = self._mlp_ln_fwd(which, feat, names, f"{pre}.ln", out, w0=w0)
+        return dict(frames=frames, a1=a1, a2=a2, a3=a3, acts=acts, stats=stats, names=names, pre=pre, w0=w0, a1_bits=a1_bits, a2_bits=a2_bits)
+
+    def _encoder_bwd_bf16(self, which, ctx, demb):
+        P, G = self.ps.p, self.ps.g
+        pre, a1, a2, a3 = ctx["pre"], ctx["a1"], ctx["a2"], ctx["a3"]
+        dout = demb[:, 0:64] if which == "static" else demb[:, 64:128]
+        N = a3.shape[0]
+        da3 = self.hbuf(f"{which}.da3h", *a3.shape)
+        if which == "static":
+            dss = self._mlp_ln_bwd(which, ctx["acts"], ctx["stats"], ctx["names"], f"{pre}.ln", dout, self.buf("static.dss", N, 128))
+            ops.spatial_softmax_nhwc_bf16_bwd(a3, dss, da3, temperature=self.dims.spatial_softmax_temp, relu_gate=True)
+        else:
+            acts, names, w0 = ctx["acts"], ctx["names"], ctx["w0"]
+            d = self.buf(f"{which}.mlp_dz", *acts[-1].shape)
+            ops.layernorm_bwd(dout, acts[-1], ctx["stats"], P[f"{pre}.ln.weight"], G[f"{pre}.ln.weight"], G[f"{pre}.ln.bias"], dz=d)
+            for i in (2, 1):
+                nd = self.buf(f"{which}.mlp_d{i}", *acts[i].shape)
+                self._linear_bwd(names[i], acts[i], d, nd, gate=acts[i])
+                d = nd
+            PP = a3.shape[1] * a3.shape[2]
+            dw0 = self.buf("gripper.dw7p", *w0.shape)
+            self.gemm_bwd(d, acts[0], dw0, transA=True)
+            g7 = G[f"{pre}.conv_model.7.weight"]
+            ops.strided_copy(g7.view(-1, 64, PP).transpose(1, 2), dw0.view(-1, PP, 64), accumulate=True)
+            self.bias_grad(d, G[f"{pre}.conv_model.7.bias"])
+            self.gemm_bwd(d, w0, da3.view(N, -1), gate=acts[0])  # bf16 result, gated by the bf16 activation (conv3's ReLU)
+        # weight gradients come with the bias gradients (a ones row in the same tensor-core pass): no column-sum launches
+        ops.conv2d_bf16_wgrad(a2, da3, G[f"{pre}.conv_model.4.weight"], 1, beta=1.0, db=G[f"{pre}.conv_model.4.bias"])
+        da2 = ops.conv2d_bf16_dgrad(da3, P[f"{pre}.conv_model.4.weight"], self.hbuf(f"{which}.da2h", *a2.shape), 1, ctx["a2_bits"])
+        ops.conv2d_bf16_wgrad(a1, da2, G[f"{pre}.conv_model.2.weight"], 2, beta=1.0, db=G[f"{pre}.conv_model.2.bias"])
+        da1 = ops.conv2d_bf16_dgrad(da2, P[f"{pre}.conv_model.2.weight"], self.hbuf(f"{which}.da1h", *a1.shape), 2, ctx["a1_bits"])
+        n0 = 0
+        for f in ctx["frames"]:
+            ops.conv2d_bf16_wgrad(f, da1[n0 : n0 + f.shape[0]], G[f"{pre}.conv_model.0.weight"], 4, beta=1.0, db=G[f"{pre}.conv_model.0.bias"])
             n0 += f.shape[0]
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -661,6 +761,7 @@ class HulcEngine:
         P, G, ps = self.ps.p, self.ps.g, self.ps
         self._step_shapes.clear()
         self._new_generation()
+        self._bias_jobs = []
         if seed is not None:
             self.rng_dev.fill_(int(seed))
         else:
@@ -873,24 +974,24 @@ class HulcEngine:
         _mark("bwd/action_decoder")
         # heads
         self.gemm_bwd(dheads_p, h1_all, ps.heads_gw, transA=True, beta=1.0)
-        colsum(dheads_p, ps.heads_gb, beta=1.0)
+        self.bias_grad(dheads_p, ps.heads_gb)
         dh1 = self.gemm_bwd(dheads_p, ps.heads_w, self.buf("dec.dh1", S * nB, H))
         # layer 1
         dpre1, dgh1 = self._rnn_bwd("dec.l1", dh1, P[f"{rp}.weight_hh_l1"], hb[1], 0, S, nB, kind=kind, saved=sv1)
         self.gemm_bwd(dgh1, hb[1][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l1"], transA=True, beta=1.0)
         self.gemm_bwd(dpre1, h0_all, G[f"{rp}.weight_ih_l1"], transA=True, beta=1.0)
-        colsum(dpre1, G[f"{rp}.bias_ih_l1"], beta=1.0)
-        colsum(dgh1, G[f"{rp}.bias_hh_l1"], beta=1.0)
+        self.bias_grad(dpre1, G[f"{rp}.bias_ih_l1"])
+        self.bias_grad(dgh1, G[f"{rp}.bias_hh_l1"])
         dh0 = self.gemm_bwd(dpre1, P[f"{rp}.weight_ih_l1"], self.buf("dec.dh0", S * nB, H))
         # layer 0
         dpre0, dgh0 = self._rnn_bwd("dec.l0", dh0, P[f"{rp}.weight_hh_l0"], hb[0], 0, S, nB, kind=kind, saved=sv0)
         self.gemm_bwd(dgh0, hb[0][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l0"], transA=True, beta=1.0)
-        colsum(dgh0, G[f"{rp}.bias_hh_l0"], beta=1.0)
+        self.bias_grad(dgh0, G[f"{rp}.bias_hh_l0"])
         g_ih0 = G[f"{rp}.weight_ih_l0"]
         self.gemm_bwd(dpre0, percep_tm.view(S * nB, C), g_ih0[:, PF : PF + C], transA=True, beta=1.0)
         dconst = self.buf("dec.dconst", nB, Gn * H)
         colsum(dpre0.view(S, nB * Gn * H), dconst.view(-1))
-        colsum(dconst, G[f"{rp}.bias_ih_l0"], beta=1.0)
+        self.bias_grad(dconst, G[f"{rp}.bias_ih_l0"])
         self.gemm_bwd(dconst, goal, g_ih0[:, PF + C :], transA=True, beta=1.0)
         self.gemm_bwd(dconst, w_goal, dgoal)
         dplan = None
@@ -948,7 +1049,7 @@ class HulcEngine:
             g0 = G["plan_proposal.fc_model.0.weight"]
             self.gemm_bwd(d, emb3[:, 0, :], g0[:, :128], transA=True, beta=1.0)
             self.gemm_bwd(d, goal, g0[:, 128:], transA=True, beta=1.0)
-            colsum(d, G["plan_proposal.fc_model.0.bias"], beta=1.0)
+            self.bias_grad(d, G["plan_proposal.fc_model.0.bias"])
             self.gemm_bwd(d, w0[:, :128], demb3[:, 0, :], beta=1.0)
             self.gemm_bwd(d, w0[:, 128:], dgoal, beta=1.0)
 
@@ -964,6 +1065,8 @@ class HulcEngine:
         # perceptual encoders
         self._encoder_bwd("static", ctx_s, demb)
         self._encoder_bwd("gripper", ctx_g, demb)
+        _mark("bwd/bias_gradients")
+        self._flush_bias_grads()
         _mark(None)
         return out
 
@@ -1018,13 +1121,13 @@ class HulcEngine:
             dctx = self._linear_bwd(f"{pre}.self_attn.out_proj", c["ctx"], do, self.buf(f"tr{l}.dctx", T, D))
             dqkv = ops.attention_bwd(c["qkv"], c["probs"], dctx, self.buf(f"tr{l}.dqkv", T, 3 * D), nB, S, Hh, drop(f"l{l}.attn", 1 + 4 * l))
             self.gemm_bwd(dqkv, c["x"], G[f"{pre}.self_attn.in_proj_weight"], transA=True, beta=1.0)
-            colsum(dqkv, G[f"{pre}.self_attn.in_proj_bias"], beta=1.0)
+            self.bias_grad(dqkv, G[f"{pre}.self_attn.in_proj_bias"])
             dy = self.gemm_bwd(dqkv, P[f"{pre}.self_attn.in_proj_weight"], self.buf(f"tr{l}.dx", T, D), addend=dz1)
         dx0 = dy
         d = drop("in", 0)
         if d.p > 0:
             dx0 = ops.dropout_apply(dx0, self.buf("tr.dx0d", T, D), d)
-        colsum(dx0.view(nB, S * D), G["plan_recognition.position_embeddings.weight"][:S].view(-1), beta=1.0)
+        self.bias_grad(dx0.view(nB, S * D), G["plan_recognition.position_embeddings.weight"][:S].view(-1))
         ops.strided_copy(demb3, dx0.view(nB, S, D), accumulate=True)
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -1068,8 +1171,8 @@ class HulcEngine:
                 hprev = (hb[2 : S + 2] if d else hb[0:S])[:, :, d * H : (d + 1) * H].reshape(S * nB, H)
                 self.gemm_bwd(dpre, hprev, G[f"{rp}.weight_hh_l{l}{sfx}"], transA=True, beta=1.0)
                 self.gemm_bwd(dpre, inp, G[f"{rp}.weight_ih_l{l}{sfx}"], transA=True, beta=1.0)
-                colsum(dpre, G[f"{rp}.bias_ih_l{l}{sfx}"], beta=1.0)
-                colsum(dpre, G[f"{rp}.bias_hh_l{l}{sfx}"], beta=1.0)
+                self.bias_grad(dpre, G[f"{rp}.bias_ih_l{l}{sfx}"])
+                self.bias_grad(dpre, G[f"{rp}.bias_hh_l{l}{sfx}"])
                 self.gemm_bwd(dpre, P[f"{rp}.weight_ih_l{l}{sfx}"], dinp, beta=float(d))
             dabove = dinp
         ops.strided_copy(demb3.transpose(0, 1), dabove.view(S, nB, 128), accumulate=True)

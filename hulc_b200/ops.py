@@ -187,6 +187,35 @@ def colsum(X, out=None, beta=0.0):
     return out
 
 
+_colsum_tables: Dict[tuple, tuple] = {}
+
+
+def colsum_multi(jobs):
+    """jobs: list of (X [rows, cols] view with contiguous rows, out [cols], beta).  One launch for all of them (hulc_colsum_multi); the
+    device-side job table is cached per set of pointers (persistent buffers: built once, also valid inside a captured graph)."""
+    import struct
+
+    if not jobs:
+        return
+    rows_, key, blk = [], [], 0
+    for X, out, beta in jobs:
+        _chk(X, out)
+        r, c = X.shape
+        assert out.numel() == c and out.is_contiguous()
+        bits = struct.unpack("<i", struct.pack("<f", float(beta)))[0]
+        rows_.append([X.data_ptr(), out.data_ptr(), r, c, _rowmajor(X), bits, blk, 0])
+        key.append((X.data_ptr(), out.data_ptr(), r, c, _rowmajor(X), bits))
+        blk += (c + 31) // 32
+    key = (str(jobs[0][0].device), tuple(key))
+    ent = _colsum_tables.get(key)
+    if ent is None:
+        if len(_colsum_tables) > 64:
+            _colsum_tables.clear()
+        ent = _colsum_tables[key] = (torch.tensor(rows_, dtype=torch.int64, device=jobs[0][0].device), blk)
+    table, total = ent
+    _L().hulc_colsum_multi(_ptr(table), len(jobs), total, _stream())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # GRU gates
 # ----------------------------------------------------------------------------------------------------------------------
@@ -299,6 +328,64 @@ def conv2d_tc_wgrad(x, dy, dw, stride, beta=0.0, db=None):
     ws = workspace(x.device)
     _L().hulc_conv2d_tc_wgrad(_ptr(x), _ptr(dy), _ptr(dw), float(beta), _ptr(db), N, CIN, H, W, COUT, KS, stride, int(nchw), _ptr(ws), ws.numel() * 4, _stream())
     return dw
+
+
+# bf16 activations between the conv layers (bf16 path): layer 1 reads the fp32 NCHW frames, layers 2 / 3 bf16 NHWC; outputs bf16 NHWC
+def conv2d_bf16_fwd(x, w, b, stride, y, relu=True, relu_bits=None):
+    _chk(w, b)
+    COUT, CIN, KS, _ = w.shape
+    _chk(x, dtype=torch.float32 if CIN == 3 else torch.bfloat16)
+    _chk(y, dtype=torch.bfloat16)
+    _chk(relu_bits, dtype=torch.int32)
+    assert x.is_contiguous() and w.is_contiguous() and y.is_contiguous()
+    N, H, W = (x.shape[0], x.shape[2], x.shape[3]) if CIN == 3 else (x.shape[0], x.shape[1], x.shape[2])
+    assert tuple(y.shape) == (N, _conv_out(H, KS, stride), _conv_out(W, KS, stride), COUT), y.shape
+    ws = workspace(x.device)
+    _L().hulc_conv2d_bf16_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, CIN, H, W, COUT, KS, stride, int(relu), _ptr(relu_bits), _ptr(ws), ws.numel() * 4, _stream())
+    return y
+
+
+def conv2d_bf16_dgrad(dy, w, dx, stride, gate_bits):
+    _chk(w)
+    _chk(dy, dx, dtype=torch.bfloat16)
+    _chk(gate_bits, dtype=torch.int32)
+    COUT, CIN, KS, _ = w.shape
+    N, H, W, _ = dx.shape
+    assert dy.is_contiguous() and dx.is_contiguous()
+    ws = workspace(dy.device)
+    _L().hulc_conv2d_bf16_dgrad(_ptr(dy), _ptr(w), _ptr(gate_bits), _ptr(dx), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
+    return dx
+
+
+def conv2d_bf16_wgrad(x, dy, dw, stride, beta=0.0, db=None):
+    """dw = beta * dw + dL/dw (fp32); db (optional, fp32) += sum over pixels of dy, out of the same tensor-core pass."""
+    _chk(dw, db)
+    COUT, CIN, KS, _ = dw.shape
+    _chk(x, dtype=torch.float32 if CIN == 3 else torch.bfloat16)
+    _chk(dy, dtype=torch.bfloat16)
+    N, H, W = (x.shape[0], x.shape[2], x.shape[3]) if CIN == 3 else (x.shape[0], x.shape[1], x.shape[2])
+    assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
+    ws = workspace(x.device)
+    _L().hulc_conv2d_bf16_wgrad(_ptr(x), _ptr(dy), _ptr(dw), float(beta), _ptr(db), N, CIN, H, W, COUT, KS, stride, _ptr(ws), ws.numel() * 4, _stream())
+    return dw
+
+
+def spatial_softmax_nhwc_bf16_fwd(x, out, temperature=1.0):
+    _chk(x, dtype=torch.bfloat16)
+    _chk(out)
+    N, H, W, C = x.shape
+    assert x.is_contiguous() and out.is_contiguous()
+    _L().hulc_spatial_softmax_nhwc_bf16_fwd(_ptr(x), _ptr(out), N, C, H, W, 1.0 / float(temperature), _stream())
+    return out
+
+
+def spatial_softmax_nhwc_bf16_bwd(x, dout, dx, temperature=1.0, relu_gate=True):
+    _chk(x, dx, dtype=torch.bfloat16)
+    _chk(dout)
+    N, H, W, C = x.shape
+    assert x.is_contiguous() and dout.is_contiguous() and dx.is_contiguous()
+    _L().hulc_spatial_softmax_nhwc_bf16_bwd(_ptr(x), _ptr(dout), _ptr(dx), N, C, H, W, 1.0 / float(temperature), int(relu_gate), _stream())
+    return dx
 
 
 def nchw_channel_sum(x, out):

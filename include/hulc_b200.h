@@ -57,6 +57,10 @@ int hulc_launch_count(unsigned long long* out);
  * and combined in a fixed order (bit-reproducible). */
 int hulc_colsum(const float* X, int rows, int cols, int ldx, float* out, float beta, float* workspace, size_t workspace_bytes,
                 void* stream);
+/* njobs column sums in one launch: table = njobs x 8 int64 on the device — {X, out, rows, cols, ldx, float bits of beta, first block of the
+ * job, 0}; job j owns blocks [first_j, first_j + ceil(cols_j / 32)); out_j[c] = beta_j * out_j[c] + sum_r X_j[r][c].  The bias gradients
+ * (sum over rows of dY for every nn.Linear / nn.Conv2d of the backward pass) go through this once per step. */
+int hulc_colsum_multi(const void* table, int njobs, int total_blocks, void* stream);
 
 /* activation / gate selectors for hulc_gemm's `act` argument */
 #define HULC_ACT_NONE 0
@@ -241,6 +245,10 @@ int hulc_conv2d_bf16_dgrad(const void* dy, const float* w, const unsigned* gate_
                            float* workspace, size_t workspace_bytes, void* stream);
 int hulc_conv2d_bf16_wgrad(const void* x, const void* dy, float* dw, float beta, float* db, int N, int CIN, int H, int W, int COUT, int KS, int S,
                            float* workspace, size_t workspace_bytes, void* stream);
+
+/* SpatialSoftmax (vision_network.py:100-108) on a bf16 channels-last map; dx (bf16) is gated by x > 0 when relu_gate (the conv's ReLU). */
+int hulc_spatial_softmax_nhwc_bf16_fwd(const void* x, float* out, int N, int C, int H, int W, float inv_temp, void* stream);
+int hulc_spatial_softmax_nhwc_bf16_bwd(const void* x, const float* dout, void* dx, int N, int C, int H, int W, float inv_temp, int relu_gate, void* stream);
 
 /* ---- optimizer: torch.optim.Adam(lr, betas, eps), no weight decay (hulc/models/hulc.py:239-252) over a flat buffer ---------
  * g is multiplied by grad_scale first (1/world after the all-reduce); `step` is the 1-based step count, read from the device

@@ -59,7 +59,7 @@ def test_bf16_plumbing_on_the_emulator(emu, monkeypatch, model, rnn_model, p):
 
     def init(self, *a, **kw):
         orig_init(self, *a, **kw)
-        self.tc = False  # the tensor-core convolutions / persistent recurrence do not exist on the emulator: SIMT convs, per-step products
+        self.tc = self.bf16_conv = False  # the tensor-core convolutions / persistent recurrence do not exist on the emulator: SIMT convs, per-step products
 
     monkeypatch.setattr(engine.HulcEngine, "__init__", init)
     res = run_pair(model, rnn_model, B=2, S=4, p=p, device="cpu", hw=(64, 44), precision="bf16", use_idx=True)
