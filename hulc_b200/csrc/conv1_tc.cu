@@ -260,9 +260,12 @@ constexpr int kWgGroups = 7;                    // builder warps: 6 groups of Xc
 // the im2col matrix, so accumulator row 192 is sum_pixels dY = the BIAS gradient, for free), 7 = dY^T
 constexpr int kWgOnes = 6, kWgDy = 7;
 constexpr int kWgSlotB = 8 * kWgGroupB;         // 56 KB
-constexpr int kWgSlots = 3;
-constexpr int kWgBandB = 19 * 1024;             // 8 input rows x 3 channels x W floats (W <= 202)
-constexpr int kWgBands = 3;
+constexpr int kWgSlots = 2;                     // tiles being built / multiplied
+constexpr int kWgXB = 19 * 1024;                // 8 input rows x 3 channels x W floats (W <= 202)
+constexpr int kWgDyStageB = kWgKR * kRowBytes;  // the tile's dY row, fetched by the same bulk-copy thread (fp32: 128 B per pixel, bf16: 64)
+constexpr int kWgBandB = kWgXB + kWgDyStageB;   // 26 KB
+constexpr int kWgBands = 4;                     // bands in flight: the loader runs up to four tiles ahead of the builders, so no builder
+                                                // ever waits on a global-memory round trip (the dY warp used to: one per tile)
 constexpr int kWgSmem = kWgSlots * kWgSlotB + kWgBands * kWgBandB + 256 + 1024;
 static_assert(kWgSmem <= 227 * 1024, "shared memory budget");
 // warps: 0-3 epilogue (end of kernel only) | 4-5 MMA issuers | 6 band loader | 7-13 builders
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
     }
     for (int s = 0; s < kWgBands; ++s) {
       mbar_init(&bars->band_full[s], 1);
-      mbar_init(&bars->band_empty[s], kWgGroups - 1);
+      mbar_init(&bars->band_empty[s], kWgGroups);
     }
     mbar_init(&bars->done, 2);
     fence_barrier_init();
@@ -376,10 +379,12 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
         const int slot = it % kWgBands;
         mbar_wait(&bars->band_empty[slot], ((it / kWgBands) & 1) ^ 1);
         const int n = tile / p.HO, y = tile - n * p.HO;
-        expect_tx(&bars->band_full[slot], 3 * 8 * rowbytes);
+        const uint32_t dy_bytes = (uint32_t)p.WO * kCout * (p.dy_bf16 ? 2u : 4u);
+        expect_tx(&bars->band_full[slot], 3 * 8 * rowbytes + dy_bytes);
         const uint32_t dst = smem_u32(band_smem) + slot * kWgBandB;
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci) bulk_load(dst + (uint32_t)(ci * 8) * rowbytes, p.x + ((size_t)(n * 3 + ci) * p.H + 4 * y) * p.W, 8 * rowbytes, &bars->band_full[slot]);
+        bulk_load(dst + kWgXB, reinterpret_cast<const unsigned char*>(p.dy) + ((size_t)(n * p.HO + y) * p.WO) * kCout * (p.dy_bf16 ? 2 : 4), dy_bytes, &bars->band_full[slot]);
       }
     }
   } else {
@@ -395,33 +400,30 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
       mbar_wait(&bars->empty[slot], ((it / kWgSlots) & 1) ^ 1);
       constexpr int kIters = kWgKR * 8 / 32;  // 14 chunks per lane at most; all loads are issued before the first store
       float4 v[kIters];
+      mbar_wait(&bars->band_full[bslot], (it / kWgBands) & 1);
+      const uint32_t band = smem_u32(band_smem) + bslot * kWgBandB;
       if (g < 6) {
-        mbar_wait(&bars->band_full[bslot], (it / kWgBands) & 1);
-        const uint32_t band = smem_u32(band_smem) + bslot * kWgBandB;
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
           const int q = lane + 32 * i, xx = q >> 3, c = q & 7;
           const int pr = g * 4 + (c >> 1), ci = pr >> 3, ky = pr & 7;  // (ci, ky) pair of this chunk; kx half = c & 1
           if (q < nchunks) v[i] = ld_shared16(band + (uint32_t)(ci * 8 + ky) * rowbytes + (uint32_t)((xx * 4 + (c & 1) * 4) * 4));
         }
+      } else if (p.dy_bf16) {  // the staged dY row: chunk q = four bf16 = 8 bytes -> four fp32 (a 16-bit shift)
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) {
+          const int q = lane + 32 * i;
+          if (q < nchunks) {
+            uint32_t lo, hi;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(band + kWgXB + (uint32_t)q * 8u));
+            v[i] = make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xFFFF0000u), __uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+          }
+        }
       } else {
-        if (p.dy_bf16) {
-          const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(p.dy) + ((size_t)(n * p.HO + y) * p.WO) * (kCout * 2));
 #pragma unroll
-          for (int i = 0; i < kIters; ++i) {
-            const int q = lane + 32 * i;
-            if (q < nchunks) {  // four bf16 = 8 bytes -> four fp32 (a 16-bit shift)
-              const uint2 t = __ldg(src + q);
-              v[i] = make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xFFFF0000u), __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xFFFF0000u));
-            }
-          }
-        } else {
-          const float* src = p.dy + ((size_t)(n * p.HO + y) * p.WO) * kCout;
-#pragma unroll
-          for (int i = 0; i < kIters; ++i) {
-            const int q = lane + 32 * i;
-            if (q < nchunks) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)q * 4));  // rows of 32 floats are contiguous: chunk q is at q * 16 B
-          }
+        for (int i = 0; i < kIters; ++i) {
+          const int q = lane + 32 * i;
+          if (q < nchunks) v[i] = ld_shared16(band + kWgXB + (uint32_t)q * 16u);  // rows of 32 floats are contiguous: chunk q is at q * 16 B
         }
       }
 #pragma unroll
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&bars->full[slot]);
-        if (g < 6) mbar_arrive(&bars->band_empty[bslot]);
+        mbar_arrive(&bars->band_empty[bslot]);
       }
     }
   }
@@ -699,7 +701,7 @@ int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y
 int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int want_bias, int N, int H, int W, int* ctas_out,
                                    cudaStream_t st, int dy_bf16) {
   const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
-  if (HO <= 0 || WO <= 0 || WO > kWgKR || (W & 3) || (size_t)3 * 8 * W * 4 > (size_t)kWgBandB) return (int)cudaErrorNotSupported;
+  if (HO <= 0 || WO <= 0 || WO > kWgKR || (W & 3) || (size_t)3 * 8 * W * 4 > (size_t)kWgXB) return (int)cudaErrorNotSupported;
   if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(partial)) & 15) return (int)cudaErrorNotSupported;
   const long long tiles = (long long)N * HO;
   if (tiles >= (1ll << 31) || (long long)N * 3 * H * W >= (1ll << 31)) return (int)cudaErrorNotSupported;

@@ -12,14 +12,17 @@
 //     rounds it to tf32 (round-to-nearest; the tensor core itself would truncate) and keeps it in shared memory (128 KB)
 //     in the UMMA operand layout for all S steps;
 //   * per step sixteen producer warps — one per 32-wide k-block — each wait for the ONE feature tile of the previous step their
-//     k-block comes from (per-tile arrival counters in global memory, release / acquire: no grid barrier), fetch their B x 32
-//     piece of the previous hidden state (ld.global.cg, every load in flight at once), round it to tf32 and store it into the
-//     swizzled A tile; one thread issues 64 tcgen05.mma (kind::tf32, M = 64 batch rows, N = 64, fp32 accumulator in TMEM) with two
+//     k-block comes from and fetch their B x 32 piece of the previous hidden state in ONE round trip: the output slots of all S steps
+//     are pre-filled with a sentinel bit pattern (0xFFFFFFFF, a NaN no arithmetic produces) and a producer simply re-reads its 16-byte
+//     pieces (ld.relaxed.gpu, every load in flight at once) until none of their words is the sentinel — the data is its own flag, so
+//     there is no release fence, no arrival counter and no second dependent load (flag, then data) on the critical path; it rounds the
+//     values to tf32 and stores them into the swizzled A tile; one thread issues 64 tcgen05.mma (kind::tf32, M = 64 batch rows, N = 64, fp32 accumulator in TMEM) with two
 //     barrier waits and three commits per step; the CTA parks its partial tile in shared memory and after ONE cluster barrier
 //     each CTA sums the four partials of its quarter of the rows through distributed shared memory in a fixed order, applies
-//     the epilogue (addend and gate prefetched while the MMAs run), writes h_t and publishes it with a release increment.
-// Measured (scripts/dbg_rnn_trace.py): 10.3 us per step — flag propagation 2.6, L2 load 1.1, stage + MMA 4.4, reduce + store +
-// release 2.2 — against 25 us (forward, 3xTF32) / 17 us (backward) for the same step as a split-K cluster GEMM launch.
+//     the epilogue (addend and gate prefetched while the MMAs run) and writes h_t with relaxed gpu-scope stores.
+// Measured with arrival counters (release increment per CTA, acquire poll, then the loads): 10.3 us per step — flag propagation 2.6,
+// L2 load 1.1, stage + MMA 4.4, reduce + store + release 2.2 — against 25 us (forward, 3xTF32) / 17 us (backward) for the same step as a
+// split-K cluster GEMM launch; the data-as-flag hand-off removes the flag propagation and the release.
 // A single tf32 pass with round-to-nearest on both operands keeps the action logits within 0.3 of the parity tolerance
 // (rtol 1e-3 / atol 1e-4) over the 32-step chain; accumulation, addend and activation are fp32.
 #include "common.cuh"
@@ -52,8 +55,8 @@ struct RnnParams {
   const float* add; long long add_step; int ldadd;
   const float* gate; long long gate_step; int ldg;
   int act, B, S;
-  unsigned* flags;  // [kH / kFT] arrival counters, zero on entry
 };
+constexpr unsigned kSentinel = 0xFFFFFFFFu;  // "not written yet" (see the header); hulc_rnn_tc_seq fills every output slot with it before the launch
 
 struct Bars {
   uint64_t full[2];   // k-blocks 0..7 / 8..15 of the step staged (8 producer warps each)
@@ -74,13 +77,13 @@ __device__ __forceinline__ void rtrace(int, int) {}
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_relaxed16(const float* p) {  // gpu-scope relaxed: served by L2, never by a stale L1 line
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed16(float* p, float a, float b, float c, float d) {
+  asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ float4 rna4(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
 __device__ __forceinline__ void st_shared16(uint32_t addr, float4 v) {
@@ -226,16 +229,11 @@ __global__ void __launch_bounds__(kThreads, 1) rnn_seq_kernel(RnnParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = (p.act & 4) ? o[j] * (1.f - g[j] * g[j]) : (g[j] > 0.f ? o[j] : 0.f);
           }
-          *reinterpret_cast<float4*>(out + (size_t)row * p.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
+          // the values are their own "ready" flag for the next step's producers (32-bit words are written atomically)
+          st_relaxed16(out + (size_t)row * p.ldo + col, o[0], o[1], o[2], o[3]);
         }
       }
       if (e == 0) rtrace(s, 9);
-      named_bar(1, kEpiWarps * 32);  // orders the 128 threads' stores before thread 0's release (cumulative)
-      if (e == 0) {
-        rtrace(s, 10);
-        red_release_add(p.flags + tile, 1u);  // this CTA's quarter of (step s, tile) is published
-        rtrace(s, 11);
-      }
     }
   } else if (warp == kEpiWarps) {
     // ================================ MMA issuer ================================
@@ -274,31 +272,42 @@ __global__ void __launch_bounds__(kThreads, 1) rnn_seq_kernel(RnnParams p) {
     const int stage = kb & (kAStages - 1);
     const int r0 = lane >> 3, c = lane & 7;  // rows r0 + 4 i (i = 0..15), 16-byte chunk c
     const uint32_t dst = smem_u32(a_smem) + stage * kAStageBytes;
-    // the 32 columns of this k-block are outputs of ONE feature tile of the previous step
-    const unsigned* flag = p.flags + (k0 + kb * kBK) / kFT;
     for (int s = 0; s < p.S; ++s) {
       cluster_arrive();
       if (kb == 0 && lane == 0) rtrace(s, 0);
-      if (s > 0) {  // wait until that tile has published step s-1 (4 arrivals per step)
-        if (lane == 0) {
-          const unsigned need = (unsigned)(kCl * s);
-          for (unsigned spins = 0; ld_acquire(flag) < need; ++spins)
-            if (spins > (1u << 23)) __trap();  // a protocol bug must surface as a launch failure, never as a hung GPU
-        }
-        __syncwarp();
-        if (kb == 0 && lane == 0) rtrace(s, 1);
-      }
+      // this lane's 16 pieces of the previous step's output (step 0: the initial state): re-read until every word has been written
       const float* src = p.prev + s * p.prev_step + k0 + kb * kBK + c * 4;
-      float4 v[16];
+      uint4 u[16];
+      unsigned pending = 0u;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int row = r0 + 4 * i;
-#ifdef HULC_RNN_TRACE
-        v[i] = (row < p.B && !(p.act & 64)) ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)row * p.ldp)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-        v[i] = row < p.B ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)row * p.ldp)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
+        u[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + 4 * i < p.B) pending |= 1u << i;
       }
+#ifdef HULC_RNN_TRACE
+      if (p.act & 64) pending = 0u;
+#endif
+      // (1) cheap wait: every lane re-reads only its FIRST piece (rows 0..3 of the block: one row from each of the four CTAs that write this
+      //     feature tile) until it has been written — 512 bytes per warp and round, not the whole 8 KB block;
+      // (2) then all 16 pieces, every load in flight at once; any word still holding the sentinel sends that piece round again (rare).
+      if (pending & 1u) {
+        for (unsigned spins = 0;; ++spins) {
+          u[0] = ld_relaxed16(src + (size_t)r0 * p.ldp);
+          const bool ok = u[0].x != kSentinel && u[0].y != kSentinel && u[0].z != kSentinel && u[0].w != kSentinel;
+          if (__all_sync(__activemask(), ok)) break;
+          if (spins > (1u << 22)) __trap();  // a protocol bug (or a genuine 0xFFFFFFFF NaN in the state) must surface as a launch failure, never as a hung GPU
+        }
+      }
+      for (unsigned spins = 0; __any_sync(0xffffffffu, pending != 0u); ++spins) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if ((pending >> i) & 1u) u[i] = ld_relaxed16(src + (size_t)(r0 + 4 * i) * p.ldp);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (u[i].x != kSentinel && u[i].y != kSentinel && u[i].z != kSentinel && u[i].w != kSentinel) pending &= ~(1u << i);
+        if (spins > (1u << 22)) __trap();
+      }
+      if (kb == 0 && lane == 0) rtrace(s, 1);
       // stage w is shared by warps w (first half of the step) and w + 8 (second half): the second user waits until the MMAs of
       // the first half have read it; the first user needs no wait — the cluster barrier that ended the previous step is
       // only passed once every MMA of that step has completed
@@ -306,7 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) rnn_seq_kernel(RnnParams p) {
       if (kb == 0 && lane == 0) rtrace(s, 2);
       if (lane == 0) rtrace(s, 48 + kb);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) st_shared16(dst + swz(r0 + 4 * i, c), rna4(v[i]));
+      for (int i = 0; i < 16; ++i)
+        st_shared16(dst + swz(r0 + 4 * i, c), rna4(make_float4(__uint_as_float(u[i].x), __uint_as_float(u[i].y), __uint_as_float(u[i].z), __uint_as_float(u[i].w))));
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->full[kb >> 3]);
@@ -324,6 +334,16 @@ __global__ void __launch_bounds__(kThreads, 1) rnn_seq_kernel(RnnParams p) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_d, 64);
   }
+}
+
+// every output slot (S steps x B rows x kH columns) := the sentinel
+__global__ void fill_sentinel_kernel(float* out0, long long out_step, int ldo, int B, int S) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (int)(i % (kH / 4));
+  const long long rs = i / (kH / 4);
+  const int row = (int)(rs % B), s = (int)(rs / B);
+  if (s >= S) return;
+  *reinterpret_cast<uint4*>(out0 + s * out_step + (long long)row * ldo + q * 4) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
 }
 
 template <bool TRANSW>
@@ -382,11 +402,12 @@ HULC_API int hulc_rnn_tc_seq(const float* W, int ldw, int transW, const float* p
     max_clusters = n;
   }
   if (max_clusters < kH / kFT) return (int)cudaErrorLaunchOutOfResources;
-  unsigned* flags = reinterpret_cast<unsigned*>(workspace + 1024);
-  HULC_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (kH / kFT), st));
+  // the hand-off between steps is by address: step s reads what step s - 1 wrote
+  if (S > 1 && (prev0 + prev_step != out0 || prev_step != out_step || ldp != ldo)) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(fill_sentinel_kernel, dim3(hulc_cdiv((long long)S * B * (kH / 4), 256)), dim3(256), 0, st, out0, out_step, ldo, B, S);
   RnnParams p;
   p.W = W; p.ldw = ldw; p.prev = prev0; p.prev_step = prev_step; p.ldp = ldp; p.out = out0; p.out_step = out_step; p.ldo = ldo;
   p.add = add0; p.add_step = add_step; p.ldadd = ldadd; p.gate = gate0; p.gate_step = gate_step; p.ldg = ldg;
-  p.act = act; p.B = B; p.S = S; p.flags = flags;
+  p.act = act; p.B = B; p.S = S;
   return transW ? launch_seq<true>(p, st) : launch_seq<false>(p, st);
 }

@@ -636,6 +636,36 @@ __global__ void frames_u8_tail_kernel(const unsigned char* __restrict__ src, flo
   long long i = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (((float)src[i] / 255.0f) - mean) / stdv;
 }
+// RandomShiftsAug (hulc/utils/transforms.py:8-29) + scale + normalise in one pass: the reference pads the frame by `pad` replicated pixels and
+// samples it on a grid displaced by an integer number of pixels (sx, sy) in [0, 2 pad] drawn per frame — i.e. out[y][x] = in[clamp(y + sy - pad)]
+// [clamp(x + sx - pad)].  shifts: [N][2] = (sx, sy) injected, or NULL: drawn from Philox(seed, site, frame).  4 pixels of a row per thread.
+__global__ void frames_u8_shift_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int N, int C, int H, int W, int pad,
+                                       const int* __restrict__ shifts, unsigned long long seed, const unsigned long long* seed_ptr, unsigned site, float mean,
+                                       float stdv) {
+  const int Wq = (W + 3) / 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * C * H * Wq) return;
+  const int xq = (int)(i % Wq);
+  const long long r = i / Wq;
+  const int y = (int)(r % H);
+  const long long nc = r / H;
+  const int n = (int)(nc / C);
+  int sx, sy;
+  if (shifts) {
+    sx = shifts[2 * n]; sy = shifts[2 * n + 1];
+  } else {  // torch.randint(0, 2 pad + 1): uniform integers, two per frame
+    const uint4 rnd = philox4x32(rng_seed(seed, seed_ptr), site, (unsigned long long)n);
+    sx = (int)(rnd.x % (unsigned)(2 * pad + 1)); sy = (int)(rnd.y % (unsigned)(2 * pad + 1));
+  }
+  const int cy = min(max(y + sy - pad, 0), H - 1);
+  const unsigned char* row = src + ((size_t)nc * H + cy) * W;
+  float* out = dst + ((size_t)nc * H + y) * W + xq * 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int x = xq * 4 + e;
+    if (x < W) out[e] = (((float)row[min(max(x + sx - pad, 0), W - 1)] / 255.0f) - mean) / stdv;
+  }
+}
 
 }  // namespace
 
@@ -646,6 +676,16 @@ HULC_API int hulc_frames_u8_to_f32(const unsigned char* src, float* dst, long lo
   long long n16 = ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(dst)) & 15) ? 0 : n / 16;
   if (n16 > 0) HULC_LAUNCH(frames_u8_kernel, dim3(hulc_cdiv(n16, 256)), dim3(256), 0, st, reinterpret_cast<const uint4*>(src), reinterpret_cast<float4*>(dst), n16, mean, stdv);
   if (n16 * 16 < n) HULC_LAUNCH(frames_u8_tail_kernel, dim3(hulc_cdiv(n - n16 * 16, 256)), dim3(256), 0, st, src, dst, n16 * 16, n, mean, stdv);
+  HULC_RETURN_LAST();
+}
+
+HULC_API int hulc_frames_u8_shift_to_f32(const unsigned char* src, float* dst, int N, int C, int H, int W, int pad, const int* shifts, unsigned long long seed,
+                                         unsigned site, float mean, float stdv, void* stream) {
+  if (N <= 0) return 0;
+  if (!src || !dst || stdv == 0.f || pad < 0) return (int)cudaErrorInvalidValue;
+  const long long n = (long long)N * C * H * ((W + 3) / 4);
+  HULC_LAUNCH(frames_u8_shift_kernel, dim3(hulc_cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, src, dst, N, C, H, W, pad, shifts, seed, g_hulc_rng_offset_ptr, site, mean,
+              stdv);
   HULC_RETURN_LAST();
 }
 

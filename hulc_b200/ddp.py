@@ -46,6 +46,23 @@ class FlatGradientSync:
         self._work = dist.all_reduce(self.engine.ps.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         return self._work
 
+    def sync_head(self):
+        """Overlapped variant, part 1: start the all-reduce of everything behind the perceptual encoders' gradients (97 % of the bytes; final
+        once the decoder / prior / posterior / goal-encoder backward is done, see HulcEngine.capture_split).  NCCL runs on its own stream,
+        ordered after the work already queued on the current stream, so the encoders' backward that follows overlaps it."""
+        if self.world == 1:
+            return None
+        split = self.engine.encoder_grad_split()
+        self._work = dist.all_reduce(self.engine.ps.grad[split:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return self._work
+
+    def sync_tail(self):
+        """Part 2, after the encoders' backward: the remaining (small) slice."""
+        if self.world == 1:
+            return None
+        split = self.engine.encoder_grad_split()
+        dist.all_reduce(self.engine.ps.grad[:split], op=dist.ReduceOp.SUM, group=self.group)
+
     def step(self, lr: Optional[float] = None):
         """Adam on the averaged gradient: waits for an outstanding async all-reduce first."""
         if self._work is not None:

@@ -180,6 +180,8 @@ class HulcEngine:
         self._twins: Dict[tuple, list] = {}     # (ptr, shape, strides) of an fp32 tensor -> [bf16 twin, generation it is valid for, byte range]
         self._twin_gen = 0
         self._bias_jobs: list = []
+        self.augment_pad: Dict[str, int] = {}   # camera -> RandomShiftsAug pad (set_augmentation); empty: no device-side augmentation
+        self._aug_ctx = None
         self._bf16_only: set = set()            # keys whose fp32 storage was never written this step (the producer emitted bf16 only)
         self.dropout_p = float(dims.dropout_p) if model != "mcil" else 0.0
         self.kl_beta, self.kl_alpha, self.clip_beta, self.gripper_alpha = float(kl_beta), float(kl_balancing_mix), float(clip_beta), float(dims.gripper_alpha)
@@ -377,6 +379,9 @@ class HulcEngine:
     def bias_grad(self, dy, gb):
         """gb += column sums of dy (the bias gradient of a Linear / conv layer).  Deferred: all of a backward pass's bias gradients are summed
         by ONE launch at its end (`_flush_bias_grads`; every dy lives in its own persistent buffer until then)."""
+        if dy.shape[0] > 16384:  # (conv maps of the fp32-activation path: ~10^6 rows) — the row-split, ticketed reduction, right away
+            colsum(dy, gb, beta=1.0)
+            return
         self._bias_jobs.append((dy, gb, 1.0))
 
     def _flush_bias_grads(self):
@@ -424,14 +429,31 @@ class HulcEngine:
     # ------------------------------------------------------------------------------------------------------------------
     _CONVS = ((0, 4), (2, 2), (4, 1))
 
+    def set_augmentation(self, static_pad: int = 10, gripper_pad: int = 4):
+        """Apply the reference's training-time RandomShiftsAug (conf/datamodule/transforms/rand_shift.yaml:2-22: pad 10 / 4) on the device to
+        uint8 frames of TRAINING steps, fused with their scale + normalise pass.  0 disables it for a camera.  Validation / inference never shift."""
+        self.augment_pad = {"static": int(static_pad), "gripper": int(gripper_pad)}
+
     def _normalised_frames(self, which, frames: List[torch.Tensor]) -> List[torch.Tensor]:
         """uint8 frames (as read from disk) are scaled / normalised on the device into a persistent fp32 buffer — the
-        deterministic part of the reference's image transforms (conf/datamodule/transforms/rand_shift.yaml:3-22); fp32
-        frames (the reference's batch contract) pass through untouched."""
+        deterministic part of the reference's image transforms (conf/datamodule/transforms/rand_shift.yaml:3-22) and, in training steps
+        with `set_augmentation`, its RandomShiftsAug (one random whole-pixel shift per frame); fp32 frames (the reference's batch contract)
+        pass through untouched."""
         out = []
+        aug = self._aug_ctx
+        pad = self.augment_pad.get(which, 0) if aug is not None else 0
+        n0 = 0
         for i, f in enumerate(frames):
             if f.dtype == torch.uint8:
-                f = ops.frames_u8_to_f32(f.contiguous(), self.buf(f"{which}.frames{i}", *f.shape))
+                dst = self.buf(f"{which}.frames{i}", *f.shape)
+                if pad > 0:
+                    sh = aug["shifts"].get(which) if aug["shifts"] is not None else None
+                    ops.frames_u8_shift_to_f32(f.contiguous(), dst, pad, shifts=None if sh is None else sh[n0 : n0 + f.shape[0]].contiguous(), seed=aug["seed"],
+                                               site=400 + 2 * i + (which == "gripper"))
+                    f = dst
+                else:
+                    f = ops.frames_u8_to_f32(f.contiguous(), dst)
+            n0 += f.shape[0]
             out.append(f)
         return out
 
@@ -748,7 +770,8 @@ class HulcEngine:
 
     def _step(self, batch: Dict[str, Dict], *, plan_idx=None, plan_u=None, plan_eps=None, dropout_masks=None, seed: Optional[int] = None,
               backward: bool = True, plan_from: str = "posterior", emb_override: Optional[torch.Tensor] = None,
-              goal_override: Optional[torch.Tensor] = None, with_clip: bool = True) -> Dict[str, torch.Tensor]:
+              goal_override: Optional[torch.Tensor] = None, with_clip: bool = True, defer_encoder_bwd: bool = False,
+              aug_shifts: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """One fused forward(+backward) over `batch` (the reference's {"vis": ..., "lang": ...} contract).  Gradients of
         total_loss land in `self.ps.grad` (zeroed first).  Randomness: `plan_idx[m]` / `plan_u[m]` / `plan_eps[m]` and
         `dropout_masks` (dict site -> uint8 keep mask over the whole batch, modalities concatenated in batch order)
@@ -789,6 +812,8 @@ class HulcEngine:
 
         if backward:
             ps.zero_grad()
+        # device-side RandomShiftsAug: training steps only; aug_shifts = {"static" | "gripper": [frames, 2] int32 (sx, sy)} injects the draws
+        self._aug_ctx = dict(shifts=aug_shifts, seed=seed) if (backward and self.augment_pad) else None
         losses = self.buf("losses", 16, zero=True)  # per modality m: [4m] nll, [4m+1] ce, [4m+2] kl, [4m+3] clip
         losses.zero_()  # slots of a modality order / count seen on an earlier step must not leak into this step's totals
         lview = lambda i: losses[i : i + 1]
@@ -1061,14 +1086,34 @@ class HulcEngine:
             else:
                 self._mlp_ln_bwd(f"goal.{m}", acts, stats, names, ln, dgoal[b0 : b0 + Bm], demb3[b0 : b0 + Bm, S - 1, :], dx_beta=1.0)
 
+        if defer_encoder_bwd:
+            # data-parallel overlap: everything but the perceptual encoders' gradients (97 % of the gradient bytes) is final here — the
+            # caller starts their all-reduce, then runs `finish_backward()` (the conv stack's backward) underneath it
+            self._flush_bias_grads()
+            self._tail = (ctx_s, ctx_g, demb)
+            _mark(None)
+            return out
+        self._tail = (ctx_s, ctx_g, demb)
+        self.finish_backward()
+        return out
+
+    @torch.no_grad()
+    def finish_backward(self):
+        """Backward of the perceptual encoders (the last block of the step; see `defer_encoder_bwd`)."""
+        ctx_s, ctx_g, demb = self._tail
+        self._tail = None
         _mark("bwd/perceptual_encoders")
-        # perceptual encoders
         self._encoder_bwd("static", ctx_s, demb)
         self._encoder_bwd("gripper", ctx_g, demb)
         _mark("bwd/bias_gradients")
         self._flush_bias_grads()
         _mark(None)
-        return out
+
+    def encoder_grad_split(self) -> int:
+        """Element offset in the flat gradient buffer below which the perceptual encoders' gradients (and `logit_scale`) live: the layout
+        is the reference's registration order, encoders first."""
+        first = next(k for k in self.ps.keys if not (k.startswith("perceptual_encoder.") or k == "logit_scale"))
+        return self.ps.offsets[first][0]
 
     # ------------------------------------------------------------------------------------------------------------------
     # posterior: transformer (plan_recognition_net.py:94-117)
@@ -1462,6 +1507,25 @@ class HulcEngine:
         if optimizer:
             self.ps.step_count -= 1  # the capture itself did not execute the update
         return StepGraph(self, g, out, optimizer, ops.launch_count() - n0, namespace=("train", self.batch_signature(batch)))
+
+    def capture_split(self, batch):
+        """Two graphs for data-parallel training: (1) forward + the backward of everything but the perceptual encoders, (2) the encoders'
+        backward.  Between the two replays the caller launches the all-reduce of the already-final part of the gradient
+        (`encoder_grad_split()` onwards), which then overlaps the conv stack's backward (hulc_b200.ddp.FlatGradientSync)."""
+        seed0 = self.rng_dev.clone()
+        self.step(batch)
+        self.rng_dev.copy_(seed0)
+        torch.cuda.synchronize(self.device)
+        ns = ("train", self.batch_signature(batch))
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g1):
+            out = self.step(batch, defer_encoder_bwd=True)
+        n1 = ops.launch_count()
+        with torch.cuda.graph(g2):
+            with self._buffers(ns):
+                self.finish_backward()
+        return StepGraph(self, g1, out, False, n1 - n0, namespace=ns), StepGraph(self, g2, out, False, ops.launch_count() - n1, namespace=ns)
 
     def check_nan_flag(self):
         """The reference asserts on NaNs inside world_to_tcp_frame every step (gripper_control.py:35), which stalls the

@@ -563,6 +563,11 @@ class Hulc(_Base):
         self.rollout_step_counter += 1
         return action
 
+    def enable_device_augmentation(self, static_pad: int = 10, gripper_pad: int = 4):
+        """Run the training transforms of conf/datamodule/transforms/rand_shift.yaml on the device for uint8 frames: RandomShiftsAug (pad 10 / 4)
+        fused with scale + normalise — the datamodule then only has to hand over the stored uint8 frames."""
+        self.engine.set_augmentation(static_pad, gripper_pad)
+
     def enable_cuda_graph_inference(self, flag: bool = True):
         """Replay `step`'s per-control-step work (encoders, one decoder step, sampling, frame change) from one CUDA graph."""
         self.engine.enable_infer_graph(flag)

@@ -528,6 +528,17 @@ def frames_u8_to_f32(src, dst, mean=0.5, std=0.5):
     return dst
 
 
+def frames_u8_shift_to_f32(src, dst, pad, shifts=None, seed=0, site=0, mean=0.5, std=0.5):
+    """RandomShiftsAug + scale + normalise of uint8 frames [N, C, H, W] (hulc_frames_u8_shift_to_f32); shifts [N, 2] int32 (sx, sy) or Philox."""
+    _chk(src, dtype=torch.uint8)
+    _chk(dst)
+    _chk(shifts, dtype=torch.int32)
+    N, C, H, W = src.shape
+    assert src.is_contiguous() and dst.is_contiguous() and tuple(dst.shape) == (N, C, H, W) and (shifts is None or tuple(shifts.shape) == (N, 2))
+    _L().hulc_frames_u8_shift_to_f32(_ptr(src), _ptr(dst), N, C, H, W, int(pad), _ptr(shifts), int(seed), int(site), float(mean), float(std), _stream())
+    return dst
+
+
 def scale_(x, alpha):
     _chk(x)
     assert x.is_contiguous()

@@ -172,6 +172,12 @@ int hulc_scale_dev(float* x, long long n, const float* alpha_ptr, void* stream);
  * Normalize(0.5, 0.5), conf/datamodule/transforms/rand_shift.yaml:3-22; hulc/utils/transforms.py:8-29) — lets the host hand over the
  * uint8 frames it read from disk (4x fewer PCIe bytes).  The random-shift augmentation stays with the data pipeline. */
 int hulc_frames_u8_to_f32(const unsigned char* src, float* dst, long long n, float mean, float stdv, void* stream);
+/* The training-time image pipeline of the reference on the device (conf/datamodule/transforms/rand_shift.yaml:2-22): RandomShiftsAug
+ * (hulc/utils/transforms.py:8-29: replicate-pad by `pad`, shift by (sx, sy) in [0, 2 pad] whole pixels per frame) fused with the scale +
+ * normalise of hulc_frames_u8_to_f32.  src uint8 [N][C][H][W] -> dst fp32 [N][C][H][W]; shifts [N][2] (sx, sy) int32 on the device, or NULL to
+ * draw them from the Philox stream (seed, site) — one pair per frame, like torch.randint in the reference. */
+int hulc_frames_u8_shift_to_f32(const unsigned char* src, float* dst, int N, int C, int H, int W, int pad, const int* shifts, unsigned long long seed,
+                                unsigned site, float mean, float stdv, void* stream);
 
 /* ---- world_to_tcp_frame (decoders/utils/gripper_control.py:16-36) ----------------------------------------------------------
  * actions [n,7], robot_obs [n,obs_dim] (euler XYZ at 3:6) -> out [n,7].  *nan_flag is OR-ed with 1 if any output is NaN

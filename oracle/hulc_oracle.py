@@ -420,6 +420,20 @@ def clip_loss(sd: SD, seq_feat: torch.Tensor, goal: torch.Tensor, mask: Optional
     return loss * 0 if skip else loss
 
 
+def random_shifts_aug(frames_u8: torch.Tensor, shifts: torch.Tensor, pad: int, mean: float = 0.5, std: float = 0.5) -> torch.Tensor:
+    """The training-time image pipeline of conf/datamodule/transforms/rand_shift.yaml:2-22 on uint8 frames [N, C, H, W]: RandomShiftsAug
+    (hulc/utils/transforms.py:8-29) -> ScaleImageTensor (/255) -> Normalize(mean, std).  The reference replicate-pads by `pad` and bilinearly
+    samples a grid displaced by shifts[n] = (sx, sy) whole pixels of the PADDED image (align_corners=False puts every sample on a pixel
+    centre), i.e. it crops the padded frame at offset (sy, sx): out[y][x] = in[clamp(y + sy - pad)][clamp(x + sx - pad)]."""
+    N, C, H, W = frames_u8.shape
+    ys = (torch.arange(H).view(1, H) + shifts[:, 1].view(N, 1) - pad).clamp(0, H - 1)  # [N, H]
+    xs = (torch.arange(W).view(1, W) + shifts[:, 0].view(N, 1) - pad).clamp(0, W - 1)  # [N, W]
+    x = frames_u8.float()
+    x = torch.gather(x, 2, ys.view(N, 1, H, 1).expand(N, C, H, W))
+    x = torch.gather(x, 3, xs.view(N, 1, 1, W).expand(N, C, H, W))
+    return ((x / 255.0) - mean) / std
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # the training step
 # ----------------------------------------------------------------------------------------------------------------------

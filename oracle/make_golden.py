@@ -471,7 +471,36 @@ def run_infer_case(name):
     print(f"[golden] {name}: {T} steps, {len(plans)} plans, |a|max={float(actions.abs().max()):.3f}  ({time.time() - t0:.1f}s)")
 
 
+def run_aug_case(name="aug_random_shifts"):
+    """RandomShiftsAug of the UNMODIFIED reference (hulc/utils/transforms.py:8-29; drawn shifts injected through a patched torch.randint), followed
+    by the yaml's ScaleImageTensor + Normalize(0.5, 0.5), on seeded uint8 frames of both cameras; pins oracle.random_shifts_aug (an exact crop of
+    the replicate-padded frame; the reference's bilinear grid_sample lands within 6e-5 of it) and writes a sub-sampled fixture."""
+    from hulc.utils.transforms import RandomShiftsAug
+
+    fx = {}
+    for cam, (h, pad, n) in {"static": (200, 10, 3), "gripper": (84, 4, 4)}.items():
+        g = torch.Generator().manual_seed(17 + h)
+        x = torch.randint(0, 256, (n, 3, h, h), generator=g, dtype=torch.uint8)
+        sh = torch.randint(0, 2 * pad + 1, (n, 2), generator=g)
+        orig = torch.randint
+        torch.randint = lambda *a, **k: sh.view(n, 1, 1, 2).to(k.get("dtype", torch.float32))
+        try:
+            ref = RandomShiftsAug(pad)(x)
+        finally:
+            torch.randint = orig
+        ref = ((ref / 255.0) - 0.5) / 0.5
+        mine = O.random_shifts_aug(x, sh, pad)
+        err = float((mine - ref).abs().max())
+        assert err < 1e-4, f"{name}/{cam}: oracle != reference ({err:.2e})"
+        fx[f"{cam}_shifts"], fx[f"{cam}_out_sub"] = sh.numpy().astype(np.int32), ref[:, :, ::7, ::5].numpy()
+        print(f"[golden] {name}/{cam}: {n} frames {h}x{h}, pad {pad}: max |oracle - reference| = {err:.2e}")
+    np.savez_compressed(GOLDEN / f"{name}.npz", **fx)
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES) + list(VAL_CASES) + list(INFER_CASES) + list(AUTOCAST_CASES)
+    names = sys.argv[1:] or list(CASES) + list(VAL_CASES) + list(INFER_CASES) + list(AUTOCAST_CASES) + ["aug_random_shifts"]
     for n in names:
+        if n == "aug_random_shifts":
+            run_aug_case(n)
+            continue
         (run_val_case if n in VAL_CASES else run_infer_case if n in INFER_CASES else run_autocast_case if n in AUTOCAST_CASES else run_case)(n)

@@ -38,6 +38,9 @@ def _worker(rank, world, port, emu_path, q):
         class Eng:  # the part of HulcEngine the sync object touches
             lr = 1e-2
 
+            def encoder_grad_split(self):  # chunked variant: [split, end) is reduced first (asynchronously), [0, split) afterwards
+                return self.ps.offsets["logit_scale"][0]
+
         eng = Eng()
         eng.ps = ParamStore(SPEC, "cpu")
         # ranks start from different weights: the broadcast must make them rank 0's
@@ -56,7 +59,11 @@ def _worker(rank, world, port, emu_path, q):
             mine = _grads(rank, step)
             for k in SPEC:
                 eng.ps.g[k].copy_(mine[k])
-            sync.sync(async_op=bool(step & 1))
+            if step == 2:  # the overlapped two-chunk exchange (HulcEngine.capture_split)
+                sync.sync_head()
+                sync.sync_tail()
+            else:
+                sync.sync(async_op=bool(step & 1))
             sync.step()
             allg = [_grads(r, step) for r in range(world)]
             for k in SPEC:
