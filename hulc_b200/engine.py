@@ -395,7 +395,8 @@ class HulcEngine:
         self.bias_grad(dy, G[name + ".bias"])
         if not need_dx:
             return None
-        return self.gemm_bwd(dy, P[name + ".weight"], dx, beta=dx_beta, gate=gate, act=act, addend=addend, drop=drop)
+        # bf16 path: dx usually is the dy of the next layer down (a product operand again): let the epilogue write its bf16 twin too
+        return self.gemm_bwd(dy, P[name + ".weight"], dx, beta=dx_beta, gate=gate, act=act, addend=addend, drop=drop, out="both")
 
     def _mlp_ln_fwd(self, tag, x, names, ln, out, w0=None):
         """x -> [Linear+ReLU]* -> Linear -> LayerNorm written into `out` (a 2-D view).  Saves activations under `tag`.
@@ -1513,10 +1514,12 @@ class HulcEngine:
         backward.  Between the two replays the caller launches the all-reduce of the already-final part of the gradient
         (`encoder_grad_split()` onwards), which then overlaps the conv stack's backward (hulc_b200.ddp.FlatGradientSync)."""
         seed0 = self.rng_dev.clone()
-        self.step(batch)
+        ns = ("train", self.batch_signature(batch))
+        self.step(batch, defer_encoder_bwd=True)  # eager warm-up in the same two parts (buffers, cached job tables of the bias-gradient launches)
+        with self._buffers(ns):
+            self.finish_backward()
         self.rng_dev.copy_(seed0)
         torch.cuda.synchronize(self.device)
-        ns = ("train", self.batch_signature(batch))
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
         with torch.cuda.graph(g1):
