@@ -180,6 +180,8 @@ class HulcEngine:
         self._twins: Dict[tuple, list] = {}     # (ptr, shape, strides) of an fp32 tensor -> [bf16 twin, generation it is valid for, byte range]
         self._twin_gen = 0
         self._bias_jobs: list = []
+        self._side, self._side_dirty = None, False
+        self.overlap_wgrad = os.environ.get("HULC_B200_OVERLAP_WGRAD", "1") != "0"  # Linear weight gradients on a side stream (gemm_wgrad)
         self.augment_pad: Dict[str, int] = {}   # camera -> RandomShiftsAug pad (set_augmentation); empty: no device-side augmentation
         self._aug_ctx = None
         self._bf16_only: set = set()            # keys whose fp32 storage was never written this step (the producer emitted bf16 only)
@@ -280,6 +282,46 @@ class HulcEngine:
         M, K = (A.shape[1], A.shape[0]) if kw.get("transA") else A.shape
         N = B.shape[0] if kw.get("transB") else B.shape[1]
         return gemm(A, B, C, tc=self._tc_mode(M, N, K, "bwd"), **kw)
+
+    def gemm_wgrad(self, dy, x, gw, beta=0.0):
+        """gw = beta * gw + dy^T x — the weight gradient of a Linear layer.  Nothing downstream in the backward chain depends on it, so in the
+        tensor-core modes it is launched on a side stream (a fork inside the captured graph) and runs BESIDE the data-gradient chain, whose
+        products are small and latency-bound; the operands (bf16 twins) are prepared on the main stream first.  `_join_side` re-joins."""
+        M, K, N = dy.shape[1], dy.shape[0], x.shape[1]
+        side = self._side_stream()
+        if side is None:
+            return self.gemm_bwd(dy, x, gw, transA=True, beta=beta)
+        if self.bf16:
+            A16, B16 = self._tw(dy), self._tw(x)
+            if not ops.gemm_bf16_ok(A16, B16):
+                return self.gemm_bwd(dy, x, gw, transA=True, beta=beta)
+        else:
+            mode = self._tc_mode(M, N, K, "bwd")
+            if not mode or not ops._tc_ok(dy, x, M, N, K, True, False):  # the CUDA-core kernel shares the split-K workspace with the main stream
+                return self.gemm_bwd(dy, x, gw, transA=True, beta=beta)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            if self.bf16:
+                ops.gemm_bf16(A16, B16, gw, None, transA=True, beta=beta)
+            else:
+                gemm(dy, x, gw, transA=True, beta=beta, tc=mode)
+        self._side_dirty = True
+        return gw
+
+    def _side_stream(self):
+        if not self.tc or self.device.type != "cuda" or not self.overlap_wgrad:
+            return None
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()  # ("cuda" has no index: compare resolved ones)
+        if self._side is None or self._side.device.index != idx:
+            self._join_side()
+            self._side = torch.cuda.Stream(device=torch.device("cuda", idx))
+        return self._side
+
+    def _join_side(self):
+        """The main stream waits for the weight-gradient products on the side stream (end of a backward pass / before gradients are consumed)."""
+        if self._side_dirty:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_dirty = False
 
     def gemm_rec(self, A, B, C, role, **kw):
         """The per-step products of the recurrences that do not run in the persistent kernel (GRU, windows above 32 steps)."""
@@ -391,7 +433,7 @@ class HulcEngine:
     def _linear_bwd(self, name, x, dy, dx=None, *, gate=None, dx_beta=0.0, need_dx=True, act=0, addend=None, drop=NO_DROP):
         """Gradients of y = x W^T + b: accumulates dW, db; returns dx = dy W (optionally gated by the producer's ReLU)."""
         P, G = self.ps.p, self.ps.g
-        self.gemm_bwd(dy, x, G[name + ".weight"], transA=True, beta=1.0)
+        self.gemm_wgrad(dy, x, G[name + ".weight"], beta=1.0)
         self.bias_grad(dy, G[name + ".bias"])
         if not need_dx:
             return None
@@ -588,7 +630,7 @@ class HulcEngine:
             da3 = self.buf("gripper.da3", *a3.shape)
             PP = a3.shape[1] * a3.shape[2]
             dw0 = self.buf("gripper.dw7p", *w0.shape)
-            self.gemm_bwd(d, acts[0], dw0, transA=True)
+            self.gemm_bwd(d, acts[0], dw0, transA=True)  # (main stream: the permuting copy below reads dw0 right away)
             g7 = G[f"{pre}.conv_model.7.weight"]
             ops.strided_copy(g7.view(-1, 64, PP).transpose(1, 2), dw0.view(-1, PP, 64), accumulate=True)
             self.bias_grad(d, G[f"{pre}.conv_model.7.bias"])
@@ -656,7 +698,7 @@ class HulcEngine:
                 d = nd
             PP = a3.shape[1] * a3.shape[2]
             dw0 = self.buf("gripper.dw7p", *w0.shape)
-            self.gemm_bwd(d, acts[0], dw0, transA=True)
+            self.gemm_bwd(d, acts[0], dw0, transA=True)  # (main stream: the permuting copy below reads dw0 right away)
             g7 = G[f"{pre}.conv_model.7.weight"]
             ops.strided_copy(g7.view(-1, 64, PP).transpose(1, 2), dw0.view(-1, PP, 64), accumulate=True)
             self.bias_grad(d, G[f"{pre}.conv_model.7.bias"])
@@ -683,6 +725,24 @@ class HulcEngine:
         pre3 = pre.view(S, B, -1)
         saved = self.buf(f"{tag}.saved", S, B, 4 * H) if kind == "gru" else None
         gh = self.buf(f"{tag}.gh", B, 3 * H) if kind == "gru" else None
+        if self.bf16 and self.persistent_rnn and kind != "gru" and ops.rnn_seq_bf16_ok(B, H):
+            # bf16 path: one persistent launch (csrc/rnn_push_tc.cu) with the bf16 copy of W_hh resident and the state exchanged as bf16, what
+            # the reference's nn.RNN does under 16-bit autocast; any window length.  The exchange buffer doubles as the bf16 twin of the
+            # hidden states for the products that consume them (next layer's input product, the weight gradients).
+            x16 = self.hbuf(f"{tag}.x16", (S + 1) * B * H)
+            st, sp = hbuf.stride(0), pre3.stride(0)
+            act = TANH if kind == "tanh" else RELU
+            self._written(hbuf)
+            if reverse:
+                ops.rnn_seq_bf16(self._tw(w_hh), h(S + 1), x16, h(S), pre3[S - 1], S, out_step=-st, add_step=-sp, act=act)
+            else:
+                ops.rnn_seq_bf16(self._tw(w_hh), h(0), x16, h(1), pre3[0], S, out_step=st, add_step=sp, act=act)
+                if col0 == 0 and hbuf.shape[2] == H:
+                    x3 = x16.view(S + 1, B, H)
+                    for lo in (0, 1):  # h_{t-1} (slots 0..S-1) and h_t (slots 1..S) as [S*B, H] operands
+                        t32 = hbuf[lo : lo + S].view(S * B, H)
+                        self._twins[self._key(t32)] = [x3[lo : lo + S].view(S * B, H), self._twin_gen, self._span(t32)]
+            return saved
         if self.tc and self.persistent_rnn and kind != "gru" and ops.rnn_tc_seq_ok(B, H) and S <= 32:
             # one persistent launch for the whole chain (W_hh resident in shared memory, csrc/rnn_tc.cu).  Forward only up to 32
             # steps: the kernel makes ONE tf32 pass per step, whose rounding of W_hh accumulates along the chain — 0.28 of the
@@ -725,6 +785,17 @@ class HulcEngine:
         # Elman: dpre_t = (dh_above_t + dpre_{t+1} W_hh) * act'(h_t); slot S (or slot 0 for reverse) of dbuf stays zero
         dbuf = self.buf(f"{tag}.dpre", S + 1, B, H, zero=True)
         act = GATE_TANH if kind == "tanh" else 0
+        if self.bf16 and self.persistent_rnn and ops.rnn_seq_bf16_ok(B, H):
+            sd, sh, sa = dbuf.stride(0), hbuf.stride(0), B * dh_above.stride(0)
+            x16 = self.hbuf(f"{tag}.dx16", (S + 1) * B * H)
+            self._written(dbuf)
+            if reverse:
+                ops.rnn_seq_bf16(self._tw(w_hh), dbuf[0], x16, dbuf[1], ab(0), S, out_step=sd, add_step=sa, gate0=h(1), gate_step=sh, act=act, transW=True)
+            else:
+                ops.rnn_seq_bf16(self._tw(w_hh), dbuf[S], x16, dbuf[S - 1], ab(S - 1), S, out_step=-sd, add_step=-sa, gate0=h(S), gate_step=-sh, act=act,
+                                 transW=True)
+            d = (dbuf[1:] if reverse else dbuf[:S]).reshape(S * B, H)
+            return d, d
         if self.tc and self.persistent_rnn and ops.rnn_tc_seq_ok(B, H):
             sd, sh, sa = dbuf.stride(0), hbuf.stride(0), B * dh_above.stride(0)
             if reverse:
@@ -999,30 +1070,30 @@ class HulcEngine:
 
         _mark("bwd/action_decoder")
         # heads
-        self.gemm_bwd(dheads_p, h1_all, ps.heads_gw, transA=True, beta=1.0)
+        self.gemm_wgrad(dheads_p, h1_all, ps.heads_gw, beta=1.0)
         self.bias_grad(dheads_p, ps.heads_gb)
         dh1 = self.gemm_bwd(dheads_p, ps.heads_w, self.buf("dec.dh1", S * nB, H))
         # layer 1
         dpre1, dgh1 = self._rnn_bwd("dec.l1", dh1, P[f"{rp}.weight_hh_l1"], hb[1], 0, S, nB, kind=kind, saved=sv1)
-        self.gemm_bwd(dgh1, hb[1][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l1"], transA=True, beta=1.0)
-        self.gemm_bwd(dpre1, h0_all, G[f"{rp}.weight_ih_l1"], transA=True, beta=1.0)
+        self.gemm_wgrad(dgh1, hb[1][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l1"], beta=1.0)
+        self.gemm_wgrad(dpre1, h0_all, G[f"{rp}.weight_ih_l1"], beta=1.0)
         self.bias_grad(dpre1, G[f"{rp}.bias_ih_l1"])
         self.bias_grad(dgh1, G[f"{rp}.bias_hh_l1"])
         dh0 = self.gemm_bwd(dpre1, P[f"{rp}.weight_ih_l1"], self.buf("dec.dh0", S * nB, H))
         # layer 0
         dpre0, dgh0 = self._rnn_bwd("dec.l0", dh0, P[f"{rp}.weight_hh_l0"], hb[0], 0, S, nB, kind=kind, saved=sv0)
-        self.gemm_bwd(dgh0, hb[0][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l0"], transA=True, beta=1.0)
+        self.gemm_wgrad(dgh0, hb[0][0:S].view(S * nB, H), G[f"{rp}.weight_hh_l0"], beta=1.0)
         self.bias_grad(dgh0, G[f"{rp}.bias_hh_l0"])
         g_ih0 = G[f"{rp}.weight_ih_l0"]
-        self.gemm_bwd(dpre0, percep_tm.view(S * nB, C), g_ih0[:, PF : PF + C], transA=True, beta=1.0)
+        self.gemm_wgrad(dpre0, percep_tm.view(S * nB, C), g_ih0[:, PF : PF + C], beta=1.0)
         dconst = self.buf("dec.dconst", nB, Gn * H)
         colsum(dpre0.view(S, nB * Gn * H), dconst.view(-1))
         self.bias_grad(dconst, G[f"{rp}.bias_ih_l0"])
-        self.gemm_bwd(dconst, goal, g_ih0[:, PF + C :], transA=True, beta=1.0)
+        self.gemm_wgrad(dconst, goal, g_ih0[:, PF + C :], beta=1.0)
         self.gemm_bwd(dconst, w_goal, dgoal)
         dplan = None
         if PF:
-            self.gemm_bwd(dconst, plan, g_ih0[:, :PF], transA=True, beta=1.0)
+            self.gemm_wgrad(dconst, plan, g_ih0[:, :PF], beta=1.0)
             dplan = self.gemm_bwd(dconst, w_plan, self.buf("dplan", nB, PF))
         dpercep = self.gemm_bwd(dpre0, w_pc, self.buf("dec.dpercep", S * nB, C))
         ops.strided_copy(demb3[:, :, self.percep_lo :].transpose(0, 1), dpercep.view(S, nB, C), accumulate=True)
@@ -1073,8 +1144,8 @@ class HulcEngine:
                 self._linear_bwd(n, x, d, nd, gate=x)
                 d = nd
             g0 = G["plan_proposal.fc_model.0.weight"]
-            self.gemm_bwd(d, emb3[:, 0, :], g0[:, :128], transA=True, beta=1.0)
-            self.gemm_bwd(d, goal, g0[:, 128:], transA=True, beta=1.0)
+            self.gemm_wgrad(d, emb3[:, 0, :], g0[:, :128], beta=1.0)
+            self.gemm_wgrad(d, goal, g0[:, 128:], beta=1.0)
             self.bias_grad(d, G["plan_proposal.fc_model.0.bias"])
             self.gemm_bwd(d, w0[:, :128], demb3[:, 0, :], beta=1.0)
             self.gemm_bwd(d, w0[:, 128:], dgoal, beta=1.0)
@@ -1091,6 +1162,7 @@ class HulcEngine:
             # data-parallel overlap: everything but the perceptual encoders' gradients (97 % of the gradient bytes) is final here — the
             # caller starts their all-reduce, then runs `finish_backward()` (the conv stack's backward) underneath it
             self._flush_bias_grads()
+            self._join_side()
             self._tail = (ctx_s, ctx_g, demb)
             _mark(None)
             return out
@@ -1108,6 +1180,7 @@ class HulcEngine:
         self._encoder_bwd("gripper", ctx_g, demb)
         _mark("bwd/bias_gradients")
         self._flush_bias_grads()
+        self._join_side()
         _mark(None)
 
     def encoder_grad_split(self) -> int:
@@ -1166,7 +1239,7 @@ class HulcEngine:
                               drop=drop(f"l{l}.drop1", 2 + 4 * l))
             dctx = self._linear_bwd(f"{pre}.self_attn.out_proj", c["ctx"], do, self.buf(f"tr{l}.dctx", T, D))
             dqkv = ops.attention_bwd(c["qkv"], c["probs"], dctx, self.buf(f"tr{l}.dqkv", T, 3 * D), nB, S, Hh, drop(f"l{l}.attn", 1 + 4 * l))
-            self.gemm_bwd(dqkv, c["x"], G[f"{pre}.self_attn.in_proj_weight"], transA=True, beta=1.0)
+            self.gemm_wgrad(dqkv, c["x"], G[f"{pre}.self_attn.in_proj_weight"], beta=1.0)
             self.bias_grad(dqkv, G[f"{pre}.self_attn.in_proj_bias"])
             dy = self.gemm_bwd(dqkv, P[f"{pre}.self_attn.in_proj_weight"], self.buf(f"tr{l}.dx", T, D), addend=dz1)
         dx0 = dy
@@ -1215,8 +1288,8 @@ class HulcEngine:
                 dpre, _ = self._rnn_bwd(f"bi.l{l}{d}", dabove[:, d * H : (d + 1) * H], P[f"{rp}.weight_hh_l{l}{sfx}"], hb, d * H, S, nB,
                                         kind="tanh", reverse=bool(d))
                 hprev = (hb[2 : S + 2] if d else hb[0:S])[:, :, d * H : (d + 1) * H].reshape(S * nB, H)
-                self.gemm_bwd(dpre, hprev, G[f"{rp}.weight_hh_l{l}{sfx}"], transA=True, beta=1.0)
-                self.gemm_bwd(dpre, inp, G[f"{rp}.weight_ih_l{l}{sfx}"], transA=True, beta=1.0)
+                self.gemm_wgrad(dpre, hprev, G[f"{rp}.weight_hh_l{l}{sfx}"], beta=1.0)
+                self.gemm_wgrad(dpre, inp, G[f"{rp}.weight_ih_l{l}{sfx}"], beta=1.0)
                 self.bias_grad(dpre, G[f"{rp}.bias_ih_l{l}{sfx}"])
                 self.bias_grad(dpre, G[f"{rp}.bias_hh_l{l}{sfx}"])
                 self.gemm_bwd(dpre, P[f"{rp}.weight_ih_l{l}{sfx}"], dinp, beta=float(d))

@@ -251,6 +251,35 @@ def rnn_tc_seq(W, prev0, out0, add0, S: int, *, prev_step: int, out_step: int, a
                          _rowmajor(gate0) if gate0 is not None else 0, int(act), B, H, int(S), _ptr(ws), ws.numel() * 4, _stream())
 
 
+_push_clusters = None
+
+
+def rnn_seq_bf16_ok(B: int, H: int) -> bool:
+    """hulc_rnn_seq_bf16 takes hidden size 2048, at most 64 sequences, on a device that holds its 32 four-CTA clusters at once."""
+    global _push_clusters
+    if not rnn_tc_seq_ok(B, H):
+        return False
+    if _push_clusters is None:
+        import ctypes
+        out = (ctypes.c_int * 2)()
+        _L().hulc_rnn_push_max_clusters(ctypes.addressof(out))
+        _push_clusters = (out[0], out[1])
+    return _push_clusters[0] >= 32
+
+
+def rnn_seq_bf16(W16, prev0, x16, out0, add0, S: int, *, out_step: int, add_step: int, gate0=None, gate_step: int = 0, act: int = 0,
+                 transW: bool = False):
+    """bf16 variant of `rnn_tc_seq` (hulc_rnn_seq_bf16): W16 is the bf16 copy of weight_hh, x16 a bf16 workspace of (S + 1) * B * H elements
+    through which the hidden state travels between the steps; the fp32 result of step s lands in out0 + s * out_step."""
+    _chk(prev0, out0, add0, gate0)
+    _chk(W16, x16, dtype=torch.bfloat16)
+    B, H = prev0.shape
+    assert x16.numel() >= (S + 1) * B * H and x16.is_contiguous() and W16.stride(1) == 1
+    _L().hulc_rnn_seq_bf16(_ptr(W16), W16.stride(0), int(transW), _ptr(prev0), _rowmajor(prev0), _ptr(x16), _ptr(out0), int(out_step),
+                           _rowmajor(out0) if out0 is not None else 0, _ptr(add0), int(add_step), _rowmajor(add0), _ptr(gate0), int(gate_step),
+                           _rowmajor(gate0) if gate0 is not None else 0, int(act), B, H, int(S), _stream())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # convolutions
 # ----------------------------------------------------------------------------------------------------------------------

@@ -90,6 +90,18 @@ int hulc_rnn_tc_seq(const float* W, int ldw, int transW, const float* prev0, lon
                     int ldo, const float* add0, long long add_step, int ldadd, const float* gate0, long long gate_step, int ldg, int act,
                     int B, int H, int S, float* workspace, size_t workspace_bytes, void* stream);
 
+/* bf16 variant (reference under 16-bit autocast, conf/trainer/play_trainer.yaml:3): W16 is the bf16 copy of weight_hh [H, ldw]; the
+ * hidden state travels between the steps as bf16 through x16 (workspace, (S + 1) * B * H bf16; slot 0 is filled from the fp32 initial
+ * state prev0 [B, ldp]); the fp32 result of step s goes to out0 + s * out_step (may be NULL).  add / gate / act / transW as above. */
+int hulc_rnn_seq_bf16(const void* W16, int ldw, int transW, const float* prev0, int ldp, void* x16, float* out0, long long out_step, int ldo,
+                      const float* add0, long long add_step, int ldadd, const float* gate0, long long gate_step, int ldg, int act, int B, int H,
+                      int S, void* stream);
+
+/* Diagnostics: number of 4-CTA clusters of the second-generation recurrence kernels (csrc/rnn_push_tc.cu) the current device can hold
+ * at once (they need 32 co-resident; fewer: hulc_rnn_seq_bf16 returns cudaErrorLaunchOutOfResources, hulc_rnn_tc_seq runs its first kernel).
+ * out[0]: bf16 kernel, out[1]: tf32 kernel. */
+int hulc_rnn_push_max_clusters(int* out);
+
 /* ---- convolutions of the perceptual encoders -------------------------------------------------------------------------
  * perceptual_encoders/vision_network.py:36-47 and vision_network_gripper.py:11-17: nn.Conv2d (valid, NCHW) + ReLU for
  * the three layer shapes (3->32 k8 s4, 32->64 k4 s2, 64->64 k3 s1).  x [N,CIN,H,W], w [COUT,CIN,KS,KS], y [N,COUT,HO,WO].
