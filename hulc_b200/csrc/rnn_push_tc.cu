@@ -117,17 +117,14 @@ __device__ __forceinline__ void st_async16(uint32_t raddr, uint32_t rbar, uint32
 __device__ __forceinline__ void mbar_arrive_expect(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// wait for a phase completed by a peer CTA's st.async traffic: acquire at cluster scope
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spins = 0;; ++spins) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    if (ok) return;
-    if (spins > (1u << 26)) __trap();
-  }
+// 32 lanes x 16 columns of fp32 from TMEM
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 template <typename E>
 __device__ __forceinline__ bool piece_ready(const uint4& u) {
@@ -259,29 +256,29 @@ __global__ void __launch_bounds__(Cfg<E, ISSUERS>::kThreads, 1) rnn_push_kernel(
       mbar_wait(&bars->tmem_full, s & 1);
       tc_fence_after_sync();
       if (threadIdx.x == 0) ptrace(s, 4);
-      // push: columns [RO j, RO j + RO) of this feature's row go to owner j, 32 columns per pass (register budget)
+      // push: columns [RO j, RO j + RO) of this feature's row go to owner j, 16 columns per pass (register budget)
 #pragma unroll
-      for (int pass = 0; pass < NB / 32; ++pass) {
-        uint32_t v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pass * 32), v);
+      for (int pass = 0; pass < NB / 16; ++pass) {
+        uint32_t v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pass * 16), v);
         if (ISSUERS == 2) {  // the second issuer's accumulator (odd k-blocks)
-          uint32_t v2[32];
-          tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(NB + pass * 32), v2);
+          uint32_t v2[16];
+          tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(NB + pass * 16), v2);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
         } else {
           tmem_ld_wait();
         }
-        if (pass == NB / 32 - 1) {
+        if (pass == NB / 16 - 1) {
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tmem_empty);
         }
         if (sender) {
 #pragma unroll
-          for (int jj = 0; jj < 32 / RO; ++jj) {
-            const uint32_t j = (uint32_t)(pass * (32 / RO) + jj);
+          for (int jj = 0; jj < 16 / RO; ++jj) {
+            const uint32_t j = (uint32_t)(pass * (16 / RO) + jj);
             const uint32_t dst = mapa(my_slot, j) + (uint32_t)buf * kRecvBytes, bar = mapa(bar_u, j) + (uint32_t)buf * 8u;
 #pragma unroll
             for (int q = 0; q < PP; ++q)
@@ -291,7 +288,9 @@ __global__ void __launch_bounds__(Cfg<E, ISSUERS>::kThreads, 1) rnn_push_kernel(
       }
       if (threadIdx.x == 0) ptrace(s, 5);
       // reduce: the 4 partials of rows row0 .. row0 + 7, feature f, summed in a fixed order
-      mbar_wait_cluster(&bars->recv[buf], (s >> 1) & 1);
+      // (a plain try_wait: the transaction-count completion orders the st.async data before the phase flip, as for TMA traffic; an
+      //  acquire at cluster scope makes ptxas emit CCTL.IVALL — an L1 flush per step that sent every later local / read-only load to L2)
+      mbar_wait(&bars->recv[buf], (s >> 1) & 1);
       if (threadIdx.x == 0) {
         ptrace(s, 6);
         mbar_arrive_expect(&bars->recv[buf], kRecvBytes);  // arm the barrier for step s + 2 (nobody can be there before this step's result is out)
@@ -307,21 +306,39 @@ __global__ void __launch_bounds__(Cfg<E, ISSUERS>::kThreads, 1) rnn_push_kernel(
         o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
         o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
       }
-      E* xo = const_cast<E*>(xg) + (long long)(s + 1) * p.x_step;
-      float* out = p.out ? p.out + s * p.out_step : nullptr;
+      E* xo = const_cast<E*>(xg) + (long long)(s + 1) * p.x_step + (long long)row0 * p.ldx + col;
+      // (the activation / gate kind is uniform: select the loop once, not per element)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) o[r] += ad[r];
+      if ((p.act & 3) == 1) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) o[r] = fmaxf(o[r], 0.f);
+      } else if ((p.act & 3) == 2) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) o[r] = tanhf(o[r]);
+      }
+      if (p.gate) {
+        if (p.act & 4) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) o[r] *= 1.f - gt[r] * gt[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) o[r] = gt[r] > 0.f ? o[r] : 0.f;
+        }
+      }
+      // the value is its own "ready" flag for the next step's producers: these stores go out first
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const int row = row0 + r;
-        if (row < p.B) {
-          float y = o[r] + ad[r];
-          if ((p.act & 3) == 1) y = fmaxf(y, 0.f);
-          else if ((p.act & 3) == 2) y = tanhf(y);
-          if (p.gate) y = (p.act & 4) ? y * (1.f - gt[r] * gt[r]) : (gt[r] > 0.f ? y : 0.f);
-          // the value is its own "ready" flag for the next step's producers
-          if (kBf) st_relaxed_b16(reinterpret_cast<__nv_bfloat16*>(xo) + (size_t)row * p.ldx + col, __float2bfloat16_rn(y));
-          else st_relaxed_f32(reinterpret_cast<float*>(xo) + (size_t)row * p.ldx + col, y);
-          if (out) out[(size_t)row * p.ldo + col] = y;
+        if (row0 + r < p.B) {
+          if (kBf) st_relaxed_b16(reinterpret_cast<__nv_bfloat16*>(xo) + (long long)r * p.ldx, __float2bfloat16_rn(o[r]));
+          else st_relaxed_f32(reinterpret_cast<float*>(xo) + (long long)r * p.ldx, o[r]);
         }
+      }
+      if (p.out) {
+        float* out = p.out + s * p.out_step + (long long)row0 * p.ldo + col;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (row0 + r < p.B) out[(long long)r * p.ldo] = o[r];
       }
       if (threadIdx.x == 0) ptrace(s, 7);
     }
@@ -476,7 +493,7 @@ int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 int poll_mode() {
-  static int mode = env_int("HULC_B200_RNN_POLL", 0);
+  static int mode = env_int("HULC_B200_RNN_POLL", 1);  // 1: wait on the first piece, then fetch all (less L2 polling traffic; measured 3-4 % faster than polling every piece)
   return mode;
 }
 int issuers() {
