@@ -253,24 +253,31 @@ __global__ void __launch_bounds__(kThr, 1) conv1_band_fwd_kernel(C1Params p, int
 // k 128..191 into accumulator 1 — and the accumulators stay in TMEM across ALL tiles of the CTA: each CTA writes one partial
 // [192 x 32] at the end, which the existing reduction sums over CTAs in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kWgKR = 56;                       // k-rows (pixels) per tile, multiple of 8
+constexpr int kWgKR = 56;                       // k-rows per tile, multiple of 8
 constexpr int kWgGroupB = kWgKR * kRowBytes;    // one 32-element group of a tile: 7 KB
-constexpr int kWgGroups = 7;                    // builder warps: 6 groups of Xcol^T + 1 group of dY^T
-// slot = 8 groups: 0-5 Xcol^T, 6 = a constant group whose element 0 is 1 for every real pixel (k = 192: a row of ones appended to
-// the im2col matrix, so accumulator row 192 is sum_pixels dY = the BIAS gradient, for free), 7 = dY^T
-constexpr int kWgOnes = 6, kWgDy = 7;
-constexpr int kWgSlotB = 8 * kWgGroupB;         // 56 KB
-constexpr int kWgSlots = 2;                     // tiles being built / multiplied
+// The contraction runs over PIXEL GROUPS, not pixels: with kx = 4 a + b the window element x[ci][4 oy + ky][4 ox + kx] is
+// Xp[ci][4 oy + ky][ox + a][b], Xp[..][j][b] = x[..][4 j + b] — the input row cut into W/4 = WO + 1 groups of 4 floats.  So
+//   dW[co][ci][ky][4 a + b] = sum_j Xp[ci][4 oy + ky][j][b] * dY_a[j][co],   dY_0[j] = dY[oy][j],  dY_1[j] = dY[oy][j - 1]
+// and the two halves of the kernel window (a = 0, 1) share ONE staged operand of 96 columns (ci, ky, b) instead of an im2col matrix of
+// 192 in which every input value appears twice; the shift moves into the small operand (dY staged twice, one k-row apart) and both
+// halves ride in one instruction of N = 64.  Per tile the builders write 35 KB instead of 49 KB and the tensor core reads 42 KB of
+// operands instead of 70 KB — the first kernel spent its time on exactly that shared-memory traffic (≈190 KB per tile at 128 B/clk).
+// slot = 6 groups: 0-2 Xp^T of channel ci (column = 4 ky + b), 3 = a constant group whose element 0 is 1 (accumulator row 96 = sum over
+// the pixels of dY = the BIAS gradient, for free), 4 = dY_0^T, 5 = dY_1^T
+constexpr int kWgOnes = 3, kWgDy = 4;
+constexpr int kWgSlotB = 6 * kWgGroupB;         // 42 KB
+constexpr int kWgSlots = 2;                     // tiles being built / multiplied; slot s belongs to issuer s
 constexpr int kWgXB = 19 * 1024;                // 8 input rows x 3 channels x W floats (W <= 202)
 constexpr int kWgDyStageB = kWgKR * kRowBytes;  // the tile's dY row, fetched by the same bulk-copy thread (fp32: 128 B per pixel, bf16: 64)
 constexpr int kWgBandB = kWgXB + kWgDyStageB;   // 26 KB
 constexpr int kWgBands = 4;                     // bands in flight: the loader runs up to four tiles ahead of the builders, so no builder
-                                                // ever waits on a global-memory round trip (the dY warp used to: one per tile)
+                                                // ever waits on a global-memory round trip
 constexpr int kWgSmem = kWgSlots * kWgSlotB + kWgBands * kWgBandB + 256 + 1024;
 static_assert(kWgSmem <= 227 * 1024, "shared memory budget");
-// warps: 0-3 epilogue (end of kernel only) | 4-5 MMA issuers | 6 band loader | 7-13 builders
+// warps: 0-3 epilogue (end of kernel only) | 4-5 MMA issuers | 6 band loader | 7-12 Xp builders (two per channel) | 13-16 dY builders (two per half)
+constexpr int kWgXBuilders = 6, kWgDyBuilders = 4, kWgBuilders = kWgXBuilders + kWgDyBuilders;
 constexpr int kWgLoader = kEpiWarps + 2, kWgBuilder0 = kWgLoader + 1;
-constexpr int kWgThr = (kWgBuilder0 + kWgGroups) * 32;
+constexpr int kWgThr = (kWgBuilder0 + kWgBuilders) * 32;
 
 struct C1WgParams {
   const float* x;    // [N, 3, H, W]
@@ -278,7 +285,7 @@ struct C1WgParams {
   int dy_bf16;
   float* partial;    // [gridDim.x][192][32]
   float* bias_partial;  // [gridDim.x][32] or null
-  int N, H, W, HO, WO, KR;  // KR = WO rounded up to 8
+  int N, H, W, HO, WO, KR;  // KR = WO + 1 pixel groups rounded up to 8
 };
 
 struct C1WgBars {
@@ -300,23 +307,23 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgSlots; ++s) {
-      mbar_init(&bars->full[s], kWgGroups);
-      mbar_init(&bars->empty[s], 2);
+      mbar_init(&bars->full[s], kWgBuilders);
+      mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < kWgBands; ++s) {
       mbar_init(&bars->band_full[s], 1);
-      mbar_init(&bars->band_empty[s], kWgGroups);
+      mbar_init(&bars->band_empty[s], kWgBuilders);
     }
     mbar_init(&bars->done, 2);
     fence_barrier_init();
   }
-  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 64);
-  // k-rows past WO are never written by the builders and must contribute zero
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, 128);
+  // k-rows the builders never write must contribute zero: pixel groups past WO, row WO of dY_0, row 0 of dY_1
   for (int i = threadIdx.x; i < kWgSlots * kWgSlotB / 16; i += kWgThr) reinterpret_cast<float4*>(slot_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  for (int i = threadIdx.x; i < kWgSlots * p.WO; i += kWgThr) {  // the constant ones group of every slot
-    const int s_ = i / p.WO, xx = i - s_ * p.WO;
-    *reinterpret_cast<float*>(slot_smem + s_ * kWgSlotB + kWgOnes * kWgGroupB + swz32(xx, 0)) = 1.0f;
+  for (int i = threadIdx.x; i < kWgSlots * (p.WO + 1); i += kWgThr) {  // the constant ones group of every slot
+    const int s_ = i / (p.WO + 1), j = i - s_ * (p.WO + 1);
+    *reinterpret_cast<float*>(slot_smem + s_ * kWgSlotB + kWgOnes * kWgGroupB + swz32(j, 0)) = 1.0f;
   }
   fence_proxy_async();
   tc_fence_before_sync();
@@ -329,44 +336,45 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
     // ================================ epilogue: once, after the last tile ================================
     mbar_wait(&bars->done, 0);
     tc_fence_after_sync();
-    const int r = warp * 32 + lane;
+    const int m = warp * 32 + lane;  // accumulator row: (ci, ky, b) for m < 96, the bias row at 96
     float* dst = p.partial + (size_t)blockIdx.x * (kKtot * kCout);
 #pragma unroll
-    for (int acc = 0; acc < 2; ++acc) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * kCout), v);
+    for (int a = 0; a < 2; ++a) {  // columns [32 a, 32 a + 32): the kx half a of the window
+      uint32_t v[32], v1[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kCout), v);
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(64 + a * kCout), v1);
       tmem_ld_wait();
-      const int k = acc * kBM + r;
-      if (k == kKtot && p.bias_partial) {  // the ones row: sum over this CTA's pixels of dY
+      float o[32];
 #pragma unroll
-        for (int j = 0; j < kCout; ++j) p.bias_partial[(size_t)blockIdx.x * kCout + j] = my_tiles ? __uint_as_float(v[j]) : 0.f;
+      for (int j = 0; j < 32; ++j) o[j] = (my_tiles > 0 ? __uint_as_float(v[j]) : 0.f) + (my_tiles > 1 ? __uint_as_float(v1[j]) : 0.f);  // issuer 1 ran only if there were two tiles
+      if (m == 96 && a == 0 && p.bias_partial) {  // the ones row: sum over this CTA's pixels of dY
+#pragma unroll
+        for (int j = 0; j < kCout; ++j) p.bias_partial[(size_t)blockIdx.x * kCout + j] = o[j];
       }
-      if (k < kKtot) {
+      if (m < 96) {
+        const int k = (m >> 5) * 64 + ((m >> 2) & 7) * 8 + 4 * a + (m & 3);  // (ci, ky, kx = 4 a + b)
 #pragma unroll
-        for (int j = 0; j < kCout; j += 4)
-          *reinterpret_cast<float4*>(dst + (size_t)k * kCout + j) =
-              my_tiles ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kCout; j += 4) *reinterpret_cast<float4*>(dst + (size_t)k * kCout + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
       }
     }
   } else if (warp < kWgLoader) {
-    // ================================ MMA issuers: me = 0 -> k 0..127, me = 1 -> k 128..191 (+ two phantom groups) ================================
+    // ================================ MMA issuers: issuer me takes the tiles of slot me (it = me, me + 2, ...) into accumulator me ================================
     if (lane == 0) {
       const int me = warp - kEpiWarps;
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, kCout, true, true);
-      const uint32_t sb = smem_u32(slot_smem);
-      const uint32_t d = tmem_base + (uint32_t)(me * kCout);
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, 2 * kCout, true, true);
+      const uint32_t sb = smem_u32(slot_smem) + me * kWgSlotB;
+      const uint32_t d = tmem_base + (uint32_t)(me * 2 * kCout);
       const int ksteps = p.KR >> 3;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int slot = it % kWgSlots;
-        mbar_wait(&bars->full[slot], (it / kWgSlots) & 1);
+      for (int it = me; it < my_tiles; it += 2) {
+        mbar_wait(&bars->full[me], (it >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t a = sb + slot * kWgSlotB + me * 4 * kWgGroupB, b = sb + slot * kWgSlotB + kWgDy * kWgGroupB;
+        const uint32_t a = sb, b = sb + kWgDy * kWgGroupB;
         for (int k = 0; k < ksteps; ++k) {
           // MN-major operands: 8 k-rows per MMA = two 512-byte swizzle atoms (SBO), 32-element groups kWgGroupB apart (LBO)
           const uint64_t da = make_smem_desc(a + k * 1024, kWgGroupB, 512u, 1u), db = make_smem_desc(b + k * 1024, kWgGroupB, 512u, 1u);
-          umma_tf32(d, da, db, idesc, (uint32_t)(it != 0 || k != 0));
+          umma_tf32(d, da, db, idesc, (uint32_t)(it >= 2 || k != 0));
         }
-        umma_commit(&bars->empty[slot]);
+        umma_commit(&bars->empty[me]);
       }
       umma_commit(&bars->done);
     }
@@ -388,31 +396,32 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
       }
     }
   } else {
-    // ================================ builders: warp g fills group g of every tile slot ================================
-    const int g = warp - kWgBuilder0;  // 0..5: Xcol^T groups, 6: dY^T
+    // ================================ builders ================================
+    // warps 0-5: channel ci = bw / 2, every other 32-chunk batch of group ci; warps 6-9: window half a = (bw - 6) / 2, every other batch of dY_a^T
+    const int bw = warp - kWgBuilder0;
+    const bool is_x = bw < kWgXBuilders;
+    const int grp = is_x ? (bw >> 1) : kWgDy + ((bw - kWgXBuilders) >> 1), half = bw & 1;
+    const int shift = is_x ? 0 : ((bw - kWgXBuilders) >> 1);  // dY_1 sits one k-row further down
     const uint32_t rowbytes = (uint32_t)p.W * 4;
-    const int nchunks = p.WO * 8;      // 16-byte chunks of one group: pixel x = q / 8, chunk c = q % 8
+    const int nchunks = (is_x ? p.WO + 1 : p.WO) * 8;  // 16-byte chunks of one group: k-row = q / 8, chunk c = q % 8
+    constexpr int kIters = kWgKR * 8 / 64;             // 7 chunks per lane at most; all loads are issued before the first store
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
       const int slot = it % kWgSlots, bslot = it % kWgBands;
-      const int n = tile / p.HO, y = tile - n * p.HO;
-      const uint32_t dst = smem_u32(slot_smem) + slot * kWgSlotB + (g < 6 ? g : kWgDy) * kWgGroupB;
+      const uint32_t dst = smem_u32(slot_smem) + slot * kWgSlotB + grp * kWgGroupB;
       mbar_wait(&bars->empty[slot], ((it / kWgSlots) & 1) ^ 1);
-      constexpr int kIters = kWgKR * 8 / 32;  // 14 chunks per lane at most; all loads are issued before the first store
       float4 v[kIters];
       mbar_wait(&bars->band_full[bslot], (it / kWgBands) & 1);
       const uint32_t band = smem_u32(band_smem) + bslot * kWgBandB;
-      if (g < 6) {
+      if (is_x) {
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
-          const int q = lane + 32 * i, xx = q >> 3, c = q & 7;
-          const int pr = g * 4 + (c >> 1), ci = pr >> 3, ky = pr & 7;  // (ci, ky) pair of this chunk; kx half = c & 1
-          if (q < nchunks) v[i] = ld_shared16(band + (uint32_t)(ci * 8 + ky) * rowbytes + (uint32_t)((xx * 4 + (c & 1) * 4) * 4));
+          const int q = lane + 32 * (2 * i + half), j = q >> 3, c = q & 7;  // column 4 c + b of group ci: input row ky = c, floats 4 j .. 4 j + 3
+          if (q < nchunks) v[i] = ld_shared16(band + (uint32_t)(grp * 8 + c) * rowbytes + (uint32_t)j * 16u);
         }
       } else if (p.dy_bf16) {  // the staged dY row: chunk q = four bf16 = 8 bytes -> four fp32 (a 16-bit shift)
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
-          const int q = lane + 32 * i;
+          const int q = lane + 32 * (2 * i + half);
           if (q < nchunks) {
             uint32_t lo, hi;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(band + kWgXB + (uint32_t)q * 8u));
@@ -422,14 +431,14 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
       } else {
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
-          const int q = lane + 32 * i;
+          const int q = lane + 32 * (2 * i + half);
           if (q < nchunks) v[i] = ld_shared16(band + kWgXB + (uint32_t)q * 16u);  // rows of 32 floats are contiguous: chunk q is at q * 16 B
         }
       }
 #pragma unroll
       for (int i = 0; i < kIters; ++i) {
-        const int q = lane + 32 * i;
-        if (q < nchunks) st_shared16(dst + swz32(q >> 3, q & 7), v[i]);
+        const int q = lane + 32 * (2 * i + half);
+        if (q < nchunks) st_shared16(dst + swz32((q >> 3) + shift, q & 7), v[i]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(kWgThr, 1) conv1_band_wgrad_kernel(C1WgParams 
   __syncthreads();
   if (warp == kEpiWarps) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -701,7 +710,7 @@ int hulc_conv1_band_fwd(const float* x, const float* w, const float* b, float* y
 int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* partial, size_t partial_bytes, int want_bias, int N, int H, int W, int* ctas_out,
                                    cudaStream_t st, int dy_bf16) {
   const int HO = (H - 8) / 4 + 1, WO = (W - 8) / 4 + 1;
-  if (HO <= 0 || WO <= 0 || WO > kWgKR || (W & 3) || (size_t)3 * 8 * W * 4 > (size_t)kWgXB) return (int)cudaErrorNotSupported;
+  if (HO <= 0 || WO <= 0 || WO + 1 > kWgKR || (W & 3) || (size_t)3 * 8 * W * 4 > (size_t)kWgXB) return (int)cudaErrorNotSupported;
   if ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(dy) | reinterpret_cast<size_t>(partial)) & 15) return (int)cudaErrorNotSupported;
   const long long tiles = (long long)N * HO;
   if (tiles >= (1ll << 31) || (long long)N * 3 * H * W >= (1ll << 31)) return (int)cudaErrorNotSupported;
@@ -709,7 +718,7 @@ int hulc_conv1_band_wgrad_partials(const float* x, const float* dy, float* parti
   if ((size_t)ctas * (kKtot + 1) * kCout * sizeof(float) > partial_bytes) return (int)cudaErrorNotSupported;
   C1WgParams p;
   p.x = x; p.dy = dy; p.dy_bf16 = dy_bf16; p.partial = partial; p.bias_partial = want_bias ? partial + (size_t)ctas * kKtot * kCout : nullptr;  // bias partials follow the weight partials
-  p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.KR = (WO + 7) & ~7;
+  p.N = N; p.H = H; p.W = W; p.HO = HO; p.WO = WO; p.KR = (WO + 1 + 7) & ~7;  // WO + 1 = W / 4 pixel groups per input row
   HULC_TRY(cudaFuncSetAttribute(conv1_band_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
   HULC_LAUNCH(conv1_band_wgrad_kernel, dim3(ctas), dim3(kWgThr), kWgSmem, st, p, (int)tiles);
   *ctas_out = ctas;

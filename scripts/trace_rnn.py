@@ -13,6 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 lib = ctypes.CDLL(str(ROOT / "hulc_b200" / "lib" / "libhulc_trace.so"))
 H, B, S = 2048, 64, 32
 transW = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+tf32 = len(sys.argv) > 2 and sys.argv[2] == "tf32"  # the fp32-state variant behind hulc_rnn_tc_seq (needs HULC_B200_RNN_GEN=2)
 g = torch.Generator().manual_seed(0)
 W16 = ((torch.rand(H, H, generator=g) * 2 - 1) / H ** 0.5).cuda().to(torch.bfloat16)
 pre = (torch.randn(S, B, H, generator=g) * 0.5).cuda()
@@ -22,7 +23,18 @@ vp, ll, ci = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
 fn = lib.hulc_rnn_seq_bf16
 fn.argtypes = [vp, ci, ci, vp, ci, vp, vp, ll, ci, vp, ll, ci, vp, ll, ci, ci, ci, ci, ci, vp]
 fn.restype = ci
+W32 = W16.float()
+ws = torch.zeros(1 << 20, device="cuda")
+fn32 = lib.hulc_rnn_tc_seq
+fn32.argtypes = [vp, ci, ci, vp, ll, ci, vp, ll, ci, vp, ll, ci, vp, ll, ci, ci, ci, ci, ci, vp, ctypes.c_size_t, vp]
+fn32.restype = ci
 for it in range(3):
+    if tf32:
+        hbuf.zero_()
+        rc = fn32(W32.data_ptr(), H, transW, hbuf[0].data_ptr(), hbuf.stride(0), H, hbuf[1].data_ptr(), hbuf.stride(0), H, pre[0].data_ptr(), pre.stride(0), H,
+                  None, 0, 0, 1, B, H, S, ws.data_ptr(), ws.numel() * 4, None)
+        assert rc == 0, rc
+        continue
     rc = fn(W16.data_ptr(), H, transW, hbuf[0].data_ptr(), H, x16.data_ptr(), hbuf[1].data_ptr(), hbuf.stride(0), H, pre[0].data_ptr(), pre.stride(0), H,
             None, 0, 0, 1, B, H, S, None)
     assert rc == 0, rc

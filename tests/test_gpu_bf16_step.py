@@ -74,7 +74,9 @@ def test_bf16_step_within_the_references_own_bf16_deviation(name, golden_dir):
         if rel > worst[1]:
             worst = (k, rel)
         # (two sequences per modality: single bf16 roundings move the small bias / LayerNorm gradients visibly; the full batch averages them out)
-        assert rel < (0.1 if B >= 4 else 0.3), f"|grad {k}| = {float(g.norm()):.4e}, reference {gn:.4e}"
+        # a one-element parameter (logit_scale) has no averaging at all: its "norm" is the bare scalar, a difference of nearly cancelling terms
+        bound = 0.1 if B >= 4 else (0.5 if g.numel() == 1 else 0.3)
+        assert rel < bound, f"|grad {k}| = {float(g.norm()):.4e}, reference {gn:.4e}"
     print(name, {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in rep.items()}, "worst |grad| deviation", worst)
 
 

@@ -290,3 +290,45 @@ def test_set_kl_beta_and_losses_slots(env):
         out = m.last_outputs
         ref = O.training_step(sd, {"vis": host["vis"]}, plan_u={"vis": noise["vis"]["u"]}, kl_beta=0.05)
         np.testing.assert_allclose(float(out["total_loss"]), float(ref["total_loss"]), rtol=1e-3, atol=1e-4)
+
+
+def test_kl_schedule_callbacks_drive_the_step(env):
+    """hulc/utils/kl_callbacks.py:9-60 (conf/callbacks/kl_schedule/*.yaml): the schedules' values against the reference formulas (the sigmoid in
+    float32 like torch.sigmoid on a float tensor) and the hook driving `set_kl_beta` on the module, whose next step scales the KL term."""
+    from hulc_b200.utils.kl_callbacks import KLConstantSchedule, KLLinearSchedule, KLSigmoidSchedule
+
+    lin, sig = KLLinearSchedule(10, 50, 0.01), KLSigmoidSchedule(10, 50, 0.01)
+    for epoch in (0, 9, 10, 11, 30, 49, 50, 51, 200):
+        if epoch < 10:
+            want_l = want_s = 0.0
+        elif epoch > 50:
+            want_l = want_s = 0.01
+        else:
+            want_l = 0.01 * (epoch - 10) / 40
+            want_s = torch.sigmoid(torch.Tensor([(epoch - 30.0) / (40 / 12)])).item() * 0.01
+        assert lin._anneal_fn(epoch) == want_l
+        assert sig._anneal_fn(epoch) == want_s
+    m, sd = _build(env)
+    host, batch = _batch(env)
+    noise = {k: synthetic.plan_noise(2, 4, k) for k in host}
+    pu = {k: noise[k]["u"].to(batch[k]["actions"].device) for k in batch}
+
+    class _Epoch:  # what the trainer exposes to the hook: pl_module.current_epoch
+        def __init__(self, module, epoch):
+            self.module, self.current_epoch = module, epoch
+
+        def set_kl_beta(self, v):
+            self.module.set_kl_beta(v)
+
+    with torch.no_grad():
+        KLConstantSchedule().on_train_epoch_start(None, _Epoch(m, 30))
+        assert m.kl_beta == 0.01  # untouched
+        m.training_step(batch, 0, plan_u=pu)
+        kl_full = float(m.last_outputs["kl_loss"])
+        lin.on_train_epoch_start(None, _Epoch(m, 30))  # half way up the ramp
+        assert m.kl_beta == 0.005 and m.engine.kl_beta == 0.005
+        m.training_step(batch, 1, plan_u=pu)
+        np.testing.assert_allclose(float(m.last_outputs["kl_loss"]), 0.5 * kl_full, rtol=1e-5)
+        lin.on_train_epoch_start(None, _Epoch(m, 3))  # before the ramp: the KL term is switched off
+        m.training_step(batch, 2, plan_u=pu)
+        assert float(m.last_outputs["kl_loss"]) == 0.0
