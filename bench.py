@@ -225,6 +225,18 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     elman = eng.rnn_model == "rnn_decoder"
     if not elman:
         pass  # GRU decoder: per-step GEMM + gate kernels (not timed one by one here)
+    elif eng.bf16 and eng.persistent_rnn and ops.rnn_seq_bf16_ok(nB, H):
+        # bf16 mode: the whole chain of one layer is one persistent launch of the push kernel (csrc/rnn_push_tc.cu), bf16 W_hh and state
+        st, sp = hb.stride(0), pre1.view(S, nB, -1).stride(0)
+        pre3 = pre1.view(S, nB, -1)
+        w16 = eng._tw(whh)
+        x16, dx16 = B_["dec.l1.x16"], B_["dec.l1.dx16"]
+        cands[f"rnn_seq_fwd_{S}steps"] = (lambda: ops.rnn_seq_bf16(w16, hb[0], x16, hb[1], pre3[0], S, out_step=st, add_step=sp, act=1), 2.0 * nB * H * H * S, 2)
+        dbuf = B_["dec.l1.dpre"]
+        sd = dbuf.stride(0)
+        dh = big_a.view(S, nB, H)
+        cands[f"rnn_seq_bwd_{S}steps"] = (lambda: ops.rnn_seq_bf16(w16, dbuf[S], dx16, dbuf[S - 1], dh[S - 1], S, out_step=-sd, add_step=-dh.stride(0),
+                                                                   gate0=hb[S], gate_step=-st, act=0, transW=True), 2.0 * nB * H * H * S, 2)
     elif eng.tc and eng.persistent_rnn:
         # the whole 32-step chain of one layer is one persistent launch (csrc/rnn_tc.cu); 2 layers forward + 2 backward per step
         st, sp = hb.stride(0), pre1.view(S, nB, -1).stride(0)
@@ -286,6 +298,9 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
             "conv3_fwd": f2(N, 64, 23) + f2(N, 64, 21), "conv3_wgrad": f2(N, 64, 23) + f2(N, 64, 21), "conv3_dgrad": f2(N, 64, 21) + (1 + 1 / 16) * f2(N, 64, 23),
         })
     if eng.bf16:  # bf16 operands, fp32 result
+        # recurrence: bf16 W_hh once, per step the fp32 addend in, the fp32 result + its bf16 exchange copy out (+ the fp32 gate in BPTT)
+        abytes[f"rnn_seq_fwd_{S}steps"] = 2.0 * H * H + 10.0 * S * nB * H
+        abytes[f"rnn_seq_bwd_{S}steps"] = 2.0 * H * H + 14.0 * S * nB * H
         abytes["dense_wgrad_2048^3"] = 2.0 * 2 * S * nB * H + 4.0 * H * H
         abytes["dense_fwd_2048^3"] = 2.0 * (S * nB * H + H * H) + 4.0 * S * nB * H
     top = max(res, key=lambda k: res[k]["ms"] * res[k]["per_step"])
@@ -294,23 +309,24 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     gbs = abytes[top] / (r["ms"] * 1e-3) / 1e9
     # the kernel runs tf32 operands: its tensor ceiling is half the measured bf16 rate; it is HBM-bound when its arithmetic
     # intensity is below that ridge
-    is_bf16_kernel = eng.bf16 and (top.startswith("dense") or (eng.bf16_conv and top.startswith(("conv2", "conv3"))))
+    is_bf16_kernel = eng.bf16 and (top.startswith(("dense", "rnn_seq")) or (eng.bf16_conv and top.startswith(("conv2", "conv3"))))
     tf32_peak = peaks["tf_burst"] / (1.0 if is_bf16_kernel else 2.0)
     hbm_bound = (r["flops"] / abytes[top]) < (tf32_peak * 1e12) / (peaks["hbm"] * 1e9)
     kern = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "gbs": round(abytes[k] / (v["ms"] * 1e-3) / 1e9, 1),
                 "per_step": v["per_step"], "share_of_step": round(v["share"], 4)} for k, v in res.items()}
     traffic = None
-    tp = ROOT / "profiles" / "r01_traffic.json"  # dram bytes per launch from the committed ncu --set full capture of the same kernels
+    tp = ROOT / "profiles" / "r02_traffic.json"  # dram bytes per launch from the committed ncu --set full captures of the same kernels
     if tp.exists():
-        traffic = json.loads(tp.read_text())["kernels"].get(top, {}).get("dram_bytes_per_launch")
-    common = {"kernel": top, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram read+write bytes per launch)" if traffic else None, "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
+        traffic = json.loads(tp.read_text()).get("bf16" if eng.bf16 else "tf32", {}).get(top, {}).get("dram_bytes_per_launch")
+    peak_note = ("the kernel runs bf16 operands (kind::f16)" if is_bf16_kernel else "the kernel runs tf32 operands, whose tensor-core peak is half of it")
+    common = {"kernel": top, "traffic": traffic, "traffic_source": "profiles/r02_traffic.json (ncu --set full, dram read+write bytes per launch)" if traffic else None, "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
               "algorithmic_bytes_per_launch": abytes[top], "algorithmic_flops_per_launch": r["flops"], "kernels": kern,
               "step": {"tensor_frac": None, "hbm_frac": None}}
     if hbm_bound:
         return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                 "peak_source": f"{peaks['src']} HBM copy bandwidth (MEASURED_PEAKS.json hbm_gbs)", **common}
     return {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tflops / peaks["tf_burst"],
-            "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); the kernel runs tf32 operands, whose tensor-core peak is half of it", **common}
+            "peak_source": f"{peaks['src']} bf16 dense burst (kernel timed alone); {peak_note}", **common}
 
 
 def eager_b200(torch, args, dev):

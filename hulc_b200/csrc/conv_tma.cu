@@ -343,6 +343,24 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gate + off));
         }
       }
+      // the sign-mask words of all the tile's chunks: loaded here, before the accumulator wait — inside the chunk loop each was a dependent
+      // DRAM round trip (the masks were written a whole forward pass ago), four per tile for the stride-2 data gradient: ~3 us of latency
+      // per tile, which was the kernel's time
+      unsigned gmw[BN / 32];
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        gmw[c0 >> 5] = 0xFFFFFFFFu;
+        if (p.gate_bits && valid0) {
+          size_t off = off0 + c0;
+          bool valid = true;
+          if (p.scatter) {
+            const int oy = 2 * (y0 + yl) + (c0 >> 6), ox = 2 * xx + ((c0 >> 5) & 1);
+            valid = oy < p.out_H && ox < p.out_W;
+            off = (((size_t)n * p.out_H + oy) * p.out_W + ox) * 32;
+          }
+          if (valid) gmw[c0 >> 5] = __ldg(p.gate_bits + (off >> 5));
+        }
+      }
       mbar_wait(&bars->tmem_full[a], (it >> 1) & 1);
       tc_fence_after_sync();
 #pragma unroll
@@ -371,8 +389,8 @@ __global__ void __launch_bounds__((kEpiWarps + NI + 1) * 32, 1) conv_band_kernel
         if (valid) {
           // word of the sign masks for this (pixel, 32-channel chunk): `off` is the element offset of the chunk's first channel
           const size_t word = off >> 5;
-          unsigned gm = 0xFFFFFFFFu, om = 0u;
-          if (p.gate_bits) gm = __ldg(p.gate_bits + word);
+          const unsigned gm = gmw[c0 >> 5];
+          unsigned om = 0u;
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
