@@ -47,6 +47,8 @@ CASES = {
     "mcil_b2s8": ("mcil", "rnn_decoder", 2, 8, 0.0),
     "hulc_b4s32": ("hulc", "rnn_decoder", 4, 32, 0.0),  # full window, small batch
     "hulc_b32s32": ("hulc", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 2 shape
+    "mcil_b32s32": ("mcil", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 4 shape
+    "gcbc_b32s64": ("gcbc", "rnn_decoder", 32, 64, 0.0),  # BASELINE config 5 shape (window 64)
 }
 
 
@@ -111,7 +113,7 @@ def injected_randomness(u_queue, eps_queue, mask_queue, p):
 def run_case(name):
     model, rnn_model, B, S, p = CASES[name]
     t0 = time.time()
-    net = build_reference(model, rnn_model, p, 32)
+    net = build_reference(model, rnn_model, p, max(32, S))
     batch = synthetic.make_batch(B, S, seed=1)
     noise = {m: synthetic.plan_noise(B, S, m) for m in batch}
     masks = {m: synthetic.dropout_masks(B, S, m, p) for m in batch} if p > 0 else None

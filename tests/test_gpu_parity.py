@@ -75,6 +75,8 @@ GOLDEN = {
     "mcil_b2s8": ("mcil", "rnn_decoder", 2, 8, 0.0),
     "hulc_b4s32": ("hulc", "rnn_decoder", 4, 32, 0.0),
     "hulc_b32s32": ("hulc", "rnn_decoder", 32, 32, 0.0),
+    "mcil_b32s32": ("mcil", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 4 at its full shape
+    "gcbc_b32s64": ("gcbc", "rnn_decoder", 32, 64, 0.0),  # BASELINE config 5 at its full shape
 }
 
 
@@ -86,8 +88,8 @@ def test_step_matches_reference_fixture(name, golden_dir, precision):
     model, rnn_model, B, S, p = GOLDEN[name]
     tf32 = precision == "tf32"
     fx = np.load(golden_dir / f"{name}.npz")
-    eng = HulcEngine(model, rnn_model, device="cuda", dropout_p=p, precision=precision)
-    eng.load_state_dict(synthetic.make_state_dict(model, rnn_model))
+    eng = HulcEngine(model, rnn_model, max_window=max(32, S), device="cuda", dropout_p=p, precision=precision)
+    eng.load_state_dict(synthetic.make_state_dict(model, rnn_model, max_window=max(32, S)))
     batch = synthetic.make_batch(B, S, seed=1, device="cuda")
     mods = list(batch)
     noise = {m: synthetic.plan_noise(B, S, m) for m in mods}
