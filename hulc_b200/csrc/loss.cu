@@ -607,6 +607,68 @@ HULC_API int hulc_sum(const float* x, int n, float* out, float scale, void* stre
   HULC_RETURN_LAST();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Auxiliary losses of the ablation configs (hulc/models/hulc.py:567-648): mean cosine distance between the regressed and the
+// true language embedding (BC-Z), binary cross entropy with logits over matching / rolled pairs (MIA).  One small CTA each;
+// rows are reduced by warps in a fixed order, so the results are deterministic.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cosine_loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ tgt, int ldt, float* __restrict__ dpred,
+                                                         int ldd, float* __restrict__ loss, int B, int D, float grad_scale) {
+  __shared__ float row_loss[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = warp; b < B; b += nw) {
+    const float* p = pred + (size_t)b * ldp;
+    const float* g = tgt + (size_t)b * ldt;
+    float pg = 0.f, pp = 0.f, gg = 0.f;
+    for (int j = lane; j < D; j += 32) { pg += p[j] * g[j]; pp += p[j] * p[j]; gg += g[j] * g[j]; }
+    pg = warp_sum(pg); pp = warp_sum(pp); gg = warp_sum(gg);
+    const float np_ = sqrtf(pp), ng = sqrtf(gg), cosv = pg / (np_ * ng);
+    // d(1 - cos)/dp = -(g / (|p||g|) - cos * p / |p|^2), averaged over the B rows
+    const float k = grad_scale / (float)B;
+    for (int j = lane; j < D; j += 32) dpred[(size_t)b * ldd + j] = -k * (g[j] / (np_ * ng) - cosv * p[j] / pp);
+    if (lane == 0) row_loss[b] = 1.f - cosv;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += row_loss[b];
+    loss[0] = acc / (float)B;
+  }
+}
+
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ x, float* __restrict__ dx, float* __restrict__ loss, int n_pos, int n_neg,
+                                                        float grad_scale) {
+  __shared__ float part[256];
+  const int n = n_pos + n_neg;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i], y = i < n_pos ? 1.f : 0.f;
+    acc += fmaxf(v, 0.f) - v * y + log1pf(expf(-fabsf(v)));  // the numerically stable form torch uses
+    dx[i] = grad_scale * (1.f / (1.f + expf(-v)) - y) / (float)n;
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)blockDim.x; ++i) t += part[i];
+    loss[0] = t / (float)n;
+  }
+}
+
+// See include/hulc_b200.h.
+HULC_API int hulc_cosine_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int ldd, float* loss, int B, int D, float grad_scale,
+                              void* stream) {
+  if (B <= 0 || D <= 0) return 0;
+  if (B > 256) return (int)cudaErrorInvalidValue;
+  HULC_LAUNCH(cosine_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, pred, ldp, target, ldt, dpred, ldd, loss, B, D, grad_scale);
+  HULC_RETURN_LAST();
+}
+HULC_API int hulc_bce_logits_loss(const float* logits, float* dlogits, float* loss, int n_pos, int n_neg, float grad_scale, void* stream) {
+  if (n_pos + n_neg <= 0) return 0;
+  HULC_LAUNCH(bce_logits_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, logits, dlogits, loss, n_pos, n_neg, grad_scale);
+  HULC_RETURN_LAST();
+}
+
 HULC_API int hulc_clip_loss(const float* im, const float* tx, const float* logit_scale, const unsigned char* mask, float* loss, float* d_im,
                             float* d_tx, float* d_logit_scale, int n, int D, float grad_scale, void* stream) {
   if (n <= 0) return 0;

@@ -187,6 +187,7 @@ class HulcEngine:
         self._bf16_only: set = set()            # keys whose fp32 storage was never written this step (the producer emitted bf16 only)
         self.dropout_p = float(dims.dropout_p) if model != "mcil" else 0.0
         self.kl_beta, self.kl_alpha, self.clip_beta, self.gripper_alpha = float(kl_beta), float(kl_balancing_mix), float(clip_beta), float(dims.gripper_alpha)
+        self.bc_z_beta, self.mia_beta = 1.0, 1.0  # conf/loss/default.yaml:4-5 (the module overwrites them from its constructor arguments)
         self.nhead, self.nlayers, self.lr = dims.nhead, dims.nlayers, lr
         self.discrete = dims.discrete
         self.plan_features = dims.plan_features
@@ -429,6 +430,73 @@ class HulcEngine:
     def _flush_bias_grads(self):
         jobs, self._bias_jobs = self._bias_jobs, []
         ops.colsum_multi(jobs)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # BC-Z / MIA auxiliary heads (hulc/models/hulc.py:567-648; bc_z_lang_decoder.py:5-20, mia_lang_discriminator.py:5-21) — ablation
+    # configs, language modality only.  A few tiny products: they run on the exact-fp32 kernels in every precision mode.
+    # ------------------------------------------------------------------------------------------------------------------
+    def _aux_heads_fwd(self, d, mask, sf, im2, tx2, d_im2, d_tx2, Bm):
+        P = self.ps.p
+        active = True
+        if mask is not None:  # (a host sync: the module keeps CUDA graphs off while these heads are on)
+            if not bool(mask.all()):
+                if bool(mask.any()):
+                    raise NotImplementedError("use_for_aux_lang_loss keeps only part of the batch: the reference's BC-Z loss indexes with the mask twice "
+                                              "(hulc.py:592-594) and fails there; MIA would need the kept rows compacted")
+                active = False  # hulc.py:583-590 / 626-633: dummy forward, loss * 0 -> no loss, no gradient
+        losses = self.buf("aux.losses", 2)
+        losses.zero_()
+        ctx = {"losses": losses, "active": active}
+        if not active:
+            return ctx
+        Ha = self.dims.aux_hidden
+        if self.dims.bc_z:
+            lang = d["lang"].contiguous()
+            h = gemm(sf, P["bc_z_lang_decoder.mlp.0.weight"], self.buf("bcz.h", Bm, Ha), transB=True, bias=P["bc_z_lang_decoder.mlp.0.bias"], act=RELU)
+            pred = gemm(h, P["bc_z_lang_decoder.mlp.2.weight"], self.buf("bcz.pred", Bm, lang.shape[1]), transB=True, bias=P["bc_z_lang_decoder.mlp.2.bias"])
+            dpred = self.buf("bcz.dpred", *pred.shape)
+            ops.cosine_loss(pred, lang, dpred, losses[0:1], grad_scale=self.bc_z_beta)
+            ctx.update(bcz_h=h, bcz_dpred=dpred)
+        if self.dims.mia:
+            Dc = im2.shape[1]
+            x = self.buf("mia.x", 2 * Bm, 2 * Dc)  # rows [0, Bm): (im_i, tx_i); rows [Bm, 2 Bm): (im_i, tx_{i-1}) = torch.roll(tx, 1, 0)
+            ops.strided_copy(x[:Bm, :Dc], im2), ops.strided_copy(x[:Bm, Dc:], tx2), ops.strided_copy(x[Bm:, :Dc], im2)
+            ops.strided_copy(x[Bm : Bm + 1, Dc:], tx2[Bm - 1 : Bm])
+            if Bm > 1:
+                ops.strided_copy(x[Bm + 1 :, Dc:], tx2[: Bm - 1])
+            hm = gemm(x, P["mia_lang_discriminator.mlp.0.weight"], self.buf("mia.h", 2 * Bm, Ha), transB=True, bias=P["mia_lang_discriminator.mlp.0.bias"], act=RELU)
+            logit = gemm(hm, P["mia_lang_discriminator.mlp.3.weight"], self.buf("mia.logit", 2 * Bm, 1), transB=True, bias=P["mia_lang_discriminator.mlp.3.bias"])
+            dlogit = self.buf("mia.dlogit", 2 * Bm, 1)
+            ops.bce_logits_loss(logit.view(-1), dlogit.view(-1), losses[1:2], Bm, Bm, grad_scale=self.mia_beta)
+            ctx.update(mia_x=x, mia_h=hm, mia_dlogit=dlogit)
+        return ctx
+
+    def _aux_heads_bwd(self, ctx, sf, dseq, d_im2, d_tx2, Bm, *, mia_only):
+        if not ctx["active"]:
+            return
+        P, G = self.ps.p, self.ps.g
+
+        def lin_bwd(name, x, dy, dx, gate=None, dx_beta=0.0):
+            gemm(dy, x, G[name + ".weight"], transA=True, beta=1.0)
+            self.bias_grad(dy, G[name + ".bias"])
+            return gemm(dy, P[name + ".weight"], dx, beta=dx_beta, gate=gate)
+
+        if mia_only:
+            if not self.dims.mia:
+                return
+            x, hm, dlogit = ctx["mia_x"], ctx["mia_h"], ctx["mia_dlogit"]
+            Dc = d_im2.shape[1]
+            dhm = lin_bwd("mia_lang_discriminator.mlp.3", hm, dlogit, self.buf("mia.dh", *hm.shape), gate=hm)
+            dx = lin_bwd("mia_lang_discriminator.mlp.0", x, dhm, self.buf("mia.dx", *x.shape))
+            ops.strided_copy(d_im2, dx[:Bm, :Dc], accumulate=True), ops.strided_copy(d_im2, dx[Bm:, :Dc], accumulate=True)
+            ops.strided_copy(d_tx2, dx[:Bm, Dc:], accumulate=True)
+            ops.strided_copy(d_tx2[Bm - 1 : Bm], dx[Bm : Bm + 1, Dc:], accumulate=True)
+            if Bm > 1:
+                ops.strided_copy(d_tx2[: Bm - 1], dx[Bm + 1 :, Dc:], accumulate=True)
+        elif self.dims.bc_z:
+            h, dpred = ctx["bcz_h"], ctx["bcz_dpred"]
+            dh = lin_bwd("bc_z_lang_decoder.mlp.2", h, dpred, self.buf("bcz.dh", *h.shape), gate=h)
+            lin_bwd("bc_z_lang_decoder.mlp.0", sf, dh, dseq, dx_beta=1.0)
 
     def _linear_bwd(self, name, x, dy, dx=None, *, gate=None, dx_beta=0.0, need_dx=True, act=0, addend=None, drop=NO_DROP):
         """Gradients of y = x W^T + b: accumulates dW, db; returns dx = dy W (optionally gated by the producer's ReLU)."""
@@ -1028,7 +1096,7 @@ class HulcEngine:
 
         _mark("fwd/clip_aux")
         # ---- CLIP auxiliary loss (hulc.py:650-695, proj_vis_lang.py:23-27), language modality only --------------------------------
-        clip_ctx = None
+        clip_ctx = aux_ctx = None
         if self.model != "mcil" and with_clip:
             for i, (m, b0, Bm) in enumerate(zip(mods, b0s, Bs)):
                 if "lang" not in m:
@@ -1044,6 +1112,8 @@ class HulcEngine:
                 d_im2, d_tx2 = self.buf("clip.dim2", Bm, Dc), self.buf("clip.dtx2", Bm, Dc)
                 ops.clip_loss(im2, tx2, P["logit_scale"].view(1), mask8, lview(4 * i + 3), d_im2, d_tx2, G["logit_scale"].view(1), grad_scale=self.clip_beta)
                 clip_ctx = (i, b0, Bm, sf, gl, im1, tx1, d_im2, d_tx2)
+                if self.dims.bc_z or self.dims.mia:
+                    aux_ctx = self._aux_heads_fwd(batch[m], mask, sf, im2, tx2, d_im2, d_tx2, Bm)
 
         _mark("totals")
         # ---- totals (hulc.py:464-491,525) ------------------------------------------------------------------------------------------
@@ -1052,6 +1122,13 @@ class HulcEngine:
         kl_m = self.kl_beta * L[:, 2] if self.model != "gcbc" else torch.zeros_like(L[:, 2])
         clip = L[:, 3].sum() if (self.model != "mcil" and with_clip) else None
         total = (act_m + kl_m).sum() / n_mod
+        if aux_ctx is not None:  # hulc.py:500-519: beta * loss, added before the CLIP term
+            if self.dims.bc_z:
+                out["lang_pred_loss"] = aux_ctx["losses"][0]
+                total = total + self.bc_z_beta * aux_ctx["losses"][0]
+            if self.dims.mia:
+                out["lang_contrastive_loss"] = aux_ctx["losses"][1]
+                total = total + self.mia_beta * aux_ctx["losses"][1]
         if clip is not None:
             total = total + self.clip_beta * clip
             out["lang_clip_loss"] = clip
@@ -1104,10 +1181,14 @@ class HulcEngine:
         dseq.zero_()
         if clip_ctx is not None:
             i, b0, Bm, sf, gl, im1, tx1, d_im2, d_tx2 = clip_ctx
+            if aux_ctx is not None:  # the MIA gradient joins d_im2 / d_tx2 before they go back through the shared projection head
+                self._aux_heads_bwd(aux_ctx, sf, dseq[b0 : b0 + Bm], d_im2, d_tx2, Bm, mia_only=True)
             d_im1 = self._linear_bwd("proj_vis_lang.mlp_im.2", im1, d_im2, self.buf("clip.dim1", *im1.shape), gate=im1)
             self._linear_bwd("proj_vis_lang.mlp_im.0", sf, d_im1, dseq[b0 : b0 + Bm])
             d_tx1 = self._linear_bwd("proj_vis_lang.mlp_lang.2", tx1, d_tx2, self.buf("clip.dtx1", *tx1.shape), gate=tx1)
             self._linear_bwd("proj_vis_lang.mlp_lang.0", gl, d_tx1, dgoal[b0 : b0 + Bm], dx_beta=1.0)
+            if aux_ctx is not None:  # BC-Z: accumulates into the sequence feature's gradient after the CLIP head wrote it
+                self._aux_heads_bwd(aux_ctx, sf, dseq[b0 : b0 + Bm], d_im2, d_tx2, Bm, mia_only=False)
 
         _mark("bwd/latent_plan_kl")
         # latent plan

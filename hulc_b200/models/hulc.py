@@ -242,15 +242,18 @@ class Hulc(_Base):
         precision: str = "tf32",
     ):
         super().__init__()
-        if state_recons or use_bc_z_auxiliary_loss or use_mia_auxiliary_loss:
-            raise NotImplementedError("state reconstruction / BC-Z / MIA auxiliary losses are off in every shipped model yaml and are not built (DESIGN.md, out of scope)")
+        if state_recons:
+            raise NotImplementedError("state_recons needs the proprio encoder that conf/model/perceptual_encoder/gripper_cam.yaml disables (concat_encoders.py:46-50); not built")
+        if bool(use_bc_z_auxiliary_loss) != (bc_z_lang_decoder not in (None, {}, "none")) or bool(use_mia_auxiliary_loss) != (mia_lang_discriminator not in (None, {}, "none")):
+            raise NotImplementedError("use_bc_z_auxiliary_loss / use_mia_auxiliary_loss go together with their networks (model/bc_z_lang_decoder, model/mia_lang_discriminator)")
         birnn = str(_get(plan_recognition, "_target_", "")).endswith("PlanRecognitionBiRNNNetwork")
         model = "mcil" if birnn else self.MODEL
         if bool(use_clip_auxiliary_loss) != (model != "mcil"):
             raise NotImplementedError("CLIP auxiliary loss is on for hulc/gcbc and off for mcil in the shipped configs")
         # every size of the network comes from the config tree (hulc.py:86-187 wires the sub-configs the same way); values the kernels
         # cannot honour raise NotImplementedError naming the key
-        dims = dims_from_configs(model, perceptual_encoder, plan_proposal, plan_recognition, language_goal, visual_goal, action_decoder, distribution, proj_vis_lang)
+        dims = dims_from_configs(model, perceptual_encoder, plan_proposal, plan_recognition, language_goal, visual_goal, action_decoder, distribution, proj_vis_lang,
+                                 bc_z_lang_decoder=bc_z_lang_decoder, mia_lang_discriminator=mia_lang_discriminator)
         self._check_optimizer_config(optimizer)
         dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.engine = HulcEngine(device=dev, kl_beta=kl_beta, kl_balancing_mix=kl_balancing_mix, clip_beta=clip_auxiliary_loss_beta,
@@ -261,6 +264,9 @@ class Hulc(_Base):
         self._register_reference_buffers(model)
         self._init_parameters()
         self.use_clip_auxiliary_loss, self.clip_auxiliary_loss_beta = use_clip_auxiliary_loss, clip_auxiliary_loss_beta
+        self.use_bc_z_auxiliary_loss, self.bc_z_auxiliary_loss_beta = bool(use_bc_z_auxiliary_loss), bc_z_auxiliary_loss_beta
+        self.use_mia_auxiliary_loss, self.mia_auxiliary_loss_beta = bool(use_mia_auxiliary_loss), mia_auxiliary_loss_beta
+        self.engine.bc_z_beta, self.engine.mia_beta = float(bc_z_auxiliary_loss_beta), float(mia_auxiliary_loss_beta)
         self.kl_beta, self.kl_balancing_mix = kl_beta, kl_balancing_mix
         self.modality_scope = "vis"
         self.optimizer_config, self.lr_scheduler = optimizer, lr_scheduler
@@ -418,7 +424,10 @@ class Hulc(_Base):
     def enable_cuda_graphs(self, flag: bool = True):
         """Replay the training step from a CUDA graph captured per distinct set of input buffers (the batch tensors are the
         graph's static inputs: a loader that re-uses its device staging buffers hits the same graph every step).  At most
-        `max_graphs` graphs are kept; every batch shape has its own activation buffers (HulcEngine.step)."""
+        `max_graphs` graphs are kept; every batch shape has its own activation buffers (HulcEngine.step).  With the BC-Z / MIA heads on the
+        step stays eager: they inspect `use_for_aux_lang_loss` on the host every step, like the reference (hulc.py:581, 624)."""
+        if flag and (self.engine.dims.bc_z or self.engine.dims.mia):
+            flag = False
         self._graphs = {} if flag else None
 
     def fused_step(self, batch, **inject) -> Dict[str, torch.Tensor]:
@@ -470,6 +479,10 @@ class Hulc(_Base):
             self.log(f"train/kl_loss_scaled_{m}", out[f"kl_loss_{m}"], on_step=False, on_epoch=True, batch_size=bs)
             self.log(f"train/action_loss_{m}", out[f"action_loss_{m}"], on_step=False, on_epoch=True, batch_size=bs)
             self.log(f"train/total_loss_{m}", out[f"action_loss_{m}"] + out[f"kl_loss_{m}"], on_step=False, on_epoch=True, batch_size=bs)
+        if "lang_pred_loss" in out:  # hulc.py:500-509
+            self.log("train/pred_lang", self.bc_z_auxiliary_loss_beta * out["lang_pred_loss"], on_step=False, on_epoch=True, sync_dist=True)
+        if "lang_contrastive_loss" in out:  # hulc.py:510-519
+            self.log("train/lang_contrastive", self.mia_auxiliary_loss_beta * out["lang_contrastive_loss"], on_step=False, on_epoch=True, sync_dist=True)
         if "lang_clip_loss" in out:
             self.log("train/lang_clip_loss", self.clip_auxiliary_loss_beta * out["lang_clip_loss"], on_step=False, on_epoch=True, sync_dist=True)
         self.log("train/kl_loss", kl, on_step=False, on_epoch=True, batch_size=total_bs)

@@ -671,6 +671,20 @@ def clip_loss(im, tx, logit_scale, mask, loss, d_im, d_tx, d_logit_scale, grad_s
                         float(grad_scale), _stream())
 
 
+def cosine_loss(pred, target, dpred, loss, grad_scale=1.0):
+    """loss[0] = mean cosine distance of the rows of pred / target [B, D]; dpred = grad_scale * its gradient (hulc_cosine_loss)."""
+    _chk(pred, target, dpred, loss)
+    B, D = pred.shape
+    _L().hulc_cosine_loss(_ptr(pred), _rowmajor(pred), _ptr(target), _rowmajor(target), _ptr(dpred), _rowmajor(dpred), _ptr(loss), B, D, float(grad_scale), _stream())
+
+
+def bce_logits_loss(logits, dlogits, loss, n_pos: int, n_neg: int, grad_scale=1.0):
+    """Binary cross entropy with logits over n_pos scores labelled 1 followed by n_neg labelled 0 (hulc_bce_logits_loss)."""
+    _chk(logits, dlogits, loss)
+    assert logits.is_contiguous() and dlogits.is_contiguous() and logits.numel() == n_pos + n_neg
+    _L().hulc_bce_logits_loss(_ptr(logits), _ptr(dlogits), _ptr(loss), int(n_pos), int(n_neg), float(grad_scale), _stream())
+
+
 def set_rng_offset(t: Optional[torch.Tensor]):
     """Point the library's device-resident RNG offset at a 1-element int64 tensor (None clears it)."""
     if t is not None:

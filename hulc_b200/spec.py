@@ -46,6 +46,10 @@ class ModelDims:
     gripper_alpha: float = 1.0
     clip_hidden: int = 128              # ProjVisLang's hidden width (proj_vis_lang.py:10-21, fixed in the reference)
     clip_out: int = 32
+    # ablation blocks, all off in the shipped model YAMLs
+    bc_z: bool = False                  # use_bc_z_auxiliary_loss + bc_z_lang_decoder (hulc.py:567-604, bc_z_lang_decoder.py:5-20)
+    mia: bool = False                   # use_mia_auxiliary_loss + mia_lang_discriminator (hulc.py:606-648, mia_lang_discriminator.py:5-21)
+    aux_hidden: int = 512               # hidden width of both auxiliary MLPs (fixed in the reference)
 
     @classmethod
     def shipped(cls, model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: int = 32, **kw) -> "ModelDims":
@@ -108,7 +112,7 @@ def _require(cfg, path: str, key: str, allowed, default):
 
 
 def dims_from_configs(model: str, perceptual_encoder, plan_proposal, plan_recognition, language_goal, visual_goal, action_decoder, distribution,
-                      proj_vis_lang=None) -> ModelDims:
+                      proj_vis_lang=None, bc_z_lang_decoder=None, mia_lang_discriminator=None) -> ModelDims:
     """Every size of the network from the config tree; raises on anything the kernels cannot run."""
     d = ModelDims.shipped(model)
     # ---- perceptual encoders (concat_encoders.py:20-57, vision_network.py:17-53, vision_network_gripper.py:24-47) ----
@@ -168,8 +172,11 @@ def dims_from_configs(model: str, perceptual_encoder, plan_proposal, plan_recogn
                     max_window=int(_get(plan_recognition, "max_position_embeddings", 32)))
     # ---- action decoder (logistic_decoder_rnn.py:27-83) ----------------------------------------------------------------
     ad = action_decoder
-    if not str(_get(ad, "_target_", "LogisticDecoderRNN")).endswith("LogisticDecoderRNN"):
-        raise NotImplementedError(f"action_decoder._target_={_get(ad, '_target_')!r}: only LogisticDecoderRNN is built (DeterministicDecoder: DESIGN.md, out of scope)")
+    target = str(_get(ad, "_target_", "LogisticDecoderRNN"))
+    if not target.endswith("LogisticDecoderRNN"):
+        # (the reference's DeterministicDecoder cannot be constructed: deterministic_decoder.py:33 evaluates the name `rnn_decoder`, which that
+        #  module never imports — NameError in the unmodified reference, so there is nothing to be a drop-in for)
+        raise NotImplementedError(f"action_decoder._target_={_get(ad, '_target_')!r}: LogisticDecoderRNN is the decoder the reference can build")
     rnn_model = _require(ad, "action_decoder", "rnn_model", ("rnn_decoder", "gru_decoder"), "rnn_decoder")
     _require(ad, "action_decoder", "num_layers", (2,), 2)
     _require(ad, "action_decoder", "policy_rnn_dropout_p", (0, 0.0), 0.0)
@@ -187,8 +194,27 @@ def dims_from_configs(model: str, perceptual_encoder, plan_proposal, plan_recogn
         raise NotImplementedError("action_decoder.act_{min,max}_bound: one bound shared by all action dimensions")
     d = replace(d, rnn_model=rnn_model, dec_hidden=int(_get(ad, "hidden_size", 2048)), n_mix=int(_get(ad, "n_mixtures", 10)), num_classes=int(_get(ad, "num_classes", 10)),
                 log_scale_min=float(_get(ad, "log_scale_min", -7.0)), act_min=float(lo[0]), act_max=float(hi[0]), gripper_alpha=float(_get(ad, "gripper_alpha", 1.0)))
+    return _aux_heads(d, model, proj_vis_lang, bc_z_lang_decoder, mia_lang_discriminator)
+
+
+def _aux_heads(d: ModelDims, model: str, proj_vis_lang, bc_z_lang_decoder, mia_lang_discriminator) -> ModelDims:
     if d.dec_hidden % 4 or d.prior_hidden % 4 or d.ffn_hidden % 4 or d.fc_hidden % 4:
         raise NotImplementedError("hidden sizes must be multiples of 4 (16-byte rows)")
+    # ---- BC-Z language regression head / MIA discriminator (bc_z_lang_decoder.py:5-20, mia_lang_discriminator.py:5-21) --
+    if bc_z_lang_decoder not in (None, {}, "none"):
+        if model == "mcil":
+            raise NotImplementedError("bc_z_lang_decoder is built for hulc / gcbc")
+        if int(_get(bc_z_lang_decoder, "in_features", d.fc_hidden)) != d.fc_hidden or int(_get(bc_z_lang_decoder, "lang_dim", d.lang_in)) != d.lang_in:
+            raise NotImplementedError("bc_z_lang_decoder: in_features = plan_recognition.fc_hidden_size, lang_dim = language_goal.in_features (conf/model/bc_z_lang_decoder/default.yaml)")
+        d = replace(d, bc_z=True)
+    if mia_lang_discriminator not in (None, {}, "none"):
+        if model == "mcil":
+            raise NotImplementedError("mia_lang_discriminator is built for hulc / gcbc")
+        _require(mia_lang_discriminator, "mia_lang_discriminator", "dropout_p", (0, 0.0), 0.0)
+        od = int(_get(proj_vis_lang, "output_dim", 32))
+        if int(_get(mia_lang_discriminator, "in_features", od)) != od or int(_get(mia_lang_discriminator, "lang_dim", od)) != od:
+            raise NotImplementedError("mia_lang_discriminator: in_features = lang_dim = proj_vis_lang.output_dim (conf/model/mia_lang_discriminator/default.yaml)")
+        d = replace(d, mia=True)
     # ---- CLIP projection head (proj_vis_lang.py:7-27) ------------------------------------------------------------------
     if model != "mcil":
         if proj_vis_lang is None:
@@ -271,4 +297,8 @@ def param_spec(model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: 
         lin("action_decoder.gripper_fc", 2, d.dec_hidden)
         lin("proj_vis_lang.mlp_im.0", d.clip_hidden, d.fc_hidden), lin("proj_vis_lang.mlp_im.2", d.clip_out, d.clip_hidden)
         lin("proj_vis_lang.mlp_lang.0", d.clip_hidden, G), lin("proj_vis_lang.mlp_lang.2", d.clip_out, d.clip_hidden)
+    if d.bc_z:
+        lin("bc_z_lang_decoder.mlp.0", d.aux_hidden, d.fc_hidden), lin("bc_z_lang_decoder.mlp.2", d.lang_in, d.aux_hidden)
+    if d.mia:
+        lin("mia_lang_discriminator.mlp.0", d.aux_hidden, 2 * d.clip_out), lin("mia_lang_discriminator.mlp.3", 1, d.aux_hidden)
     return spec

@@ -45,8 +45,11 @@ def model_config(
     max_window: int = 32,
     dropout_p: float = 0.1,
     target_root: str = "hulc",
+    bc_z: bool = False,
+    mia: bool = False,
 ) -> AttrDict:
-    """Resolved `conf/model/<model>.yaml`.  `target_root` is the package the `_target_` strings point into."""
+    """Resolved `conf/model/<model>.yaml`.  `target_root` is the package the `_target_` strings point into.  The ablation switches select
+    `model/bc_z_lang_decoder=default` (+ use_bc_z_auxiliary_loss) and `model/mia_lang_discriminator=default` (+ use_mia_auxiliary_loss)."""
     r = target_root
     action_space = 7
     act_max = [1.0] * 7
@@ -191,6 +194,13 @@ def model_config(
         cfg["use_clip_auxiliary_loss"] = False
     elif model != "hulc":
         raise ValueError(model)
+    if bc_z:  # conf/model/bc_z_lang_decoder/default.yaml
+        cfg["bc_z_lang_decoder"] = dict(_target_=f"{r}.models.auxiliary_loss_networks.bc_z_lang_decoder.BCZLangDecoder", in_features=4096, lang_dim=384)
+        cfg["use_bc_z_auxiliary_loss"] = True
+    if mia:  # conf/model/mia_lang_discriminator/default.yaml
+        cfg["mia_lang_discriminator"] = dict(_target_=f"{r}.models.auxiliary_loss_networks.mia_lang_discriminator.MIALangDiscriminator", in_features=32, lang_dim=32,
+                                             dropout_p=0.0)
+        cfg["use_mia_auxiliary_loss"] = True
     cfg["_target_"] = top
     cfg["_recursive_"] = False
     return _attr(cfg)
@@ -339,7 +349,7 @@ def dropout_masks(
     return m
 
 
-def make_state_dict(model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: int = 32, salt: int = 0) -> Dict[str, torch.Tensor]:
-    """Seeded parameters for `param_spec` (fp32, CPU)."""
-    sd = {k: torch.empty(s, dtype=torch.float32) for k, s in param_spec(model, rnn_model, max_window).items()}
+def make_state_dict(model: str = "hulc", rnn_model: str = "rnn_decoder", max_window: int = 32, salt: int = 0, dims=None) -> Dict[str, torch.Tensor]:
+    """Seeded parameters for `param_spec` (fp32, CPU); `dims` (spec.ModelDims) selects a non-shipped variant."""
+    sd = {k: torch.empty(s, dtype=torch.float32) for k, s in param_spec(model, rnn_model, max_window, dims=dims).items()}
     return fill_state_dict_(sd, salt)

@@ -241,6 +241,15 @@ int hulc_plan_cont_bwd(const float* pr_state, const float* pp_state, const float
 int hulc_clip_loss(const float* im, const float* tx, const float* logit_scale, const unsigned char* mask, float* loss, float* d_im,
                    float* d_tx, float* d_logit_scale, int n, int D, float grad_scale, void* stream);
 
+/* ---- auxiliary losses of the ablation configs ------------------------------------------------------------------------------------
+ * hulc_cosine_loss: Hulc.bc_z_auxiliary_loss (hulc/models/hulc.py:567-604) on the BCZLangDecoder output: loss[0] = mean_b (1 - cos(pred_b, target_b)),
+ *   dpred = grad_scale * d loss / d pred.  pred, target [B, D] with leading dimensions; B <= 256.
+ * hulc_bce_logits_loss: the binary cross entropy with logits of Hulc.mia_auxiliary_loss (hulc.py:606-648) over n_pos matching scores (label 1)
+ *   followed by n_neg rolled-pair scores (label 0): loss[0] = mean, dlogits = grad_scale * d loss / d logits. */
+int hulc_cosine_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int ldd, float* loss, int B, int D, float grad_scale,
+                     void* stream);
+int hulc_bce_logits_loss(const float* logits, float* dlogits, float* loss, int n_pos, int n_neg, float grad_scale, void* stream);
+
 /* ---- bf16 path (BASELINE config 3: the reference trains under 16-bit autocast, conf/trainer/play_trainer.yaml:3) ------------------
  * hulc_cast_bf16(_rows): y = bf16(x), round to nearest even — what torch.autocast does to the inputs of every nn.Linear / nn.Conv2d.
  * hulc_gemm_bf16: the nn.Linear products (forward x W^T, data gradient dY W, weight gradient dY^T x — the same call sites as hulc_gemm)

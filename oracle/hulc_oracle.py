@@ -420,6 +420,40 @@ def clip_loss(sd: SD, seq_feat: torch.Tensor, goal: torch.Tensor, mask: Optional
     return loss * 0 if skip else loss
 
 
+def bc_z_loss(sd: SD, seq_feat: torch.Tensor, gt_lang: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Hulc.bc_z_auxiliary_loss (hulc.py:567-604) with BCZLangDecoder (bc_z_lang_decoder.py:5-20): regress the language embedding from the
+    sequence feature, mean cosine distance.  The reference indexes `seq_vis_feat` with the mask TWICE (hulc.py:592-594), which only works
+    when the mask keeps every sequence; an all-false mask runs a dummy forward on the first sequence and multiplies the loss by 0."""
+    if mask is not None:
+        if not bool(mask.any()):
+            return 0.0 * bc_z_loss(sd, seq_feat[0:1], gt_lang[0:1])
+        if not bool(mask.all()):
+            raise IndexError("the reference applies use_for_aux_lang_loss twice to seq_vis_feat (hulc.py:592-594): partial masks fail there")
+    pred = linear(sd, "bc_z_lang_decoder.mlp.2", torch.relu(linear(sd, "bc_z_lang_decoder.mlp.0", seq_feat)))
+    cos = (pred * gt_lang).sum(-1) / (torch.linalg.norm(pred, dim=1) * torch.linalg.norm(gt_lang, dim=1))
+    return (1 - cos).mean()
+
+
+def mia_loss(sd: SD, seq_feat: torch.Tensor, goal: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Hulc.mia_auxiliary_loss (hulc.py:606-648) with MIALangDiscriminator (mia_lang_discriminator.py:5-21): a discriminator over
+    [projected image feature | projected language feature] scores matching pairs against pairs whose language row is rolled by one
+    (torch.roll(lang, 1, 0)); binary cross entropy with logits over the 2B scores."""
+    if mask is not None:
+        if not bool(mask.any()):
+            return 0.0 * mia_loss(sd, seq_feat[0:1], goal[0:1])
+        seq_feat, goal = seq_feat[mask], goal[mask]
+    im = linear(sd, "proj_vis_lang.mlp_im.2", torch.relu(linear(sd, "proj_vis_lang.mlp_im.0", seq_feat)))
+    tx = linear(sd, "proj_vis_lang.mlp_lang.2", torch.relu(linear(sd, "proj_vis_lang.mlp_lang.0", goal)))
+
+    def disc(a, b):
+        return linear(sd, "mia_lang_discriminator.mlp.3", torch.relu(linear(sd, "mia_lang_discriminator.mlp.0", torch.cat([a, b], -1))))
+
+    pos, neg = disc(im, tx), disc(im, torch.roll(tx, shifts=1, dims=0))
+    pred = torch.cat([pos, neg], 0)
+    labels = torch.cat([torch.ones_like(pos), torch.zeros_like(neg)], 0)
+    return F.binary_cross_entropy_with_logits(pred, labels)
+
+
 def random_shifts_aug(frames_u8: torch.Tensor, shifts: torch.Tensor, pad: int, mean: float = 0.5, std: float = 0.5) -> torch.Tensor:
     """The training-time image pipeline of conf/datamodule/transforms/rand_shift.yaml:2-22 on uint8 frames [N, C, H, W]: RandomShiftsAug
     (hulc/utils/transforms.py:8-29) -> ScaleImageTensor (/255) -> Normalize(mean, std).  The reference replicate-pads by `pad` and bilinearly
@@ -451,6 +485,8 @@ def training_step(
     kl_beta: float = 0.01,
     kl_alpha: float = 0.8,
     clip_beta: float = 3.0,
+    bc_z_beta: Optional[float] = None,
+    mia_beta: Optional[float] = None,
 ) -> Dict[str, torch.Tensor]:
     """Hulc.training_step (hulc.py:390-537) + lmp_train (hulc.py:254-299); GCBC.training_step (gcbc.py:50-181) for
     model="gcbc"; conf/model/mcil.yaml for model="mcil".  Returns every loss plus the intermediates the kernel tests
@@ -510,7 +546,15 @@ def training_step(
         kl_tot, act_tot = kl_tot + kl, act_tot + act_loss
         if "lang" in m and model != "mcil":
             clip = clip + clip_loss(sd, seq_feat, goal, d.get("use_for_aux_lang_loss"))
+            if bc_z_beta is not None:
+                out["lang_pred_loss"] = out.get("lang_pred_loss", 0.0) + bc_z_loss(sd, seq_feat, d["lang"], d.get("use_for_aux_lang_loss"))
+            if mia_beta is not None:
+                out["lang_contrastive_loss"] = out.get("lang_contrastive_loss", 0.0) + mia_loss(sd, seq_feat, goal, d.get("use_for_aux_lang_loss"))
     total = tot / n_mod
+    if bc_z_beta is not None and "lang_pred_loss" in out:  # hulc.py:500-509
+        total = total + bc_z_beta * out["lang_pred_loss"]
+    if mia_beta is not None and "lang_contrastive_loss" in out:  # hulc.py:510-519
+        total = total + mia_beta * out["lang_contrastive_loss"]
     if model != "mcil":
         total = total + clip_beta * clip
         out["lang_clip_loss"] = clip

@@ -49,13 +49,16 @@ CASES = {
     "hulc_b32s32": ("hulc", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 2 shape
     "mcil_b32s32": ("mcil", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 4 shape
     "gcbc_b32s64": ("gcbc", "rnn_decoder", 32, 64, 0.0),  # BASELINE config 5 shape (window 64)
+    # ablation blocks: BC-Z + MIA auxiliary losses next to the CLIP loss.  (model/action_decoder=deterministic cannot be
+    # pinned: DeterministicDecoder.__init__ raises NameError in the unmodified reference, deterministic_decoder.py:33.)
+    "hulc_aux_b4s8": ("hulc", "rnn_decoder", 4, 8, 0.0, dict(bc_z=True, mia=True)),
 }
 
 
-def build_reference(model, rnn_model, dropout_p, max_window):
+def build_reference(model, rnn_model, dropout_p, max_window, **variant):
     import importlib
 
-    cfg = synthetic.model_config(model, rnn_model, max_window, dropout_p, target_root="hulc")
+    cfg = synthetic.model_config(model, rnn_model, max_window, dropout_p, target_root="hulc", **variant)
     cfg = copy.deepcopy(cfg)
     target = cfg.pop("_target_")
     cfg.pop("_recursive_")
@@ -111,9 +114,10 @@ def injected_randomness(u_queue, eps_queue, mask_queue, p):
 
 
 def run_case(name):
-    model, rnn_model, B, S, p = CASES[name]
+    model, rnn_model, B, S, p = CASES[name][:5]
+    variant = CASES[name][5] if len(CASES[name]) > 5 else {}
     t0 = time.time()
-    net = build_reference(model, rnn_model, p, max(32, S))
+    net = build_reference(model, rnn_model, p, max(32, S), **variant)
     batch = synthetic.make_batch(B, S, seed=1)
     noise = {m: synthetic.plan_noise(B, S, m) for m in batch}
     masks = {m: synthetic.dropout_masks(B, S, m, p) for m in batch} if p > 0 else None
@@ -150,6 +154,7 @@ def run_case(name):
     out = O.training_step(
         sd, batch, model=model, rnn_model=rnn_model, dropout_p=p,
         plan_u={m: noise[m]["u"] for m in batch}, plan_eps={m: noise[m]["eps"] for m in batch}, dropout_masks=masks,
+        bc_z_beta=1.0 if variant.get("bc_z") else None, mia_beta=1.0 if variant.get("mia") else None,
     )
     out["total_loss"].backward()
 
@@ -160,7 +165,7 @@ def run_case(name):
     close(out["total_loss"].detach(), loss_ref.detach(), "total_loss", 1e-5, 1e-6)
     fx = {"total_loss": loss_ref.detach()}
     for k in ("train/kl_loss", "train/action_loss", "train/lang_clip_loss", "train/kl_loss_scaled_vis", "train/kl_loss_scaled_lang",
-              "train/action_loss_vis", "train/action_loss_lang"):
+              "train/action_loss_vis", "train/action_loss_lang", "train/pred_lang", "train/lang_contrastive"):
         if k in logged:
             fx[k.replace("train/", "")] = logged[k]
     close(out["action_loss"].detach(), logged["train/action_loss"], "action_loss", 1e-5, 1e-6)
@@ -168,6 +173,10 @@ def run_case(name):
         close(out["kl_loss"].detach(), logged["train/kl_loss"], "kl_loss", 1e-5, 1e-7)
     if model != "mcil":
         close(3.0 * out["lang_clip_loss"].detach(), logged["train/lang_clip_loss"], "clip", 1e-5, 1e-6)
+    if variant.get("bc_z"):
+        close(out["lang_pred_loss"].detach(), logged["train/pred_lang"], "bc-z loss", 1e-5, 1e-6)
+    if variant.get("mia"):
+        close(out["lang_contrastive_loss"].detach(), logged["train/lang_contrastive"], "mia loss", 1e-5, 1e-6)
     nseq = min(B, 2)
     for m in batch:
         lp, ls, mu, grip, act = captured[m]

@@ -14,14 +14,20 @@ def _cat_masks(masks, mods):
     return {k: torch.cat([masks[m][k] for m in mods], 0).to(torch.uint8).contiguous() for k in masks[mods[0]]}
 
 
-def run_pair(model, rnn_model, B, S, p, device, hw=(200, 84), use_idx=False, seed=1, max_window=32, precision="fp32"):
+def run_pair(model, rnn_model, B, S, p, device, hw=(200, 84), use_idx=False, seed=1, max_window=32, precision="fp32", aux=False, aux_mask=None):
+    """aux: the BC-Z and MIA auxiliary heads next to the CLIP loss (ablation configs, hulc.py:567-648); aux_mask: use_for_aux_lang_loss of the
+    language modality (None keeps the batch's all-true mask)."""
     from hulc_b200.engine import HulcEngine
+    from hulc_b200.spec import ModelDims
 
-    sd = synthetic.make_state_dict(model, rnn_model, max_window=max_window)
+    dims = ModelDims.shipped(model, rnn_model, max_window, bc_z=True, mia=True, **({} if model == "mcil" else {"dropout_p": float(p)})) if aux else None
+    sd = synthetic.make_state_dict(model, rnn_model, max_window=max_window, dims=dims)
     if hw != (200, 84):  # reduced frames (emulator speed): the gripper flatten-FC shrinks with them
         k = ((((hw[1] - 8) // 4 + 1) - 4) // 2 + 1) - 2
         sd["perceptual_encoder.rgb_gripper_encoder.conv_model.7.weight"] = sd["perceptual_encoder.rgb_gripper_encoder.conv_model.7.weight"][:, : 64 * k * k].contiguous()
     batch = synthetic.make_batch(B, S, seed=seed, static_hw=hw[0], gripper_hw=hw[1])
+    if aux_mask is not None:
+        batch["lang"]["use_for_aux_lang_loss"] = aux_mask
     mods = list(batch)
     noise = {m: synthetic.plan_noise(B, S, m) for m in mods}
     masks = {m: synthetic.dropout_masks(B, S, m, p) for m in mods} if p > 0 else None
@@ -29,10 +35,10 @@ def run_pair(model, rnn_model, B, S, p, device, hw=(200, 84), use_idx=False, see
     # oracle (CPU autograd)
     sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     ref = O.training_step(sd_o, batch, model=model, rnn_model=rnn_model, dropout_p=p, plan_u={m: noise[m]["u"] for m in mods},
-                          plan_eps={m: noise[m]["eps"] for m in mods}, dropout_masks=masks)
+                          plan_eps={m: noise[m]["eps"] for m in mods}, dropout_masks=masks, bc_z_beta=1.0 if aux else None, mia_beta=1.0 if aux else None)
     ref["total_loss"].backward()
 
-    eng = HulcEngine(model, rnn_model, max_window=max_window, device=device, dropout_p=p, precision=precision)
+    eng = HulcEngine(model, rnn_model, max_window=max_window, device=device, dropout_p=p, precision=precision, dims=dims)
     if hw != (200, 84):
         from hulc_b200.engine import ParamStore
         eng.spec["perceptual_encoder.rgb_gripper_encoder.conv_model.7.weight"] = tuple(sd["perceptual_encoder.rgb_gripper_encoder.conv_model.7.weight"].shape)
@@ -59,8 +65,9 @@ def compare(res, rtol=1e-3, atol=1e-4, grad_rtol=2e-3, inter_rtol=None, inter_at
     ref, out, eng, sd_o, mods, B, S, model = (res[k] for k in ("ref", "out", "eng", "sd_o", "mods", "B", "S", "model"))
     cpu = lambda t: t.detach().float().cpu()
     report = {}
-    for k in ("total_loss", "action_loss", "kl_loss", "lang_clip_loss"):
-        if k in ref and k in out:
+    for k in ("total_loss", "action_loss", "kl_loss", "lang_clip_loss", "lang_pred_loss", "lang_contrastive_loss"):
+        if k in ref or k in out:
+            assert k in ref and k in out, f"{k}: reported by only one side"
             a, b = float(cpu(out[k])), float(ref[k])
             report[k] = (a, b)
             np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=k)

@@ -77,6 +77,7 @@ GOLDEN = {
     "hulc_b32s32": ("hulc", "rnn_decoder", 32, 32, 0.0),
     "mcil_b32s32": ("mcil", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 4 at its full shape
     "gcbc_b32s64": ("gcbc", "rnn_decoder", 32, 64, 0.0),  # BASELINE config 5 at its full shape
+    "hulc_aux_b4s8": ("hulc", "rnn_decoder", 4, 8, 0.0),  # BC-Z + MIA auxiliary heads next to the CLIP loss (ablation configs)
 }
 
 
@@ -88,8 +89,11 @@ def test_step_matches_reference_fixture(name, golden_dir, precision):
     model, rnn_model, B, S, p = GOLDEN[name]
     tf32 = precision == "tf32"
     fx = np.load(golden_dir / f"{name}.npz")
-    eng = HulcEngine(model, rnn_model, max_window=max(32, S), device="cuda", dropout_p=p, precision=precision)
-    eng.load_state_dict(synthetic.make_state_dict(model, rnn_model, max_window=max(32, S)))
+    from hulc_b200.spec import ModelDims
+
+    dims = ModelDims.shipped(model, rnn_model, max(32, S), bc_z=True, mia=True, dropout_p=p) if "_aux_" in name else None
+    eng = HulcEngine(model, rnn_model, max_window=max(32, S), device="cuda", dropout_p=p, precision=precision, dims=dims)
+    eng.load_state_dict(synthetic.make_state_dict(model, rnn_model, max_window=max(32, S), dims=dims))
     batch = synthetic.make_batch(B, S, seed=1, device="cuda")
     mods = list(batch)
     noise = {m: synthetic.plan_noise(B, S, m) for m in mods}
@@ -112,6 +116,9 @@ def test_step_matches_reference_fixture(name, golden_dir, precision):
         np.testing.assert_allclose(out["kl_loss"].item(), fx["kl_loss"], rtol=RTOL, atol=ATOL)
     if "lang_clip_loss" in fx.files:  # the reference logs beta * loss
         np.testing.assert_allclose(3.0 * out["lang_clip_loss"].item(), fx["lang_clip_loss"], rtol=RTOL, atol=ATOL)
+    if "pred_lang" in fx.files:
+        np.testing.assert_allclose(out["lang_pred_loss"].item(), fx["pred_lang"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(out["lang_contrastive_loss"].item(), fx["lang_contrastive"], rtol=RTOL, atol=ATOL)
     heads = out["heads_tm"].transpose(0, 1).cpu()  # (nB, S, n)
     nm = eng.n_dims * eng.n_mix
     for i, m in enumerate(mods):

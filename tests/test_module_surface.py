@@ -332,3 +332,34 @@ def test_kl_schedule_callbacks_drive_the_step(env):
         lin.on_train_epoch_start(None, _Epoch(m, 3))  # before the ramp: the KL term is switched off
         m.training_step(batch, 2, plan_u=pu)
         assert float(m.last_outputs["kl_loss"]) == 0.0
+
+
+def test_bc_z_and_mia_heads_through_the_module(env):
+    """use_bc_z_auxiliary_loss / use_mia_auxiliary_loss with their networks (conf/model/{bc_z_lang_decoder,mia_lang_discriminator}/default.yaml):
+    the module builds the extra parameters under the reference's keys, logs train/pred_lang and train/lang_contrastive (hulc.py:500-519) and
+    its total matches the oracle; the flags without their networks are refused."""
+    from hulc_b200.models.hulc import Hulc
+    from hulc_b200.spec import ModelDims
+
+    dev, precision, hw = env
+    m = Hulc(**_cfg("hulc", hw, 0.0, bc_z=True, mia=True), device=dev, precision=precision)
+    dims = ModelDims.shipped("hulc", bc_z=True, mia=True, dropout_p=0.0)
+    sd = _state_dict("hulc", hw, dims=dims)
+    assert {"bc_z_lang_decoder.mlp.0.weight", "bc_z_lang_decoder.mlp.2.bias", "mia_lang_discriminator.mlp.0.weight", "mia_lang_discriminator.mlp.3.bias"} <= set(m.state_dict())
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("spatial_softmax" in k or "action_decoder" in k for k in missing), (missing, unexpected)  # (only reference buffers are absent)
+    host, batch = _batch(env, B=3)
+    noise = {k: synthetic.plan_noise(3, 4, k) for k in host}
+    with torch.no_grad():
+        m.training_step(batch, 0, plan_u={k: noise[k]["u"].to(batch[k]["actions"].device) for k in batch})
+    assert set(m.logged) == REF_TRAIN_KEYS | {"train/pred_lang", "train/lang_contrastive"}
+    ref = O.training_step(sd, host, plan_u={k: noise[k]["u"] for k in host}, bc_z_beta=1.0, mia_beta=1.0)
+    out = m.last_outputs
+    for k in ("total_loss", "lang_pred_loss", "lang_contrastive_loss", "lang_clip_loss"):
+        np.testing.assert_allclose(float(out[k]), float(ref[k]), rtol=1e-3, atol=1e-4, err_msg=k)
+    m.enable_cuda_graphs(True)
+    assert m._graphs is None  # these heads read the mask on the host every step: the step stays eager
+    cfg = _cfg("hulc", hw, 0.0)
+    cfg.use_bc_z_auxiliary_loss = True
+    with pytest.raises(NotImplementedError):
+        Hulc(**cfg, device=dev, precision=precision)

@@ -13,11 +13,14 @@ CASES = {
     "hulc_gru_b2s8": ("hulc", "gru_decoder", 2, 8, 0.0),
     "gcbc_b2s8": ("gcbc", "rnn_decoder", 2, 8, 0.0),
     "mcil_b2s8": ("mcil", "rnn_decoder", 2, 8, 0.0),
+    "hulc_aux_b4s8": ("hulc", "rnn_decoder", 4, 8, 0.0),  # BC-Z + MIA auxiliary heads on (ablation configs, hulc.py:567-648)
 }
 
 
-def run_oracle(model, rnn_model, B, S, p, plan_idx=None):
-    sd = synthetic.make_state_dict(model, rnn_model)
+def run_oracle(model, rnn_model, B, S, p, plan_idx=None, aux=False):
+    from hulc_b200.spec import ModelDims
+
+    sd = synthetic.make_state_dict(model, rnn_model, dims=ModelDims.shipped(model, rnn_model, bc_z=True, mia=True) if aux else None)
     for v in sd.values():
         v.requires_grad_(True)
     batch = synthetic.make_batch(B, S, seed=1)
@@ -26,6 +29,7 @@ def run_oracle(model, rnn_model, B, S, p, plan_idx=None):
     out = O.training_step(
         sd, batch, model=model, rnn_model=rnn_model, dropout_p=p, plan_idx=plan_idx,
         plan_u={m: noise[m]["u"] for m in batch}, plan_eps={m: noise[m]["eps"] for m in batch}, dropout_masks=masks,
+        bc_z_beta=1.0 if aux else None, mia_beta=1.0 if aux else None,
     )
     out["total_loss"].backward()
     return sd, out
@@ -35,8 +39,11 @@ def run_oracle(model, rnn_model, B, S, p, plan_idx=None):
 def test_oracle_matches_reference_fixture(name, golden_dir):
     model, rnn_model, B, S, p = CASES[name]
     fx = np.load(golden_dir / f"{name}.npz")
-    sd, out = run_oracle(model, rnn_model, B, S, p)
+    sd, out = run_oracle(model, rnn_model, B, S, p, aux="_aux_" in name)
     np.testing.assert_allclose(out["total_loss"].item(), fx["total_loss"], rtol=1e-5, atol=1e-6)
+    if "pred_lang" in fx.files:  # the reference logs beta * loss (beta = 1, conf/loss/default.yaml)
+        np.testing.assert_allclose(out["lang_pred_loss"].item(), fx["pred_lang"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out["lang_contrastive_loss"].item(), fx["lang_contrastive"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(out["action_loss"].item(), fx["action_loss"], rtol=1e-5, atol=1e-6)
     if "kl_loss" in fx:
         np.testing.assert_allclose(out["kl_loss"].item(), fx["kl_loss"], rtol=1e-5, atol=1e-7)
