@@ -51,7 +51,7 @@ CASES = {
     "gcbc_b32s64": ("gcbc", "rnn_decoder", 32, 64, 0.0),  # BASELINE config 5 shape (window 64)
     # ablation blocks: BC-Z + MIA auxiliary losses next to the CLIP loss.  (model/action_decoder=deterministic cannot be
     # pinned: DeterministicDecoder.__init__ raises NameError in the unmodified reference, deterministic_decoder.py:33.)
-    "hulc_aux_b4s8": ("hulc", "rnn_decoder", 4, 8, 0.0, dict(bc_z=True, mia=True)),
+    "hulc_aux_b4s32": ("hulc", "rnn_decoder", 4, 32, 0.0, dict(bc_z=True, mia=True)),
 }
 
 

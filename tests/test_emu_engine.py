@@ -29,7 +29,7 @@ def test_emu_step_matches_oracle(emu, monkeypatch, model, rnn_model, p):
 def test_emu_step_with_bc_z_and_mia_heads(emu, monkeypatch, mask):
     """The ablation configs' auxiliary heads (hulc.py:567-648): BC-Z language regression (cosine distance) and the MIA discriminator (BCE over
     matching / rolled pairs) next to the CLIP loss — losses and every gradient against the oracle, whose restatement is pinned to the
-    unmodified reference by the fixture hulc_aux_b4s8.  An all-false use_for_aux_lang_loss switches both off (loss * 0 in the reference)."""
+    unmodified reference by the fixture hulc_aux_b4s32.  An all-false use_for_aux_lang_loss switches both off (loss * 0 in the reference)."""
     import torch
 
     from hulc_b200 import engine

@@ -77,7 +77,7 @@ GOLDEN = {
     "hulc_b32s32": ("hulc", "rnn_decoder", 32, 32, 0.0),
     "mcil_b32s32": ("mcil", "rnn_decoder", 32, 32, 0.0),  # BASELINE config 4 at its full shape
     "gcbc_b32s64": ("gcbc", "rnn_decoder", 32, 64, 0.0),  # BASELINE config 5 at its full shape
-    "hulc_aux_b4s8": ("hulc", "rnn_decoder", 4, 8, 0.0),  # BC-Z + MIA auxiliary heads next to the CLIP loss (ablation configs)
+    "hulc_aux_b4s32": ("hulc", "rnn_decoder", 4, 32, 0.0),  # BC-Z + MIA auxiliary heads next to the CLIP loss (ablation configs)
 }
 
 

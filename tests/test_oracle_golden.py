@@ -13,7 +13,7 @@ CASES = {
     "hulc_gru_b2s8": ("hulc", "gru_decoder", 2, 8, 0.0),
     "gcbc_b2s8": ("gcbc", "rnn_decoder", 2, 8, 0.0),
     "mcil_b2s8": ("mcil", "rnn_decoder", 2, 8, 0.0),
-    "hulc_aux_b4s8": ("hulc", "rnn_decoder", 4, 8, 0.0),  # BC-Z + MIA auxiliary heads on (ablation configs, hulc.py:567-648)
+    "hulc_aux_b4s32": ("hulc", "rnn_decoder", 4, 32, 0.0),  # BC-Z + MIA auxiliary heads on (ablation configs, hulc.py:567-648)
 }
 
 
