@@ -322,6 +322,10 @@ def dominant_kernel_roofline(torch, eng, batch, peaks, step_ms):
     common = {"kernel": top, "traffic": traffic, "traffic_source": "profiles/r02_traffic.json (ncu --set full, dram read+write bytes per launch)" if traffic else None, "ms_per_launch": r["ms"], "launches_per_step": r["per_step"], "share_of_step": r["share"],
               "algorithmic_bytes_per_launch": abytes[top], "algorithmic_flops_per_launch": r["flops"], "kernels": kern,
               "step": {"tensor_frac": None, "hbm_frac": None}}
+    if top.startswith("rnn_seq"):  # a chain of S dependent 64 x 2048 x 2048 products: latency per dependent step is the figure that describes it
+        common["note"] = (f"{S} dependent steps in one persistent launch: {r['ms'] * 1e3 / S:.2f} us per dependent step; a latency chain, neither the tensor nor the "
+                          "HBM roof bounds it (DESIGN.md section 4)")
+        common["us_per_dependent_step"] = r["ms"] * 1e3 / S
     if hbm_bound:
         return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                 "peak_source": f"{peaks['src']} HBM copy bandwidth (MEASURED_PEAKS.json hbm_gbs)", **common}

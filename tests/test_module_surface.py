@@ -240,7 +240,8 @@ def test_optimizer_checkpoint_is_torch_adam_layout(env):
     m2.training_step(batch, 2, seed=12).backward()
     opt2.step()
     for k, v in m2.state_dict().items():
-        assert torch.equal(v, cont[k]), k
+        # (equal up to the summation order of the fp32 atomics in the conv bias gradients, which differs from run to run)
+        torch.testing.assert_close(v, cont[k], rtol=1e-5, atol=1e-8, msg=k)
     # without the optimizer state the same step lands elsewhere (zero moments, step = 1)
     m3, _ = _build(env)
     m3.load_state_dict(msd, strict=False)
