@@ -23,6 +23,7 @@ from .ops import Drop, NO_DROP, gemm, colsum
 from .spec import ModelDims, param_spec
 
 RELU, TANH, GATE_TANH = 1, 2, 4
+_TRACE_CASTS = os.environ.get("HULC_B200_TRACE_CASTS", "0") == "1"
 _POISON = bool(int(os.environ.get("HULC_B200_POISON", "0")))
 # HULC_B200_NVTX=1: one NVTX range per block of the step (encoders, goal, prior, posterior, plan, decoder, losses, and their backward
 # counterparts), so a timeline (nsys / ncu --nvtx) reads in the reference's vocabulary
@@ -368,6 +369,9 @@ class HulcEngine:
             ent[1] = self._twin_gen
         elif ent[1] != self._twin_gen:
             assert key not in self._bf16_only
+            if _TRACE_CASTS:  # development aid: which activations still reach a product as fp32 (one cast launch each)
+                name = next((n for n, b in self._bufs.items() if b.data_ptr() <= t.data_ptr() < b.data_ptr() + b.numel() * b.element_size()), "?")
+                print(f"[cast] {name} {tuple(t.shape)}")
             ops.cast_bf16(t, ent[0])
             ent[1] = self._twin_gen
         return ent[0]
