@@ -32,6 +32,16 @@ constexpr int kBK16 = 64;                           // bf16 elements per k-block
 constexpr int kATile16 = kBM * kRowBytes;           // 16 KB
 constexpr int kGroupB = 64 * kRowBytes;             // one MN-major group: 64 k-rows x 128 B
 constexpr int kThreadsG = (kEpiWarps + 2) * 32;
+// The same kernel serves fp32 operands consumed as tf32 (TF = true; hulc_gemm_tc's 1-pass products): a k-block row is still 128 bytes (32 floats),
+// the stage layout and byte counts are identical, only the MN-major layout differs — 32-element groups under SWIZZLE_128B_BASE32B, which the TMA
+// writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (scripts/micro/tma_mn_probe.cu) — and the instruction kind.
+template <bool TF>
+struct Elem {
+  static constexpr int kBK = TF ? 32 : 64;            // elements per k-block (128 bytes)
+  static constexpr int kG = TF ? 32 : 64;             // rows of an MN-major group = k-rows per k-block
+  static constexpr int kGroupBytes = kG * kRowBytes;  // 4 KB / 8 KB
+  static constexpr uint32_t kMnStep = TF ? 1024u : 2048u;  // bytes between the k-slices of consecutive MMAs in an MN-major tile (8 / 16 k-rows)
+};
 
 template <int BN>
 struct GCfg {
@@ -69,8 +79,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 // operand slice of one MMA (K = 16 bf16) inside a stage tile
-template <bool MN>
+template <bool MN, bool TF = false>
 __device__ __forceinline__ uint64_t desc16(uint32_t tile) {
+  if (MN && TF) return make_smem_desc(tile, (uint32_t)Elem<true>::kGroupBytes, 512u, 1u);  // SWIZZLE_128B_BASE32B: 4-row atoms, k-step + 8 k-rows = 1024 B
   if (MN) return make_smem_desc(tile, (uint32_t)kGroupB, 1024u, 2u);  // k-step: + 16 k-rows = 2048 B
   return make_smem_desc(tile, 16u, 1024u, 2u);                        // k-step: + 32 B inside the 128-byte row
 }
@@ -283,7 +294,7 @@ struct BfEpilogue {
   }
 };
 
-template <int BN, int CLUSTER, bool A_MN, bool B_MN>
+template <int BN, int CLUSTER, bool A_MN, bool B_MN, bool TF = false>
 __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, BfEpilogue ep,
                                                                   int num_tiles, int kb_per_split) {
   using Cfg = GCfg<BN>;
@@ -348,10 +359,10 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
   } else if (warp == kEpiWarps) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
-      constexpr uint32_t kAStep = (A_MN ? 2048u : 32u) >> 4, kBStep = (B_MN ? 2048u : 32u) >> 4;
+      constexpr uint32_t idesc = TF ? make_idesc_tf32(kBM, BN, A_MN, B_MN) : make_idesc_bf16(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t kAStep = (A_MN ? Elem<TF>::kMnStep : 32u) >> 4, kBStep = (B_MN ? Elem<TF>::kMnStep : 32u) >> 4;
       const uint32_t s0 = smem_u32(smem);
-      const uint64_t a0 = desc16<A_MN>(s0), b0 = desc16<B_MN>(s0 + kATile16);
+      const uint64_t a0 = desc16<A_MN, TF>(s0), b0 = desc16<B_MN, TF>(s0 + kATile16);
       int j = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int a = it & 1;
@@ -364,7 +375,10 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
           tc_fence_after_sync();
           const uint32_t soff = (uint32_t)(stage * Cfg::kStage) >> 4;
 #pragma unroll
-          for (int k = 0; k < kBK16 / 16; ++k) umma_bf16(d_tmem, a0 + (soff + k * kAStep), b0 + (soff + k * kBStep), idesc, (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < 4; ++k) {  // 4 MMAs per 128-byte k-block: K = 16 bf16 or 8 tf32 each
+            if (TF) umma_tf32(d_tmem, a0 + (soff + k * kAStep), b0 + (soff + k * kBStep), idesc, (uint32_t)((kb | k) != 0));
+            else umma_bf16(d_tmem, a0 + (soff + k * kAStep), b0 + (soff + k * kBStep), idesc, (uint32_t)((kb | k) != 0));
+          }
           umma_commit(&bars->empty[stage]);
           if (kb == kb_per_split - 1) umma_commit(&bars->tmem_full[a]);
         }
@@ -384,17 +398,18 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
           const int stage = j % S;
           mbar_wait(&bars->empty[stage], ((j / S) & 1) ^ 1);
           const uint32_t dstA = smem_u32(smem) + stage * Cfg::kStage, dstB = dstA + kATile16;
-          const int k0 = (kb0 + kb) * kBK16;
+          using El = Elem<TF>;
+          const int k0 = (kb0 + kb) * El::kBK;
           tma::expect_tx(&bars->full[stage], (uint32_t)Cfg::kStage);
           if (A_MN) {
 #pragma unroll
-            for (int g = 0; g < kBM / 64; ++g) tma::load_2d(dstA + g * kGroupB, &mapA, &bars->full[stage], m0 + g * 64, k0);
+            for (int g = 0; g < kBM / El::kG; ++g) tma::load_2d(dstA + g * El::kGroupBytes, &mapA, &bars->full[stage], m0 + g * El::kG, k0);
           } else {
             tma::load_2d(dstA, &mapA, &bars->full[stage], k0, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g) tma::load_2d(dstB + g * kGroupB, &mapB, &bars->full[stage], n0 + g * 64, k0);
+            for (int g = 0; g < BN / El::kG; ++g) tma::load_2d(dstB + g * El::kGroupBytes, &mapB, &bars->full[stage], n0 + g * El::kG, k0);
           } else {
             tma::load_2d(dstB, &mapB, &bars->full[stage], k0, n0);
           }
@@ -460,8 +475,8 @@ __global__ void cast_bf16_rows_kernel(const float* __restrict__ x, int ldx, __nv
 // Tile width and k-slices of a product.  Clusters of 8 / 4 / 2 CTAs of this kernel (one CTA per SM) fit 15 / 33 / 74 at a time on the
 // 148 SMs (measured for gemm_tc_kernel, same shared-memory footprint): a skinny product takes the combination that puts the most CTAs
 // to work in one wave.
-inline void choose_config(int M, int N, int K, int& bn, int& splits) {
-  const int num_kb = hulc_cdiv(K, kBK16), tiles_m = hulc_cdiv(M, kBM);
+inline void choose_config(int M, int N, int K, int& bn, int& splits, int bk = kBK16) {
+  const int num_kb = hulc_cdiv(K, bk), tiles_m = hulc_cdiv(M, kBM);
   static const int kClusters[3] = {8, 4, 2}, kCap[3] = {15, 33, 74};
   splits = 1;
   bn = N > 64 ? 128 : 64;
@@ -479,6 +494,20 @@ inline void choose_config(int M, int N, int K, int& bn, int& splits) {
   }
 }
 
+// fp32 operand (consumed as tf32): 32 floats per k-block row; MN-major tiles are 32 x 32 boxes under the ATOM_32B flavour of the 128-byte swizzle
+int operand_map_f32(CUtensorMap* m, const float* p, int rows, int K, int ld, bool mn_major, int box_rows) {
+  if (mn_major) {  // stored K x rows
+    const uint64_t dims[2] = {(uint64_t)rows, (uint64_t)K};
+    const uint64_t strides[1] = {(uint64_t)ld * 4};
+    const uint32_t box[2] = {32, 32};
+    return tma::make_map(m, p, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  }
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  const uint64_t strides[1] = {(uint64_t)ld * 4};
+  const uint32_t box[2] = {32, (uint32_t)box_rows};
+  return tma::make_map(m, p, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int operand_map(CUtensorMap* m, const __nv_bfloat16* p, int rows, int K, int ld, bool mn_major, int box_rows) {
   if (mn_major) {  // stored K x rows
     const uint64_t dims[2] = {(uint64_t)rows, (uint64_t)K};
@@ -492,10 +521,10 @@ int operand_map(CUtensorMap* m, const __nv_bfloat16* p, int rows, int K, int ld,
   return tma::make_map(m, p, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
 
-template <int BN, int CLUSTER, bool A_MN, bool B_MN>
+template <int BN, int CLUSTER, bool A_MN, bool B_MN, bool TF = false>
 int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const BfEpilogue& ep, int tiles, int kbps, cudaStream_t st) {
   using Cfg = GCfg<BN>;
-  auto kfn = gemm_bf16_kernel<BN, CLUSTER, A_MN, B_MN>;
+  auto kfn = gemm_bf16_kernel<BN, CLUSTER, A_MN, B_MN, TF>;
   HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   if (CLUSTER == 1) {
     HULC_LAUNCH(kfn, dim3(min(kNumSMs, tiles)), dim3(kThreadsG), Cfg::kSmem, st, ma, mb, ep, tiles, kbps);
@@ -515,36 +544,57 @@ int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const BfEpilogue& e
   HULC_RETURN_LAST();
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, BfEpilogue ep, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, bool TF = false, typename T = __nv_bfloat16>
+int launch(const T* A, const T* B, int M, int N, int K, int lda, int ldb, BfEpilogue ep, cudaStream_t st) {
   CUtensorMap ma, mb;
-  if (operand_map(&ma, A, M, K, lda, A_MN, kBM) != 0 || operand_map(&mb, B, N, K, ldb, B_MN, BN) != 0) return (int)cudaErrorInvalidValue;
+  if constexpr (TF) {
+    if (operand_map_f32(&ma, A, M, K, lda, A_MN, kBM) != 0 || operand_map_f32(&mb, B, N, K, ldb, B_MN, BN) != 0) return (int)cudaErrorInvalidValue;
+  } else {
+    if (operand_map(&ma, A, M, K, lda, A_MN, kBM) != 0 || operand_map(&mb, B, N, K, ldb, B_MN, BN) != 0) return (int)cudaErrorInvalidValue;
+  }
   const int tiles_m = hulc_cdiv(M, kBM), tiles_n = hulc_cdiv(N, BN);
-  const int kbps = hulc_cdiv(hulc_cdiv(K, kBK16), ep.splits);
+  const int kbps = hulc_cdiv(hulc_cdiv(K, Elem<TF>::kBK), ep.splits);
   const int tiles = tiles_m * tiles_n * ep.splits;
   ep.BN = BN; ep.tiles_n = tiles_n;
   if constexpr (BN <= 128) {
     switch (ep.splits) {
-      case 8: return launch_one<BN, 8, A_MN, B_MN>(ma, mb, ep, tiles, kbps, st);
-      case 4: return launch_one<BN, 4, A_MN, B_MN>(ma, mb, ep, tiles, kbps, st);
-      case 2: return launch_one<BN, 2, A_MN, B_MN>(ma, mb, ep, tiles, kbps, st);
+      case 8: return launch_one<BN, 8, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
+      case 4: return launch_one<BN, 4, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
+      case 2: return launch_one<BN, 2, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
       default: break;
     }
   }
-  return launch_one<BN, 1, A_MN, B_MN>(ma, mb, ep, tiles, kbps, st);
+  return launch_one<BN, 1, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
 }
 
-template <int BN>
-int dispatch_layout(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, int transA, int transB, const BfEpilogue& ep, cudaStream_t st) {
+template <int BN, bool TF = false, typename T = __nv_bfloat16>
+int dispatch_layout(const T* A, const T* B, int M, int N, int K, int lda, int ldb, int transA, int transB, const BfEpilogue& ep, cudaStream_t st) {
   // op(A) is M x K: stored M x K (transA = 0: K-major) or K x M (transA = 1: MN-major).  op(B)^T is N x K: B stored N x K
   // (transB = 1, the torch Linear weight: K-major) or K x N (transB = 0: MN-major).
-  if (!transA && transB) return launch<BN, false, false>(A, B, M, N, K, lda, ldb, ep, st);
-  if (!transA && !transB) return launch<BN, false, true>(A, B, M, N, K, lda, ldb, ep, st);
-  if (transA && transB) return launch<BN, true, false>(A, B, M, N, K, lda, ldb, ep, st);
-  return launch<BN, true, true>(A, B, M, N, K, lda, ldb, ep, st);
+  if (!transA && transB) return launch<BN, false, false, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
+  if (!transA && !transB) return launch<BN, false, true, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
+  if (transA && transB) return launch<BN, true, false, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
+  return launch<BN, true, true, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
 }
 
 }  // namespace
+
+// fp32 operands consumed as tf32 (one pass), TMA-fed: the kernel behind hulc_gemm_tc's 1-pass products (gemm_tc.cu).  Same contract as hulc_gemm_tc
+// (dropout applied in the epilogue with hulc_apply_dropout_rows' element indexing); cudaErrorNotSupported = operands the TMA cannot address.
+int hulc_gemm_tf32_tma(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta,
+                       const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate, int ldg, float drop_p,
+                       unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, cudaStream_t st) {
+  if ((reinterpret_cast<size_t>(A) & 15) || (reinterpret_cast<size_t>(B) & 15) || (lda & 3) || (ldb & 3)) return (int)cudaErrorNotSupported;
+  BfEpilogue ep{};
+  ep.C = C; ep.Cb = nullptr; ep.M = M; ep.N = N; ep.ldc = ldc; ep.ldcb = 0; ep.alpha = alpha; ep.beta = beta; ep.bias = bias;
+  ep.addend = addend; ep.ldadd = ldadd; ep.add_mod = add_mod; ep.act = act; ep.gate = gate; ep.gate_b = nullptr; ep.ldg = ldg;
+  ep.drop = make_drop(drop_p, drop_seed, drop_site, drop_keep);
+  int bn;
+  choose_config(M, N, K, bn, ep.splits, Elem<true>::kBK);
+  if (bn == 256) return dispatch_layout<256, true, float>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
+  if (bn == 128) return dispatch_layout<128, true, float>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
+  return dispatch_layout<64, true, float>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
+}
 
 // y = bf16(x) for n contiguous elements (x 32-byte aligned, y 16-byte aligned) — the cast that makes an fp32 tensor a GEMM operand.
 HULC_API int hulc_cast_bf16(const float* x, void* y, long long n, void* stream) {

@@ -295,6 +295,11 @@ HULC_API int hulc_tc_trace_read(unsigned long long* host_out) {
 // storage, M / N for the transposed storage); otherwise cudaErrorInvalidValue (callers use hulc_gemm for such shapes).
 // Skinny products (few output tiles, long K — the recurrent steps, the prior / goal MLPs, the decoder heads) are split along
 // K over a thread-block cluster and reduced through distributed shared memory; the workspace is not used.
+// gemm_bf16_tc.cu: the TMA-fed kernel with fp32 operands consumed as tf32 (one pass)
+int hulc_gemm_tf32_tma(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta,
+                       const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate, int ldg, float drop_p,
+                       unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, cudaStream_t st);
+
 HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                           float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate,
                           int ldg, float drop_p, unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, int passes,
@@ -303,6 +308,17 @@ HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N
   if (K <= 0 || !A || !B || !C || (passes != 1 && passes != 3)) return (int)cudaErrorInvalidValue;
   if ((reinterpret_cast<size_t>(A) & 15) || (reinterpret_cast<size_t>(B) & 15) || (lda & 3) || (ldb & 3)) return (int)cudaErrorInvalidValue;
   if (((transA ? M : K) & 3) || ((transB ? K : N) & 3)) return (int)cudaErrorInvalidValue;
+  if (passes == 1) {
+    // one-pass products (the backward GEMMs of tf32 mode): operands by TMA — twice the L2 -> shared-memory delivery rate of the cp.async producers
+    // below (64 vs 30 B/clk/SM measured), same arithmetic (the tensor core truncates the fp32 containers either way).  HULC_B200_GEMM_TF32_TMA=0
+    // keeps the cp.async kernel.
+    static const bool use_tma = [] { const char* e = getenv("HULC_B200_GEMM_TF32_TMA"); return !(e && e[0] == '0'); }();
+    if (use_tma) {
+      const int rc = hulc_gemm_tf32_tma(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bias, addend, ldadd, add_mod, act, gate, ldg, drop_p, drop_seed,
+                                        drop_site, drop_keep, (cudaStream_t)stream);
+      if (rc != (int)cudaErrorNotSupported) return rc;
+    }
+  }
   TcEpilogue ep;
   ep.C = C; ep.M = M; ep.N = N; ep.ldc = ldc; ep.alpha = alpha; ep.beta = beta; ep.bias = bias; ep.addend = addend; ep.ldadd = ldadd;
   ep.add_mod = add_mod; ep.act = act; ep.gate = gate; ep.ldg = ldg;

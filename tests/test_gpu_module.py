@@ -31,7 +31,8 @@ def _same_training(losses, sd, ref_losses, ref_sd, n=2, lr=2e-4):
     np.testing.assert_allclose(losses, ref_losses, rtol=1e-5)
     for k in ref_sd:
         diff = (sd[k].float() - ref_sd[k].float()).abs()
-        assert float(diff.max()) <= 3 * n * lr and float((diff > 1e-6).float().mean()) < 1e-2, k
+        # (a count, not only a fraction: one moved element of a 32-element bias is already 3 % of it)
+        assert float(diff.max()) <= 3 * n * lr and int((diff > 1e-6).sum()) <= max(2, int(1e-2 * diff.numel())), k
 
 
 def _steps(m, dev, n=2, B=2, S=8):

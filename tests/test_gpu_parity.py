@@ -202,7 +202,8 @@ def test_cuda_graph_replay_matches_eager():
     # parameters: identical up to the order of fp32 atomics in the bias / LayerNorm-gain gradient sums, which Adam's
     # normalisation turns into at most a few times lr on a handful of near-zero-gradient elements
     diff = (b.ps.flat - a.ps.flat).abs()
-    assert float(diff.max()) <= 3 * 3 * b.lr and float((diff > 1e-6).float().mean()) < 3e-3
+    # (measured: 0.2-0.35 % of the elements move by more than 1e-6 over the three updates, depending on the products' summation split)
+    assert float(diff.max()) <= 3 * 3 * b.lr and float((diff > 1e-6).float().mean()) < 6e-3
 
 
 def test_no_cpu_fallback(monkeypatch):
