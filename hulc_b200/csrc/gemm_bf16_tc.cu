@@ -43,19 +43,27 @@ struct Elem {
   static constexpr uint32_t kMnStep = TF ? 1024u : 2048u;  // bytes between the k-slices of consecutive MMAs in an MN-major tile (8 / 16 k-rows)
 };
 
-template <int BN>
+// P3 (fp32 operands only): 3xTF32 — the TMA lands the raw fp32 tiles (the tensor core reads them as their tf32 truncation, "hi"); four splitter
+// warps write the residual x - tf32(x) of every 16-byte chunk into a second ("lo") copy of the stage, and the issuer adds lo*hi + hi*lo (side
+// accumulator) to hi*hi: fp32-level accuracy, the arithmetic of hulc_gemm_tc's 3-pass kernel with its operands delivered by TMA.
+template <int BN, bool P3 = false>
 struct GCfg {
   static constexpr int kBTile = BN * kRowBytes;
-  static constexpr int kStage = kATile16 + kBTile;
+  static constexpr int kHi = kATile16 + kBTile;          // what the TMA delivers per stage
+  static constexpr int kStage = (P3 ? 2 : 1) * kHi;
   static constexpr int kStagesRaw = (200 * 1024) / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmem = kStages * kStage + 1024 + 256;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static_assert(kStages >= 3, "pipeline depth");
+  static constexpr int kAcc = (P3 ? 2 : 1) * BN;         // TMEM columns of one accumulator buffer (main + side)
+  static constexpr int kTmemCols = 2 * kAcc < 32 ? 32 : 2 * kAcc;
+  static constexpr int kSplitWarps = P3 ? 4 : 0;
+  static constexpr int kThreads = kThreadsG + kSplitWarps * 32;
+  static_assert(kStages >= 3 && kTmemCols <= 512, "pipeline depth / TMEM columns");
 };
 
 struct GBars {
   uint64_t full[8];
+  uint64_t split[8];   // (3xTF32) the lo tiles of the stage are written
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
@@ -294,10 +302,12 @@ struct BfEpilogue {
   }
 };
 
-template <int BN, int CLUSTER, bool A_MN, bool B_MN, bool TF = false>
-__global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, BfEpilogue ep,
-                                                                  int num_tiles, int kb_per_split) {
-  using Cfg = GCfg<BN>;
+template <int BN, int CLUSTER, bool A_MN, bool B_MN, bool TF = false, bool P3 = false>
+__global__ void __launch_bounds__((GCfg<BN, P3>::kThreads), 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                                BfEpilogue ep, int num_tiles, int kb_per_split) {
+  static_assert(!P3 || TF, "the 3-pass split exists for fp32 operands");
+  using Cfg = GCfg<BN, P3>;
+  constexpr int kThr = Cfg::kThreads;
   constexpr int S = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->split[s], 4);
       mbar_init(&bars->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -329,13 +340,21 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
       const int a = it & 1;
       mbar_wait(&bars->tmem_full[a], (it >> 1) & 1);
       tc_fence_after_sync();
-      if constexpr (CLUSTER > 1) asm volatile("bar.sync 1, %0;" ::"n"(kThreadsG) : "memory");  // producers are done with the stage buffers (see tc_pipeline.cuh)
+      if constexpr (CLUSTER > 1) asm volatile("bar.sync 1, %0;" ::"n"(kThr) : "memory");  // producers are done with the stage buffers (see tc_pipeline.cuh)
       const int row = warp * 32 + lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN + c0), r);
-        tmem_ld_wait();
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * Cfg::kAcc + c0), r);
+        if constexpr (P3) {  // + the side accumulator (cross terms)
+          uint32_t r2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * Cfg::kAcc + BN + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        } else {
+          tmem_ld_wait();
+        }
         if constexpr (CLUSTER > 1) {
           float* prow = reinterpret_cast<float*>(smem) + (size_t)row * (BN + 4) + c0;
 #pragma unroll
@@ -368,20 +387,46 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
         const int a = it & 1;
         mbar_wait(&bars->tmem_empty[a], ((it >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * Cfg::kAcc);
         for (int kb = 0; kb < kb_per_split; ++kb, ++j) {
           const int stage = j % S;
-          mbar_wait(&bars->full[stage], (j / S) & 1);
+          mbar_wait(P3 ? &bars->split[stage] : &bars->full[stage], (j / S) & 1);
           tc_fence_after_sync();
           const uint32_t soff = (uint32_t)(stage * Cfg::kStage) >> 4;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 MMAs per 128-byte k-block: K = 16 bf16 or 8 tf32 each
-            if (TF) umma_tf32(d_tmem, a0 + (soff + k * kAStep), b0 + (soff + k * kBStep), idesc, (uint32_t)((kb | k) != 0));
-            else umma_bf16(d_tmem, a0 + (soff + k * kAStep), b0 + (soff + k * kBStep), idesc, (uint32_t)((kb | k) != 0));
+            const uint32_t first = (uint32_t)((kb | k) != 0);
+            const uint64_t da = a0 + (soff + k * kAStep), db = b0 + (soff + k * kBStep);
+            if constexpr (P3) {
+              constexpr uint32_t kLo = (uint32_t)Cfg::kHi >> 4;  // the lo copy of a tile sits kHi bytes behind it
+              umma_tf32(d_tmem + BN, da + kLo, db, idesc, first);
+              umma_tf32(d_tmem + BN, da, db + kLo, idesc, 1u);
+              umma_tf32(d_tmem, da, db, idesc, first);
+            } else if (TF) {
+              umma_tf32(d_tmem, da, db, idesc, first);
+            } else {
+              umma_bf16(d_tmem, da, db, idesc, first);
+            }
           }
           umma_commit(&bars->empty[stage]);
           if (kb == kb_per_split - 1) umma_commit(&bars->tmem_full[a]);
         }
+      }
+    }
+  } else if (P3 && warp >= kEpiWarps + 2) {
+    // ================================ splitters (3xTF32): lo = x - tf32(x), chunk by chunk, smem -> smem ================================
+    const int stid = threadIdx.x - (kEpiWarps + 2) * 32;  // 0..127
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kb_per_split; ++kb, ++j) {
+        const int stage = j % S;
+        mbar_wait(&bars->full[stage], (j / S) & 1);
+        const uint32_t hi = smem_u32(smem) + stage * Cfg::kStage;
+#pragma unroll 4
+        for (int i = stid; i < Cfg::kHi / 16; i += 128) lo_chunk(hi + (uint32_t)i * 16u, hi + (uint32_t)Cfg::kHi + (uint32_t)i * 16u);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->split[stage]);
       }
     }
   } else {
@@ -400,7 +445,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
           const uint32_t dstA = smem_u32(smem) + stage * Cfg::kStage, dstB = dstA + kATile16;
           using El = Elem<TF>;
           const int k0 = (kb0 + kb) * El::kBK;
-          tma::expect_tx(&bars->full[stage], (uint32_t)Cfg::kStage);
+          tma::expect_tx(&bars->full[stage], (uint32_t)Cfg::kHi);
           if (A_MN) {
 #pragma unroll
             for (int g = 0; g < kBM / El::kG; ++g) tma::load_2d(dstA + g * El::kGroupBytes, &mapA, &bars->full[stage], m0 + g * El::kG, k0);
@@ -419,7 +464,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_bf16_kernel(const __grid_co
   }
 
   if constexpr (CLUSTER > 1) {
-    if (warp >= kEpiWarps && (int)blockIdx.x < num_tiles) asm volatile("bar.sync 1, %0;" ::"n"(kThreadsG) : "memory");
+    if (warp >= kEpiWarps && (int)blockIdx.x < num_tiles) asm volatile("bar.sync 1, %0;" ::"n"(kThr) : "memory");
     static_assert(kBM * (BN + 4) * 4 <= Cfg::kStages * Cfg::kStage, "partial tile must fit in the stage buffers");
     cluster_sync_all();  // all partial tiles of the cluster are in place
     if (warp < kEpiWarps && (int)blockIdx.x < num_tiles) {
@@ -521,18 +566,18 @@ int operand_map(CUtensorMap* m, const __nv_bfloat16* p, int rows, int K, int ld,
   return tma::make_map(m, p, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
 
-template <int BN, int CLUSTER, bool A_MN, bool B_MN, bool TF = false>
+template <int BN, int CLUSTER, bool A_MN, bool B_MN, bool TF = false, bool P3 = false>
 int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const BfEpilogue& ep, int tiles, int kbps, cudaStream_t st) {
-  using Cfg = GCfg<BN>;
-  auto kfn = gemm_bf16_kernel<BN, CLUSTER, A_MN, B_MN, TF>;
+  using Cfg = GCfg<BN, P3>;
+  auto kfn = gemm_bf16_kernel<BN, CLUSTER, A_MN, B_MN, TF, P3>;
   HULC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   if (CLUSTER == 1) {
-    HULC_LAUNCH(kfn, dim3(min(kNumSMs, tiles)), dim3(kThreadsG), Cfg::kSmem, st, ma, mb, ep, tiles, kbps);
+    HULC_LAUNCH(kfn, dim3(min(kNumSMs, tiles)), dim3(Cfg::kThreads), Cfg::kSmem, st, ma, mb, ep, tiles, kbps);
     HULC_RETURN_LAST();
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles);  // one work item per CTA; consecutive CTAs = the k-slices of one output tile = one cluster
-  cfg.blockDim = dim3(kThreadsG);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -544,7 +589,7 @@ int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const BfEpilogue& e
   HULC_RETURN_LAST();
 }
 
-template <int BN, bool A_MN, bool B_MN, bool TF = false, typename T = __nv_bfloat16>
+template <int BN, bool A_MN, bool B_MN, bool TF = false, typename T = __nv_bfloat16, bool P3 = false>
 int launch(const T* A, const T* B, int M, int N, int K, int lda, int ldb, BfEpilogue ep, cudaStream_t st) {
   CUtensorMap ma, mb;
   if constexpr (TF) {
@@ -558,23 +603,23 @@ int launch(const T* A, const T* B, int M, int N, int K, int lda, int ldb, BfEpil
   ep.BN = BN; ep.tiles_n = tiles_n;
   if constexpr (BN <= 128) {
     switch (ep.splits) {
-      case 8: return launch_one<BN, 8, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
-      case 4: return launch_one<BN, 4, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
-      case 2: return launch_one<BN, 2, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
+      case 8: return launch_one<BN, 8, A_MN, B_MN, TF, P3>(ma, mb, ep, tiles, kbps, st);
+      case 4: return launch_one<BN, 4, A_MN, B_MN, TF, P3>(ma, mb, ep, tiles, kbps, st);
+      case 2: return launch_one<BN, 2, A_MN, B_MN, TF, P3>(ma, mb, ep, tiles, kbps, st);
       default: break;
     }
   }
-  return launch_one<BN, 1, A_MN, B_MN, TF>(ma, mb, ep, tiles, kbps, st);
+  return launch_one<BN, 1, A_MN, B_MN, TF, P3>(ma, mb, ep, tiles, kbps, st);
 }
 
-template <int BN, bool TF = false, typename T = __nv_bfloat16>
+template <int BN, bool TF = false, typename T = __nv_bfloat16, bool P3 = false>
 int dispatch_layout(const T* A, const T* B, int M, int N, int K, int lda, int ldb, int transA, int transB, const BfEpilogue& ep, cudaStream_t st) {
   // op(A) is M x K: stored M x K (transA = 0: K-major) or K x M (transA = 1: MN-major).  op(B)^T is N x K: B stored N x K
   // (transB = 1, the torch Linear weight: K-major) or K x N (transB = 0: MN-major).
-  if (!transA && transB) return launch<BN, false, false, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
-  if (!transA && !transB) return launch<BN, false, true, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
-  if (transA && transB) return launch<BN, true, false, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
-  return launch<BN, true, true, TF, T>(A, B, M, N, K, lda, ldb, ep, st);
+  if (!transA && transB) return launch<BN, false, false, TF, T, P3>(A, B, M, N, K, lda, ldb, ep, st);
+  if (!transA && !transB) return launch<BN, false, true, TF, T, P3>(A, B, M, N, K, lda, ldb, ep, st);
+  if (transA && transB) return launch<BN, true, false, TF, T, P3>(A, B, M, N, K, lda, ldb, ep, st);
+  return launch<BN, true, true, TF, T, P3>(A, B, M, N, K, lda, ldb, ep, st);
 }
 
 }  // namespace
@@ -583,7 +628,7 @@ int dispatch_layout(const T* A, const T* B, int M, int N, int K, int lda, int ld
 // (dropout applied in the epilogue with hulc_apply_dropout_rows' element indexing); cudaErrorNotSupported = operands the TMA cannot address.
 int hulc_gemm_tf32_tma(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta,
                        const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate, int ldg, float drop_p,
-                       unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, cudaStream_t st) {
+                       unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, int passes, cudaStream_t st) {
   if ((reinterpret_cast<size_t>(A) & 15) || (reinterpret_cast<size_t>(B) & 15) || (lda & 3) || (ldb & 3)) return (int)cudaErrorNotSupported;
   BfEpilogue ep{};
   ep.C = C; ep.Cb = nullptr; ep.M = M; ep.N = N; ep.ldc = ldc; ep.ldcb = 0; ep.alpha = alpha; ep.beta = beta; ep.bias = bias;
@@ -591,6 +636,10 @@ int hulc_gemm_tf32_tma(const float* A, const float* B, float* C, int M, int N, i
   ep.drop = make_drop(drop_p, drop_seed, drop_site, drop_keep);
   int bn;
   choose_config(M, N, K, bn, ep.splits, Elem<true>::kBK);
+  if (passes == 3) {  // (hi + lo stages and two accumulators per buffer: tiles of at most 128 columns)
+    if (bn >= 128) return dispatch_layout<128, true, float, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
+    return dispatch_layout<64, true, float, true>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
+  }
   if (bn == 256) return dispatch_layout<256, true, float>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
   if (bn == 128) return dispatch_layout<128, true, float>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);
   return dispatch_layout<64, true, float>(A, B, M, N, K, lda, ldb, transA, transB, ep, st);

@@ -298,7 +298,7 @@ HULC_API int hulc_tc_trace_read(unsigned long long* host_out) {
 // gemm_bf16_tc.cu: the TMA-fed kernel with fp32 operands consumed as tf32 (one pass)
 int hulc_gemm_tf32_tma(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta,
                        const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate, int ldg, float drop_p,
-                       unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, cudaStream_t st);
+                       unsigned long long drop_seed, unsigned drop_site, const unsigned char* drop_keep, int passes, cudaStream_t st);
 
 HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                           float alpha, float beta, const float* bias, const float* addend, int ldadd, int add_mod, int act, const float* gate,
@@ -308,14 +308,15 @@ HULC_API int hulc_gemm_tc(const float* A, const float* B, float* C, int M, int N
   if (K <= 0 || !A || !B || !C || (passes != 1 && passes != 3)) return (int)cudaErrorInvalidValue;
   if ((reinterpret_cast<size_t>(A) & 15) || (reinterpret_cast<size_t>(B) & 15) || (lda & 3) || (ldb & 3)) return (int)cudaErrorInvalidValue;
   if (((transA ? M : K) & 3) || ((transB ? K : N) & 3)) return (int)cudaErrorInvalidValue;
-  if (passes == 1) {
-    // one-pass products (the backward GEMMs of tf32 mode): operands by TMA — twice the L2 -> shared-memory delivery rate of the cp.async producers
+  {
+    // operands by TMA — twice the L2 -> shared-memory delivery rate of the cp.async producers
     // below (64 vs 30 B/clk/SM measured), same arithmetic (the tensor core truncates the fp32 containers either way).  HULC_B200_GEMM_TF32_TMA=0
     // keeps the cp.async kernel.
-    static const bool use_tma = [] { const char* e = getenv("HULC_B200_GEMM_TF32_TMA"); return !(e && e[0] == '0'); }();
-    if (use_tma) {
+    // HULC_B200_GEMM_TF32_TMA: 0 = cp.async kernels for everything, 1 = TMA for the one-pass products only, 3 (default) = also for 3xTF32
+    static const int use_tma = [] { const char* e = getenv("HULC_B200_GEMM_TF32_TMA"); return e ? atoi(e) : 3; }();
+    if (use_tma >= passes) {
       const int rc = hulc_gemm_tf32_tma(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bias, addend, ldadd, add_mod, act, gate, ldg, drop_p, drop_seed,
-                                        drop_site, drop_keep, (cudaStream_t)stream);
+                                        drop_site, drop_keep, passes, (cudaStream_t)stream);
       if (rc != (int)cudaErrorNotSupported) return rc;
     }
   }

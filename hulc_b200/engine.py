@@ -266,7 +266,7 @@ class HulcEngine:
         # thresholds from scripts/dbg_gemm_small.py (B200, back-to-back launches): the 1-pass kernel beats the CUDA-core one
         # from K = 64 up (and at K = 32 when there are >= 8 row tiles); the 3-pass kernel only on many rows or big products
         if role == "bwd":
-            return 1 if (K >= 64 or M >= 1024) else 0
+            return 1  # the TMA-fed one-pass kernel costs ~5 us for the smallest product; the CUDA-core kernel it used to lose to at K < 64 takes ~10
         return 3 if K >= 64 and (M >= 256 or 2.0 * M * N * K >= 1e8) else 0
 
     def gemm_fwd(self, A, B, C=None, out="f32", **kw):
