@@ -263,11 +263,11 @@ class HulcEngine:
         products, whose outputs are held to the fp32 parity tolerance)."""
         if not self.tc or N < 32 or K < 32:
             return 0
-        # thresholds from scripts/dbg_gemm_small.py (B200, back-to-back launches): the 1-pass kernel beats the CUDA-core one
-        # from K = 64 up (and at K = 32 when there are >= 8 row tiles); the 3-pass kernel only on many rows or big products
+        # Both flavours run on the TMA-fed kernel (csrc/gemm_bf16_tc.cu, fp32 operands): ~5-7 us for the smallest product inside a graph, which the
+        # CUDA-core kernel (~10 us) only beats below these sizes.  (With the cp.async kernels of round 1 the thresholds were K >= 64 and M >= 256.)
         if role == "bwd":
-            return 1  # the TMA-fed one-pass kernel costs ~5 us for the smallest product; the CUDA-core kernel it used to lose to at K < 64 takes ~10
-        return 3 if K >= 64 and (M >= 256 or 2.0 * M * N * K >= 1e8) else 0
+            return 1
+        return 3
 
     def gemm_fwd(self, A, B, C=None, out="f32", **kw):
         """out (bf16 mode only): "f32" writes C; "bf16" writes only C's bf16 twin (C stays a handle: for activations that are consumed by
