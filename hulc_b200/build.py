@@ -29,6 +29,16 @@ def nvcc() -> str:
 
 
 def build(verbose: bool = False, force: bool = False) -> Path:
+    """(Serialised with a file lock: concurrent callers — parallel test workers — wait for the first one's build.)"""
+    import fcntl
+
+    OBJ.mkdir(parents=True, exist_ok=True)
+    with open(OBJ / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build(verbose, force)
+
+
+def _build(verbose: bool = False, force: bool = False) -> Path:
     OBJ.mkdir(parents=True, exist_ok=True)
     LIB.parent.mkdir(parents=True, exist_ok=True)
     srcs = sorted(CSRC.glob("*.cu"))

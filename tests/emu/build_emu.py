@@ -12,6 +12,16 @@ OUT = HERE / "_build"
 
 
 def build(verbose=False) -> Path:
+    """(Serialised with a file lock: the test workers of a parallel run all ask for the library at start-up.)"""
+    import fcntl
+
+    OUT.mkdir(exist_ok=True)
+    with open(OUT / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build(verbose)
+
+
+def _build(verbose=False) -> Path:
     OUT.mkdir(exist_ok=True)
     srcs = sorted(p for p in CSRC.glob("*.cu") if "_tc" not in p.stem and "_tma" not in p.stem) + [HERE / "cuda_emu.cc"]  # tcgen05 / TMA kernels are not emulated
     deps = srcs + sorted(CSRC.glob("*.cuh")) + [HERE / "cuda_emu.h"]
