@@ -311,6 +311,35 @@ def test_clip_loss(K, masked):
     torch.testing.assert_close(d_ls[0], ls.grad, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("B,D,ld", [(5, 384, 384), (1, 20, 24), (64, 33, 40)])
+def test_cosine_loss(K, B, D, ld):
+    """hulc_cosine_loss: the BC-Z language-regression loss (hulc.py:596-601) — mean cosine distance of the rows, and its gradient."""
+    g = torch.Generator().manual_seed(B + D)
+    pred = torch.randn(B, ld, generator=g)[:, :D].requires_grad_(True)  # rows with a leading dimension
+    tgt = torch.randn(B, ld, generator=g)[:, :D]
+    loss, dpred = torch.full((1,), 7.0), torch.zeros(B, ld)[:, :D]
+    K.cosine_loss(pred.detach(), tgt, dpred, loss, grad_scale=1.5)
+    cos = (pred * tgt).sum(-1) / (torch.linalg.norm(pred, dim=1) * torch.linalg.norm(tgt, dim=1))
+    ref = (1 - cos).mean()
+    (1.5 * ref).backward()
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dpred, pred.grad, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("n_pos,n_neg", [(4, 4), (1, 1), (300, 300)])
+def test_bce_logits_loss(K, n_pos, n_neg):
+    """hulc_bce_logits_loss: binary_cross_entropy_with_logits over matching (label 1) and rolled (label 0) pairs (hulc.py:637-645)."""
+    g = torch.Generator().manual_seed(n_pos)
+    x = (torch.randn(n_pos + n_neg, generator=g) * 4).requires_grad_(True)  # large logits exercise the log1p(exp(-|x|)) form
+    loss, dx = torch.full((1,), -3.0), torch.zeros(n_pos + n_neg)
+    K.bce_logits_loss(x.detach(), dx, loss, n_pos, n_neg, grad_scale=0.5)
+    labels = torch.cat([torch.ones(n_pos), torch.zeros(n_neg)])
+    ref = F.binary_cross_entropy_with_logits(x, labels)
+    (0.5 * ref).backward()
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dx, x.grad, rtol=1e-4, atol=1e-7)
+
+
 def test_gru_gates(K):
     g = torch.Generator().manual_seed(8)
     B, H = 3, 40
